@@ -1,0 +1,191 @@
+/* scdef_b200 — C ABI of the B200-native scDEF training hot path.
+ *
+ * The reference (cbg-ethz/scDEF) has no FFI: its seam is the pair of jitted Python
+ * callables built in `_get_or_build_learn_grad_fns`
+ * (src/scdef/models/_scdef.py:2808-2856) and consumed by `local_update` / `global_update`
+ * (3087-3163).  This header is what a maintainer would bind (ctypes) to replace them:
+ *
+ *   scdef_elbo_grad   <->  local_loss_grad / global_loss_grad   (_scdef.py:2848-2849;
+ *                          objective 2822-2846, batch_elbo 2148-2181, elbo 1823-2146,
+ *                          jax_utils.py:6-46)
+ *   scdef_adam_local  <->  optax.adam(local_lr) update + apply over local_params
+ *                          (_scdef.py:3079, 3112-3116) + frozen-z snap-back (3248-3255)
+ *   scdef_adam_global <->  optax.adam(lr) update + apply + freeze_w restore + clip_params
+ *                          (_scdef.py:3080, 3149-3162, 3034-3042)
+ *   scdef_posterior   <->  set_posterior_means / set_posterior_variances (3394-3476)
+ *   scdef_row_stats   <->  the per-cell constants of load_adata (482-504) that the hot
+ *                          path needs (library size, sum_g lgamma(x+1))
+ *
+ * Conventions: every pointer marked "device" is caller-owned contiguous CUDA memory
+ * (PyTorch `data_ptr()`), 16-byte aligned.  All calls enqueue on the caller's stream and
+ * return immediately; there are no hidden host syncs, no cudaMalloc, no CPU fallback.
+ * Return value 0 = success, negative = SCDEF_E*.  Not thread-safe per ctx.
+ * Variational blocks are stored as the reference stores them: a stacked pair
+ * [mu, rho = log sigma] along axis 0, float32.
+ */
+#ifndef SCDEF_B200_H
+#define SCDEF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCDEF_ABI_VERSION 3
+#define SCDEF_MAX_LAYERS 8
+
+#define SCDEF_OK 0
+#define SCDEF_EINVAL -1     /* bad argument / shape */
+#define SCDEF_EALIGN -2     /* pointer not 16-byte aligned */
+#define SCDEF_EUNSUPPORTED -3 /* shape outside what the kernels support */
+#define SCDEF_EWORKSPACE -4 /* workspace too small */
+#define SCDEF_ECUDA -5      /* CUDA launch / runtime error (see scdef_last_error) */
+
+#define SCDEF_PASS_LOCAL 1  /* gradients w.r.t. local_params  (argnums=2) */
+#define SCDEF_PASS_GLOBAL 2 /* gradients w.r.t. global_params (argnums=3) */
+
+#define SCDEF_NOISE_PHILOX 0   /* counter-based N(0,1), generated inside the kernels */
+#define SCDEF_NOISE_EXPLICIT 1 /* caller-provided draws (parity tests) */
+
+#define SCDEF_LIK_AUTO 0
+#define SCDEF_LIK_SIMT 1 /* fp32 CUDA-core likelihood kernel (any shape)               */
+#define SCDEF_LIK_TC 2   /* tcgen05 / TMEM split-bf16 likelihood kernel (K0 <= 128)     */
+
+typedef struct scdef_ctx scdef_ctx;
+
+/* Static description of the model (what `elbo` reads from `self`). */
+typedef struct scdef_model_desc {
+  int32_t abi_version;      /* = SCDEF_ABI_VERSION */
+  int32_t n_layers;         /* L */
+  int32_t layer_sizes[SCDEF_MAX_LAYERS]; /* K_0 (bottom) ... K_{L-1} */
+  int64_t n_cells;          /* rows of the local tensors held by THIS rank */
+  int32_t n_genes;          /* G */
+  int32_t n_batches;        /* nb >= 1 */
+  int32_t use_brd;          /* _scdef.py:1936, 1982, 2014 */
+  int32_t marginalize_alpha;/* _scdef.py:1972 */
+  int32_t supervised_layer; /* sscDEF pinned layer (_sscdef.py:484) or -1 */
+  float alpha_floor;        /* 0.1 (_scdef.py:2068) / 1.0 (_sscdef.py:506) */
+  float top_alpha, brd, brd_mean, shrinkage_shape, shrinkage_rate;
+  float cell_scale_shape, gene_scale_shape;
+  /* device constants */
+  const float* X;                 /* (N,G) row-major counts, resident; NULL if batches are streamed */
+  const int32_t* batch_id;        /* (N) batch of each cell (argmax of batch_indices_onehot) */
+  const float* batch_lib_ratio;   /* (N)      _scdef.py:500-504 */
+  const float* cell_alpha_factor; /* (N)      _scdef.py:1279-1281 */
+  const float* gene_ratio;        /* (nb,G)   _scdef.py:521-524, 568-573 (broadcast if scalar) */
+  const float* x_lgamma_rowsum;   /* (N) sum_g lgamma(x+1) or NULL (computed per batch) */
+  int32_t* row_slot;              /* (N) scratch owned by the library between calls; caller fills -1 once */
+  /* W priors, w_priors[l] = [shape, rate] (_scdef.py:1258-1277; _iscdef.py:442-450):
+     matrix (K_l, K_{l-1}) device pointers, or NULL -> the scalar is used */
+  const float* w_prior_shape[SCDEF_MAX_LAYERS];
+  const float* w_prior_rate[SCDEF_MAX_LAYERS];
+  float w_prior_shape_scalar[SCDEF_MAX_LAYERS];
+  float w_prior_rate_scalar[SCDEF_MAX_LAYERS];
+  const float* fixed_top_z;       /* sscDEF (N, K_t) constant z of the pinned layer, or NULL */
+} scdef_model_desc;
+
+/* One set of per-block device pointers: parameters, gradients or Adam moments.
+   Layouts: cell_scale (2,R,1), z (2,R,sumK), gene_scale (2,nb,G), brd (2,K0,1),
+   W[l] (2,K_l,K_{l-1}) with K_{-1}=G, ard (2,K0,1), alpha (2,1,1).
+   R = n_cells for parameters/moments; R = B (minibatch slot order) for local gradients. */
+typedef struct scdef_blocks {
+  float* cell_scale;
+  float* z;
+  float* gene_scale;
+  float* brd;
+  float* W[SCDEF_MAX_LAYERS];
+  float* ard;
+  float* alpha;
+} scdef_blocks;
+
+/* Noise of one `elbo_grad` call (= one `rng_input` of the reference, _scdef.py:3231). */
+typedef struct scdef_noise {
+  int32_t mode;     /* SCDEF_NOISE_* */
+  int32_t coupling; /* 1: blocks of identical shape share their draws within an MC sample, as
+                       the reference's single-key sampling does; 0: independent */
+  uint64_t seed;    /* philox key */
+  uint64_t step;    /* philox key, the per-iteration split */
+  /* explicit draws, leading axis S (device): */
+  const float* eps_cell_scale; /* (S,B,1)    */
+  const float* eps_z;          /* (S,B,sumK) */
+  const float* eps_gene_scale; /* (S,nb,G)   */
+  const float* eps_brd;        /* (S,K0,1)   */
+  const float* eps_W[SCDEF_MAX_LAYERS]; /* (S,K_l,K_{l-1}) */
+  const float* eps_ard;        /* (S,K0,1)   */
+  const float* eps_alpha;      /* (S,1,1)    */
+} scdef_noise;
+
+/* Per-call arguments of the objective (the non-array arguments of `objective`). */
+typedef struct scdef_call {
+  int32_t pass;          /* SCDEF_PASS_LOCAL | SCDEF_PASS_GLOBAL */
+  int32_t num_samples;   /* S */
+  int32_t batch;         /* B = number of minibatch rows on this rank (may be 0) */
+  int32_t lik_impl;      /* SCDEF_LIK_* */
+  float annealing;       /* annealing_parameter */
+  float stop_gradients[SCDEF_MAX_LAYERS]; /* 0/1 per layer (_scdef.py:3064-3066) */
+  float stop_cell_budgets, stop_gene_budgets;
+  float alpha;
+  float scale;           /* N_total / B_total  (_scdef.py:2143); under data parallelism the
+                            GLOBAL cell and minibatch counts */
+  float global_weight;   /* weight of the cell-independent terms (priors/entropies of the global
+                            blocks) in loss and global gradients: 1 on one GPU, 1/R on R ranks so
+                            the all-reduce sum restores them */
+  const int64_t* indices;/* device (B) rows of this rank's local tensors */
+  const float* X_batch;  /* device (B,G) counts of the minibatch, or NULL -> gathered from desc.X */
+} scdef_call;
+
+int scdef_abi_version(void);
+int scdef_ctx_create(const scdef_model_desc* desc, scdef_ctx** out);
+void scdef_ctx_destroy(scdef_ctx* ctx);
+const char* scdef_last_error(scdef_ctx* ctx);
+
+/* Scratch needed by scdef_elbo_grad for minibatches up to B_max rows and S samples. */
+size_t scdef_workspace_bytes(scdef_ctx* ctx, int B_max, int S, int lik_impl);
+
+/* loss = -(1/S) sum_s ELBO_s and its gradient w.r.t. the local or the global blocks.
+   `loss_out` (device double[2]): [0] += cell-dependent part, [1] += global part * global_weight;
+   the caller zeroes it.  `grads`: for PASS_LOCAL only cell_scale (2,B,1) and z (2,B,sumK) are
+   written (minibatch slot order; every other row of the reference's dense gradient is 0);
+   for PASS_GLOBAL all global blocks are written (overwritten, not accumulated). */
+int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* params,
+                    const scdef_noise* noise, double* loss_out, const scdef_blocks* grads,
+                    void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Dense Adam over ALL n_cells rows of the local blocks (optax semantics: rows outside the
+   minibatch see a zero gradient but their moments decay and they still move).  `grads` is the
+   compact (2,B,.) output of scdef_elbo_grad, `indices` the same minibatch rows.
+   `freeze_z_layers[l] != 0` keeps the z columns of layer l unchanged (_scdef.py:3248-3255).
+   Locals are never clipped (clip_params skips a 2-element list, _scdef.py:3038). */
+int scdef_adam_local(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blocks* grads,
+                     const scdef_blocks* m, const scdef_blocks* v, const int64_t* indices,
+                     int B, int64_t step, float lr, float b1, float b2, float eps,
+                     const int32_t* freeze_z_layers, void* cuda_stream);
+
+/* Adam over the global blocks, then freeze_w restore (W blocks keep their values, moments
+   still update) and clip_params: mu <= 1e4, rho <= 10 on gene_scale, brd and every W
+   (not ard, not alpha). */
+int scdef_adam_global(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blocks* grads,
+                      const scdef_blocks* m, const scdef_blocks* v, int64_t step, float lr,
+                      float b1, float b2, float eps, int freeze_w, void* cuda_stream);
+
+/* E[v] = exp(mu + sigma^2/2) and Var[v] of every block, on the device (`means`/`vars` have the
+   shape of one half of each block; either may be NULL). */
+int scdef_posterior(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blocks* means,
+                    const scdef_blocks* vars, void* cuda_stream);
+
+/* Per-cell constants from a resident count matrix: lib[n] = sum_g x, lgam[n] = sum_g lgamma(x+1). */
+int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam,
+                    void* cuda_stream);
+
+/* Writes the N(0,1) draws the kernels would use for one block in PHILOX mode (debug / parity):
+   block_kind 0 cell_scale, 1 z layer `layer`, 2 gene_scale, 3 brd, 4 W layer `layer`, 5 ard,
+   6 alpha; out is (S, rows, cols). */
+int scdef_noise_fill(scdef_ctx* ctx, const scdef_noise* noise, int block_kind, int layer, int S,
+                     int B, float* out, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCDEF_B200_H */

@@ -1,0 +1,173 @@
+// K8: fused Adam (optax.adam semantics, `_scdef.py:3079-3082, 3112-3116, 3149-3162`) and the
+// posterior summaries (`_scdef.py:3394-3476`).  HBM-bound: 24 B/param (read p,m,v; write p,m,v)
+// plus the gradient (dense for globals, minibatch-sparse for locals).
+#pragma once
+#include "common.cuh"
+
+namespace scdef {
+
+struct AdamHyper {
+  float lr, b1, b2, eps, bc1, bc2;  // bc = 1 - b^t
+};
+
+__device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, const AdamHyper& h,
+                                          bool write_p, float clip_hi) {
+  m = h.b1 * m + (1.f - h.b1) * g;
+  v = h.b2 * v + (1.f - h.b2) * g * g;
+  float mh = m / h.bc1, vh = v / h.bc2;
+  float pn = p - h.lr * (mh / (sqrtf(vh) + h.eps));
+  if (write_p) p = fminf(pn, clip_hi);  // clip_params lower bounds (-1e10) can never bind after fminf of finite
+}
+
+// ---- globals: a table of segments, one per block --------------------------------------------
+struct AdamSeg {
+  float *p, *m, *v;
+  const float* g;
+  int n_half;      // elements of one half (mu or rho)
+  int clip;        // clip_params applies (mu<=1e4, rho<=10)
+  int frozen;      // freeze_w: parameters keep their value, moments still update
+};
+struct AdamSegTable {
+  AdamSeg s[SCDEF_MAX_LAYERS + 4];
+  int n;
+};
+
+// grid = (blocks, n_segments)
+__global__ void __launch_bounds__(256) k_adam_global(const AdamSegTable tab, const AdamHyper h) {
+  const AdamSeg& sg = tab.s[blockIdx.y];
+  const int total = 2 * sg.n_half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float p = sg.p[i], m = sg.m[i], v = sg.v[i];
+    float hi = INFINITY;
+    if (sg.clip) hi = (i < sg.n_half) ? 1e4f : 10.f;
+    float lo = sg.clip ? -1e10f : -INFINITY;
+    adam_elem(p, m, v, sg.g[i], h, !sg.frozen, hi);
+    if (!sg.frozen) p = fmaxf(p, lo);
+    else if (sg.clip) p = fmaxf(fminf(p, hi), lo);  // clip_params still runs on the restored W
+    sg.p[i] = p;
+    sg.m[i] = m;
+    sg.v[i] = v;
+  }
+}
+
+// ---- locals: dense over all N rows; gradient rows come from the minibatch via row_slot -------
+__global__ void k_set_slots(int32_t* row_slot, const int64_t* idx, int B, int clear) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < B) row_slot[idx[j]] = clear ? -1 : j;
+}
+
+struct AdamLocalArgs {
+  float *p, *m, *v;      // (2, N, C)
+  const float* g;        // (2, B, C) compact
+  const int32_t* row_slot;
+  long long N;
+  int C, B;
+  int n_frozen;          // frozen column ranges [lo, hi)
+  int frozen_lo[SCDEF_MAX_LAYERS], frozen_hi[SCDEF_MAX_LAYERS];
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_adam_local(const AdamLocalArgs a, const AdamHyper h) {
+  const long long half = a.N * a.C;
+  const long long nvec = 2 * half / VEC;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nvec;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t * VEC;
+    const int hsel = i >= half;
+    const long long rem = i - (hsel ? half : 0);
+    const long long n = rem / a.C;
+    const int c0 = (int)(rem - n * a.C);
+    float p[VEC], m[VEC], v[VEC], g[VEC];
+    if (VEC == 4) {
+      float4 p4 = *reinterpret_cast<const float4*>(a.p + i);
+      float4 m4 = *reinterpret_cast<const float4*>(a.m + i);
+      float4 v4 = *reinterpret_cast<const float4*>(a.v + i);
+      p[0] = p4.x; p[1] = p4.y; p[2] = p4.z; p[3] = p4.w;
+      m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
+      v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+    } else {
+      p[0] = a.p[i]; m[0] = a.m[i]; v[0] = a.v[i];
+    }
+    const int slot = a.row_slot[n];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) g[q] = 0.f;
+    if (slot >= 0) {
+      const float* gp = a.g + ((long long)hsel * a.B + slot) * a.C + c0;
+      if (VEC == 4) {
+        float4 g4 = *reinterpret_cast<const float4*>(gp);
+        g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+      } else {
+        g[0] = gp[0];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      bool frozen = false;
+      for (int f = 0; f < a.n_frozen; ++f) frozen |= (c0 + q >= a.frozen_lo[f]) && (c0 + q < a.frozen_hi[f]);
+      adam_elem(p[q], m[q], v[q], g[q], h, !frozen, INFINITY);
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(a.p + i) = make_float4(p[0], p[1], p[2], p[3]);
+      *reinterpret_cast<float4*>(a.m + i) = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(a.v + i) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      a.p[i] = p[0]; a.m[i] = m[0]; a.v[i] = v[0];
+    }
+  }
+}
+
+// ---- posterior summaries ----------------------------------------------------------------------
+struct PostSeg {
+  const float* p;   // (2, n)
+  float* mean;      // (n) or nullptr
+  float* var;       // (n) or nullptr
+  long long n;
+};
+struct PostSegTable {
+  PostSeg s[SCDEF_MAX_LAYERS + 6];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) k_posterior(const PostSegTable tab) {
+  const PostSeg& sg = tab.s[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float mu = sg.p[i], ls = sg.p[sg.n + i];
+    float s2 = expf(ls);
+    s2 *= s2;
+    if (sg.mean) sg.mean[i] = expf(mu + 0.5f * s2);
+    if (sg.var) sg.var[i] = (expf(s2) - 1.f) * expf(2.f * mu + s2);
+  }
+}
+
+// ---- per-cell constants of a resident count matrix ---------------------------------------------
+__global__ void __launch_bounds__(256) k_row_stats(const float* X, long long n_rows, int G, float* lib,
+                                                   float* lgam) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  float sl = 0.f, sg = 0.f;
+  for (int g = lane; g < G; g += 32) {
+    float x = X[row * G + g];
+    sl += x;
+    if (x > 1.5f) sg += lgammaf(x + 1.f);
+  }
+  sl = warp_sum(sl);
+  sg = warp_sum(sg);
+  if (lane == 0) {
+    if (lib) lib[row] = sl;
+    if (lgam) lgam[row] = sg;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_noise_fill(float* out, int S, int per, PhiloxKey key, NoiseTag tag) {
+  const long long total = (long long)S * per;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    int s = (int)(e / per);
+    int i = (int)(e - (long long)s * per);
+    out[e] = philox_normal(key, tag, (uint32_t)s, (uint32_t)i);
+  }
+}
+
+}  // namespace scdef

@@ -1,0 +1,556 @@
+// C ABI of scdef_b200 (include/scdef_b200.h): host-side orchestration of the kernels.
+// Every entry point only enqueues work on the caller's stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+#include "common.cuh"
+#include "kernels_small.cuh"
+#include "lik_simt.cuh"
+#include "adam.cuh"
+#include "lik_tc.cuh"
+
+using namespace scdef;
+
+struct scdef_ctx {
+  scdef_model_desc d;
+  int L, Kt, K0;
+  int K[SCDEF_MAX_LAYERS], off[SCDEF_MAX_LAYERS + 1], out_dim[SCDEF_MAX_LAYERS];
+  int sm_count;
+  char err[512];
+};
+
+namespace {
+
+enum { BLK_C = 0, BLK_S = 1, BLK_TAU = 2, BLK_OM = 3, BLK_A = 4, BLK_W = 5, BLK_Z = 5 + SCDEF_MAX_LAYERS };
+
+int fail(scdef_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+int check_launch(scdef_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, SCDEF_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  return SCDEF_OK;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Workspace layout: per block a sample buffer and a dELBO/dv buffer, (S, rows, cols) floats.
+struct Plan {
+  size_t smp[MAX_BLOCKS], G[MAX_BLOCKS];
+  int rows[MAX_BLOCKS], cols[MAX_BLOCKS];
+  size_t tc_off, tc_bytes;  // scratch of the tcgen05 likelihood kernel
+  size_t total;
+};
+
+Plan make_plan(const scdef_ctx* c, int B, int S, int lik_impl) {
+  Plan p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < MAX_BLOCKS; ++i) p.rows[i] = p.cols[i] = 0;
+  p.rows[BLK_C] = B; p.cols[BLK_C] = 1;
+  p.rows[BLK_S] = c->d.n_batches; p.cols[BLK_S] = c->d.n_genes;
+  p.rows[BLK_TAU] = c->K0; p.cols[BLK_TAU] = 1;
+  p.rows[BLK_OM] = c->K0; p.cols[BLK_OM] = 1;
+  p.rows[BLK_A] = 1; p.cols[BLK_A] = 1;
+  for (int l = 0; l < c->L; ++l) {
+    p.rows[BLK_W + l] = c->K[l]; p.cols[BLK_W + l] = c->out_dim[l];
+    p.rows[BLK_Z + l] = B; p.cols[BLK_Z + l] = c->K[l];
+  }
+  size_t o = 0;
+  for (int i = 0; i < MAX_BLOCKS; ++i) {
+    size_t n = (size_t)S * p.rows[i] * p.cols[i] * sizeof(float);
+    if (i == BLK_W && lik_impl == SCDEF_LIK_TC) n = 0;  // W_0 samples never hit HBM
+    p.smp[i] = o; o += align_up(n);
+    p.G[i] = o; o += align_up(n);
+  }
+  p.tc_off = o;
+  p.tc_bytes = (lik_impl == SCDEF_LIK_TC) ? lik_tc_workspace_bytes(B, S, c->K0, c->d.n_genes, c->d.n_batches) : 0;
+  o += align_up(p.tc_bytes);
+  p.total = o;
+  return p;
+}
+
+NoiseTag make_tag(const scdef_noise* nz, int blk, int rows, int cols) {
+  NoiseTag t;
+  if (nz->coupling) { t.a = (uint32_t)rows; t.b = (uint32_t)cols; }
+  else { t.a = 0x80000000u | (uint32_t)blk; t.b = 0u; }
+  return t;
+}
+
+PhiloxKey make_key(const scdef_noise* nz) {
+  PhiloxKey k;
+  k.k0 = (uint32_t)(nz->seed ^ (nz->seed >> 32)) ^ (uint32_t)(nz->step >> 32) * 0x85EBCA6Bu;
+  k.k1 = (uint32_t)nz->step;
+  return k;
+}
+
+int resolve_lik_impl(const scdef_ctx* c, int requested) {
+  if (requested == SCDEF_LIK_AUTO) return lik_tc_supported(c->K0, c->d.n_genes, c->d.n_batches) ? SCDEF_LIK_TC : SCDEF_LIK_SIMT;
+  return requested;
+}
+
+}  // namespace
+
+extern "C" {
+
+int scdef_abi_version(void) { return SCDEF_ABI_VERSION; }
+
+int scdef_ctx_create(const scdef_model_desc* desc, scdef_ctx** out) {
+  if (!desc || !out) return SCDEF_EINVAL;
+  if (desc->abi_version != SCDEF_ABI_VERSION) return SCDEF_EINVAL;
+  if (desc->n_layers < 1 || desc->n_layers > SCDEF_MAX_LAYERS) return SCDEF_EINVAL;
+  if (desc->n_genes < 1 || desc->n_batches < 1 || desc->n_cells < 0) return SCDEF_EINVAL;
+  scdef_ctx* c = new (std::nothrow) scdef_ctx;
+  if (!c) return SCDEF_EINVAL;
+  memset(c, 0, sizeof(*c));
+  c->d = *desc;
+  c->L = desc->n_layers;
+  c->off[0] = 0;
+  for (int l = 0; l < c->L; ++l) {
+    if (desc->layer_sizes[l] < 1) { delete c; return SCDEF_EINVAL; }
+    c->K[l] = desc->layer_sizes[l];
+    c->off[l + 1] = c->off[l] + c->K[l];
+    c->out_dim[l] = l == 0 ? desc->n_genes : desc->layer_sizes[l - 1];
+  }
+  c->Kt = c->off[c->L];
+  c->K0 = c->K[0];
+  if (c->K0 > 256) { delete c; return SCDEF_EUNSUPPORTED; }
+  int dev = 0;
+  c->sm_count = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) c->sm_count = n;
+  }
+  cudaGetLastError();
+  *out = c;
+  return SCDEF_OK;
+}
+
+void scdef_ctx_destroy(scdef_ctx* ctx) { delete ctx; }
+
+const char* scdef_last_error(scdef_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+size_t scdef_workspace_bytes(scdef_ctx* ctx, int B_max, int S, int lik_impl) {
+  if (!ctx || B_max < 0 || S < 1) return 0;
+  return make_plan(ctx, B_max < 1 ? 1 : B_max, S, resolve_lik_impl(ctx, lik_impl)).total + 256;
+}
+
+int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* params,
+                    const scdef_noise* noise, double* loss_out, const scdef_blocks* grads,
+                    void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!ctx) return SCDEF_EINVAL;
+  if (!call || !params || !noise || !loss_out || !grads || !workspace)
+    return fail(ctx, SCDEF_EINVAL, "null argument");
+  const int pass = call->pass;
+  if (pass != SCDEF_PASS_LOCAL && pass != SCDEF_PASS_GLOBAL) return fail(ctx, SCDEF_EINVAL, "bad pass %d", pass);
+  const int S = call->num_samples, B = call->batch;
+  if (S < 1 || B < 0) return fail(ctx, SCDEF_EINVAL, "bad S=%d or B=%d", S, B);
+  if (B > 0 && !call->indices) return fail(ctx, SCDEF_EINVAL, "indices is null");
+  if (B > 0 && !call->X_batch && !ctx->d.X) return fail(ctx, SCDEF_EINVAL, "no counts: X_batch and desc.X are both null");
+  if (((uintptr_t)workspace & 15) != 0) return fail(ctx, SCDEF_EALIGN, "workspace not 16-byte aligned");
+  const int lik_impl = resolve_lik_impl(ctx, call->lik_impl);
+  if (lik_impl == SCDEF_LIK_TC && !lik_tc_supported(ctx->K0, ctx->d.n_genes, ctx->d.n_batches))
+    return fail(ctx, SCDEF_EUNSUPPORTED, "tcgen05 likelihood kernel does not take K0=%d", ctx->K0);
+  const Plan plan = make_plan(ctx, B < 1 ? 1 : B, S, lik_impl);
+  if (plan.total > workspace_bytes)
+    return fail(ctx, SCDEF_EWORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, plan.total);
+  if (noise->mode == SCDEF_NOISE_EXPLICIT) {
+    bool ok = noise->eps_cell_scale && noise->eps_z && noise->eps_gene_scale;
+    if (ctx->d.use_brd) ok = ok && noise->eps_brd && noise->eps_ard;
+    if (ctx->d.marginalize_alpha) ok = ok && noise->eps_alpha;
+    for (int l = 0; l < ctx->L; ++l) ok = ok && noise->eps_W[l];
+    if (!ok) return fail(ctx, SCDEF_EINVAL, "explicit noise: missing eps pointer");
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  char* ws = (char*)workspace;
+  const scdef_model_desc& d = ctx->d;
+  const int L = ctx->L, K0 = ctx->K0, G = d.n_genes, nb = d.n_batches;
+  const bool global_pass = pass == SCDEF_PASS_GLOBAL;
+  const bool explicit_noise = noise->mode == SCDEF_NOISE_EXPLICIT;
+  const float gw = call->global_weight, scale = call->scale, anneal = call->annealing;
+  const PhiloxKey key = make_key(noise);
+  const float* sg = call->stop_gradients;
+  const bool lik_on = !(sg[0] != 0.f);
+  const bool tc = (lik_impl == SCDEF_LIK_TC);
+  auto smp = [&](int b) { return (float*)(ws + plan.smp[b]); };
+  auto Gb = [&](int b) { return (float*)(ws + plan.G[b]); };
+
+  // ---- block table ----------------------------------------------------------------------
+  BlockTable all;
+  memset(&all, 0, sizeof(all));
+  auto fill = [&](int blk, const float* base, int rows, int cols, int ld, int col0, bool local,
+                  const float* eps, int eps_ld, int eps_col0, float mu_hi, float ent_w, bool stopped,
+                  bool active, float* gbase, int g_rows, int g_ld, int g_col0) {
+    BlockDesc& b = all.b[blk];
+    const long long half = (long long)(local ? d.n_cells : rows) * ld;
+    b.mu = base; b.rho = base ? base + half : nullptr;
+    b.gather = local ? call->indices : nullptr;
+    b.eps = explicit_noise ? eps : nullptr;
+    b.fixed = nullptr;
+    b.smp = smp(blk); b.G = Gb(blk);
+    b.gmu = gbase; b.grho = gbase ? gbase + (long long)g_rows * g_ld : nullptr;
+    b.rows = rows; b.cols = cols; b.ld = ld; b.col0 = col0;
+    b.eps_ld = eps_ld; b.eps_col0 = eps_col0; b.g_ld = g_ld; b.g_col0 = g_col0;
+    b.tag = make_tag(noise, blk, rows, cols);
+    b.mu_hi = mu_hi; b.ent_weight = ent_w; b.g_weight = 1.f;
+    b.stopped = stopped; b.active = active;
+  };
+  const bool st0 = sg[0] != 0.f;
+  fill(BLK_C, params->cell_scale, B, 1, 1, 0, true, noise->eps_cell_scale, 1, 0, LOG_1E6, scale,
+       st0 || call->stop_cell_budgets != 0.f, true, grads->cell_scale, B, 1, 0);
+  fill(BLK_S, params->gene_scale, nb, G, G, 0, false, noise->eps_gene_scale, G, 0, INFINITY, gw,
+       st0 || call->stop_gene_budgets != 0.f, true, grads->gene_scale, nb, G, 0);
+  fill(BLK_TAU, params->brd, K0, 1, 1, 0, false, noise->eps_brd, 1, 0, LOG_1E6, gw, st0, d.use_brd != 0,
+       grads->brd, K0, 1, 0);
+  fill(BLK_OM, params->ard, K0, 1, 1, 0, false, noise->eps_ard, 1, 0, LOG_1E6, gw, false, d.use_brd != 0,
+       grads->ard, K0, 1, 0);
+  fill(BLK_A, params->alpha, 1, 1, 1, 0, false, noise->eps_alpha, 1, 0, LOG_1E6, gw, false,
+       d.marginalize_alpha != 0, grads->alpha, 1, 1, 0);
+  for (int l = 0; l < L; ++l) {
+    const bool stl = sg[l] != 0.f;
+    fill(BLK_W + l, params->W[l], ctx->K[l], ctx->out_dim[l], ctx->out_dim[l], 0, false, noise->eps_W[l],
+         ctx->out_dim[l], 0, LOG_1E6, anneal * gw, stl, true, grads->W[l], ctx->K[l], ctx->out_dim[l], 0);
+    const bool pinned = (l == d.supervised_layer) && d.fixed_top_z;
+    fill(BLK_Z + l, params->z, B, ctx->K[l], ctx->Kt, ctx->off[l], true, noise->eps_z, ctx->Kt, ctx->off[l],
+         LOG_1E6, pinned ? 0.f : anneal * scale, stl || pinned, true, grads->z, B, ctx->Kt, ctx->off[l]);
+    if (pinned) all.b[BLK_Z + l].fixed = d.fixed_top_z;
+  }
+
+  int rc;
+  // ---- K1 sampling (+ entropy values) ----------------------------------------------------
+  if (B > 0 || true) {
+    BlockTable t;
+    memset(&t, 0, sizeof(t));
+    size_t max_el = 1;
+    auto add = [&](int blk) {
+      const BlockDesc& b = all.b[blk];
+      if (!b.active || b.rows * b.cols == 0) return;
+      if (tc && blk == BLK_W) return;  // W_0 is sampled inside the fused kernel
+      t.b[t.n++] = b;
+      size_t n = (size_t)S * b.rows * b.cols;
+      if (n > max_el) max_el = n;
+    };
+    if (B > 0) add(BLK_C);
+    add(BLK_S); add(BLK_TAU); add(BLK_OM); add(BLK_A);
+    for (int l = 0; l < L; ++l) { add(BLK_W + l); if (B > 0) add(BLK_Z + l); }
+    size_t gx = (max_el + 255) / 256;
+    if (gx > (size_t)ctx->sm_count * 16) gx = (size_t)ctx->sm_count * 16;
+    k_sample<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key, loss_out, gw);
+    if ((rc = check_launch(ctx, "k_sample"))) return rc;
+  }
+
+  // ---- scale priors ------------------------------------------------------------------------
+  {
+    SimplePriorTable t;
+    memset(&t, 0, sizeof(t));
+    auto set = [&](int i, int blk, float a, const float* rate, const int64_t* gather, float rate_scale,
+                   float weight, int is_cell, bool active, bool want_G) {
+      SimplePrior& p = t.p[i];
+      p.smp = smp(blk); p.G = want_G ? Gb(blk) : nullptr;
+      p.rate = rate; p.gather = gather;
+      p.rows = all.b[blk].rows; p.cols = all.b[blk].cols;
+      p.a = a; p.lgam_a = lgammaf(a); p.rate_scale = rate_scale; p.weight = weight;
+      p.is_cell = is_cell; p.active = active && p.rows * p.cols > 0;
+    };
+    set(0, BLK_C, d.cell_scale_shape, d.batch_lib_ratio, call->indices, d.cell_scale_shape, scale, 1, B > 0, !global_pass);
+    set(1, BLK_S, d.gene_scale_shape, d.gene_ratio, nullptr, d.gene_scale_shape, gw, 0, true, global_pass);
+    set(2, BLK_TAU, d.brd, nullptr, nullptr, d.brd / d.brd_mean, gw, 0, d.use_brd != 0, global_pass);
+    set(3, BLK_OM, d.shrinkage_shape, nullptr, nullptr, d.shrinkage_rate, gw, 0, d.use_brd != 0, global_pass);
+    set(4, BLK_A, 2.f, nullptr, nullptr, 2.f / fmaxf(call->alpha, 1e-8f), gw, 0, d.marginalize_alpha != 0, global_pass);
+    size_t max_el = (size_t)S * (size_t)((size_t)nb * G > (size_t)B ? (size_t)nb * G : (size_t)B);
+    size_t gx = (max_el + 255) / 256;
+    if (gx > (size_t)ctx->sm_count * 8) gx = (size_t)ctx->sm_count * 8;
+    if (gx < 1) gx = 1;
+    k_scale_priors<<<dim3((unsigned)gx, 5), 256, 0, st>>>(t, S, loss_out);
+    if ((rc = check_launch(ctx, "k_scale_priors"))) return rc;
+  }
+
+  // ---- W priors ----------------------------------------------------------------------------
+  for (int l = 0; l < L; ++l) {
+    if (tc && l == 0) continue;  // fused into the tcgen05 kernel
+    WPriorArgs a;
+    memset(&a, 0, sizeof(a));
+    a.smp_W = smp(BLK_W + l);
+    a.G_W = global_pass ? Gb(BLK_W + l) : nullptr;
+    a.P = d.w_prior_shape[l]; a.R = d.w_prior_rate[l];
+    a.P_scalar = d.w_prior_shape_scalar[l]; a.R_scalar = d.w_prior_rate_scalar[l];
+    a.smp_tau = smp(BLK_TAU); a.smp_om = smp(BLK_OM);
+    a.G_tau = Gb(BLK_TAU); a.G_om = Gb(BLK_OM);
+    a.rows = ctx->K[l]; a.cols = ctx->out_dim[l];
+    a.mode = (d.use_brd && l == 0) ? 1 : ((d.use_brd && l == 1) ? 2 : 0);
+    a.K_l = (float)ctx->K[l];
+    a.weight = gw;
+    int warps = S * a.rows;
+    k_wprior<<<(warps + 7) / 8, 256, 0, st>>>(a, S, loss_out);
+    if ((rc = check_launch(ctx, "k_wprior"))) return rc;
+  }
+
+  if (B > 0) {
+    // ---- hierarchy ---------------------------------------------------------------------------
+    HierArgs h;
+    memset(&h, 0, sizeof(h));
+    h.L = L;
+    int wtot = 0;
+    for (int l = 0; l < L; ++l) {
+      h.K[l] = ctx->K[l]; h.off[l] = ctx->off[l];
+      h.smp_z[l] = smp(BLK_Z + l); h.G_z[l] = Gb(BLK_Z + l);
+      h.smp_W[l] = smp(BLK_W + l); h.G_W[l] = Gb(BLK_W + l);
+      if (l >= 1) {
+        h.wld[l] = ctx->K[l - 1] | 1;
+        h.woff[l] = wtot;
+        wtot += ctx->K[l] * h.wld[l];
+      }
+    }
+    h.off[L] = ctx->Kt;
+    h.wtot = wtot;
+    h.smp_a = d.marginalize_alpha ? smp(BLK_A) : nullptr;
+    h.G_a = (d.marginalize_alpha && global_pass) ? Gb(BLK_A) : nullptr;
+    h.caf = d.cell_alpha_factor; h.idx = call->indices;
+    h.B = B; h.pass = pass;
+    const bool root_frozen = sg[L - 1] > 0.5f;
+    h.top_layer = root_frozen ? L - 2 : L - 1;
+    h.alpha = call->alpha; h.alpha_floor = d.alpha_floor; h.top_alpha = d.top_alpha;
+    h.lgam_top = lgammaf(d.top_alpha); h.scale = scale;
+    // enough CTAs to fill the GPU, at least one round of 8 cells each
+    int chunks = (ctx->sm_count * 2 + S - 1) / S;
+    int max_chunks = (B + HIER_WARPS - 1) / HIER_WARPS;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    h.cells_per_block = ((B + chunks - 1) / chunks + HIER_WARPS - 1) / HIER_WARPS * HIER_WARPS;
+    chunks = (B + h.cells_per_block - 1) / h.cells_per_block;
+    size_t smem = ((size_t)2 * wtot + (size_t)3 * HIER_WARPS * ctx->Kt) * sizeof(float);
+    if (smem > 200 * 1024) return fail(ctx, SCDEF_EUNSUPPORTED, "hierarchy needs %zu B of shared memory", smem);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_hier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_hier<<<dim3(chunks, S), HIER_WARPS * 32, smem, st>>>(h, S, loss_out);
+    if ((rc = check_launch(ctx, "k_hier"))) return rc;
+
+    // ---- likelihood ----------------------------------------------------------------------------
+    if (lik_on) {
+      const float* Xp = call->X_batch ? call->X_batch : d.X;
+      const int64_t* idx_x = call->X_batch ? nullptr : call->indices;
+      k_x_lgamma<<<(B + 7) / 8, 256, 0, st>>>(Xp, idx_x, d.x_lgamma_rowsum, call->indices, B, G, scale, loss_out);
+      if ((rc = check_launch(ctx, "k_x_lgamma"))) return rc;
+      if (tc) {
+        LikTcArgs a;
+        memset(&a, 0, sizeof(a));
+        a.mu_W0 = params->W[0]; a.rho_W0 = params->W[0] + (long long)K0 * G;
+        a.eps_W0 = explicit_noise ? noise->eps_W[0] : nullptr;
+        a.key = key; a.tag = all.b[BLK_W].tag;
+        a.smp_z0 = smp(BLK_Z); a.smp_c = smp(BLK_C); a.smp_s = smp(BLK_S);
+        a.smp_tau = smp(BLK_TAU); a.smp_om = smp(BLK_OM);
+        a.X = Xp; a.idx_x = idx_x; a.idx = call->indices; a.batch_id = d.batch_id;
+        a.G_z0 = Gb(BLK_Z); a.G_c = Gb(BLK_C); a.G_s = Gb(BLK_S);
+        a.G_tau = Gb(BLK_TAU); a.G_om = Gb(BLK_OM);
+        a.gmu_W0 = grads->W[0]; a.grho_W0 = grads->W[0] ? grads->W[0] + (long long)K0 * G : nullptr;
+        a.P = d.w_prior_shape[0]; a.R = d.w_prior_rate[0];
+        a.P_scalar = d.w_prior_shape_scalar[0]; a.R_scalar = d.w_prior_rate_scalar[0];
+        a.use_brd = d.use_brd; a.B = B; a.G = G; a.K0 = K0; a.nb = nb; a.pass = pass; a.S = S;
+        a.scale = scale; a.global_weight = gw; a.anneal = anneal; a.w0_stopped = st0;
+        a.ws = ws + plan.tc_off; a.ws_bytes = plan.tc_bytes;
+        if ((rc = lik_tc_launch(a, loss_out, ctx->sm_count, st))) return fail(ctx, rc, "lik_tc_launch failed");
+        if ((rc = check_launch(ctx, "k_lik_tc"))) return rc;
+      } else {
+        LikArgs a;
+        memset(&a, 0, sizeof(a));
+        a.smp_z0 = smp(BLK_Z); a.smp_W0 = smp(BLK_W); a.smp_c = smp(BLK_C); a.smp_s = smp(BLK_S);
+        a.X = Xp; a.idx_x = idx_x; a.idx = call->indices; a.batch_id = d.batch_id;
+        a.G_z0 = Gb(BLK_Z); a.G_c = Gb(BLK_C); a.G_W0 = Gb(BLK_W); a.G_s = Gb(BLK_S);
+        a.B = B; a.G = G; a.K0 = K0; a.nb = nb; a.pass = pass; a.scale = scale;
+        size_t smem = ((size_t)LT * (K0 + 1) + (size_t)K0 * LW_LD + (size_t)LT * LQ_LD) * sizeof(float);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_lik_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dim3 grid((G + LT - 1) / LT, (B + LT - 1) / LT, S);
+        k_lik_simt<<<grid, 256, smem, st>>>(a, S, loss_out);
+        if ((rc = check_launch(ctx, "k_lik_simt"))) return rc;
+      }
+    }
+  }
+
+  // ---- (mu, rho) gradients of the blocks of this pass ------------------------------------------
+  {
+    BlockTable t;
+    memset(&t, 0, sizeof(t));
+    size_t max_el = 1;
+    auto add = [&](int blk) {
+      const BlockDesc& b = all.b[blk];
+      if (!b.gmu || b.rows * b.cols == 0) return;
+      if (tc && blk == BLK_W && lik_on && B > 0 && global_pass) return;  // written by the fused kernel
+      t.b[t.n++] = b;
+      size_t n = (size_t)b.rows * b.cols;
+      if (n > max_el) max_el = n;
+    };
+    if (global_pass) {
+      add(BLK_S); add(BLK_TAU); add(BLK_OM); add(BLK_A);
+      for (int l = 0; l < L; ++l) add(BLK_W + l);
+    } else if (B > 0) {
+      add(BLK_C);
+      for (int l = 0; l < L; ++l) add(BLK_Z + l);
+    }
+    if (t.n > 0) {
+      size_t gx = (max_el + 255) / 256;
+      if (gx > (size_t)ctx->sm_count * 16) gx = (size_t)ctx->sm_count * 16;
+      k_finish<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key);
+      if ((rc = check_launch(ctx, "k_finish"))) return rc;
+    }
+  }
+  return SCDEF_OK;
+}
+
+int scdef_adam_local(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blocks* grads,
+                     const scdef_blocks* m, const scdef_blocks* v, const int64_t* indices, int B,
+                     int64_t step, float lr, float b1, float b2, float eps,
+                     const int32_t* freeze_z_layers, void* cuda_stream) {
+  if (!ctx) return SCDEF_EINVAL;
+  if (!params || !grads || !m || !v || step < 1) return fail(ctx, SCDEF_EINVAL, "bad argument");
+  if (B > 0 && !indices) return fail(ctx, SCDEF_EINVAL, "indices is null");
+  if (!ctx->d.row_slot) return fail(ctx, SCDEF_EINVAL, "desc.row_slot is null");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  AdamHyper h;
+  h.lr = lr; h.b1 = b1; h.b2 = b2; h.eps = eps;
+  h.bc1 = (float)(1.0 - pow((double)b1, (double)step));
+  h.bc2 = (float)(1.0 - pow((double)b2, (double)step));
+  const long long N = ctx->d.n_cells;
+  if (N == 0) return SCDEF_OK;
+  int rc;
+  if (B > 0) {
+    k_set_slots<<<(B + 255) / 256, 256, 0, st>>>(ctx->d.row_slot, indices, B, 0);
+    if ((rc = check_launch(ctx, "k_set_slots"))) return rc;
+  }
+  for (int which = 0; which < 2; ++which) {
+    AdamLocalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = which ? params->z : params->cell_scale;
+    a.m = which ? m->z : m->cell_scale;
+    a.v = which ? v->z : v->cell_scale;
+    a.g = which ? grads->z : grads->cell_scale;
+    a.row_slot = ctx->d.row_slot;
+    a.N = N; a.C = which ? ctx->Kt : 1; a.B = B;
+    if (which && freeze_z_layers)
+      for (int l = 0; l < ctx->L; ++l)
+        if (freeze_z_layers[l]) { a.frozen_lo[a.n_frozen] = ctx->off[l]; a.frozen_hi[a.n_frozen] = ctx->off[l + 1]; a.n_frozen++; }
+    const long long total = 2 * N * a.C;
+    const bool vec4 = (a.C % 4 == 0) && (((uintptr_t)a.p | (uintptr_t)a.m | (uintptr_t)a.v | (uintptr_t)a.g) % 16 == 0);
+    long long nthreads = vec4 ? total / 4 : total;
+    long long blocks = (nthreads + 255) / 256;
+    long long cap = (long long)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    if (vec4) k_adam_local<4><<<(unsigned)blocks, 256, 0, st>>>(a, h);
+    else k_adam_local<1><<<(unsigned)blocks, 256, 0, st>>>(a, h);
+    if ((rc = check_launch(ctx, "k_adam_local"))) return rc;
+  }
+  if (B > 0) {
+    k_set_slots<<<(B + 255) / 256, 256, 0, st>>>(ctx->d.row_slot, indices, B, 1);
+    if ((rc = check_launch(ctx, "k_set_slots(clear)"))) return rc;
+  }
+  return SCDEF_OK;
+}
+
+int scdef_adam_global(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blocks* grads,
+                      const scdef_blocks* m, const scdef_blocks* v, int64_t step, float lr, float b1,
+                      float b2, float eps, int freeze_w, void* cuda_stream) {
+  if (!ctx) return SCDEF_EINVAL;
+  if (!params || !grads || !m || !v || step < 1) return fail(ctx, SCDEF_EINVAL, "bad argument");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  AdamHyper h;
+  h.lr = lr; h.b1 = b1; h.b2 = b2; h.eps = eps;
+  h.bc1 = (float)(1.0 - pow((double)b1, (double)step));
+  h.bc2 = (float)(1.0 - pow((double)b2, (double)step));
+  AdamSegTable t;
+  memset(&t, 0, sizeof(t));
+  int max_n = 1;
+  auto add = [&](float* p, const float* g, float* mm, float* vv, int n_half, int clip, int frozen) {
+    AdamSeg& s = t.s[t.n++];
+    s.p = p; s.g = g; s.m = mm; s.v = vv; s.n_half = n_half; s.clip = clip; s.frozen = frozen;
+    if (2 * n_half > max_n) max_n = 2 * n_half;
+  };
+  const int K0 = ctx->K0, G = ctx->d.n_genes, nb = ctx->d.n_batches;
+  add(params->gene_scale, grads->gene_scale, m->gene_scale, v->gene_scale, nb * G, 1, 0);
+  add(params->brd, grads->brd, m->brd, v->brd, K0, 1, 0);
+  for (int l = 0; l < ctx->L; ++l)
+    add(params->W[l], grads->W[l], m->W[l], v->W[l], ctx->K[l] * ctx->out_dim[l], 1, freeze_w ? 1 : 0);
+  add(params->ard, grads->ard, m->ard, v->ard, K0, 0, 0);
+  add(params->alpha, grads->alpha, m->alpha, v->alpha, 1, 0, 0);
+  for (int i = 0; i < t.n; ++i)
+    if (!t.s[i].p || !t.s[i].g || !t.s[i].m || !t.s[i].v) return fail(ctx, SCDEF_EINVAL, "null block pointer");
+  int gx = (max_n + 255) / 256;
+  if (gx > ctx->sm_count * 8) gx = ctx->sm_count * 8;
+  k_adam_global<<<dim3(gx, t.n), 256, 0, st>>>(t, h);
+  return check_launch(ctx, "k_adam_global");
+}
+
+int scdef_posterior(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blocks* means,
+                    const scdef_blocks* vars, void* cuda_stream) {
+  if (!ctx) return SCDEF_EINVAL;
+  if (!params) return fail(ctx, SCDEF_EINVAL, "null params");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  PostSegTable t;
+  memset(&t, 0, sizeof(t));
+  long long max_n = 1;
+  auto add = [&](const float* p, float* mean, float* var, long long n) {
+    if (!p || (!mean && !var) || n == 0) return;
+    PostSeg& s = t.s[t.n++];
+    s.p = p; s.mean = mean; s.var = var; s.n = n;
+    if (n > max_n) max_n = n;
+  };
+  const long long N = ctx->d.n_cells;
+  const int K0 = ctx->K0, G = ctx->d.n_genes, nb = ctx->d.n_batches;
+#define MV(f) (means ? means->f : nullptr), (vars ? vars->f : nullptr)
+  add(params->cell_scale, MV(cell_scale), N);
+  add(params->z, MV(z), N * ctx->Kt);
+  add(params->gene_scale, MV(gene_scale), (long long)nb * G);
+  add(params->brd, MV(brd), K0);
+  for (int l = 0; l < ctx->L; ++l) add(params->W[l], MV(W[l]), (long long)ctx->K[l] * ctx->out_dim[l]);
+  add(params->ard, MV(ard), K0);
+  add(params->alpha, MV(alpha), 1);
+#undef MV
+  if (t.n == 0) return SCDEF_OK;
+  long long gx = (max_n + 255) / 256;
+  if (gx > (long long)ctx->sm_count * 16) gx = (long long)ctx->sm_count * 16;
+  k_posterior<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t);
+  return check_launch(ctx, "k_posterior");
+}
+
+int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam, void* cuda_stream) {
+  if (!X || n_rows < 0 || n_genes < 1) return SCDEF_EINVAL;
+  if (n_rows == 0) return SCDEF_OK;
+  long long blocks = (n_rows + 7) / 8;
+  k_row_stats<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(X, n_rows, n_genes, lib, lgam);
+  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+}
+
+int scdef_noise_fill(scdef_ctx* ctx, const scdef_noise* noise, int block_kind, int layer, int S, int B,
+                     float* out, void* cuda_stream) {
+  if (!ctx) return SCDEF_EINVAL;
+  if (!noise || !out || S < 1) return fail(ctx, SCDEF_EINVAL, "bad argument");
+  int blk, rows, cols;
+  const int K0 = ctx->K0;
+  switch (block_kind) {
+    case 0: blk = BLK_C; rows = B; cols = 1; break;
+    case 1: if (layer < 0 || layer >= ctx->L) return fail(ctx, SCDEF_EINVAL, "bad layer");
+            blk = BLK_Z + layer; rows = B; cols = ctx->K[layer]; break;
+    case 2: blk = BLK_S; rows = ctx->d.n_batches; cols = ctx->d.n_genes; break;
+    case 3: blk = BLK_TAU; rows = K0; cols = 1; break;
+    case 4: if (layer < 0 || layer >= ctx->L) return fail(ctx, SCDEF_EINVAL, "bad layer");
+            blk = BLK_W + layer; rows = ctx->K[layer]; cols = ctx->out_dim[layer]; break;
+    case 5: blk = BLK_OM; rows = K0; cols = 1; break;
+    case 6: blk = BLK_A; rows = 1; cols = 1; break;
+    default: return fail(ctx, SCDEF_EINVAL, "bad block kind");
+  }
+  if (rows * cols == 0) return SCDEF_OK;
+  long long total = (long long)S * rows * cols;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
+  k_noise_fill<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(out, S, rows * cols, make_key(noise),
+                                                                          make_tag(noise, blk, rows, cols));
+  return check_launch(ctx, "k_noise_fill");
+}
+
+}  // extern "C"

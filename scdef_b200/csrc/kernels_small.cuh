@@ -1,0 +1,386 @@
+// Generic per-block kernels: reparameterised sampling, scale priors, W priors, the
+// hierarchical z priors, and the final (mu, rho) gradient assembly.
+// Math: SURVEY.md Appendix A.1-A.5; reference `_scdef.py:1850-2094`, `jax_utils.py:6-46`.
+#pragma once
+#include "common.cuh"
+
+namespace scdef {
+
+// -----------------------------------------------------------------------------------------
+// K1: v = clip(exp(clip(mu) + exp(clip(rho)) * eps), 1e-15, 1e15) for every block and MC
+// sample; the s == 0 slice also accumulates the LogNormal entropies (jax_utils.py:6-18).
+// grid = (ceil(max_elems/256), n_blocks)
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sample(const BlockTable tab, int S, PhiloxKey key,
+                                                double* loss_out, float global_weight) {
+  __shared__ double red[32];
+  const BlockDesc& b = tab.b[blockIdx.y];
+  const int per = b.rows * b.cols;
+  const long long total = (long long)S * per;
+  double ent = 0.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    int s = (int)(e / per);
+    int i = (int)(e - (long long)s * per);
+    int r = i / b.cols, c = i - r * b.cols;
+    long long row = b.gather ? b.gather[r] : r;
+    float v;
+    if (b.fixed) {
+      v = b.fixed[row * b.cols + c];
+    } else {
+      float mu = b.mu[row * b.ld + b.col0 + c];
+      float rho = b.rho[row * b.ld + b.col0 + c];
+      float mut = fminf(fmaxf(mu, LOG_1E_10), b.mu_hi);
+      float rhot = fminf(fmaxf(rho, LOG_1E_10), LOG_1E10);
+      float eps = b.eps ? b.eps[((long long)s * b.rows + r) * b.eps_ld + b.eps_col0 + c]
+                        : philox_normal(key, b.tag, (uint32_t)s, (uint32_t)i);
+      v = fminf(fmaxf(expf(mut + expf(rhot) * eps), V_LO), V_HI);
+      if (s == 0) ent += (double)(mut + rhot + HALF_LOG_2PI_PLUS_HALF);
+    }
+    b.smp[e] = v;
+  }
+  // entropy value: ent_weight already holds w_H * scale_H (* global_weight for global blocks)
+  double tot = block_sum_d(ent, red);
+  if (threadIdx.x == 0 && tot != 0.0 && b.active) {
+    bool is_local = b.gather != nullptr;
+    atomicAdd(&loss_out[is_local ? 0 : 1], -tot * (double)b.ent_weight);
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// Final assembly (A.1): d loss/d mu = -1[mu in clip] ( (1/S) sum_s 1[v in clip] G v + w_H ),
+//                       d loss/d rho = -1[rho in clip]( (1/S) sum_s 1[..] G v eps sigma + w_H ).
+// grid = (ceil(max_elems/256), n_blocks); only blocks of the requested pass are in `tab`.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finish(const BlockTable tab, int S, PhiloxKey key) {
+  const BlockDesc& b = tab.b[blockIdx.y];
+  const int per = b.rows * b.cols;
+  const float invS = 1.f / (float)S;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+    int r = i / b.cols, c = i - r * b.cols;
+    float dmu = 0.f, drho = 0.f;
+    if (b.active && !b.stopped) {
+      long long row = b.gather ? b.gather[r] : r;
+      float mu = b.mu[row * b.ld + b.col0 + c];
+      float rho = b.rho[row * b.ld + b.col0 + c];
+      bool in_mu = (mu >= LOG_1E_10) && (mu <= b.mu_hi);
+      bool in_rho = (rho >= LOG_1E_10) && (rho <= LOG_1E10);
+      float sigma = expf(fminf(fmaxf(rho, LOG_1E_10), LOG_1E10));
+      float gv = 0.f, gve = 0.f;
+      for (int s = 0; s < S; ++s) {
+        long long e = (long long)s * per + i;
+        float v = b.smp[e];
+        if (v > V_LO && v < V_HI) {
+          float eps = b.eps ? b.eps[((long long)s * b.rows + r) * b.eps_ld + b.eps_col0 + c]
+                            : philox_normal(key, b.tag, (uint32_t)s, (uint32_t)i);
+          float t = b.G[e] * v;
+          gv += t;
+          gve += t * eps;
+        }
+      }
+      dmu = in_mu ? -(gv * invS * b.g_weight + b.ent_weight) : 0.f;
+      drho = in_rho ? -(gve * sigma * invS * b.g_weight + b.ent_weight) : 0.f;
+    }
+    b.gmu[(long long)r * b.g_ld + b.g_col0 + c] = dmu;
+    b.grho[(long long)r * b.g_ld + b.g_col0 + c] = drho;
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// Scale priors (A.4 last lines; `_scdef.py:1946-1990`): Gamma(shape a, rate b_e) on the
+// samples of cell_scale, gene_scale, brd, ard, alpha.  STORES G (first writer of these buffers).
+// -----------------------------------------------------------------------------------------
+struct SimplePrior {
+  const float* smp;
+  float* G;          // nullptr -> value only
+  const float* rate; // per-element rate factor (gathered through `gather` by row) or nullptr
+  const int64_t* gather;
+  int rows, cols;
+  float a, lgam_a, rate_scale; // rate = rate_scale * (rate ? rate[...] : 1)
+  float weight;      // multiplies value and G: scale (cell part) or global_weight
+  int is_cell;       // accumulate into loss_out[0] (cell part) or [1]
+  int active;
+};
+struct SimplePriorTable {
+  SimplePrior p[5];
+};
+
+__global__ void __launch_bounds__(256) k_scale_priors(const SimplePriorTable tab, int S, double* loss_out) {
+  __shared__ double red[32];
+  const SimplePrior& p = tab.p[blockIdx.y];
+  if (!p.active) return;
+  const int per = p.rows * p.cols;
+  const long long total = (long long)S * per;
+  double val = 0.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(e % per);
+    float b = p.rate_scale;
+    if (p.rate) {
+      int r = i / p.cols, c = i - r * p.cols;
+      long long row = p.gather ? p.gather[r] : r;
+      b *= p.rate[row * p.cols + c];
+    }
+    float v = p.smp[e];
+    val += (double)gamma_lp(v, logf(v), p.a, b, p.lgam_a, logf(b));
+    if (p.G) p.G[e] = p.weight * ((p.a - 1.f) / v - b);
+  }
+  double tot = block_sum_d(val, red);
+  if (threadIdx.x == 0) atomicAdd(&loss_out[p.is_cell ? 0 : 1], -tot * (double)p.weight / (double)S);
+}
+
+// -----------------------------------------------------------------------------------------
+// W priors (A.4; `_scdef.py:2014-2044`).  One warp per (s, row k).  STORES G_W; atomically
+// adds the brd/ard terms.  mode 0: A=P, B=R*K_l.  mode 1 (l=0, BRD): A=P/tau_k,
+// B=R*K0/(tau_k*omega_k).  mode 2 (l=1, BRD): A=P, B=R*K1/tau_col.
+// -----------------------------------------------------------------------------------------
+struct WPriorArgs {
+  const float* smp_W;  // (S, rows, cols)
+  float* G_W;          // (S, rows, cols) or nullptr (value only)
+  const float* P;      // (rows, cols) or nullptr
+  const float* R;
+  float P_scalar, R_scalar;
+  const float* smp_tau; // (S, K0)
+  const float* smp_om;  // (S, K0)
+  float* G_tau;         // (S, K0) or nullptr
+  float* G_om;
+  int rows, cols, mode;
+  float K_l;
+  float weight;         // global_weight
+};
+
+__global__ void __launch_bounds__(256) k_wprior(const WPriorArgs a, int S, double* loss_out) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nrows = S * a.rows;
+  double val = 0.0;
+  if (warp < nrows) {
+    const int s = warp / a.rows, k = warp - s * a.rows;
+    const float* w_row = a.smp_W + ((long long)s * a.rows + k) * a.cols;
+    float* g_row = a.G_W ? a.G_W + ((long long)s * a.rows + k) * a.cols : nullptr;
+    float tau = 1.f, om = 1.f;
+    if (a.mode == 1) {
+      tau = a.smp_tau[s * a.rows + k];
+      om = a.smp_om[s * a.rows + k];
+    }
+    const bool scalar_P = (a.P == nullptr);
+    float A_row = 0.f, lgam_row = 0.f, psi_row = 0.f;
+    if (scalar_P) {
+      A_row = (a.mode == 1) ? a.P_scalar / tau : a.P_scalar;
+      lgam_row = lgammaf(A_row);
+      if (a.mode == 1) psi_row = digammaf(A_row);
+    }
+    float acc_tau = 0.f, acc_om = 0.f;
+    for (int c = lane; c < a.cols; c += 32) {
+      float w = w_row[c];
+      float lw = logf(w);
+      float P = scalar_P ? a.P_scalar : a.P[k * a.cols + c];
+      float R = a.R ? a.R[k * a.cols + c] : a.R_scalar;
+      float A, Bm, lg;
+      if (a.mode == 1) {
+        A = scalar_P ? A_row : P / tau;
+        Bm = R * a.K_l / (tau * om);
+        lg = scalar_P ? lgam_row : lgammaf(A);
+        float lB = logf(Bm);
+        if (g_row) {
+          float psi = scalar_P ? psi_row : digammaf(A);
+          float dA = lw - psi + lB;
+          float dB = -w + A / Bm;
+          acc_tau += dA * (-A / tau) + dB * (-Bm / tau);
+          acc_om += dB * (-Bm / om);
+        }
+        val += (double)gamma_lp(w, lw, A, Bm, lg, lB);
+      } else {
+        A = P;
+        lg = scalar_P ? lgam_row : lgammaf(A);
+        if (a.mode == 2) {
+          float tc = a.smp_tau[s * a.cols + c];
+          Bm = R * a.K_l / tc;
+          if (g_row) atomicAdd(&a.G_tau[s * a.cols + c], a.weight * (-w + A / Bm) * (-Bm / tc));
+        } else {
+          Bm = R * a.K_l;
+        }
+        val += (double)gamma_lp(w, lw, A, Bm, lg, logf(Bm));
+      }
+      if (g_row) g_row[c] = a.weight * ((A - 1.f) / w - Bm);
+    }
+    if (a.mode == 1 && g_row) {
+      acc_tau = warp_sum(acc_tau);
+      acc_om = warp_sum(acc_om);
+      if (lane == 0) {
+        atomicAdd(&a.G_tau[s * a.rows + k], a.weight * acc_tau);
+        atomicAdd(&a.G_om[s * a.rows + k], a.weight * acc_om);
+      }
+    }
+  }
+  double tot = block_sum_d(val, red);
+  if (threadIdx.x == 0) atomicAdd(&loss_out[1], -tot * (double)a.weight / (double)S);
+}
+
+// -----------------------------------------------------------------------------------------
+// K5: hierarchical z priors (A.4; `_scdef.py:2047-2094`).  grid = (cell chunks, S), 8 warps,
+// one warp per cell.  W_l (l>=1) samples of this MC sample live in shared memory (row stride
+// padded to an odd number of words so that both access directions are conflict-free).
+// LOCAL pass: stores G_z (all layers).  GLOBAL pass: accumulates dW_l = z_l^T P_{l-1} in shared
+// memory and adds it to G_W; adds the alpha gradient when alpha is marginalised.
+// -----------------------------------------------------------------------------------------
+struct HierArgs {
+  int L;
+  int K[SCDEF_MAX_LAYERS];
+  int off[SCDEF_MAX_LAYERS + 1];
+  int wld[SCDEF_MAX_LAYERS];   // padded row stride of W_l in smem (l >= 1)
+  int woff[SCDEF_MAX_LAYERS];  // offset of W_l in the smem W area (l >= 1)
+  int wtot;                    // floats in the smem W area
+  const float* smp_z[SCDEF_MAX_LAYERS];  // (S,B,K_l)
+  const float* smp_W[SCDEF_MAX_LAYERS];  // (S,K_l,K_{l-1}), l>=1
+  float* G_z[SCDEF_MAX_LAYERS];          // LOCAL
+  float* G_W[SCDEF_MAX_LAYERS];          // GLOBAL (l>=1)
+  const float* smp_a;  // (S) or nullptr
+  float* G_a;          // (S) GLOBAL & marginalize
+  const float* caf;    // (N) cell_alpha_factor
+  const int64_t* idx;  // (B)
+  int B, pass, cells_per_block, top_layer; // top_layer = index of the "active top" layer
+  float alpha, alpha_floor, top_alpha, lgam_top, scale;
+};
+
+constexpr int HIER_WARPS = 8;
+
+__global__ void __launch_bounds__(HIER_WARPS * 32) k_hier(const HierArgs a, int S, double* loss_out) {
+  extern __shared__ float sm[];
+  __shared__ double red[32];
+  const int Kt = a.off[a.L];
+  float* Wsm = sm;                       // [wtot]
+  float* GWsm = Wsm + a.wtot;            // [wtot] (GLOBAL only, else unused but allocated)
+  float* zs = GWsm + a.wtot;             // [HIER_WARPS][Kt]
+  float* Ps = zs + HIER_WARPS * Kt;      // [HIER_WARPS][Kt]  P_l at off[l]
+  float* gzs = Ps + HIER_WARPS * Kt;     // [HIER_WARPS][Kt]
+  const int s = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool global_pass = (a.pass == SCDEF_PASS_GLOBAL);
+
+  for (int l = 1; l < a.L; ++l) {
+    const int rows = a.K[l], cols = a.K[l - 1];
+    const float* src = a.smp_W[l] + (long long)s * rows * cols;
+    for (int e = tid; e < rows * cols; e += blockDim.x) {
+      int j = e / cols, k = e - j * cols;
+      Wsm[a.woff[l] + j * a.wld[l] + k] = src[e];
+    }
+  }
+  if (global_pass)
+    for (int e = tid; e < a.wtot; e += blockDim.x) GWsm[e] = 0.f;
+  __syncthreads();
+
+  const float alpha_value = a.smp_a ? a.smp_a[s] : a.alpha;
+  const int j_begin = blockIdx.x * a.cells_per_block;
+  const int j_end = min(a.B, j_begin + a.cells_per_block);
+  double val = 0.0;
+  float dal_acc = 0.f;
+  float* z = zs + warp * Kt;
+  float* P = Ps + warp * Kt;
+  float* gz = gzs + warp * Kt;
+
+  for (int j0 = j_begin; j0 < j_end; j0 += HIER_WARPS) {
+    const int j = j0 + warp;
+    const bool valid = j < j_end;
+    if (valid) {
+      for (int l = 0; l < a.L; ++l)
+        for (int k = lane; k < a.K[l]; k += 32)
+          z[a.off[l] + k] = a.smp_z[l][((long long)s * a.B + j) * a.K[l] + k];
+      const float caf = a.caf[a.idx[j]];
+      const float araw = alpha_value * caf;
+      const float al = fmaxf(araw, a.alpha_floor);
+      const float lgam_al = lgammaf(al);
+      const float log_al = logf(al);
+      const float psi_al = a.G_a ? digammaf(al) : 0.f;
+      __syncwarp();
+      float dal = 0.f;
+      for (int l = a.L - 1; l >= 0; --l) {
+        const int Kl = a.K[l];
+        const bool top = (l == a.top_layer);
+        for (int k = lane; k < Kl; k += 32) {
+          float zz = z[a.off[l] + k];
+          float lz = logf(zz);
+          float g;
+          if (top) {
+            val += (double)gamma_lp(zz, lz, a.top_alpha, a.top_alpha, a.lgam_top, logf(a.top_alpha));
+            g = (a.top_alpha - 1.f) / zz - a.top_alpha;
+          } else {
+            float m = 1.f;
+            if (l < a.L - 1) {
+              const int Ku = a.K[l + 1];
+              const float* Wl = Wsm + a.woff[l + 1];
+              const int ld = a.wld[l + 1];
+              const float* zu = z + a.off[l + 1];
+              m = 0.f;
+              for (int u = 0; u < Ku; ++u) m = fmaf(zu[u], Wl[u * ld + k], m);
+            }
+            float rate = al / m;
+            float lrate = log_al - logf(m);
+            val += (double)gamma_lp(zz, lz, al, rate, lgam_al, lrate);
+            g = (al - 1.f) / zz - rate;
+            if (l < a.L - 1) P[a.off[l] + k] = rate * (zz / m - 1.f);
+            dal += lz - psi_al + lrate + 1.f - zz / m;
+          }
+          gz[a.off[l] + k] = g;
+        }
+      }
+      if (a.G_a && araw > a.alpha_floor) dal_acc += dal * caf;
+      __syncwarp();
+      if (!global_pass) {
+        // children -> parents: G_{z_l}[u] += sum_k P_{l-1}[k] W_l[u][k]  (layer l-1 ordinary)
+        for (int l = 1; l < a.L; ++l) {
+          if (l - 1 == a.top_layer) continue;
+          const int Kl = a.K[l], Kc = a.K[l - 1];
+          const float* Wl = Wsm + a.woff[l];
+          const int ld = a.wld[l];
+          const float* Pc = P + a.off[l - 1];
+          for (int u = lane; u < Kl; u += 32) {
+            float acc = 0.f;
+            for (int k = 0; k < Kc; ++k) acc = fmaf(Pc[k], Wl[u * ld + k], acc);
+            gz[a.off[l] + u] += acc;
+          }
+        }
+        __syncwarp();
+        for (int l = 0; l < a.L; ++l)
+          for (int k = lane; k < a.K[l]; k += 32)
+            a.G_z[l][((long long)s * a.B + j) * a.K[l] + k] = a.scale * gz[a.off[l] + k];
+      }
+    }
+    if (global_pass) {
+      __syncthreads();
+      const int nvalid = min(HIER_WARPS, j_end - j0);
+      for (int l = 1; l < a.L; ++l) {
+        if (l - 1 == a.top_layer) continue;
+        const int rows = a.K[l], cols = a.K[l - 1], ld = a.wld[l];
+        for (int e = tid; e < rows * cols; e += blockDim.x) {
+          int u = e / cols, k = e - u * cols;
+          float acc = 0.f;
+          for (int w = 0; w < nvalid; ++w) acc = fmaf(zs[w * Kt + a.off[l] + u], Ps[w * Kt + a.off[l - 1] + k], acc);
+          GWsm[a.woff[l] + u * ld + k] += acc;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  if (global_pass) {
+    for (int l = 1; l < a.L; ++l) {
+      if (l - 1 == a.top_layer) continue;
+      const int rows = a.K[l], cols = a.K[l - 1], ld = a.wld[l];
+      float* dst = a.G_W[l] + (long long)s * rows * cols;
+      for (int e = tid; e < rows * cols; e += blockDim.x) {
+        int u = e / cols, k = e - u * cols;
+        atomicAdd(&dst[e], a.scale * GWsm[a.woff[l] + u * ld + k]);
+      }
+    }
+    if (a.G_a) {
+      dal_acc = warp_sum(dal_acc);
+      if (lane == 0 && dal_acc != 0.f) atomicAdd(&a.G_a[s], a.scale * dal_acc);
+    }
+  }
+  double tot = block_sum_d(val, red);
+  if (tid == 0) atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)S);
+}
+
+}  // namespace scdef

@@ -1,0 +1,100 @@
+"""GPU parity: the CUDA path (through the C ABI) vs the float64 oracle on the same inputs and
+the same injected noise.  Tolerance: 1e-4 relative on the loss, 1e-4 on max|g-g_ref|/max|g_ref|
+per gradient tensor (BASELINE.json north_star)."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import elbo_closed
+from oracle.elbo_ref import Noise
+from tests.helpers import make_engine, noise_to_spec, rel_err, small_problem
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _run_case(N, G, Ks, nb, B, S, sg, scb=0.0, sgb=0.0, use_brd=True, marg=False, anneal=1.3,
+              resident=True, lik_impl=0, seed=0, couple=False, **hyper):
+    X, batch, model, lp, gp = small_problem(N, G, Ks, nb, seed=seed, use_brd=use_brd,
+                                            marginalize_alpha=marg, **hyper)
+    eng = make_engine(X, batch, model, lp, gp, resident=resident)
+    idx = np.random.RandomState(seed).permutation(N)[:B]
+    noise = Noise.draw(S, B, nb, G, Ks, seed=seed + 7, dtype=torch.float32, couple_like_reference=couple)
+    ref_loss, ref_gl, ref_gg = elbo_closed.loss_and_grads(
+        model, X[idx], idx, lp, gp, noise, anneal, sg, scb, sgb, model.alpha)
+    idx_d = torch.as_tensor(idx, dtype=torch.int64, device="cuda")
+    Xb = None if resident else torch.as_tensor(X[idx], device="cuda").contiguous()
+    spec = noise_to_spec(noise)
+    kw = dict(num_samples=S, annealing=anneal, stop_gradients=sg, stop_cell_budgets=scb,
+              stop_gene_budgets=sgb, alpha=model.alpha, X_batch=Xb, lik_impl=lik_impl)
+    out = {}
+    eng.elbo_grad("local", idx_d, spec, **kw)
+    out["loss_local"] = eng.loss_value()
+    gl = [g[:, :B].cpu().numpy() for g in eng.local_grad.views]
+    eng.elbo_grad("global", idx_d, spec, **kw)
+    out["loss_global"] = eng.loss_value()
+    gg = [g.cpu().numpy() for g in eng.glob_grad.views]
+    errs = {"loss_local": abs(out["loss_local"] - ref_loss) / abs(ref_loss),
+            "loss_global": abs(out["loss_global"] - ref_loss) / abs(ref_loss)}
+    for name, g, r in zip(("cell_scale", "z"), gl, ref_gl):
+        r = r[:, idx]
+        if np.abs(r).max() == 0:
+            assert np.abs(g).max() == 0, name
+        else:
+            errs["g_" + name] = rel_err(g, r)
+    names = ["gene_scale", "brd"] + [f"W{l}" for l in range(len(Ks))] + ["ard", "alpha"]
+    for name, g, r in zip(names, gg, ref_gg):
+        if np.abs(r).max() == 0:
+            assert np.abs(g).max() == 0, name
+        else:
+            errs["g_" + name] = rel_err(g, r)
+    bad = {k: v for k, v in errs.items() if not (v <= TOL)}
+    assert not bad, f"parity failures {bad} (all: {errs})"
+    return errs
+
+
+def test_c1_shape_full_batch():
+    # BASELINE config C1: 200 x 120, layers [10,5,2], full batch
+    _run_case(200, 120, (10, 5, 2), 1, 200, 4, [0, 0, 0])
+
+
+@pytest.mark.parametrize("sg", [[0, 0, 0], [1, 0, 0], [0, 0, 1], [1, 1, 0], [0, 1, 0]])
+@pytest.mark.parametrize("use_brd", [True, False])
+def test_stop_gradient_phases(sg, use_brd):
+    _run_case(96, 70, (9, 5, 2), 1, 40, 3, sg, use_brd=use_brd)
+
+
+@pytest.mark.parametrize("scb,sgb", [(1.0, 0.0), (0.0, 1.0), (1.0, 1.0)])
+def test_budget_freezes(scb, sgb):
+    _run_case(96, 70, (9, 5, 2), 1, 40, 3, [0, 0, 0], scb=scb, sgb=sgb)
+
+
+@pytest.mark.parametrize("nb", [2, 3, 11])
+def test_batches(nb):
+    _run_case(120, 75, (8, 4, 1), nb, 50, 3, [0, 0, 0])
+
+
+def test_marginalize_alpha():
+    _run_case(96, 70, (9, 5, 2), 1, 40, 3, [0, 0, 0], marg=True)
+    _run_case(96, 70, (9, 5, 2), 2, 40, 3, [0, 0, 1], marg=True, use_brd=False)
+
+
+def test_streamed_batch_equals_resident():
+    _run_case(96, 70, (9, 5, 2), 1, 40, 3, [0, 0, 0], resident=False)
+
+
+def test_reference_noise_coupling():
+    _run_case(96, 70, (9, 5, 1), 1, 40, 3, [0, 0, 0], couple=True)
+
+
+def test_ragged_shapes_and_single_layer():
+    _run_case(70, 131, (13,), 1, 33, 2, [0])            # L = 1
+    _run_case(70, 67, (17, 3), 1, 1, 2, [0, 0])          # B = 1
+    _run_case(150, 257, (33, 16, 6, 3, 1), 2, 65, 2, [0, 0, 0, 0, 0])
+    _run_case(300, 190, (100, 60, 30, 10), 1, 129, 2, [0, 0, 0, 0])  # the C5 ladder
+
+
+def test_default_ladder_and_s1():
+    _run_case(130, 90, (20, 10, 5, 1), 1, 64, 1, [0, 0, 0, 0])
