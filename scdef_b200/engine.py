@@ -113,7 +113,7 @@ class Engine:
         self.Kt = sum(self.Ks)
         self.G, self.nb, self.N = int(n_genes), int(n_batches), int(n_cells)
         dev = self.device
-        f32 = lambda a: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(dev, torch.float32).contiguous()
+        f32 = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.array(a, copy=True))).to(dev, torch.float32).contiguous()
         self.X = None if X is None else (X if isinstance(X, torch.Tensor) else torch.as_tensor(np.asarray(X)))
         if self.X is not None:
             self.X = self.X.to(dev, torch.float32).contiguous()
@@ -307,6 +307,11 @@ class Engine:
         self._check(rc, "scdef_elbo_grad")
         self._keep = keep  # explicit-noise tensors must outlive the enqueued kernels
         return self.loss_buf
+
+    def local_grads(self, B: int) -> List[torch.Tensor]:
+        """Views of the compact local gradient written by the last LOCAL pass: (2,B,1), (2,B,sumK)."""
+        c, z = self.local_grad.views
+        return [c.reshape(-1)[: 2 * B].view(2, B, 1), z.reshape(-1)[: 2 * B * self.Kt].view(2, B, self.Kt)]
 
     def loss_value(self) -> float:
         return float(self.loss_buf.sum().item())

@@ -32,7 +32,7 @@ def _run_case(N, G, Ks, nb, B, S, sg, scb=0.0, sgb=0.0, use_brd=True, marg=False
     out = {}
     eng.elbo_grad("local", idx_d, spec, **kw)
     out["loss_local"] = eng.loss_value()
-    gl = [g[:, :B].cpu().numpy() for g in eng.local_grad.views]
+    gl = [g.cpu().numpy() for g in eng.local_grads(B)]
     eng.elbo_grad("global", idx_d, spec, **kw)
     out["loss_global"] = eng.loss_value()
     gg = [g.cpu().numpy() for g in eng.glob_grad.views]
