@@ -1,0 +1,76 @@
+"""Minibatch stream — `data_stream`, `/root/reference/src/scdef/models/_scdef.py:3167-3173`.
+
+Index selection is the reference's, bit for bit: `np.random.RandomState(0)`, a fresh
+`permutation(n_cells)` per epoch, contiguous slices of `batch_size`, short last slice.  The
+permutation is drawn on the host (it IS NumPy's algorithm) and uploaded once per epoch; batches
+are device views of it.  With the counts resident in HBM nothing else moves per step; in
+"host" placement the rows `X[batch_idx]` are gathered into pinned memory and copied each step,
+as the reference does (`jnp.array(self.X[batch_idx])`).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import dist as _dist
+
+
+class MinibatchStream:
+    def __init__(self, n_total: int, global_batch: int, shard: _dist.ShardInfo, device,
+                 host_X=None, n_local=None, start=None, pinned_slots: int = 3):
+        self.n_total, self.gb, self.shard, self.device = int(n_total), int(global_batch), shard, device
+        self.rng = np.random.RandomState(0)
+        num_complete, leftover = divmod(self.n_total, self.gb)
+        self.num_batches = num_complete + bool(leftover)
+        if shard.world > 1 and (n_local is None or start is None):
+            raise ValueError("sharded stream needs n_local and start")
+        self.n_local = self.n_total if n_local is None else int(n_local)
+        self.start = 0 if start is None else int(start)
+        self.host_X = host_X
+        self.h2d_bytes = 0
+        self._slots, self._events, self._slot_i = [], [], 0
+        if host_X is not None:
+            G = host_X.shape[1]
+            cap = min(self.gb, self.n_total)
+            for _ in range(pinned_slots):
+                self._slots.append(torch.empty((cap, G), dtype=torch.float32).pin_memory())
+                self._events.append(None)
+            self._dev_slots = [torch.empty((cap, G), dtype=torch.float32, device=device) for _ in range(pinned_slots)]
+
+    def new_epoch(self):
+        perm = self.rng.permutation(self.n_total)
+        bounds = np.minimum(np.arange(self.num_batches + 1, dtype=np.int64) * self.gb, self.n_total)
+        self.n_glob = np.diff(bounds)
+        if self.shard.world == 1:
+            local, offs = perm, bounds
+        else:
+            m = (perm >= self.start) & (perm < self.start + self.n_local)
+            local = perm[m] - self.start
+            offs = np.concatenate([[0], np.cumsum(np.add.reduceat(m.astype(np.int64), bounds[:-1]))])
+        self.perm_host = np.ascontiguousarray(local, dtype=np.int64)
+        self.offs = offs
+        self.perm_dev = torch.from_numpy(self.perm_host).to(self.device, non_blocking=False)
+        self.h2d_bytes += self.perm_host.nbytes
+
+    def indices_host(self, it: int) -> np.ndarray:
+        return self.perm_host[self.offs[it] : self.offs[it + 1]]
+
+    def batch(self, it: int):
+        """(device int64 indices of this rank, device X rows or None, global minibatch size)."""
+        idx = self.perm_dev[self.offs[it] : self.offs[it + 1]]
+        Xb = None
+        if self.host_X is not None:
+            rows = self.indices_host(it)
+            k = self._slot_i
+            self._slot_i = (k + 1) % len(self._slots)
+            if self._events[k] is not None:
+                self._events[k].synchronize()  # the copy that last used this pinned slot is done
+            pin = self._slots[k][: len(rows)]
+            np.take(self.host_X, rows, axis=0, out=pin.numpy())
+            Xb = self._dev_slots[k][: len(rows)]
+            Xb.copy_(pin, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._events[k] = ev
+            self.h2d_bytes += pin.numel() * 4
+        return idx, Xb, int(self.n_glob[it])

@@ -1,0 +1,173 @@
+"""CPU: host logic of the drop-in class, the minibatch stream, the ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import host_ref
+from scdef_b200 import MiniAnnData, scDEF, _lib
+from scdef_b200.dist import ShardInfo, local_members
+from scdef_b200.synth import synth_counts_numpy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model(N=200, G=120, nb=1, **kw):
+    X, b = synth_counts_numpy(N, G, n_batches=nb, seed=0)
+    obs = {"batch": np.array([f"b{i}" for i in range(max(nb, 1))])[b]} if nb > 1 else None
+    return X, b, scDEF(MiniAnnData(X, obs=obs), batch_key="batch" if nb > 1 else None, **kw)
+
+
+def test_geometric_ladder_golden_values():
+    # /root/reference/tests/test_sscdef.py:55-83 and SURVEY.md §8c
+    _, _, m = _model(20, 10)
+    assert m.layer_sizes == [100, 40, 16, 6, 3, 1]
+    assert host_ref.geometric_layer_sizes(100, 1, 6) == [100, 40, 16, 6, 3, 1]
+    _, _, m = _model(20, 10, n_factors=20, top_factors=5, n_layers=3)
+    assert m.layer_sizes == [20, 10, 5, 1]
+    assert host_ref.geometric_layer_sizes(20, 5, 3) == [20, 10, 5, 1]
+    for nf, tf, nl in [(100, 1, 6), (50, 2, 4), (10, 1, 2), (8, 8, 3), (30, 3, 5)]:
+        _, _, m = _model(20, 10, n_factors=nf, top_factors=tf, n_layers=nl)
+        assert m.layer_sizes == host_ref.geometric_layer_sizes(nf, tf, nl)
+
+
+def test_constructor_validation_matches_reference():
+    X, _ = synth_counts_numpy(20, 10)
+    with pytest.raises(TypeError, match="AnnData"):
+        scDEF(X)
+    with pytest.raises(ValueError, match="n_factors"):
+        scDEF(MiniAnnData(X), n_factors=0)
+    with pytest.raises(ValueError, match="top_factors must be >= 1"):
+        scDEF(MiniAnnData(X), top_factors=0)
+    with pytest.raises(ValueError, match="top_factors must be <= n_factors"):
+        scDEF(MiniAnnData(X), n_factors=4, top_factors=5)
+
+
+@pytest.mark.parametrize("nb", [1, 3])
+def test_constants_match_oracle_restatement(nb):
+    X, b, m = _model(150, 60, nb=nb, layer_sizes=[10, 5, 2], seed=1)
+    ref = host_ref.build_model(X, [10, 5, 2], batch_ids=b if nb > 1 else None)
+    np.testing.assert_allclose(m.batch_lib_ratio, ref.batch_lib_ratio, rtol=1e-10)
+    np.testing.assert_allclose(np.broadcast_to(m.gene_ratio, (nb, 60)), np.broadcast_to(ref.gene_ratio, (nb, 60)), rtol=1e-10)
+    np.testing.assert_allclose(m.cell_alpha_factor, ref.cell_alpha_factor, rtol=1e-12)
+    np.testing.assert_allclose(m.gene_ratio_init, ref.gene_ratio_init, rtol=1e-10)
+    assert m.alpha == pytest.approx(ref.alpha, rel=1e-12)
+    np.testing.assert_array_equal(m.batch_indices_onehot, ref.batch_indices_onehot)
+    for l in range(3):
+        np.testing.assert_allclose(np.asarray(m.w_priors[l][0]), np.asarray(ref.w_priors[l][0]))
+    # parameter layout
+    assert [p.shape for p in m.local_params] == [(2, 150, 1), (2, 150, 17)]
+    assert [p.shape for p in m.global_params] == [(2, nb, 60), (2, 10, 1), (2, 10, 60), (2, 5, 10), (2, 2, 5), (2, 10, 1), (2, 1, 1)]
+    assert all(p.dtype == np.float32 for p in m.local_params + m.global_params)
+    # posterior summaries follow _scdef.py:3394-3476
+    np.testing.assert_allclose(m.pmeans["L0W"], host_ref.lognormal_mean(*m.global_params[2]), rtol=1e-6)
+    np.testing.assert_allclose(m.pvars["L1z"], host_ref.lognormal_var(m.local_params[1][0][:, 10:15], m.local_params[1][1][:, 10:15]), rtol=1e-6)
+
+
+def test_init_matches_reference_moments():
+    # cold-start c and s are deterministic (App. B): exact agreement with the oracle restatement
+    X, b, m = _model(150, 60, layer_sizes=[10, 5, 2], seed=1)
+    ref = host_ref.build_model(X, [10, 5, 2])
+    lp, gp = host_ref.init_var_params(ref, seed=1)
+    np.testing.assert_allclose(m.local_params[0], lp[0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m.global_params[0], gp[0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m.global_params[5], gp[5], rtol=1e-5, atol=1e-6)  # ard
+    np.testing.assert_allclose(m.global_params[6], gp[6], rtol=1e-5, atol=1e-6)  # alpha
+
+
+def test_learn_kwargs_are_strict():
+    _, _, m = _model(50, 20, layer_sizes=[4, 2])
+    with pytest.raises(TypeError, match="Unexpected keyword arguments for _learn: bogus"):
+        m._learn(bogus=1)
+    assert scDEF.learn is scDEF._learn
+
+
+def test_learn_fails_loudly_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    _, _, m = _model(50, 20, layer_sizes=[4, 2])
+    with pytest.raises(Exception, match="no CPU fallback"):
+        m._learn(n_epoch=1)
+
+
+@pytest.mark.parametrize("N,bs", [(10, 3), (257, 256), (100, None), (64, 64), (5, 8)])
+def test_minibatch_stream_is_bit_exact(N, bs):
+    """`data_stream` (_scdef.py:3167-3173): RandomState(0), permutation per epoch, short last slice."""
+    import torch
+
+    from scdef_b200.stream import MinibatchStream
+
+    bsz = N if bs is None else bs
+    st = MinibatchStream(N, bsz, ShardInfo(), torch.device("cpu"))
+    ref = host_ref.data_stream_indices(N, bs)
+    rng = np.random.RandomState(0)
+    for epoch in range(3):
+        st.new_epoch()
+        perm = rng.permutation(N)
+        for it in range(st.num_batches):
+            expect = perm[it * bsz:(it + 1) * bsz]
+            np.testing.assert_array_equal(next(ref), expect)
+            idx, Xb, n_glob = st.batch(it)
+            assert idx.dtype == torch.int64
+            np.testing.assert_array_equal(idx.numpy(), expect)
+            assert n_glob == len(expect) and Xb is None
+
+
+def test_sharded_stream_partitions_the_reference_batch():
+    import torch
+
+    from scdef_b200.stream import MinibatchStream
+
+    N, b, R = 103, 8, 4
+    counts = [26, 26, 26, 25]
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    streams = [MinibatchStream(N, b * R, ShardInfo(rank=r, world=R), torch.device("cpu"), n_local=counts[r], start=int(starts[r]))
+               for r in range(R)]
+    ref = host_ref.data_stream_indices(N, b * R)
+    for epoch in range(2):
+        for s in streams:
+            s.new_epoch()
+        for it in range(streams[0].num_batches):
+            expect = next(ref)
+            got = np.concatenate([s.batch(it)[0].numpy() + starts[r] for r, s in enumerate(streams)])
+            assert sorted(got.tolist()) == sorted(expect.tolist())
+            assert all(s.batch(it)[2] == len(expect) for s in streams)
+            for r, s in enumerate(streams):
+                np.testing.assert_array_equal(s.batch(it)[0].numpy(), local_members(expect, int(starts[r]), counts[r]))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "scdef_b200.h")).read()
+    declared = set(re.findall(r"\b(scdef_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    path = _lib.lib_path()
+    assert os.path.exists(path), "build the extension first (__graft_entry__.build())"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.scdef_abi_version() == _lib.ABI_VERSION
+    # argument validation happens before any CUDA call
+    assert lib.scdef_ctx_create(None, None) == -1
+    d = _lib.ModelDesc()
+    d.abi_version = 999
+    h = ctypes.c_void_p()
+    assert lib.scdef_ctx_create(ctypes.byref(d), ctypes.byref(h)) == -1
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors are the same size as the C structs (checked by compiling a probe)."""
+    import subprocess
+    import tempfile
+
+    src = '#include <stdio.h>\n#include "scdef_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(scdef_model_desc), sizeof(scdef_blocks), sizeof(scdef_noise), sizeof(scdef_call));return 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "p.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "p")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [ctypes.sizeof(_lib.ModelDesc), ctypes.sizeof(_lib.Blocks), ctypes.sizeof(_lib.Noise), ctypes.sizeof(_lib.Call)]
