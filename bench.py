@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the scDEF training hot path on B200 (contract: see the repo prompt / DESIGN.md §6).
+
+A "step" = one iteration of the reference's hot loop (`_scdef.py:3230-3271`): ELBO + gradient
+w.r.t. the local blocks, dense Adam over ALL cells, ELBO + gradient w.r.t. the global blocks at
+the updated locals with the same noise, Adam + clip on the globals.  Library defaults
+`batch_size=256` (per GPU), `num_samples=100` (`_scdef.py:2930-2931`).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C5]
+
+Own arm: synthetic Poisson counts of the named BASELINE.json config are generated on the device,
+the model is the public `scdef_b200.scDEF`, and both numbers are taken through `model._learn`:
+  value : counts resident in HBM (x_placement="device"), no host sync inside the timed region
+  e2e   : counts in host memory (x_placement="host"): every step gathers X[batch] into pinned
+          memory, copies it to the device, and reads the step's loss back to the host.
+Reference arm (`--impl reference`): the restated CPU oracle (torch CPU autograd, all host
+threads) on a bounded sample — the reference's JAX path cannot run in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ELBO+grad train step throughput (local pass + Adam, global pass + Adam), cells/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    bf16_burst=float(d["bf16_tflops"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1400.0, bf16_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        lo = (self.t_begin or 0.0) - 0.02
+        hi = (self.t_end or time.time()) + 0.12  # a sample is printed up to one period after it is taken
+        inside = [ln for (t, ln) in self.lines if lo <= t <= hi] or [ln for (_, ln) in self.lines[-3:]]
+        for ln in inside:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+def run_reference(args):
+    """CPU arm: restated oracle (port), all host threads, bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle.cpu_baseline import time_train_steps
+    from scdef_b200.synth import CONFIGS, synth_counts_numpy
+
+    N, G, Ks, nb, lib = CONFIGS[args.config]
+    n_sample = min(N, args.cpu_cells)
+    X, _ = synth_counts_numpy(n_sample, G, lib=lib, seed=0)
+    cores = os.cpu_count() or 1
+    r = time_train_steps(X, Ks, batch_size=min(args.batch, n_sample), num_samples=args.samples,
+                         steps=args.steps, warmup=args.warmup, threads=cores)
+    sample = (f"{args.steps} train steps (B={min(args.batch, n_sample)}, S={args.samples}) on a {n_sample}-cell slice "
+              f"of {args.config} ({N}x{G}); ELBO+grad cost is independent of N, the dense local Adam runs over the slice only")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["cells_per_s"], "unit": "cells/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config} {N}x{G} layers {Ks}", "batch_per_gpu": args.batch, "num_samples": args.samples},
+        "cpu_baseline": {"value": r["cells_per_s"], "unit": "cells/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["cells_per_s"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "steps_per_s": r["steps_per_s"],
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as td
+
+    from scdef_b200 import MiniAnnData, scDEF, _lib
+    from scdef_b200.synth import CONFIGS, synth_counts_torch
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    N, G, Ks, nb, lib = CONFIGS[args.config]
+    if args.cells:
+        N = int(args.cells)
+    n_local = N // world + (1 if rank < N % world else 0)
+    W, K, S, B = args.warmup, args.steps, args.samples, args.batch
+    peaks = _peaks()
+
+    t0 = time.time()
+    X, batch = synth_counts_torch(n_local, G, n_batches=nb, lib=lib, seed=1000 + rank, device=dev)
+    torch.cuda.synchronize()
+    t_data = time.time() - t0
+    obs = {"batch": batch.cpu().numpy()} if nb > 1 else None
+
+    def build(x, placement):
+        return scDEF(MiniAnnData(x, obs=obs), batch_key="batch" if nb > 1 else None, layer_sizes=Ks, seed=42,
+                     logginglevel=30, device=str(dev), x_placement=placement,
+                     process_group="world" if world > 1 else None, lik_impl=args.lik_impl)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize()
+
+    def timed_learn(model, per_step_readback):
+        """W warm-up + K timed steps through model._learn; returns (ms total, profile, launches, extras)."""
+        st = {}
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank)
+
+        def hook(i, eng, stream):
+            if per_step_readback and i > 0:
+                st["last_loss"] = float(eng.loss_buf.sum().item())  # D2H of the step's result
+            if i == 0:
+                sampler.start()
+                eng.profile(True)
+            if i == W:
+                barrier()
+                eng.profile_read(reset=True)
+                st["h2d0"] = stream.h2d_bytes
+                sampler.mark_begin()
+                ev0.record(torch.cuda.current_stream(dev))
+            if i == W + K:
+                ev1.record(torch.cuda.current_stream(dev))
+                barrier()
+                sampler.mark_end()
+                st["clocks"] = sampler.stop()
+                st["h2d1"] = stream.h2d_bytes
+                st["prof"], st["launches"] = eng.profile_read(reset=True)
+                eng.profile(False)
+
+        model._step_hook = hook
+        model.max_steps_per_learn = W + K
+        steps_per_epoch = max(1, math.ceil(N / (B * world)))
+        model._learn(n_epoch=math.ceil((W + K) / steps_per_epoch) + 1, num_samples=S, batch_size=B,
+                     filter=False, annotate=False)
+        model._step_hook = None
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        st["ms"] = float(t.item())
+        st["loss"] = model.elbos[-1][-1] if model.elbos and model.elbos[-1] else None
+        return st
+
+    # ---- value: counts resident in HBM ------------------------------------------------------
+    t0 = time.time()
+    model = build(X, "device")
+    t_build = time.time() - t0
+    res = timed_learn(model, per_step_readback=False)
+    ms_step = res["ms"] / K
+    cells_per_step = B * world
+    value = cells_per_step / (ms_step * 1e-3)
+    Kt, K0 = sum(Ks), Ks[0]
+
+    prof = res["prof"]
+    kinds = {}
+    for k, (ms_sum, n_timed, n_launched) in prof.items():
+        if n_timed > 0:
+            kinds[k] = dict(ms_avg=ms_sum / n_timed, launches=int(n_launched), ms_per_step=ms_sum / n_timed * n_launched / K)
+    share = {k: v["ms_per_step"] / ms_step for k, v in kinds.items()}
+
+    def roof_lik():
+        if "lik" not in kinds:
+            return None
+        flops = 4.0 * S * B * K0 * G  # per launch: forward GEMM + one backward GEMM, 2 flop/MAC
+        ach = flops / (kinds["lik"]["ms_avg"] * 1e-3) / 1e12
+        return {"kernel": "likelihood (K2-K4)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16"], "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                "algorithmic": f"4*S*B*K0*G = {flops:.3e} flop/launch", "share_of_step": share.get("lik")}
+
+    def roof_adam():
+        if "adam_local_z" not in kinds:
+            return None
+        nbytes = 2.0 * n_local * Kt * 4 * 6 + 2.0 * B * Kt * 4  # r/w p,m,v of (2,N,sumK) + minibatch grads
+        ach = nbytes / (kinds["adam_local_z"]["ms_avg"] * 1e-3) / 1e9
+        return {"kernel": "dense local Adam (K8)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["source"],
+                "algorithmic": f"24 B/param * {2 * n_local * Kt} params = {nbytes:.3e} B/launch",
+                "share_of_step": share.get("adam_local_z")}
+
+    roofs = [r for r in (roof_lik(), roof_adam()) if r]
+    roofs.sort(key=lambda r: -(r["share_of_step"] or 0))
+
+    # ---- e2e: counts in host memory, per-step H2D + loss readback -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+
+        need = n_local * G * 4
+        avail = psutil.virtual_memory().available
+        note = None
+        if avail > 2.2 * need + (8 << 30):
+            Xh = np.empty((n_local, G), dtype=np.float32)
+            step_rows = 1 << 16
+            for s in range(0, n_local, step_rows):
+                Xh[s:s + step_rows] = X[s:s + step_rows].cpu().numpy()
+            del model
+            torch.cuda.empty_cache()
+            m2 = build(Xh, "host")
+            r2 = timed_learn(m2, per_step_readback=True)
+            ms2 = r2["ms"] / K
+            e2e = {"value": cells_per_step / (ms2 * 1e-3), "unit": "cells/s",
+                   "h2d_bytes_per_step": int((r2["h2d1"] - r2["h2d0"]) / K), "d2h_bytes_per_step": 8,
+                   "ms_per_step": ms2, "path": "scDEF._learn(x_placement='host')"}
+        else:
+            note = f"host RAM {avail / 2**30:.0f} GiB too small for a {need / 2**30:.0f} GiB host copy"
+            e2e = {"value": None, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": note}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu:
+        from oracle.cpu_baseline import time_train_steps
+
+        n_s = min(n_local, args.cpu_cells)
+        Xs = X[:n_s].cpu().numpy()
+        cores = os.cpu_count() or 1
+        r = time_train_steps(Xs, Ks, batch_size=min(B, n_s), num_samples=S, steps=args.cpu_steps, warmup=1, threads=cores)
+        cpu = {"value": r["cells_per_s"], "unit": "cells/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{args.cpu_steps} train steps (B={min(B, n_s)}, S={S}) of the restated CPU oracle (torch autograd, f32) on a "
+                         f"{n_s}-cell slice; the reference's JAX path is not installable here", "ms_per_step": r["ms_per_step"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config}: {N} cells x {G} genes, layers {Ks}, {nb} batch(es), cells block-sharded over {world} GPU(s)",
+                       "batch_per_gpu": B, "num_samples": S, "step": "train (local pass + dense Adam, global pass + Adam)",
+                       "l2": "inputs larger than L2: the dense local Adam streams %.2f GB per step per GPU" % (2 * n_local * (Kt + 1) * 24 / 1e9),
+                       "lik_impl": {0: "auto", 1: "simt", 2: "tcgen05"}[args.lik_impl], "noise": "philox, reference coupling"},
+            "steps_per_s": 1e3 / ms_step, "clocks": res["clocks"], "gpu_launches": int(res["launches"]),
+            "e2e": e2e, "roofline": roofs[0] if roofs else None, "roofline_other": roofs[1:],
+            "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches_per_step": v["launches"] / K, "share": round(share[k], 4)}
+                        for k, v in kinds.items()},
+            "cpu_baseline": cpu, "final_loss": res["loss"],
+            "setup_s": {"synthetic_data": round(t_data, 1), "model_build": round(t_build, 1)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C5")
+    ap.add_argument("--samples", type=int, default=100)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--cells", type=int, default=0, help="override the number of cells (debug)")
+    ap.add_argument("--lik-impl", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-cells", type=int, default=10000)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", 1))
+        if args.gpus != world and world == 1 and args.gpus > 1:
+            # convenience: relaunch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -185,6 +185,23 @@ int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib,
 int scdef_noise_fill(scdef_ctx* ctx, const scdef_noise* noise, int block_kind, int layer, int S,
                      int B, float* out, void* cuda_stream);
 
+/* Measurement (bench.py): CUDA-event pairs recorded on the launch stream around every launch
+   of each kernel family, and a count of all kernels launched through this ABI. */
+#define SCDEF_PROF_LIK 0          /* likelihood kernel (K2-K4) */
+#define SCDEF_PROF_ADAM_LOCAL 1   /* dense Adam over the z block */
+#define SCDEF_PROF_HIER 2
+#define SCDEF_PROF_SAMPLE 3
+#define SCDEF_PROF_WPRIOR 4
+#define SCDEF_PROF_FINISH 5
+#define SCDEF_PROF_ADAM_GLOBAL 6
+#define SCDEF_PROF_PRIORS 7
+#define SCDEF_PROF_ADAM_LOCAL_C 8 /* dense Adam over the cell-scale block */
+#define SCDEF_PROF_KINDS 9
+int scdef_profile_enable(scdef_ctx* ctx, int on);
+/* Sums the elapsed ms of the (up to 256 most recent) timed launches of each kind; syncs on them. */
+int scdef_profile_read(scdef_ctx* ctx, double* ms_sum, int64_t* n_timed, int64_t* n_launched,
+                       int64_t* total_launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,8 +102,9 @@ class Call(C.Structure):
 EXPORTS = [
     "scdef_abi_version", "scdef_ctx_create", "scdef_ctx_destroy", "scdef_last_error",
     "scdef_workspace_bytes", "scdef_elbo_grad", "scdef_adam_local", "scdef_adam_global",
-    "scdef_posterior", "scdef_row_stats", "scdef_noise_fill",
+    "scdef_posterior", "scdef_row_stats", "scdef_noise_fill", "scdef_profile_enable", "scdef_profile_read",
 ]
+PROF_KINDS = ["lik", "adam_local_z", "hier", "sample", "wprior", "finish", "adam_global", "priors", "adam_local_c"]
 
 _LIB = None
 
@@ -159,6 +160,10 @@ def load():
     lib.scdef_row_stats.restype = C.c_int
     lib.scdef_noise_fill.argtypes = [C.c_void_p, C.POINTER(Noise), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.scdef_noise_fill.restype = C.c_int
+    lib.scdef_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.scdef_profile_enable.restype = C.c_int
+    lib.scdef_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.scdef_profile_read.restype = C.c_int
     got = lib.scdef_abi_version()
     if got != ABI_VERSION:
         raise ScdefLibraryError(f"ABI mismatch: library {got}, binding {ABI_VERSION}; rebuild the extension")

@@ -14,12 +14,19 @@
 
 using namespace scdef;
 
+constexpr int PROF_RING = 256;
+
 struct scdef_ctx {
   scdef_model_desc d;
   int L, Kt, K0;
   int K[SCDEF_MAX_LAYERS], off[SCDEF_MAX_LAYERS + 1], out_dim[SCDEF_MAX_LAYERS];
   int sm_count;
   char err[512];
+  // profiling: CUDA-event pairs around every launch of each kernel family, on the launch stream
+  bool prof_on, prof_ready;
+  cudaEvent_t prof_ev[SCDEF_PROF_KINDS][PROF_RING][2];
+  long long prof_count[SCDEF_PROF_KINDS];
+  long long launches;
 };
 
 namespace {
@@ -37,10 +44,27 @@ int fail(scdef_ctx* ctx, int code, const char* fmt, ...) {
 }
 
 int check_launch(scdef_ctx* ctx, const char* what) {
+  if (ctx) ctx->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, SCDEF_ECUDA, "%s: %s", what, cudaGetErrorString(e));
   return SCDEF_OK;
 }
+
+struct ProfScope {
+  scdef_ctx* c; int kind; cudaStream_t st; int slot;
+  ProfScope(scdef_ctx* c_, int kind_, cudaStream_t st_) : c(c_), kind(kind_), st(st_), slot(-1) {
+    if (c->prof_on && c->prof_ready) {
+      slot = (int)(c->prof_count[kind] % PROF_RING);
+      cudaEventRecord(c->prof_ev[kind][slot][0], st);
+    }
+  }
+  ~ProfScope() {
+    if (slot >= 0) {
+      cudaEventRecord(c->prof_ev[kind][slot][1], st);
+      c->prof_count[kind]++;
+    }
+  }
+};
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -135,7 +159,49 @@ int scdef_ctx_create(const scdef_model_desc* desc, scdef_ctx** out) {
   return SCDEF_OK;
 }
 
-void scdef_ctx_destroy(scdef_ctx* ctx) { delete ctx; }
+void scdef_ctx_destroy(scdef_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->prof_ready)
+    for (int k = 0; k < SCDEF_PROF_KINDS; ++k)
+      for (int i = 0; i < PROF_RING; ++i) { cudaEventDestroy(ctx->prof_ev[k][i][0]); cudaEventDestroy(ctx->prof_ev[k][i][1]); }
+  delete ctx;
+}
+
+int scdef_profile_enable(scdef_ctx* ctx, int on) {
+  if (!ctx) return SCDEF_EINVAL;
+  if (on && !ctx->prof_ready) {
+    for (int k = 0; k < SCDEF_PROF_KINDS; ++k)
+      for (int i = 0; i < PROF_RING; ++i)
+        if (cudaEventCreate(&ctx->prof_ev[k][i][0]) != cudaSuccess || cudaEventCreate(&ctx->prof_ev[k][i][1]) != cudaSuccess)
+          return fail(ctx, SCDEF_ECUDA, "cudaEventCreate failed");
+    ctx->prof_ready = true;
+  }
+  ctx->prof_on = on != 0;
+  return SCDEF_OK;
+}
+
+int scdef_profile_read(scdef_ctx* ctx, double* ms_sum, int64_t* n_timed, int64_t* n_launched, int64_t* total_launches, int reset) {
+  if (!ctx) return SCDEF_EINVAL;
+  for (int k = 0; k < SCDEF_PROF_KINDS; ++k) {
+    double sum = 0.0;
+    long long n = ctx->prof_count[k] < PROF_RING ? ctx->prof_count[k] : PROF_RING;
+    if (ctx->prof_ready)
+      for (long long i = 0; i < n; ++i) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ctx->prof_ev[k][i][1]) != cudaSuccess ||
+            cudaEventElapsedTime(&ms, ctx->prof_ev[k][i][0], ctx->prof_ev[k][i][1]) != cudaSuccess)
+          return fail(ctx, SCDEF_ECUDA, "profile read failed for kind %d", k);
+        sum += ms;
+      }
+    if (ms_sum) ms_sum[k] = sum;
+    if (n_timed) n_timed[k] = n;
+    if (n_launched) n_launched[k] = ctx->prof_count[k];
+    if (reset) ctx->prof_count[k] = 0;
+  }
+  if (total_launches) *total_launches = ctx->launches;
+  if (reset) ctx->launches = 0;
+  return SCDEF_OK;
+}
 
 const char* scdef_last_error(scdef_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 
@@ -244,6 +310,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     for (int l = 0; l < L; ++l) { add(BLK_W + l); if (B > 0) add(BLK_Z + l); }
     size_t gx = (max_el + 255) / 256;
     if (gx > (size_t)ctx->sm_count * 16) gx = (size_t)ctx->sm_count * 16;
+    ProfScope ps(ctx, SCDEF_PROF_SAMPLE, st);
     k_sample<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key, loss_out, gw);
     if ((rc = check_launch(ctx, "k_sample"))) return rc;
   }
@@ -270,6 +337,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     size_t gx = (max_el + 255) / 256;
     if (gx > (size_t)ctx->sm_count * 8) gx = (size_t)ctx->sm_count * 8;
     if (gx < 1) gx = 1;
+    ProfScope ps(ctx, SCDEF_PROF_PRIORS, st);
     k_scale_priors<<<dim3((unsigned)gx, 5), 256, 0, st>>>(t, S, loss_out);
     if ((rc = check_launch(ctx, "k_scale_priors"))) return rc;
   }
@@ -290,6 +358,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     a.K_l = (float)ctx->K[l];
     a.weight = gw;
     int warps = S * a.rows;
+    ProfScope ps(ctx, SCDEF_PROF_WPRIOR, st);
     k_wprior<<<(warps + 7) / 8, 256, 0, st>>>(a, S, loss_out);
     if ((rc = check_launch(ctx, "k_wprior"))) return rc;
   }
@@ -330,7 +399,10 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     size_t smem = ((size_t)2 * wtot + (size_t)3 * HIER_WARPS * ctx->Kt) * sizeof(float);
     if (smem > 200 * 1024) return fail(ctx, SCDEF_EUNSUPPORTED, "hierarchy needs %zu B of shared memory", smem);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_hier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_hier<<<dim3(chunks, S), HIER_WARPS * 32, smem, st>>>(h, S, loss_out);
+    {
+      ProfScope ps(ctx, SCDEF_PROF_HIER, st);
+      k_hier<<<dim3(chunks, S), HIER_WARPS * 32, smem, st>>>(h, S, loss_out);
+    }
     if ((rc = check_launch(ctx, "k_hier"))) return rc;
 
     // ---- likelihood ----------------------------------------------------------------------------
@@ -356,7 +428,11 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
         a.use_brd = d.use_brd; a.B = B; a.G = G; a.K0 = K0; a.nb = nb; a.pass = pass; a.S = S;
         a.scale = scale; a.global_weight = gw; a.anneal = anneal; a.w0_stopped = st0;
         a.ws = ws + plan.tc_off; a.ws_bytes = plan.tc_bytes;
-        if ((rc = lik_tc_launch(a, loss_out, ctx->sm_count, st))) return fail(ctx, rc, "lik_tc_launch failed");
+        {
+          ProfScope ps(ctx, SCDEF_PROF_LIK, st);
+          rc = lik_tc_launch(a, loss_out, ctx->sm_count, st);
+        }
+        if (rc) return fail(ctx, rc, "lik_tc_launch failed");
         if ((rc = check_launch(ctx, "k_lik_tc"))) return rc;
       } else {
         LikArgs a;
@@ -368,6 +444,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
         size_t smem = ((size_t)LT * (K0 + 1) + (size_t)K0 * LW_LD + (size_t)LT * LQ_LD) * sizeof(float);
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_lik_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid((G + LT - 1) / LT, (B + LT - 1) / LT, S);
+        ProfScope ps(ctx, SCDEF_PROF_LIK, st);
         k_lik_simt<<<grid, 256, smem, st>>>(a, S, loss_out);
         if ((rc = check_launch(ctx, "k_lik_simt"))) return rc;
       }
@@ -397,6 +474,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     if (t.n > 0) {
       size_t gx = (max_el + 255) / 256;
       if (gx > (size_t)ctx->sm_count * 16) gx = (size_t)ctx->sm_count * 16;
+      ProfScope ps(ctx, SCDEF_PROF_FINISH, st);
       k_finish<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key);
       if ((rc = check_launch(ctx, "k_finish"))) return rc;
     }
@@ -442,8 +520,11 @@ int scdef_adam_local(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blo
     long long blocks = (nthreads + 255) / 256;
     long long cap = (long long)ctx->sm_count * 32;
     if (blocks > cap) blocks = cap;
-    if (vec4) k_adam_local<4><<<(unsigned)blocks, 256, 0, st>>>(a, h);
-    else k_adam_local<1><<<(unsigned)blocks, 256, 0, st>>>(a, h);
+    {
+      ProfScope ps(ctx, which ? SCDEF_PROF_ADAM_LOCAL : SCDEF_PROF_ADAM_LOCAL_C, st);
+      if (vec4) k_adam_local<4><<<(unsigned)blocks, 256, 0, st>>>(a, h);
+      else k_adam_local<1><<<(unsigned)blocks, 256, 0, st>>>(a, h);
+    }
     if ((rc = check_launch(ctx, "k_adam_local"))) return rc;
   }
   if (B > 0) {
@@ -482,7 +563,10 @@ int scdef_adam_global(scdef_ctx* ctx, const scdef_blocks* params, const scdef_bl
     if (!t.s[i].p || !t.s[i].g || !t.s[i].m || !t.s[i].v) return fail(ctx, SCDEF_EINVAL, "null block pointer");
   int gx = (max_n + 255) / 256;
   if (gx > ctx->sm_count * 8) gx = ctx->sm_count * 8;
-  k_adam_global<<<dim3(gx, t.n), 256, 0, st>>>(t, h);
+  {
+    ProfScope ps(ctx, SCDEF_PROF_ADAM_GLOBAL, st);
+    k_adam_global<<<dim3(gx, t.n), 256, 0, st>>>(t, h);
+  }
   return check_launch(ctx, "k_adam_global");
 }
 

@@ -352,6 +352,19 @@ class Engine:
         self._check(rc, "scdef_posterior")
         return (lm.views, gm.views), (lv.views, gv.views)
 
+    def profile(self, on: bool):
+        self._check(self.lib.scdef_profile_enable(self.ctx, int(on)), "scdef_profile_enable")
+
+    def profile_read(self, reset=True):
+        """{kind: (ms_sum, n_timed, n_launched)}, total kernel launches through the ABI."""
+        n = len(_lib.PROF_KINDS)
+        ms = (C.c_double * n)()
+        nt = (C.c_int64 * n)()
+        nl = (C.c_int64 * n)()
+        tot = C.c_int64()
+        self._check(self.lib.scdef_profile_read(self.ctx, ms, nt, nl, C.byref(tot), int(reset)), "scdef_profile_read")
+        return {k: (ms[i], nt[i], nl[i]) for i, k in enumerate(_lib.PROF_KINDS)}, int(tot.value)
+
     def noise_fill(self, noise: NoiseSpec, kind: int, layer: int, S: int, B: int, shape):
         out = torch.empty((S,) + tuple(shape), dtype=torch.float32, device=self.device)
         nz = self._noise_struct(noise, [])

@@ -84,6 +84,7 @@ class scDEF:
         self.lik_impl = int(lik_impl)
         self._shard = _dist.ShardInfo.from_group(process_group)
         self.max_steps_per_learn = None  # benchmark hook: stop the hot loop after this many steps
+        self._step_hook = None           # benchmark hook: called as hook(step_index, engine) around each step
         self._engine = None
 
         self.n_cells, self.n_genes = adata.shape
@@ -693,7 +694,7 @@ class scDEF:
         limit = self.max_steps_per_learn
 
         epochs = range(n_epoch)
-        pbar = _tqdm(epochs, disable=shard.rank != 0) if _tqdm is not None else None
+        pbar = _tqdm(epochs, disable=shard.rank != 0 or self.logger.level >= 30) if _tqdm is not None else None
         try:
             for epoch in (pbar if pbar is not None else epochs):
                 if stop_gene_budgets_after_burnin and not gene_budgets_frozen and total_epochs >= min_epochs:
@@ -703,6 +704,8 @@ class scDEF:
                 stream.new_epoch()
                 n_it = 0
                 for it in range(num_batches):
+                    if self._step_hook is not None:
+                        self._step_hook(steps_done, eng, stream)
                     step_counter += 1
                     noise = NoiseSpec.philox(self.seed or 0, step_counter, self.noise_coupling)
                     idx, Xb, n_glob = stream.batch(it)
@@ -782,6 +785,8 @@ class scDEF:
         if stop_message is not None:
             self.logger.info(stop_message)
         self._noise_step = step_counter
+        if self._step_hook is not None:
+            self._step_hook(steps_done, eng, stream)
 
         self._device_summaries = eng.posterior()
         self._pull_params()
