@@ -117,8 +117,12 @@ PhiloxKey make_key(const scdef_noise* nz) {
   return k;
 }
 
+bool tc_ok(const scdef_ctx* c) {
+  return lik_tc_supported(c->K0, c->d.n_genes, c->d.n_batches) && !c->d.w_prior_shape[0] && !c->d.w_prior_rate[0];
+}
+
 int resolve_lik_impl(const scdef_ctx* c, int requested) {
-  if (requested == SCDEF_LIK_AUTO) return lik_tc_supported(c->K0, c->d.n_genes, c->d.n_batches) ? SCDEF_LIK_TC : SCDEF_LIK_SIMT;
+  if (requested == SCDEF_LIK_AUTO) return tc_ok(c) ? SCDEF_LIK_TC : SCDEF_LIK_SIMT;
   return requested;
 }
 
@@ -224,7 +228,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
   if (B > 0 && !call->X_batch && !ctx->d.X) return fail(ctx, SCDEF_EINVAL, "no counts: X_batch and desc.X are both null");
   if (((uintptr_t)workspace & 15) != 0) return fail(ctx, SCDEF_EALIGN, "workspace not 16-byte aligned");
   const int lik_impl = resolve_lik_impl(ctx, call->lik_impl);
-  if (lik_impl == SCDEF_LIK_TC && !lik_tc_supported(ctx->K0, ctx->d.n_genes, ctx->d.n_batches))
+  if (lik_impl == SCDEF_LIK_TC && !tc_ok(ctx))
     return fail(ctx, SCDEF_EUNSUPPORTED, "tcgen05 likelihood kernel does not take K0=%d", ctx->K0);
   const Plan plan = make_plan(ctx, B < 1 ? 1 : B, S, lik_impl);
   if (plan.total > workspace_bytes)
@@ -405,49 +409,56 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     }
     if ((rc = check_launch(ctx, "k_hier"))) return rc;
 
-    // ---- likelihood ----------------------------------------------------------------------------
-    if (lik_on) {
-      const float* Xp = call->X_batch ? call->X_batch : d.X;
-      const int64_t* idx_x = call->X_batch ? nullptr : call->indices;
+  }
+
+  // ---- likelihood (+ the whole W_0 path in tcgen05 mode) --------------------------------------------
+  {
+    const float* Xp = call->X_batch ? call->X_batch : d.X;
+    const int64_t* idx_x = call->X_batch ? nullptr : call->indices;
+    const bool lik_run = lik_on && B > 0;
+    if (lik_run) {
       k_x_lgamma<<<(B + 7) / 8, 256, 0, st>>>(Xp, idx_x, d.x_lgamma_rowsum, call->indices, B, G, scale, loss_out);
       if ((rc = check_launch(ctx, "k_x_lgamma"))) return rc;
-      if (tc) {
-        LikTcArgs a;
-        memset(&a, 0, sizeof(a));
-        a.mu_W0 = params->W[0]; a.rho_W0 = params->W[0] + (long long)K0 * G;
-        a.eps_W0 = explicit_noise ? noise->eps_W[0] : nullptr;
-        a.key = key; a.tag = all.b[BLK_W].tag;
-        a.smp_z0 = smp(BLK_Z); a.smp_c = smp(BLK_C); a.smp_s = smp(BLK_S);
-        a.smp_tau = smp(BLK_TAU); a.smp_om = smp(BLK_OM);
-        a.X = Xp; a.idx_x = idx_x; a.idx = call->indices; a.batch_id = d.batch_id;
-        a.G_z0 = Gb(BLK_Z); a.G_c = Gb(BLK_C); a.G_s = Gb(BLK_S);
-        a.G_tau = Gb(BLK_TAU); a.G_om = Gb(BLK_OM);
-        a.gmu_W0 = grads->W[0]; a.grho_W0 = grads->W[0] ? grads->W[0] + (long long)K0 * G : nullptr;
-        a.P = d.w_prior_shape[0]; a.R = d.w_prior_rate[0];
-        a.P_scalar = d.w_prior_shape_scalar[0]; a.R_scalar = d.w_prior_rate_scalar[0];
-        a.use_brd = d.use_brd; a.B = B; a.G = G; a.K0 = K0; a.nb = nb; a.pass = pass; a.S = S;
-        a.scale = scale; a.global_weight = gw; a.anneal = anneal; a.w0_stopped = st0;
-        a.ws = ws + plan.tc_off; a.ws_bytes = plan.tc_bytes;
-        {
-          ProfScope ps(ctx, SCDEF_PROF_LIK, st);
-          rc = lik_tc_launch(a, loss_out, ctx->sm_count, st);
-        }
-        if (rc) return fail(ctx, rc, "lik_tc_launch failed");
-        if ((rc = check_launch(ctx, "k_lik_tc"))) return rc;
-      } else {
-        LikArgs a;
-        memset(&a, 0, sizeof(a));
-        a.smp_z0 = smp(BLK_Z); a.smp_W0 = smp(BLK_W); a.smp_c = smp(BLK_C); a.smp_s = smp(BLK_S);
-        a.X = Xp; a.idx_x = idx_x; a.idx = call->indices; a.batch_id = d.batch_id;
-        a.G_z0 = Gb(BLK_Z); a.G_c = Gb(BLK_C); a.G_W0 = Gb(BLK_W); a.G_s = Gb(BLK_S);
-        a.B = B; a.G = G; a.K0 = K0; a.nb = nb; a.pass = pass; a.scale = scale;
-        size_t smem = ((size_t)LT * (K0 + 1) + (size_t)K0 * LW_LD + (size_t)LT * LQ_LD) * sizeof(float);
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_lik_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dim3 grid((G + LT - 1) / LT, (B + LT - 1) / LT, S);
+    }
+    if (tc) {
+      LikTcArgs a;
+      memset(&a, 0, sizeof(a));
+      a.mu_W0 = params->W[0]; a.rho_W0 = params->W[0] + (long long)K0 * G;
+      a.eps_W0 = explicit_noise ? noise->eps_W[0] : nullptr;
+      a.key = key; a.tag = all.b[BLK_W].tag;
+      a.smp_z0 = smp(BLK_Z); a.smp_c = smp(BLK_C); a.smp_s = smp(BLK_S);
+      a.smp_tau = smp(BLK_TAU); a.smp_om = smp(BLK_OM);
+      a.X = Xp; a.idx_x = idx_x; a.idx = call->indices; a.batch_id = d.batch_id;
+      a.G_z0 = Gb(BLK_Z); a.G_c = Gb(BLK_C); a.G_s = Gb(BLK_S);
+      a.G_tau = Gb(BLK_TAU); a.G_om = Gb(BLK_OM);
+      a.gmu_W0 = grads->W[0]; a.grho_W0 = grads->W[0] ? grads->W[0] + (long long)K0 * G : nullptr;
+      a.P = d.w_prior_shape[0]; a.R = d.w_prior_rate[0];
+      a.P_scalar = d.w_prior_shape_scalar[0]; a.R_scalar = d.w_prior_rate_scalar[0];
+      a.use_brd = d.use_brd; a.B = B; a.G = G; a.K0 = K0; a.nb = nb; a.pass = pass; a.S = S;
+      a.scale = scale; a.global_weight = gw; a.anneal = anneal; a.w0_stopped = st0; a.lik_on = lik_run;
+      a.ws = ws + plan.tc_off; a.ws_bytes = plan.tc_bytes;
+      {
+        ProfScope ps(ctx, SCDEF_PROF_LIK, st);
+        rc = lik_tc_launch(a, loss_out, ctx->sm_count, st);
+      }
+      ctx->launches += 4;
+      if (rc) return fail(ctx, rc, "lik_tc_launch failed (%d)", rc);
+      if ((rc = check_launch(ctx, "k_lik_tc"))) return rc;
+    } else if (lik_run) {
+      LikArgs a;
+      memset(&a, 0, sizeof(a));
+      a.smp_z0 = smp(BLK_Z); a.smp_W0 = smp(BLK_W); a.smp_c = smp(BLK_C); a.smp_s = smp(BLK_S);
+      a.X = Xp; a.idx_x = idx_x; a.idx = call->indices; a.batch_id = d.batch_id;
+      a.G_z0 = Gb(BLK_Z); a.G_c = Gb(BLK_C); a.G_W0 = Gb(BLK_W); a.G_s = Gb(BLK_S);
+      a.B = B; a.G = G; a.K0 = K0; a.nb = nb; a.pass = pass; a.scale = scale;
+      size_t smem = ((size_t)LT * (K0 + 1) + (size_t)K0 * LW_LD + (size_t)LT * LQ_LD) * sizeof(float);
+      if (smem > 48 * 1024) cudaFuncSetAttribute(k_lik_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      dim3 grid((G + LT - 1) / LT, (B + LT - 1) / LT, S);
+      {
         ProfScope ps(ctx, SCDEF_PROF_LIK, st);
         k_lik_simt<<<grid, 256, smem, st>>>(a, S, loss_out);
-        if ((rc = check_launch(ctx, "k_lik_simt"))) return rc;
       }
+      if ((rc = check_launch(ctx, "k_lik_simt"))) return rc;
     }
   }
 
@@ -459,7 +470,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     auto add = [&](int blk) {
       const BlockDesc& b = all.b[blk];
       if (!b.gmu || b.rows * b.cols == 0) return;
-      if (tc && blk == BLK_W && lik_on && B > 0 && global_pass) return;  // written by the fused kernel
+      if (tc && blk == BLK_W) return;  // written by the fused tcgen05 path
       t.b[t.n++] = b;
       size_t n = (size_t)b.rows * b.cols;
       if (n > max_el) max_el = n;
@@ -601,6 +612,9 @@ int scdef_posterior(scdef_ctx* ctx, const scdef_blocks* params, const scdef_bloc
   k_posterior<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t);
   return check_launch(ctx, "k_posterior");
 }
+
+/* bring-up hook (not part of the public header): dump the tcgen05 rate tile R as (S,B,G) */
+void scdef_debug_tc_dump(float* p) { lik_tc_set_debug(p); }
 
 int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam, void* cuda_stream) {
   if (!X || n_rows < 0 || n_genes < 1) return SCDEF_EINVAL;

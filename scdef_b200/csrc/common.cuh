@@ -47,22 +47,26 @@ struct NoiseTag {
   uint32_t a, b;
 };
 
-// Two standard normals for the element pair (2*pair, 2*pair+1) of block `tag`, MC sample `s`.
-__device__ __forceinline__ float2 philox_normal2(PhiloxKey key, NoiseTag tag, uint32_t s, uint32_t pair) {
-  uint4 r = philox4x32_10(make_uint4(pair, tag.a, tag.b, s), key);
-  // u in (0,1): (x + 0.5) * 2^-32
-  float u1 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f;
-  float u2 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
-  u1 = fminf(u1, 0.99999994f);
-  float rad = sqrtf(-2.0f * __logf(u1));
-  float sn, cs;
-  __sincosf(6.283185307179586f * u2, &sn, &cs);
-  return make_float2(rad * cs, rad * sn);
+// Four standard normals for the elements (4*quad .. 4*quad+3) of block `tag`, MC sample `s`:
+// one Philox call, two Box-Muller pairs.
+__device__ __forceinline__ float4 philox_normal4(PhiloxKey key, NoiseTag tag, uint32_t s, uint32_t quad) {
+  uint4 r = philox4x32_10(make_uint4(quad, tag.a, tag.b, s), key);
+  const float k = 2.3283064365386963e-10f;  // 2^-32; u in (0,1): (x + 0.5) * 2^-32
+  float u1 = fminf(((float)r.x + 0.5f) * k, 0.99999994f);
+  float u2 = ((float)r.y + 0.5f) * k;
+  float u3 = fminf(((float)r.z + 0.5f) * k, 0.99999994f);
+  float u4 = ((float)r.w + 0.5f) * k;
+  float ra = sqrtf(-2.0f * __logf(u1)), rb = sqrtf(-2.0f * __logf(u3));
+  float sa, ca, sb, cb;
+  __sincosf(6.283185307179586f * u2, &sa, &ca);
+  __sincosf(6.283185307179586f * u4, &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
 }
 
 __device__ __forceinline__ float philox_normal(PhiloxKey key, NoiseTag tag, uint32_t s, uint32_t elem) {
-  float2 n = philox_normal2(key, tag, s, elem >> 1);
-  return (elem & 1u) ? n.y : n.x;
+  float4 n = philox_normal4(key, tag, s, elem >> 2);
+  uint32_t c = elem & 3u;
+  return c == 0 ? n.x : (c == 1 ? n.y : (c == 2 ? n.z : n.w));
 }
 
 // ---------------------------------------------------------------------------------------

@@ -1,8 +1,791 @@
-// tcgen05 / TMEM fused likelihood kernel (placeholder until the kernel lands).
+// Fused Poisson-likelihood kernel on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// Math (reference `_scdef.py:2096-2136` + the W_0 parts of 2012-2045):
+//   W^s = clip(exp(mu~ + sigma eps^s))            generated IN the kernel, never written to HBM
+//   R   = z0^s W^s      (tcgen05.mma, split-bf16: hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM)
+//   Lambda = c_n s_{b(n),g} R,  ll = sum x log Lambda - Lambda,  E = x - Lambda,  Q = E / R
+//   LOCAL : dz0 = Q W^T  (second MMA, accumulated in TMEM over the CTA's gene tiles)
+//   GLOBAL: dW  = z0^T Q (second MMA), then  d mu += W (.) dW,  d rho += W (.) dW (.) sigma eps
+// The cells x genes rate matrix lives only in TMEM / registers.
+//
+// Shared-memory operand tiles use the no-swizzle UMMA canonical layout: "core matrices" of
+// 8 rows x 16 bytes (8 bf16), row r of the matrix at +16*r.  A tile [rows][cols] is a grid of
+// core matrices at  (row/8)*RS + (col/8)*128.  The SAME bytes serve as a K-major operand when
+// the contiguous dimension is the contraction dimension (LBO = 128, SBO = RS) and as an MN-major
+// operand when it is not (SBO = 128, LBO = RS), so z, W and Q are each stored once:
+//   z [cell][k0] : A of MMA1 (K-major)   and A of the GLOBAL dW MMA (MN-major, M = k0)
+//   W [k0][gene] : B of MMA1 (MN-major)  and B of the LOCAL dz MMA  (K-major,  N = k0)
+//   Q [cell][gene]: A of the LOCAL dz MMA (K-major) and B of the GLOBAL dW MMA (MN-major)
+// Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+#include <cuda_bf16.h>
+
 #include "lik_tc.cuh"
 
 namespace scdef {
-bool lik_tc_supported(int, int, int) { return false; }
-size_t lik_tc_workspace_bytes(int, int, int, int, int) { return 0; }
-int lik_tc_launch(const LikTcArgs&, double*, int, cudaStream_t) { return SCDEF_EUNSUPPORTED; }
+
+namespace {
+
+constexpr int TG = 64;    // genes per tile (MMA N of the rate GEMM)
+constexpr int CB = 256;   // cells per block: two M=128 halves
+constexpr int NT = 256;   // threads per CTA (8 warps)
+constexpr int MAX_NB = 8; // batches handled by the shared-memory column accumulators
+constexpr int SM_TARGET = 148;
+constexpr uint32_t W_RS = 1024, Q_RS = 1024;  // row-group strides of the W and Q tiles (8 col groups x 128 B)
+constexpr float V_LO_M = 1.0001e-15f, V_HI_M = 0.9999e15f;  // "inside the sample clip" with a margin for hi+lo rounding
+constexpr float LOG_V_LO = -34.538776394910684f, LOG_V_HI = 34.538776394910684f;
+
+__device__ float* g_dbg_R = nullptr;  // bring-up hook: when set, R is dumped as (S,B,G)
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  // start address [0,14), leading byte offset [16,30), stride byte offset [32,46) (all >>4),
+  // version = 1 at [46,48), no swizzle (layout_type = 0 at [61,64))
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  // c_format f32 (1<<4), a/b format bf16 (1<<7, 1<<10), a_major bit 15, b_major bit 16, N>>3 at 17, M>>4 at 24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split 8 floats into bf16 hi and lo = bf16(x - hi), packed as two 16-byte vectors
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// ---- shared-memory plan -------------------------------------------------------------------------
+struct Smem {
+  uint32_t z_hi, z_lo, w_hi, w_lo, q_hi, q_lo, misc, total;
+  uint32_t z_rs;  // row-group stride of the z tile
+};
+__host__ __device__ inline Smem plan_smem(int KP) {
+  Smem s;
+  s.z_rs = (uint32_t)(KP / 8) * 128u;
+  uint32_t zp = 32u * s.z_rs, wp = (uint32_t)(KP / 8) * W_RS, qp = 32u * Q_RS;
+  s.z_hi = 0; s.z_lo = zp; s.w_hi = 2 * zp; s.w_lo = 2 * zp + wp; s.q_hi = 2 * zp + 2 * wp; s.q_lo = s.q_hi + qp;
+  s.misc = s.q_lo + qp;
+  s.total = s.misc + 4096;
+  return s;
+}
+struct Misc {                  // lives at Smem.misc
+  uint64_t bar;
+  uint32_t tmem_base, pad;
+  double red[32];
+  float colacc[MAX_NB][TG];    // sum_k ctilde[b][k] W[k][g]      (GLOBAL)
+  float rowU[128], rowW[128];  // per-k0 sums of log W and W over the tile's genes (prior terms)
+};
+
+struct Geom {
+  int KP, n_tiles, n_chunks, NG, tiles_per_range, n_cblocks;
+};
+
+// ---- (a) z0^s block -> bf16 hi/lo planes --------------------------------------------------------
+__device__ __forceinline__ void load_z(const LikTcArgs& a, uint8_t* sm, const Smem& L, int KP, int s, int j0) {
+  const int nchunk = KP / 8;
+  const float* zs = a.smp_z0 + (long long)s * a.B * a.K0;
+  for (int t = threadIdx.x; t < CB * nchunk; t += NT) {
+    const int r = t % CB, c = t / CB;
+    const int j = j0 + r, k = c * 8;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = 0.f;
+    if (j < a.B) {
+      const float* row = zs + (long long)j * a.K0;
+      if ((a.K0 & 3) == 0) {
+        if (k + 4 <= a.K0) { float4 v = *reinterpret_cast<const float4*>(row + k); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+        if (k + 8 <= a.K0) { float4 v = *reinterpret_cast<const float4*>(row + k + 4); x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (k + e < a.K0) x[e] = row[k + e];
+      }
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const uint32_t off = (uint32_t)(r >> 3) * L.z_rs + (uint32_t)c * 128u + (uint32_t)(r & 7) * 16u;
+    *reinterpret_cast<uint4*>(sm + L.z_hi + off) = hi;
+    *reinterpret_cast<uint4*>(sm + L.z_lo + off) = lo;
+  }
+}
+
+// ---- (b) W^s tile: sample, split, and the per-row / per-column side sums ---------------------------
+template <bool GLOBAL>
+__device__ __forceinline__ void gen_w(const LikTcArgs& a, uint8_t* sm, const Smem& L, Misc* mi, int KP, int s, int g0,
+                                      const float* ctilde_s, bool want_stats, bool want_col) {
+  const int nkg = KP / 8;
+  for (int t = threadIdx.x; t < nkg * 64; t += NT) {
+    const int kk = t & 7, cg = (t >> 3) & 7, kg = t >> 6;
+    const int k = kg * 8 + kk, g = g0 + cg * 8;
+    float w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] = 0.f;
+    if (k < a.K0 && g < a.G) {
+      const long long base = (long long)k * a.G + g;
+      float4 m0 = *reinterpret_cast<const float4*>(a.mu_W0 + base), m1 = *reinterpret_cast<const float4*>(a.mu_W0 + base + 4);
+      float4 r0 = *reinterpret_cast<const float4*>(a.rho_W0 + base), r1 = *reinterpret_cast<const float4*>(a.rho_W0 + base + 4);
+      float4 e0, e1;
+      if (a.eps_W0) {
+        const float* ep = a.eps_W0 + (long long)s * a.K0 * a.G + base;
+        e0 = *reinterpret_cast<const float4*>(ep); e1 = *reinterpret_cast<const float4*>(ep + 4);
+      } else {
+        e0 = philox_normal4(a.key, a.tag, (uint32_t)s, (uint32_t)(base >> 2));
+        e1 = philox_normal4(a.key, a.tag, (uint32_t)s, (uint32_t)(base >> 2) + 1u);
+      }
+      const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      const float rho[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      const float ep[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+      float su = 0.f, sw = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float mut = fminf(fmaxf(mu[e], LOG_1E_10), LOG_1E6);
+        float sig = __expf(fminf(fmaxf(rho[e], LOG_1E_10), LOG_1E10));
+        float u = fminf(fmaxf(fmaf(sig, ep[e], mut), LOG_V_LO), LOG_V_HI);
+        w[e] = __expf(u);
+        su += u;
+        sw += w[e];
+      }
+      if (want_stats) {
+        atomicAdd(&mi->rowU[k], su);
+        atomicAdd(&mi->rowW[k], sw);
+      }
+      if (GLOBAL && want_col) {
+        for (int b = 0; b < a.nb; ++b) {
+          const float ct = ctilde_s[b * a.K0 + k];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) atomicAdd(&mi->colacc[b][cg * 8 + e], ct * w[e]);
+        }
+      }
+    }
+    uint4 hi, lo;
+    split8(w, hi, lo);
+    const uint32_t off = (uint32_t)kg * W_RS + (uint32_t)cg * 128u + (uint32_t)kk * 16u;
+    *reinterpret_cast<uint4*>(sm + L.w_hi + off) = hi;
+    *reinterpret_cast<uint4*>(sm + L.w_lo + off) = lo;
+  }
+}
+
+// ---- MMA1: R[half] = z W  (M=128, N=64, K=KP; 3 split products per k-step) ---------------------------
+__device__ __forceinline__ void issue_mma1(uint32_t sbase, const Smem& L, int KP, uint32_t tmem, int nh) {
+  const uint32_t idesc = umma_idesc(128, TG, /*A K-major*/ 0, /*B MN-major*/ 1);
+  for (int h = 0; h < nh; ++h) {
+    uint32_t acc = 0;
+    for (int ks = 0; ks < KP / 16; ++ks) {
+      const uint32_t za = (uint32_t)h * 16u * L.z_rs + (uint32_t)ks * 256u;
+      const uint32_t wb = (uint32_t)ks * 2u * W_RS;
+      const uint64_t a_hi = umma_desc(sbase + L.z_hi + za, 128u, L.z_rs), a_lo = umma_desc(sbase + L.z_lo + za, 128u, L.z_rs);
+      const uint64_t b_hi = umma_desc(sbase + L.w_hi + wb, W_RS, 128u), b_lo = umma_desc(sbase + L.w_lo + wb, W_RS, 128u);
+      umma_bf16(tmem + h * TG, a_lo, b_hi, idesc, acc);
+      umma_bf16(tmem + h * TG, a_hi, b_lo, idesc, 1u);
+      umma_bf16(tmem + h * TG, a_hi, b_hi, idesc, 1u);
+      acc = 1u;
+    }
+  }
+}
+
+// ---- epilogue 1: R -> (ll, E sums, Q tile) ---------------------------------------------------------------
+struct RowCtx {
+  bool valid;
+  float c;
+  const float* srow;
+  const float* xrow;
+};
+
+__device__ __forceinline__ void epilogue1(const LikTcArgs& a, uint8_t* sm, const Smem& L, uint32_t tmem, int s, int j0, int g0,
+                                          int nh, const RowCtx& rc, float& ll, float& esum) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = warp >> 2;
+  if (h >= nh) return;
+  const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+  const int r = h * 128 + (int)lane_base + lane;
+  const int j = j0 + r;
+#pragma unroll 1
+  for (int cc = 0; cc < TG / 16; ++cc) {
+    float R[16];
+    tmem_ld16(tmem + (lane_base << 16) + (uint32_t)(h * TG + cc * 16), R);
+    float q[16];
+    const int gb = g0 + cc * 16;
+#pragma unroll
+    for (int v4 = 0; v4 < 4; ++v4) {
+      const int g = gb + v4 * 4;
+      float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      const bool ok = rc.valid && (g < a.G);
+      if (ok) {
+        x4 = *reinterpret_cast<const float4*>(rc.xrow + g);
+        s4 = *reinterpret_cast<const float4*>(rc.srow + g);
+      }
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float Rv = R[v4 * 4 + e];
+        float qq = 0.f;
+        if (ok) {
+          const float lam = rc.c * ss[e] * Rv;
+          const float E = xs[e] - lam;
+          qq = __fdividef(E, Rv);
+          ll += (xs[e] > 0.f ? xs[e] * __logf(lam) : 0.f) - lam;
+          esum += E;
+        }
+        q[v4 * 4 + e] = qq;
+      }
+    }
+    if (g_dbg_R && rc.valid) {
+      for (int e = 0; e < 16; ++e)
+        if (gb + e < a.G) g_dbg_R[((long long)s * a.B + j) * a.G + gb + e] = R[e];
+    }
+    uint4 hi, lo;
+    const uint32_t off = (uint32_t)(r >> 3) * Q_RS + (uint32_t)(r & 7) * 16u;
+    split8(q, hi, lo);
+    *reinterpret_cast<uint4*>(sm + L.q_hi + off + (uint32_t)(cc * 2) * 128u) = hi;
+    *reinterpret_cast<uint4*>(sm + L.q_lo + off + (uint32_t)(cc * 2) * 128u) = lo;
+    split8(q + 8, hi, lo);
+    *reinterpret_cast<uint4*>(sm + L.q_hi + off + (uint32_t)(cc * 2 + 1) * 128u) = hi;
+    *reinterpret_cast<uint4*>(sm + L.q_lo + off + (uint32_t)(cc * 2 + 1) * 128u) = lo;
+  }
+}
+
+__device__ __forceinline__ RowCtx make_row(const LikTcArgs& a, int s, int j0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = (warp >> 2) * 128 + (warp & 3) * 32 + lane;
+  const int j = j0 + r;
+  RowCtx rc;
+  rc.valid = j < a.B;
+  rc.c = 1.f; rc.srow = a.smp_s; rc.xrow = a.X;
+  if (rc.valid) {
+    rc.c = a.smp_c[(long long)s * a.B + j];
+    const int b = a.batch_id[a.idx[j]];
+    rc.srow = a.smp_s + ((long long)s * a.nb + b) * a.G;
+    rc.xrow = a.X + (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
+  }
+  return rc;
+}
+
+// flush the per-tile W row sums (prior terms of W_0) to the (S,K0,2) global accumulators
+__device__ __forceinline__ void flush_rowstats(const LikTcArgs& a, Misc* mi, float* rowstats, int s) {
+  for (int k = threadIdx.x; k < a.K0; k += NT) {
+    atomicAdd(&rowstats[((long long)s * a.K0 + k) * 2 + 0], mi->rowU[k]);
+    atomicAdd(&rowstats[((long long)s * a.K0 + k) * 2 + 1], mi->rowW[k]);
+    mi->rowU[k] = 0.f;
+    mi->rowW[k] = 0.f;
+  }
+}
+
+struct TcScratch {
+  float* rowstats;  // (S,K0,2)
+  float* ctilde;    // (S,nb,K0)
+  float* colsumX;   // (nb,G)
+  float* part;      // LOCAL: (S,NG,B,K0)   GLOBAL: (n_chunks,2,K0,G)
+};
+
+// =====================================================================================================
+// LOCAL pass: CTA = (MC sample s, gene range, cell block).  dz0 accumulates in TMEM over the range.
+// =====================================================================================================
+__global__ void __launch_bounds__(NT, 1) k_lik_tc_local(const LikTcArgs a, const Geom gm, const TcScratch ws, double* loss_out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const int KP = gm.KP;
+  const Smem L = plan_smem(KP);
+  Misc* mi = reinterpret_cast<Misc*>(sm + L.misc);
+  const uint32_t sbase = smem_u32(sm);
+  const int s = blockIdx.x / gm.NG, range = blockIdx.x % gm.NG;
+  const int j0 = blockIdx.y * CB;
+  const int rows = min(CB, a.B - j0), nh = rows > 128 ? 2 : 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool want_stats = (blockIdx.y == 0);  // W-row sums are cell-independent: count them once
+
+  if (threadIdx.x == 0) { mbar_init(&mi->bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  for (int i = threadIdx.x; i < 128; i += NT) { mi->rowU[i] = 0.f; mi->rowW[i] = 0.f; }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&mi->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  load_z(a, sm, L, KP, s, j0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = mi->tmem_base;
+  const uint32_t tmem_dz = tmem + 2 * TG;  // two halves of KP columns each
+  const RowCtx rc = make_row(a, s, j0);
+  const uint32_t idesc2 = umma_idesc(128, KP, 0, 0);
+  float ll = 0.f, esum = 0.f;
+  uint32_t phase = 0;
+  const int t_begin = range * gm.tiles_per_range, t_end = min(gm.n_tiles, t_begin + gm.tiles_per_range);
+
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int g0 = tile * TG;
+    gen_w<false>(a, sm, L, mi, KP, s, g0, nullptr, want_stats, false);
+    fence_async_smem();
+    __syncthreads();
+    if (want_stats) flush_rowstats(a, mi, ws.rowstats, s);
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      issue_mma1(sbase, L, KP, tmem, nh);
+      umma_commit(&mi->bar);
+    }
+    mbar_wait(&mi->bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    epilogue1(a, sm, L, tmem, s, j0, g0, nh, rc, ll, esum);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      for (int h = 0; h < nh; ++h) {
+        uint32_t acc = (tile > t_begin) ? 1u : 0u;
+        for (int ks = 0; ks < TG / 16; ++ks) {
+          const uint32_t qa = (uint32_t)h * 16u * Q_RS + (uint32_t)ks * 256u, wb = (uint32_t)ks * 256u;
+          const uint64_t a_hi = umma_desc(sbase + L.q_hi + qa, 128u, Q_RS), a_lo = umma_desc(sbase + L.q_lo + qa, 128u, Q_RS);
+          const uint64_t b_hi = umma_desc(sbase + L.w_hi + wb, 128u, W_RS), b_lo = umma_desc(sbase + L.w_lo + wb, 128u, W_RS);
+          umma_bf16(tmem_dz + h * KP, a_lo, b_hi, idesc2, acc);
+          umma_bf16(tmem_dz + h * KP, a_hi, b_lo, idesc2, 1u);
+          umma_bf16(tmem_dz + h * KP, a_hi, b_hi, idesc2, 1u);
+          acc = 1u;
+        }
+      }
+      umma_commit(&mi->bar);
+    }
+    mbar_wait(&mi->bar, phase);  // W and Q tiles are free again, dz is up to date
+    phase ^= 1;
+    tc_fence_after();
+  }
+
+  // dz0 partial of this (s, range): TMEM -> global
+  {
+    const int h = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+    const int j = j0 + h * 128 + (int)lane_base + lane;
+    if (h < nh) {
+      float* dst = ws.part + (((long long)s * gm.NG + range) * a.B + j) * a.K0;
+      for (int cc = 0; cc < KP / 16; ++cc) {
+        float v[16];
+        tmem_ld16(tmem_dz + (lane_base << 16) + (uint32_t)(h * KP + cc * 16), v);
+        if (j < a.B) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (cc * 16 + e < a.K0) dst[cc * 16 + e] = v[e];
+        }
+      }
+      if (rc.valid) atomicAdd(&a.G_c[(long long)s * a.B + j], a.scale * esum / rc.c);
+    }
+  }
+  double tot = block_sum_d((double)ll, mi->red);
+  if (threadIdx.x == 0) atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)a.S);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// =====================================================================================================
+// GLOBAL pass: CTA = (gene tile, chunk of MC samples).  d mu / d rho of the tile accumulate in
+// registers over the chunk; per sample dW = z0^T Q comes from the second MMA.
+// =====================================================================================================
+__global__ void __launch_bounds__(NT, 1) k_lik_tc_global(const LikTcArgs a, const Geom gm, const TcScratch ws, double* loss_out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const int KP = gm.KP;
+  const Smem L = plan_smem(KP);
+  Misc* mi = reinterpret_cast<Misc*>(sm + L.misc);
+  const uint32_t sbase = smem_u32(sm);
+  const int tile = blockIdx.x % gm.n_tiles, chunk = blockIdx.x / gm.n_tiles;
+  const int g0 = tile * TG;
+  const int s_begin = (int)((long long)chunk * a.S / gm.n_chunks), s_end = (int)((long long)(chunk + 1) * a.S / gm.n_chunks);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool lik = a.lik_on != 0;
+
+  if (threadIdx.x == 0) { mbar_init(&mi->bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  for (int i = threadIdx.x; i < 128; i += NT) { mi->rowU[i] = 0.f; mi->rowW[i] = 0.f; }
+  for (int i = threadIdx.x; i < MAX_NB * TG; i += NT) (&mi->colacc[0][0])[i] = 0.f;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&mi->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = mi->tmem_base;
+  const uint32_t tmem_dw = tmem + 2 * TG;
+
+  // epilogue-2 ownership: k0 row = lane of the warp's TMEM quarter, 32 genes of the tile
+  const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+  const int k2 = (int)lane_base + lane, ch = warp >> 2;
+  const bool own = k2 < a.K0;
+  float acc_mu[32], acc_rho[32], mut[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    acc_mu[e] = 0.f; acc_rho[e] = 0.f;
+    const int g = g0 + ch * 32 + e;
+    mut[e] = (own && g < a.G) ? fminf(fmaxf(a.mu_W0[(long long)k2 * a.G + g], LOG_1E_10), LOG_1E6) : 0.f;
+  }
+  const uint32_t idesc2 = umma_idesc(128, TG, 1, 1);
+  float ll = 0.f;
+  uint32_t phase = 0;
+
+  for (int s = s_begin; s < s_end; ++s) {
+    gen_w<true>(a, sm, L, mi, KP, s, g0, ws.ctilde + (long long)s * a.nb * a.K0, true, lik);
+    if (lik) {
+      for (int cb = 0; cb < gm.n_cblocks; ++cb) {
+        const int j0 = cb * CB;
+        const int rows = min(CB, a.B - j0), nh = rows > 128 ? 2 : 1;
+        load_z(a, sm, L, KP, s, j0);
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          tc_fence_after();
+          issue_mma1(sbase, L, KP, tmem, nh);
+          umma_commit(&mi->bar);
+        }
+        const RowCtx rc = make_row(a, s, j0);
+        mbar_wait(&mi->bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        float esum = 0.f;
+        epilogue1(a, sm, L, tmem, s, j0, g0, nh, rc, ll, esum);
+        if (nh == 1 && warp >= 4) {  // rows 128..255 of the Q tile feed the dW MMA: keep them zero
+          const int r = 128 + (warp & 3) * 32 + lane;
+          const uint32_t off = (uint32_t)(r >> 3) * Q_RS + (uint32_t)(r & 7) * 16u;
+          for (int c8 = 0; c8 < 8; ++c8) {
+            *reinterpret_cast<uint4*>(sm + L.q_hi + off + c8 * 128u) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(sm + L.q_lo + off + c8 * 128u) = make_uint4(0, 0, 0, 0);
+          }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          tc_fence_after();
+          uint32_t acc = cb > 0 ? 1u : 0u;
+          const int nks = (rows + 15) / 16;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t za = (uint32_t)ks * 2u * L.z_rs, qb = (uint32_t)ks * 2u * Q_RS;
+            const uint64_t a_hi = umma_desc(sbase + L.z_hi + za, L.z_rs, 128u), a_lo = umma_desc(sbase + L.z_lo + za, L.z_rs, 128u);
+            const uint64_t b_hi = umma_desc(sbase + L.q_hi + qb, Q_RS, 128u), b_lo = umma_desc(sbase + L.q_lo + qb, Q_RS, 128u);
+            umma_bf16(tmem_dw, a_lo, b_hi, idesc2, acc);
+            umma_bf16(tmem_dw, a_hi, b_lo, idesc2, 1u);
+            umma_bf16(tmem_dw, a_hi, b_hi, idesc2, 1u);
+            acc = 1u;
+          }
+          umma_commit(&mi->bar);
+        }
+        mbar_wait(&mi->bar, phase);  // z and Q tiles are free again
+        phase ^= 1;
+        tc_fence_after();
+      }
+    } else {
+      __syncthreads();
+    }
+
+    // ---- epilogue 2: fold dW (and the W_0 prior gradient) into d mu, d rho ----
+    if (!a.w0_stopped) {
+      float dW[32];
+      if (lik) {
+        tmem_ld16(tmem_dw + (lane_base << 16) + (uint32_t)(ch * 32), dW);
+        tmem_ld16(tmem_dw + (lane_base << 16) + (uint32_t)(ch * 32 + 16), dW + 16);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) dW[e] = 0.f;
+      }
+      if (own) {
+        float A = a.P_scalar, Bm = a.R_scalar * (float)a.K0;
+        if (a.use_brd) {
+          const float tau = a.smp_tau[(long long)s * a.K0 + k2], om = a.smp_om[(long long)s * a.K0 + k2];
+          A = a.P_scalar / tau;
+          Bm = a.R_scalar * (float)a.K0 / (tau * om);
+        }
+        const uint32_t woff = (uint32_t)(k2 >> 3) * W_RS + (uint32_t)(k2 & 7) * 16u;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const uint4 hv = *reinterpret_cast<const uint4*>(sm + L.w_hi + woff + (uint32_t)(ch * 4 + c8) * 128u);
+          const uint4 lv = *reinterpret_cast<const uint4*>(sm + L.w_lo + woff + (uint32_t)(ch * 4 + c8) * 128u);
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+#pragma unroll
+            for (int q2 = 0; q2 < 2; ++q2) {
+              const int e = c8 * 8 + p * 2 + q2;
+              const float W = q2 ? (bf16hi(hw[p]) + bf16hi(lw[p])) : (bf16lo(hw[p]) + bf16lo(lw[p]));
+              if (W > V_LO_M && W < V_HI_M) {
+                const float t = a.scale * dW[e] * W + a.global_weight * (A - 1.f - Bm * W);
+                acc_mu[e] += t;
+                acc_rho[e] = fmaf(t, __logf(W) - mut[e], acc_rho[e]);
+              }
+            }
+          }
+        }
+      }
+    }
+    // ---- per-(tile, s) side outputs: W_0 row sums, likelihood gradient of the gene scale ----
+    tc_fence_before();
+    __syncthreads();
+    flush_rowstats(a, mi, ws.rowstats, s);
+    if (lik && threadIdx.x < TG && g0 + (int)threadIdx.x < a.G && a.G_s) {
+      const int g = g0 + threadIdx.x;
+      for (int b = 0; b < a.nb; ++b) {
+        const float sv = a.smp_s[((long long)s * a.nb + b) * a.G + g];
+        a.G_s[((long long)s * a.nb + b) * a.G + g] += a.scale * (ws.colsumX[(long long)b * a.G + g] / sv - mi->colacc[b][threadIdx.x]);
+        mi->colacc[b][threadIdx.x] = 0.f;
+      }
+    }
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  // partial sums of this chunk: (n_chunks, 2, K0, G)
+  if (own && !a.w0_stopped) {
+    float* pm = ws.part + (((long long)chunk * 2 + 0) * a.K0 + k2) * a.G + g0 + ch * 32;
+    float* pr = ws.part + (((long long)chunk * 2 + 1) * a.K0 + k2) * a.G + g0 + ch * 32;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      if (g0 + ch * 32 + e < a.G) {
+        *reinterpret_cast<float4*>(pm + e) = make_float4(acc_mu[e], acc_mu[e + 1], acc_mu[e + 2], acc_mu[e + 3]);
+        *reinterpret_cast<float4*>(pr + e) = make_float4(acc_rho[e], acc_rho[e + 1], acc_rho[e + 2], acc_rho[e + 3]);
+      }
+    }
+  }
+  double tot = block_sum_d((double)ll, mi->red);
+  if (threadIdx.x == 0) atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)a.S);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---- small companions ---------------------------------------------------------------------------------
+// ctilde[s][b][k] = sum_{n in batch b} c_n^s z_nk^s ;  grid = S, block = 128
+__global__ void __launch_bounds__(128) k_tc_ctilde(const LikTcArgs a, float* ctilde) {
+  const int s = blockIdx.x, k = threadIdx.x;
+  if (k >= a.K0) return;
+  float acc[MAX_NB];
+#pragma unroll
+  for (int b = 0; b < MAX_NB; ++b) acc[b] = 0.f;
+  for (int j = 0; j < a.B; ++j) {
+    const float v = a.smp_c[(long long)s * a.B + j] * a.smp_z0[((long long)s * a.B + j) * a.K0 + k];
+    const int bj = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
+#pragma unroll
+    for (int b = 0; b < MAX_NB; ++b) acc[b] += (b == bj) ? v : 0.f;
+  }
+  for (int b = 0; b < a.nb; ++b) ctilde[((long long)s * a.nb + b) * a.K0 + k] = acc[b];
+}
+
+// colsumX[b][g] = sum_{n in batch b} x_ng ;  grid over genes
+__global__ void __launch_bounds__(256) k_tc_colsum(const LikTcArgs a, float* colsumX) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.G) return;
+  float acc[MAX_NB];
+#pragma unroll
+  for (int b = 0; b < MAX_NB; ++b) acc[b] = 0.f;
+  for (int j = 0; j < a.B; ++j) {
+    const float x = a.X[(a.idx_x ? a.idx_x[j] : (long long)j) * a.G + g];
+    const int bj = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
+#pragma unroll
+    for (int b = 0; b < MAX_NB; ++b) acc[b] += (b == bj) ? x : 0.f;
+  }
+  for (int b = 0; b < a.nb; ++b) colsumX[(long long)b * a.G + g] = acc[b];
+}
+
+// G_z0[s][j][k] += scale * sum_r part[s][r][j][k]
+__global__ void __launch_bounds__(256) k_tc_dz_reduce(const LikTcArgs a, const float* part, int NG) {
+  const long long per = (long long)a.B * a.K0, total = (long long)a.S * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / per, r = i - s * per;
+    float acc = 0.f;
+    for (int q = 0; q < NG; ++q) acc += part[(s * NG + q) * per + r];
+    a.G_z0[i] += a.scale * acc;
+  }
+}
+
+// W_0 prior: value (both passes) and the brd / ard gradients (GLOBAL) from the row sums
+// U = sum_g log W, Ws = sum_g W  (`_scdef.py:2014-2028`).  one thread per (s,k)
+__global__ void __launch_bounds__(128) k_tc_w0_prior(const LikTcArgs a, const float* rowstats, double* loss_out) {
+  __shared__ double red[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double val = 0.0;
+  if (i < a.S * a.K0) {
+    const float U = rowstats[2 * (long long)i], Ws = rowstats[2 * (long long)i + 1];
+    const float Gn = (float)a.G;
+    float A = a.P_scalar, Bm = a.R_scalar * (float)a.K0, tau = 1.f, om = 1.f;
+    if (a.use_brd) {
+      tau = a.smp_tau[i]; om = a.smp_om[i];
+      A = a.P_scalar / tau;
+      Bm = a.R_scalar * (float)a.K0 / (tau * om);
+    }
+    const float lB = logf(Bm);
+    val = (double)((A - 1.f) * U - Bm * Ws) + (double)Gn * (double)(A * lB - lgammaf(A));
+    if (a.use_brd && a.pass == SCDEF_PASS_GLOBAL) {
+      const float dA = U - Gn * (digammaf(A) - lB);
+      const float dB = -Ws + Gn * A / Bm;
+      a.G_tau[i] += a.global_weight * (dA * (-A / tau) + dB * (-Bm / tau));
+      a.G_om[i] += a.global_weight * dB * (-Bm / om);
+    }
+  }
+  double tot = block_sum_d(val, red);
+  if (threadIdx.x == 0) atomicAdd(&loss_out[1], -tot * (double)a.global_weight / (double)a.S);
+}
+
+// W_0: entropy value (both passes) and, in the GLOBAL pass, the final (mu, rho) gradients from the
+// chunk partials.
+__global__ void __launch_bounds__(256) k_tc_w0_final(const LikTcArgs a, const float* part, int n_chunks, double* loss_out) {
+  __shared__ double red[32];
+  const long long n = (long long)a.K0 * a.G;
+  const float wH = a.anneal * a.global_weight, invS = 1.f / (float)a.S;
+  double ent = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float mu = a.mu_W0[i], rho = a.rho_W0[i];
+    ent += (double)(fminf(fmaxf(mu, LOG_1E_10), LOG_1E6) + fminf(fmaxf(rho, LOG_1E_10), LOG_1E10) + HALF_LOG_2PI_PLUS_HALF);
+    if (a.pass == SCDEF_PASS_GLOBAL && a.gmu_W0) {
+      float dmu = 0.f, drho = 0.f;
+      if (!a.w0_stopped) {
+        float gv = 0.f, gve = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          gv += part[((long long)c * 2 + 0) * n + i];
+          gve += part[((long long)c * 2 + 1) * n + i];
+        }
+        const bool in_mu = mu >= LOG_1E_10 && mu <= LOG_1E6, in_rho = rho >= LOG_1E_10 && rho <= LOG_1E10;
+        dmu = in_mu ? -(gv * invS + wH) : 0.f;
+        drho = in_rho ? -(gve * invS + wH) : 0.f;
+      }
+      a.gmu_W0[i] = dmu;
+      a.grho_W0[i] = drho;
+    }
+  }
+  double tot = block_sum_d(ent, red);
+  if (threadIdx.x == 0) atomicAdd(&loss_out[1], -tot * (double)wH);
+}
+
+int round_up16(int k) { return (k + 15) / 16 * 16; }
+
+// work decomposition: balance (items / 148 SMs rounded up) x (work per item)
+Geom make_geom(int B, int S, int K0, int G) {
+  Geom g;
+  g.KP = round_up16(K0);
+  g.n_tiles = (G + TG - 1) / TG;
+  g.n_cblocks = B > 0 ? (B + CB - 1) / CB : 1;
+  double best = 1e30;
+  g.n_chunks = 1;
+  for (int c = 1; c <= S; ++c) {
+    const long long items = (long long)g.n_tiles * c;
+    const double waves = (double)((items + SM_TARGET - 1) / SM_TARGET);
+    const double cost = waves * (double)((S + c - 1) / c) * (1.0 + 0.002 * c) + 0.02 * c;  // mild penalty per partial buffer
+    if (cost < best - 1e-9) { best = cost; g.n_chunks = c; }
+  }
+  best = 1e30;
+  g.NG = 1;
+  for (int ng = 1; ng <= g.n_tiles; ++ng) {
+    const long long items = (long long)S * ng * g.n_cblocks;
+    const double waves = (double)((items + SM_TARGET - 1) / SM_TARGET);
+    const double cost = waves * ((double)((g.n_tiles + ng - 1) / ng) + 1.5) + 0.01 * ng;  // +1.5: per-item z load / dz drain
+    if (cost < best - 1e-9) { best = cost; g.NG = ng; }
+  }
+  g.tiles_per_range = (g.n_tiles + g.NG - 1) / g.NG;
+  g.NG = (g.n_tiles + g.tiles_per_range - 1) / g.tiles_per_range;
+  return g;
+}
+
+size_t a256(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace
+
+bool lik_tc_supported(int K0, int G, int nb) { return K0 >= 1 && K0 <= 128 && (G % 8) == 0 && nb >= 1 && nb <= MAX_NB; }
+
+size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb) {
+  const Geom g = make_geom(B, S, K0, G);
+  size_t part_local = (size_t)S * g.NG * (size_t)(B > 0 ? B : 1) * K0 * 4;
+  size_t part_global = (size_t)g.n_chunks * 2 * K0 * G * 4;
+  return a256((size_t)S * K0 * 2 * 4) + a256((size_t)S * nb * K0 * 4) + a256((size_t)nb * G * 4) +
+         a256(part_local > part_global ? part_local : part_global) + 1024;
+}
+
+void lik_tc_set_debug(float* p) { cudaMemcpyToSymbol(g_dbg_R, &p, sizeof(p)); }
+
+int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStream_t st) {
+  (void)sm_count;
+  LikTcArgs a = a_in;
+  if (!lik_tc_supported(a.K0, a.G, a.nb) || a.P || a.R) return SCDEF_EUNSUPPORTED;
+  if (a.B <= 0) a.lik_on = 0;
+  const Geom g = make_geom(a.B, a.S, a.K0, a.G);
+  char* w = (char*)a.ws;
+  TcScratch ws;
+  ws.rowstats = (float*)w; w += a256((size_t)a.S * a.K0 * 2 * 4);
+  ws.ctilde = (float*)w;   w += a256((size_t)a.S * a.nb * a.K0 * 4);
+  ws.colsumX = (float*)w;  w += a256((size_t)a.nb * a.G * 4);
+  ws.part = (float*)w;
+  if ((size_t)(w - (char*)a.ws) > a.ws_bytes) return SCDEF_EWORKSPACE;
+  const Smem L = plan_smem(g.KP);
+  const bool global_pass = a.pass == SCDEF_PASS_GLOBAL;
+  cudaMemsetAsync(ws.rowstats, 0, (size_t)a.S * a.K0 * 2 * 4, st);
+  if (global_pass) {
+    if (a.lik_on) {
+      k_tc_ctilde<<<a.S, 128, 0, st>>>(a, ws.ctilde);
+      k_tc_colsum<<<(a.G + 255) / 256, 256, 0, st>>>(a, ws.colsumX);
+    }
+    cudaFuncSetAttribute(k_lik_tc_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(a, g, ws, loss_out);
+  } else {
+    if (a.lik_on) {
+      cudaFuncSetAttribute(k_lik_tc_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+      k_lik_tc_local<<<dim3(a.S * g.NG, g.n_cblocks), NT, L.total, st>>>(a, g, ws, loss_out);
+      long long total = (long long)a.S * a.B * a.K0;
+      int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+      k_tc_dz_reduce<<<blocks, 256, 0, st>>>(a, ws.part, g.NG);
+    } else {
+      // value only: the GLOBAL kernel without likelihood produces the W_0 row sums
+      LikTcArgs v = a;
+      v.w0_stopped = 1;
+      cudaFuncSetAttribute(k_lik_tc_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+      k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(v, g, ws, loss_out);
+    }
+  }
+  k_tc_w0_prior<<<(a.S * a.K0 + 127) / 128, 128, 0, st>>>(a, ws.rowstats, loss_out);
+  k_tc_w0_final<<<148 * 4, 256, 0, st>>>(a, ws.part, g.n_chunks, loss_out);
+  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+}
+
 }  // namespace scdef

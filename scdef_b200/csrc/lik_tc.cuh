@@ -37,6 +37,7 @@ struct LikTcArgs {
 
 bool lik_tc_supported(int K0, int G, int nb);
 size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb);
+void lik_tc_set_debug(float* p);
 int lik_tc_launch(const LikTcArgs& a, double* loss_out, int sm_count, cudaStream_t st);
 
 }  // namespace scdef
