@@ -8,14 +8,15 @@ namespace scdef {
 
 struct AdamHyper {
   float lr, b1, b2, eps, bc1, bc2;  // bc = 1 - b^t
+  float inv_bc1, inv_bc2;           // reciprocals (the kernels multiply instead of dividing)
 };
 
 __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, const AdamHyper& h,
                                           bool write_p, float clip_hi) {
   m = h.b1 * m + (1.f - h.b1) * g;
   v = h.b2 * v + (1.f - h.b2) * g * g;
-  float mh = m / h.bc1, vh = v / h.bc2;
-  float pn = p - h.lr * (mh / (sqrtf(vh) + h.eps));
+  float mh = m * h.inv_bc1, vh = v * h.inv_bc2;
+  float pn = p - h.lr * __fdividef(mh, sqrtf(vh) + h.eps);
   if (write_p) p = fminf(pn, clip_hi);  // clip_params lower bounds (-1e10) can never bind after fminf of finite
 }
 
@@ -66,52 +67,70 @@ struct AdamLocalArgs {
   int frozen_lo[SCDEF_MAX_LAYERS], frozen_hi[SCDEF_MAX_LAYERS];
 };
 
-template <int VEC>
+// grid = (blocks, 2 halves); flat vector index over one half (N*C/VEC vectors), two vectors per
+// thread per iteration so that six 16-byte loads are in flight before the first dependent use.
+template <int VEC, typename IdxT>
 __global__ void __launch_bounds__(256) k_adam_local(const AdamLocalArgs a, const AdamHyper h) {
-  const long long half = a.N * a.C;
-  const long long nvec = 2 * half / VEC;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nvec;
-       t += (long long)gridDim.x * blockDim.x) {
-    const long long i = t * VEC;
-    const int hsel = i >= half;
-    const long long rem = i - (hsel ? half : 0);
-    const long long n = rem / a.C;
-    const int c0 = (int)(rem - n * a.C);
-    float p[VEC], m[VEC], v[VEC], g[VEC];
-    if (VEC == 4) {
-      float4 p4 = *reinterpret_cast<const float4*>(a.p + i);
-      float4 m4 = *reinterpret_cast<const float4*>(a.m + i);
-      float4 v4 = *reinterpret_cast<const float4*>(a.v + i);
-      p[0] = p4.x; p[1] = p4.y; p[2] = p4.z; p[3] = p4.w;
-      m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
-      v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
-    } else {
-      p[0] = a.p[i]; m[0] = a.m[i]; v[0] = a.v[i];
-    }
-    const int slot = a.row_slot[n];
+  const IdxT C = (IdxT)a.C, CV = (IdxT)(a.C / VEC);
+  const IdxT nvec = (IdxT)a.N * CV;
+  const int hsel = blockIdx.y;
+  const long long hoff = (long long)hsel * a.N * a.C;
+  float* __restrict__ P = a.p + hoff;
+  float* __restrict__ M = a.m + hoff;
+  float* __restrict__ V = a.v + hoff;
+  const float* __restrict__ G = a.g + (long long)hsel * a.B * a.C;
+  const IdxT stride = (IdxT)gridDim.x * blockDim.x;
+  for (IdxT t0 = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; t0 < nvec; t0 += 2 * stride) {
+    float p[2][VEC], m[2][VEC], v[2][VEC], g[2][VEC];
+    IdxT tt[2] = {t0, t0 + stride};
+    int c0[2], slot[2];
+    bool live[2];
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) g[q] = 0.f;
-    if (slot >= 0) {
-      const float* gp = a.g + ((long long)hsel * a.B + slot) * a.C + c0;
+    for (int u = 0; u < 2; ++u) {
+      live[u] = tt[u] < nvec;
+      if (!live[u]) continue;
+      const IdxT i = tt[u] * VEC;
       if (VEC == 4) {
-        float4 g4 = *reinterpret_cast<const float4*>(gp);
-        g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+        float4 p4 = *reinterpret_cast<const float4*>(P + i), m4 = *reinterpret_cast<const float4*>(M + i),
+               v4 = *reinterpret_cast<const float4*>(V + i);
+        p[u][0] = p4.x; p[u][1] = p4.y; p[u][2] = p4.z; p[u][VEC - 1] = p4.w;
+        m[u][0] = m4.x; m[u][1] = m4.y; m[u][2] = m4.z; m[u][VEC - 1] = m4.w;
+        v[u][0] = v4.x; v[u][1] = v4.y; v[u][2] = v4.z; v[u][VEC - 1] = v4.w;
       } else {
-        g[0] = gp[0];
+        p[u][0] = P[i]; m[u][0] = M[i]; v[u][0] = V[i];
       }
+      const IdxT n = tt[u] / CV;
+      c0[u] = (int)((tt[u] - n * CV) * VEC);
+      slot[u] = a.row_slot[n];
     }
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) {
-      bool frozen = false;
-      for (int f = 0; f < a.n_frozen; ++f) frozen |= (c0 + q >= a.frozen_lo[f]) && (c0 + q < a.frozen_hi[f]);
-      adam_elem(p[q], m[q], v[q], g[q], h, !frozen, INFINITY);
-    }
-    if (VEC == 4) {
-      *reinterpret_cast<float4*>(a.p + i) = make_float4(p[0], p[1], p[2], p[3]);
-      *reinterpret_cast<float4*>(a.m + i) = make_float4(m[0], m[1], m[2], m[3]);
-      *reinterpret_cast<float4*>(a.v + i) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-      a.p[i] = p[0]; a.m[i] = m[0]; a.v[i] = v[0];
+    for (int u = 0; u < 2; ++u) {
+      if (!live[u]) continue;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) g[u][q] = 0.f;
+      if (slot[u] >= 0) {
+        const float* gp = G + (long long)slot[u] * C + c0[u];
+        if (VEC == 4) {
+          float4 g4 = *reinterpret_cast<const float4*>(gp);
+          g[u][0] = g4.x; g[u][1] = g4.y; g[u][2] = g4.z; g[u][VEC - 1] = g4.w;
+        } else {
+          g[u][0] = gp[0];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        bool frozen = false;
+        for (int f = 0; f < a.n_frozen; ++f) frozen |= (c0[u] + q >= a.frozen_lo[f]) && (c0[u] + q < a.frozen_hi[f]);
+        adam_elem(p[u][q], m[u][q], v[u][q], g[u][q], h, !frozen, INFINITY);
+      }
+      const IdxT i = tt[u] * VEC;
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(P + i) = make_float4(p[u][0], p[u][1], p[u][2], p[u][VEC - 1]);
+        *reinterpret_cast<float4*>(M + i) = make_float4(m[u][0], m[u][1], m[u][2], m[u][VEC - 1]);
+        *reinterpret_cast<float4*>(V + i) = make_float4(v[u][0], v[u][1], v[u][2], v[u][VEC - 1]);
+      } else {
+        P[i] = p[u][0]; M[i] = m[u][0]; V[i] = v[u][0];
+      }
     }
   }
 }

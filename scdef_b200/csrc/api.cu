@@ -506,6 +506,8 @@ int scdef_adam_local(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blo
   h.lr = lr; h.b1 = b1; h.b2 = b2; h.eps = eps;
   h.bc1 = (float)(1.0 - pow((double)b1, (double)step));
   h.bc2 = (float)(1.0 - pow((double)b2, (double)step));
+  h.inv_bc1 = (float)(1.0 / (1.0 - pow((double)b1, (double)step)));
+  h.inv_bc2 = (float)(1.0 / (1.0 - pow((double)b2, (double)step)));
   const long long N = ctx->d.n_cells;
   if (N == 0) return SCDEF_OK;
   int rc;
@@ -525,16 +527,22 @@ int scdef_adam_local(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blo
     if (which && freeze_z_layers)
       for (int l = 0; l < ctx->L; ++l)
         if (freeze_z_layers[l]) { a.frozen_lo[a.n_frozen] = ctx->off[l]; a.frozen_hi[a.n_frozen] = ctx->off[l + 1]; a.n_frozen++; }
-    const long long total = 2 * N * a.C;
-    const bool vec4 = (a.C % 4 == 0) && (((uintptr_t)a.p | (uintptr_t)a.m | (uintptr_t)a.v | (uintptr_t)a.g) % 16 == 0);
-    long long nthreads = vec4 ? total / 4 : total;
-    long long blocks = (nthreads + 255) / 256;
-    long long cap = (long long)ctx->sm_count * 32;
+    const long long half = N * a.C;
+    const bool vec4 = (a.C % 4 == 0) && ((half * 4) % 16 == 0) && ((long long)B * a.C * 4 % 16 == 0) &&
+                      (((uintptr_t)a.p | (uintptr_t)a.m | (uintptr_t)a.v | (uintptr_t)a.g) % 16 == 0);
+    const long long nvec = vec4 ? half / 4 : half;
+    long long blocks = (nvec + 511) / 512;  // two vectors per thread
+    const long long cap = (long long)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const bool small = nvec < (1LL << 30);
     {
       ProfScope ps(ctx, which ? SCDEF_PROF_ADAM_LOCAL : SCDEF_PROF_ADAM_LOCAL_C, st);
-      if (vec4) k_adam_local<4><<<(unsigned)blocks, 256, 0, st>>>(a, h);
-      else k_adam_local<1><<<(unsigned)blocks, 256, 0, st>>>(a, h);
+      dim3 grid((unsigned)blocks, 2);
+      if (vec4 && small) k_adam_local<4, uint32_t><<<grid, 256, 0, st>>>(a, h);
+      else if (vec4) k_adam_local<4, unsigned long long><<<grid, 256, 0, st>>>(a, h);
+      else if (small) k_adam_local<1, uint32_t><<<grid, 256, 0, st>>>(a, h);
+      else k_adam_local<1, unsigned long long><<<grid, 256, 0, st>>>(a, h);
     }
     if ((rc = check_launch(ctx, "k_adam_local"))) return rc;
   }
@@ -555,6 +563,8 @@ int scdef_adam_global(scdef_ctx* ctx, const scdef_blocks* params, const scdef_bl
   h.lr = lr; h.b1 = b1; h.b2 = b2; h.eps = eps;
   h.bc1 = (float)(1.0 - pow((double)b1, (double)step));
   h.bc2 = (float)(1.0 - pow((double)b2, (double)step));
+  h.inv_bc1 = (float)(1.0 / (1.0 - pow((double)b1, (double)step)));
+  h.inv_bc2 = (float)(1.0 / (1.0 - pow((double)b2, (double)step)));
   AdamSegTable t;
   memset(&t, 0, sizeof(t));
   int max_n = 1;

@@ -733,7 +733,7 @@ size_t a256(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace
 
-bool lik_tc_supported(int K0, int G, int nb) { return K0 >= 1 && K0 <= 128 && (G % 8) == 0 && nb >= 1 && nb <= MAX_NB; }
+bool lik_tc_supported(int K0, int G, int nb) { return K0 >= 1 && K0 <= 112 && (G % 8) == 0 && nb >= 1 && nb <= MAX_NB; }
 
 size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb) {
   const Geom g = make_geom(B, S, K0, G);

@@ -98,3 +98,22 @@ def test_ragged_shapes_and_single_layer():
 
 def test_default_ladder_and_s1():
     _run_case(130, 90, (20, 10, 5, 1), 1, 64, 1, [0, 0, 0, 0])
+
+
+@pytest.mark.parametrize("lik_impl", [1, 2])
+def test_both_likelihood_kernels_on_tc_eligible_shapes(lik_impl):
+    """SIMT (fp32 CUDA cores) and tcgen05 (split-bf16 tensor cores) agree with the oracle."""
+    _run_case(200, 120, (10, 5, 2), 1, 200, 3, [0, 0, 0], lik_impl=lik_impl)
+    _run_case(300, 200, (100, 60, 30, 10), 1, 257, 2, [0, 0, 0, 0], lik_impl=lik_impl)       # 2 cell blocks
+    _run_case(160, 72, (24, 6, 1), 3, 130, 2, [0, 0, 0], lik_impl=lik_impl)                   # batches
+    _run_case(100, 64, (12, 4), 1, 50, 2, [1, 0], lik_impl=lik_impl)                          # likelihood off
+    _run_case(100, 64, (12, 4), 1, 50, 2, [0, 1], use_brd=False, lik_impl=lik_impl)
+    _run_case(600, 136, (112, 3), 2, 520, 1, [0, 0], lik_impl=lik_impl, resident=False)       # K0 = 112, 3 cell blocks
+    _run_case(96, 64, (9, 5, 2), 1, 40, 3, [0, 0, 0], marg=True, couple=True, lik_impl=lik_impl)
+
+
+def test_tc_request_on_unsupported_shape_fails_loudly():
+    from scdef_b200.engine import ScdefError
+
+    with pytest.raises(ScdefError, match="tcgen05"):
+        _run_case(96, 70, (9, 5, 2), 1, 40, 3, [0, 0, 0], lik_impl=2)   # G % 8 != 0
