@@ -18,6 +18,7 @@
 //   Q [cell][gene]: A of the LOCAL dz MMA (K-major) and B of the GLOBAL dW MMA (MN-major)
 // Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "lik_tc.cuh"
 
@@ -459,13 +460,9 @@ __global__ void __launch_bounds__(NT, 1) k_lik_tc_global(const LikTcArgs a, cons
   const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
   const int k2 = (int)lane_base + lane, ch = warp >> 2;
   const bool own = k2 < a.K0;
-  float acc_mu[32], acc_rho[32], mut[32];
+  float acc_mu[32], acc_rho[32];
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    acc_mu[e] = 0.f; acc_rho[e] = 0.f;
-    const int g = g0 + ch * 32 + e;
-    mut[e] = (own && g < a.G) ? fminf(fmaxf(a.mu_W0[(long long)k2 * a.G + g], LOG_1E_10), LOG_1E6) : 0.f;
-  }
+  for (int e = 0; e < 32; ++e) { acc_mu[e] = 0.f; acc_rho[e] = 0.f; }
   const uint32_t idesc2 = umma_idesc(128, TG, 1, 1);
   float ll = 0.f;
   uint32_t phase = 0;
@@ -556,7 +553,7 @@ __global__ void __launch_bounds__(NT, 1) k_lik_tc_global(const LikTcArgs a, cons
               if (W > V_LO_M && W < V_HI_M) {
                 const float t = a.scale * dW[e] * W + a.global_weight * (A - 1.f - Bm * W);
                 acc_mu[e] += t;
-                acc_rho[e] = fmaf(t, __logf(W) - mut[e], acc_rho[e]);
+                acc_rho[e] = fmaf(t, __logf(W), acc_rho[e]);  // minus mu~ * acc_mu, folded in k_tc_w0_final
               }
             }
           }
@@ -597,6 +594,8 @@ __global__ void __launch_bounds__(NT, 1) k_lik_tc_global(const LikTcArgs a, cons
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
+
+#include "lik_tc_pipe.cuh"
 
 // ---- small companions ---------------------------------------------------------------------------------
 // ctilde[s][b][k] = sum_{n in batch b} c_n^s z_nk^s ;  grid = S, block = 128
@@ -683,11 +682,13 @@ __global__ void __launch_bounds__(256) k_tc_w0_final(const LikTcArgs a, const fl
     if (a.pass == SCDEF_PASS_GLOBAL && a.gmu_W0) {
       float dmu = 0.f, drho = 0.f;
       if (!a.w0_stopped) {
-        float gv = 0.f, gve = 0.f;
+        float gv = 0.f, glw = 0.f;
         for (int c = 0; c < n_chunks; ++c) {
           gv += part[((long long)c * 2 + 0) * n + i];
-          gve += part[((long long)c * 2 + 1) * n + i];
+          glw += part[((long long)c * 2 + 1) * n + i];
         }
+        // sum_s t_s * (sigma eps)_s  with  sigma eps = log W - mu~
+        const float gve = glw - fminf(fmaxf(mu, LOG_1E_10), LOG_1E6) * gv;
         const bool in_mu = mu >= LOG_1E_10 && mu <= LOG_1E6, in_rho = rho >= LOG_1E_10 && rho <= LOG_1E10;
         dmu = in_mu ? -(gv * invS + wH) : 0.f;
         drho = in_rho ? -(gve * invS + wH) : 0.f;
@@ -759,6 +760,8 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   ws.part = (float*)w;
   if ((size_t)(w - (char*)a.ws) > a.ws_bytes) return SCDEF_EWORKSPACE;
   const Smem L = plan_smem(g.KP);
+  const PipeSmem PL = plan_pipe_smem(g.KP);
+  static const bool mono = getenv("SCDEF_TC_MONO") != nullptr;  // A/B switch: the monolithic v2a kernels
   const bool global_pass = a.pass == SCDEF_PASS_GLOBAL;
   cudaMemsetAsync(ws.rowstats, 0, (size_t)a.S * a.K0 * 2 * 4, st);
   if (global_pass) {
@@ -766,12 +769,22 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       k_tc_ctilde<<<a.S, 128, 0, st>>>(a, ws.ctilde);
       k_tc_colsum<<<(a.G + 255) / 256, 256, 0, st>>>(a, ws.colsumX);
     }
-    cudaFuncSetAttribute(k_lik_tc_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-    k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(a, g, ws, loss_out);
+    if (a.lik_on && !mono) {
+      cudaFuncSetAttribute(k_lik_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+      k_lik_pipe<true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+    } else {
+      cudaFuncSetAttribute(k_lik_tc_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+      k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(a, g, ws, loss_out);
+    }
   } else {
     if (a.lik_on) {
-      cudaFuncSetAttribute(k_lik_tc_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-      k_lik_tc_local<<<dim3(a.S * g.NG, g.n_cblocks), NT, L.total, st>>>(a, g, ws, loss_out);
+      if (!mono) {
+        cudaFuncSetAttribute(k_lik_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+        k_lik_pipe<false><<<dim3(a.S * g.NG, g.n_cblocks), PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+      } else {
+        cudaFuncSetAttribute(k_lik_tc_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        k_lik_tc_local<<<dim3(a.S * g.NG, g.n_cblocks), NT, L.total, st>>>(a, g, ws, loss_out);
+      }
       long long total = (long long)a.S * a.B * a.K0;
       int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
       k_tc_dz_reduce<<<blocks, 256, 0, st>>>(a, ws.part, g.NG);

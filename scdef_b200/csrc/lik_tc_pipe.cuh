@@ -1,0 +1,542 @@
+// Warp-specialised, mbarrier-pipelined version of the fused likelihood kernel (included by
+// lik_tc.cu inside its anonymous namespace; uses its PTX wrappers and layouts).
+//
+// One CTA = 13 warps:
+//   warps 0-3  PRODUCERS : sample the W^s tile (Philox / explicit eps -> bf16 hi/lo, UMMA layout) and,
+//                          in the GLOBAL pass, stage z0^s blocks; side sums for the W_0 prior / gene scale
+//   warps 4-11 EPILOGUE  : TMEM -> registers, Poisson terms, Q tile back to smem; GLOBAL: fold dW
+//   warp  12   MMA ISSUER: one thread issues every tcgen05.mma and tcgen05.commit
+// Work is cut into UNITS of 128 cells x 64 genes.  W tiles, z blocks and the R accumulators are
+// double-buffered, so generating tile/sample n+1, the tensor-core work of unit u+1 and the
+// epilogue of unit u overlap.  All hand-offs are mbarriers (full/empty pairs).
+//
+//   LOCAL  CTA = (MC sample s, gene range, 256-cell block): units = (tile, half); z static in smem;
+//          dz0[half] += Q W^T accumulates in TMEM over the tiles of the range.
+//   GLOBAL CTA = (gene tile, chunk of MC samples): units = (s, 128-cell block); dW[s&1] += z0^T Q over the
+//          blocks of s; epilogue 2 folds W.dW into per-thread d mu / d rho accumulators over the chunk.
+#pragma once
+
+constexpr int PIPE_NT = 416;           // 13 warps
+constexpr int P_THREADS = 128, E_THREADS = 256;
+constexpr int UC = 128;                // cells per unit
+
+struct PipeSmem {
+  uint32_t z[2], w[2], q, misc, total;   // each z / w / q region = hi plane followed by lo plane
+  uint32_t z_rs, z_plane, w_plane, q_plane;
+};
+__host__ __device__ inline PipeSmem plan_pipe_smem(int KP) {
+  PipeSmem s;
+  s.z_rs = (uint32_t)(KP / 8) * 128u;
+  s.z_plane = 16u * s.z_rs;                 // 128 cells
+  s.w_plane = (uint32_t)(KP / 8) * W_RS;    // KP rows x 64 genes
+  s.q_plane = 16u * Q_RS;                   // 128 cells x 64 genes
+  uint32_t o = 0;
+  s.z[0] = o; o += 2 * s.z_plane;
+  s.z[1] = o; o += 2 * s.z_plane;
+  s.w[0] = o; o += 2 * s.w_plane;
+  s.w[1] = o; o += 2 * s.w_plane;
+  s.q = o; o += 2 * s.q_plane;
+  s.misc = o;
+  s.total = o + 8192;
+  return s;
+}
+
+struct PipeMisc {
+  uint64_t w_full[2], w_empty[2], z_full[2], z_empty[2], r_full[2], r_empty[2], q_full, q_empty, dw_full[2],
+      dw_empty[2], dz_full;
+  uint32_t tmem_base, pad;
+  double red[32];
+  float rowU[2][128], rowW[2][128];
+  float colacc[2][MAX_NB][TG];
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// ---- producers -------------------------------------------------------------------------------------
+// 128 cells x KP of z0^s (rows j0..j0+127) -> bf16 hi/lo planes; `nthr` cooperating threads, id `tid`
+__device__ __forceinline__ void pipe_load_z(const LikTcArgs& a, uint8_t* zbuf, uint32_t z_rs, uint32_t z_plane, int KP, int s,
+                                            int j0, int tid, int nthr) {
+  const int nchunk = KP / 8;
+  const float* zs = a.smp_z0 + (long long)s * a.B * a.K0;
+  const bool vec = (a.K0 & 3) == 0;
+  for (int t0 = tid; t0 < UC * nchunk; t0 += 4 * nthr) {
+    float x[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * nthr;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[u][e] = 0.f;
+      if (t < UC * nchunk) {
+        const int r = t % UC, c = t / UC, j = j0 + r, k = c * 8;
+        if (j < a.B) {
+          const float* row = zs + (long long)j * a.K0;
+          if (vec) {
+            if (k + 4 <= a.K0) { float4 v = *reinterpret_cast<const float4*>(row + k); x[u][0] = v.x; x[u][1] = v.y; x[u][2] = v.z; x[u][3] = v.w; }
+            if (k + 8 <= a.K0) { float4 v = *reinterpret_cast<const float4*>(row + k + 4); x[u][4] = v.x; x[u][5] = v.y; x[u][6] = v.z; x[u][7] = v.w; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (k + e < a.K0) x[u][e] = row[k + e];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * nthr;
+      if (t < UC * nchunk) {
+        const int r = t % UC, c = t / UC;
+        uint4 hi, lo;
+        split8(x[u], hi, lo);
+        const uint32_t off = (uint32_t)(r >> 3) * z_rs + (uint32_t)c * 128u + (uint32_t)(r & 7) * 16u;
+        *reinterpret_cast<uint4*>(zbuf + off) = hi;
+        *reinterpret_cast<uint4*>(zbuf + z_plane + off) = lo;
+      }
+    }
+  }
+}
+
+// W^s tile -> wbuf (hi/lo planes); row sums of (log W, W) and, GLOBAL, ctilde^T W into the stage's accumulators.
+template <bool GLOBAL>
+__device__ __forceinline__ void pipe_gen_w(const LikTcArgs& a, uint8_t* wbuf, uint32_t w_plane, PipeMisc* mi, int stage, int KP,
+                                           int s, int g0, const float* ctilde_s, bool want_stats, int tid) {
+  const int nkg = KP / 8;
+  const int kk = tid & 7, cg = (tid >> 3) & 7, lane = tid & 31;
+  const int g = g0 + cg * 8;
+  float col[MAX_NB][8];
+  if (GLOBAL) {
+#pragma unroll
+    for (int b = 0; b < MAX_NB; ++b)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) col[b][e] = 0.f;
+  }
+  for (int kg = tid >> 6; kg < nkg; kg += P_THREADS / 64) {
+    const int k = kg * 8 + kk;
+    float w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] = 0.f;
+    float su = 0.f, sw = 0.f;
+    if (k < a.K0 && g < a.G) {
+      const long long base = (long long)k * a.G + g;
+      float4 m0 = *reinterpret_cast<const float4*>(a.mu_W0 + base), m1 = *reinterpret_cast<const float4*>(a.mu_W0 + base + 4);
+      float4 r0 = *reinterpret_cast<const float4*>(a.rho_W0 + base), r1 = *reinterpret_cast<const float4*>(a.rho_W0 + base + 4);
+      float4 e0, e1;
+      if (a.eps_W0) {
+        const float* ep = a.eps_W0 + (long long)s * a.K0 * a.G + base;
+        e0 = *reinterpret_cast<const float4*>(ep); e1 = *reinterpret_cast<const float4*>(ep + 4);
+      } else {
+        e0 = philox_normal4(a.key, a.tag, (uint32_t)s, (uint32_t)(base >> 2));
+        e1 = philox_normal4(a.key, a.tag, (uint32_t)s, (uint32_t)(base >> 2) + 1u);
+      }
+      const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      const float rho[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      const float ep[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float mut = fminf(fmaxf(mu[e], LOG_1E_10), LOG_1E6);
+        float sig = __expf(fminf(fmaxf(rho[e], LOG_1E_10), LOG_1E10));
+        float u = fminf(fmaxf(fmaf(sig, ep[e], mut), LOG_V_LO), LOG_V_HI);
+        w[e] = __expf(u);
+        su += u;
+        sw += w[e];
+      }
+      if (GLOBAL) {
+#pragma unroll
+        for (int b = 0; b < MAX_NB; ++b) {
+          if (b < a.nb) {
+            const float ct = ctilde_s[b * a.K0 + k];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) col[b][e] = fmaf(ct, w[e], col[b][e]);
+          }
+        }
+      }
+    }
+    uint4 hi, lo;
+    split8(w, hi, lo);
+    const uint32_t off = (uint32_t)kg * W_RS + (uint32_t)cg * 128u + (uint32_t)kk * 16u;
+    *reinterpret_cast<uint4*>(wbuf + off) = hi;
+    *reinterpret_cast<uint4*>(wbuf + w_plane + off) = lo;
+    if (want_stats) {
+      // the 4 lanes {kk, kk+8, kk+16, kk+24} of this warp hold 4 gene chunks of the same row k
+      su += __shfl_xor_sync(0xffffffffu, su, 8); sw += __shfl_xor_sync(0xffffffffu, sw, 8);
+      su += __shfl_xor_sync(0xffffffffu, su, 16); sw += __shfl_xor_sync(0xffffffffu, sw, 16);
+      if (lane < 8 && k < a.K0) {
+        atomicAdd(&mi->rowU[stage][k], su);
+        atomicAdd(&mi->rowW[stage][k], sw);
+      }
+    }
+  }
+  if (GLOBAL) {
+    // reduce over the 8 rows kk held by lanes (lane & 7), then one atomic per (b, gene)
+#pragma unroll
+    for (int b = 0; b < MAX_NB; ++b) {
+      if (b < a.nb) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float v = col[b][e];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          if (kk == 0) atomicAdd(&mi->colacc[stage][b][cg * 8 + e], v);
+        }
+      }
+    }
+  }
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+template <bool GLOBAL>
+__global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, const Geom gm, const TcScratch ws, double* loss_out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const int KP = gm.KP;
+  const PipeSmem L = plan_pipe_smem(KP);
+  PipeMisc* mi = reinterpret_cast<PipeMisc*>(sm + L.misc);
+  const uint32_t sbase = smem_u32(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- work of this CTA ----
+  int s_fixed = 0, tile_fixed = 0, outer_begin, outer_end, j_block0 = 0, units_per_outer;
+  if (GLOBAL) {
+    tile_fixed = blockIdx.x % gm.n_tiles;
+    const int chunk = blockIdx.x / gm.n_tiles;
+    outer_begin = (int)((long long)chunk * a.S / gm.n_chunks);
+    outer_end = (int)((long long)(chunk + 1) * a.S / gm.n_chunks);
+    units_per_outer = (a.B + UC - 1) / UC;
+  } else {
+    s_fixed = blockIdx.x / gm.NG;
+    const int range = blockIdx.x % gm.NG;
+    outer_begin = range * gm.tiles_per_range;
+    outer_end = min(gm.n_tiles, outer_begin + gm.tiles_per_range);
+    j_block0 = blockIdx.y * CB;
+    units_per_outer = (min(CB, a.B - j_block0) > UC) ? 2 : 1;
+  }
+  const int n_outer = outer_end - outer_begin;
+  const int U = n_outer * units_per_outer;
+
+  // ---- prologue ----
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&mi->w_full[i], P_THREADS);
+      mbar_init(&mi->w_empty[i], GLOBAL ? E_THREADS : 1);
+      mbar_init(&mi->z_full[i], P_THREADS);
+      mbar_init(&mi->z_empty[i], 1);
+      mbar_init(&mi->r_full[i], 1);
+      mbar_init(&mi->r_empty[i], E_THREADS);
+      mbar_init(&mi->dw_full[i], 1);
+      mbar_init(&mi->dw_empty[i], E_THREADS);
+    }
+    mbar_init(&mi->q_full, E_THREADS);
+    mbar_init(&mi->q_empty, 1);
+    mbar_init(&mi->dz_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * 128; i += PIPE_NT) { (&mi->rowU[0][0])[i] = 0.f; (&mi->rowW[0][0])[i] = 0.f; }
+  for (int i = threadIdx.x; i < 2 * MAX_NB * TG; i += PIPE_NT) (&mi->colacc[0][0][0])[i] = 0.f;
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&mi->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (!GLOBAL) {  // z0^s of the 256-cell block is static: both halves staged once
+    for (int h = 0; h < units_per_outer; ++h)
+      pipe_load_z(a, sm + L.z[h], L.z_rs, L.z_plane, KP, s_fixed, j_block0 + h * UC, threadIdx.x, PIPE_NT);
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = mi->tmem_base;
+  const uint32_t tmem_acc2 = tmem + 2 * TG;  // LOCAL: dz[half] (KP cols each); GLOBAL: dW[stage] (TG cols each)
+
+  if (warp < 4) {
+    // =========================================== PRODUCERS ===========================================
+    const int tid = threadIdx.x;
+    const bool want_stats = GLOBAL ? true : (blockIdx.y == 0);
+    int u = 0;
+    for (int oi = 0; oi < n_outer; ++oi) {
+      const int st = oi & 1;
+      const int s = GLOBAL ? outer_begin + oi : s_fixed;
+      const int g0 = (GLOBAL ? tile_fixed : outer_begin + oi) * TG;
+      mbar_wait(&mi->w_empty[st], ((oi >> 1) & 1) ^ 1);
+      pipe_gen_w<GLOBAL>(a, sm + L.w[st], L.w_plane, mi, st, KP, s, g0,
+                         GLOBAL ? ws.ctilde + (long long)s * a.nb * a.K0 : nullptr, want_stats, tid);
+      fence_async_smem();
+      mbar_arrive(&mi->w_full[st]);
+      named_bar_sync(1, P_THREADS);
+      if (want_stats) {
+        for (int k = tid; k < a.K0; k += P_THREADS) {
+          atomicAdd(&ws.rowstats[((long long)s * a.K0 + k) * 2 + 0], mi->rowU[st][k]);
+          atomicAdd(&ws.rowstats[((long long)s * a.K0 + k) * 2 + 1], mi->rowW[st][k]);
+          mi->rowU[st][k] = 0.f;
+          mi->rowW[st][k] = 0.f;
+        }
+      }
+      if (GLOBAL && tid < TG) {
+        const int g = g0 + tid;
+        for (int b = 0; b < a.nb; ++b) {
+          if (g < a.G && a.G_s) {
+            const float sv = a.smp_s[((long long)s * a.nb + b) * a.G + g];
+            a.G_s[((long long)s * a.nb + b) * a.G + g] += a.scale * (ws.colsumX[(long long)b * a.G + g] / sv - mi->colacc[st][b][tid]);
+          }
+          mi->colacc[st][b][tid] = 0.f;
+        }
+      }
+      if (GLOBAL) {
+        for (int cb = 0; cb < units_per_outer; ++cb, ++u) {
+          const int zs = u & 1;
+          mbar_wait(&mi->z_empty[zs], ((u >> 1) & 1) ^ 1);
+          pipe_load_z(a, sm + L.z[zs], L.z_rs, L.z_plane, KP, s, cb * UC, tid, P_THREADS);
+          fence_async_smem();
+          mbar_arrive(&mi->z_full[zs]);
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // =========================================== MMA ISSUER ===========================================
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc(128, TG, 0, 1);
+      const uint32_t idesc2 = GLOBAL ? umma_idesc(128, TG, 1, 1) : umma_idesc(128, KP, 0, 0);
+      auto issue_mma1 = [&](int u) {
+        const int oi = u / units_per_outer, cb = u - oi * units_per_outer;
+        const int st = oi & 1, rs = u & 1, zb = GLOBAL ? (u & 1) : cb;
+        if (cb == 0) mbar_wait(&mi->w_full[st], (oi >> 1) & 1);
+        if (GLOBAL) mbar_wait(&mi->z_full[zb], (u >> 1) & 1);
+        mbar_wait(&mi->r_empty[rs], ((u >> 1) & 1) ^ 1);
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int ks = 0; ks < KP / 16; ++ks) {
+          const uint32_t za = sbase + L.z[zb] + (uint32_t)ks * 256u, wb = sbase + L.w[st] + (uint32_t)ks * 2u * W_RS;
+          const uint64_t a_hi = umma_desc(za, 128u, L.z_rs), a_lo = umma_desc(za + L.z_plane, 128u, L.z_rs);
+          const uint64_t b_hi = umma_desc(wb, W_RS, 128u), b_lo = umma_desc(wb + L.w_plane, W_RS, 128u);
+          umma_bf16(tmem + rs * TG, a_lo, b_hi, idesc1, acc);
+          umma_bf16(tmem + rs * TG, a_hi, b_lo, idesc1, 1u);
+          umma_bf16(tmem + rs * TG, a_hi, b_hi, idesc1, 1u);
+          acc = 1u;
+        }
+        umma_commit(&mi->r_full[rs]);
+      };
+      if (U > 0) issue_mma1(0);
+      for (int u = 0; u < U; ++u) {
+        if (u + 1 < U) issue_mma1(u + 1);
+        const int oi = u / units_per_outer, cb = u - oi * units_per_outer;
+        const int st = oi & 1;
+        mbar_wait(&mi->q_full, u & 1);
+        if (GLOBAL && cb == 0) mbar_wait(&mi->dw_empty[st], ((oi >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (GLOBAL) {
+          // dW[st] (+)= z0^T Q : A = z (MN-major, M = k0), B = Q (MN-major, N = genes), K = cells of the unit
+          const int rows = min(UC, a.B - cb * UC), nks = (rows + 15) / 16;
+          const int zb = u & 1;
+          uint32_t acc = cb > 0 ? 1u : 0u;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t za = sbase + L.z[zb] + (uint32_t)ks * 2u * L.z_rs, qb = sbase + L.q + (uint32_t)ks * 2u * Q_RS;
+            const uint64_t a_hi = umma_desc(za, L.z_rs, 128u), a_lo = umma_desc(za + L.z_plane, L.z_rs, 128u);
+            const uint64_t b_hi = umma_desc(qb, Q_RS, 128u), b_lo = umma_desc(qb + L.q_plane, Q_RS, 128u);
+            umma_bf16(tmem_acc2 + st * TG, a_lo, b_hi, idesc2, acc);
+            umma_bf16(tmem_acc2 + st * TG, a_hi, b_lo, idesc2, 1u);
+            umma_bf16(tmem_acc2 + st * TG, a_hi, b_hi, idesc2, 1u);
+            acc = 1u;
+          }
+          umma_commit(&mi->q_empty);
+          umma_commit(&mi->z_empty[zb]);
+          if (cb == units_per_outer - 1) umma_commit(&mi->dw_full[st]);
+        } else {
+          // dz[cb] (+)= Q W^T : A = Q (K-major), B = W (K-major, N = k0), K = genes of the tile
+          uint32_t acc = oi > 0 ? 1u : 0u;
+          for (int ks = 0; ks < TG / 16; ++ks) {
+            const uint32_t qa = sbase + L.q + (uint32_t)ks * 256u, wb = sbase + L.w[st] + (uint32_t)ks * 256u;
+            const uint64_t a_hi = umma_desc(qa, 128u, Q_RS), a_lo = umma_desc(qa + L.q_plane, 128u, Q_RS);
+            const uint64_t b_hi = umma_desc(wb, 128u, W_RS), b_lo = umma_desc(wb + L.w_plane, 128u, W_RS);
+            umma_bf16(tmem_acc2 + cb * KP, a_lo, b_hi, idesc2, acc);
+            umma_bf16(tmem_acc2 + cb * KP, a_hi, b_lo, idesc2, 1u);
+            umma_bf16(tmem_acc2 + cb * KP, a_hi, b_hi, idesc2, 1u);
+            acc = 1u;
+          }
+          umma_commit(&mi->q_empty);
+          if (cb == units_per_outer - 1) umma_commit(&mi->w_empty[st]);
+        }
+      }
+      if (!GLOBAL) umma_commit(&mi->dz_full);
+    }
+    __syncwarp();
+  } else {
+    // =========================================== EPILOGUE ===========================================
+    const int e = warp - 4;
+    const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+    const int r = (int)lane_base + lane;  // row of the unit (cell) / k0 row in epilogue 2
+    const int hc = e >> 2;                // 32-gene half of the tile
+    float ll = 0.f;
+    float esum[2] = {0.f, 0.f};
+    float acc_mu[32], acc_lw[32];
+    if (GLOBAL) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { acc_mu[i] = 0.f; acc_lw[i] = 0.f; }
+    }
+    for (int u = 0; u < U; ++u) {
+      const int oi = u / units_per_outer, cb = u - oi * units_per_outer;
+      const int st = oi & 1, rs = u & 1;
+      const int s = GLOBAL ? outer_begin + oi : s_fixed;
+      const int g0 = (GLOBAL ? tile_fixed : outer_begin + oi) * TG + hc * 32;
+      const int j = (GLOBAL ? cb * UC : j_block0 + cb * UC) + r;
+      const bool valid = j < a.B;
+      float c = 1.f;
+      const float* srow = a.smp_s;
+      const float* xrow = a.X;
+      if (valid) {
+        c = a.smp_c[(long long)s * a.B + j];
+        const int b = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
+        srow = a.smp_s + ((long long)s * a.nb + b) * a.G;
+        xrow = a.X + (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
+      }
+      float4 x4[4], s4[4];
+      auto load_xs = [&](int cc) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int g = g0 + cc * 16 + v * 4;
+          x4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          s4[v] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (valid && g < a.G) {
+            x4[v] = *reinterpret_cast<const float4*>(xrow + g);
+            s4[v] = *reinterpret_cast<const float4*>(srow + g);
+          }
+        }
+      };
+      load_xs(0);
+      mbar_wait(&mi->r_full[rs], (u >> 1) & 1);
+      tc_fence_after();
+      mbar_wait(&mi->q_empty, (u & 1) ^ 1);
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        float R[16];
+        tmem_ld16(tmem + (lane_base << 16) + (uint32_t)(rs * TG + hc * 32 + cc * 16), R);
+        float q[16];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const bool ok = valid && (g0 + cc * 16 + v * 4 < a.G);
+          const float xs[4] = {x4[v].x, x4[v].y, x4[v].z, x4[v].w}, ss[4] = {s4[v].x, s4[v].y, s4[v].z, s4[v].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float Rv = R[v * 4 + i];
+            float qq = 0.f;
+            if (ok) {
+              const float lam = c * ss[i] * Rv;
+              const float E = xs[i] - lam;
+              qq = __fdividef(E, Rv);
+              ll += (xs[i] > 0.f ? xs[i] * __logf(lam) : 0.f) - lam;
+              esum[cb & 1] += E;
+            }
+            q[v * 4 + i] = qq;
+          }
+        }
+        if (g_dbg_R && valid) {
+          for (int i = 0; i < 16; ++i)
+            if (g0 + cc * 16 + i < a.G) g_dbg_R[((long long)s * a.B + j) * a.G + g0 + cc * 16 + i] = R[i];
+        }
+        if (cc == 0) load_xs(1);
+        uint4 hi, lo;
+        const uint32_t off = L.q + (uint32_t)(r >> 3) * Q_RS + (uint32_t)(r & 7) * 16u + (uint32_t)(hc * 4 + cc * 2) * 128u;
+        split8(q, hi, lo);
+        *reinterpret_cast<uint4*>(sm + off) = hi;
+        *reinterpret_cast<uint4*>(sm + off + L.q_plane) = lo;
+        split8(q + 8, hi, lo);
+        *reinterpret_cast<uint4*>(sm + off + 128u) = hi;
+        *reinterpret_cast<uint4*>(sm + off + 128u + L.q_plane) = lo;
+      }
+      tc_fence_before();
+      mbar_arrive(&mi->r_empty[rs]);
+      fence_async_smem();
+      mbar_arrive(&mi->q_full);
+
+      if (GLOBAL && cb == units_per_outer - 1) {
+        // ---- epilogue 2: fold dW^s (and the W_0 prior gradient) into d mu, sum t log W ----
+        mbar_wait(&mi->dw_full[st], (oi >> 1) & 1);
+        tc_fence_after();
+        float dW[32];
+        tmem_ld16(tmem_acc2 + (lane_base << 16) + (uint32_t)(st * TG + hc * 32), dW);
+        tmem_ld16(tmem_acc2 + (lane_base << 16) + (uint32_t)(st * TG + hc * 32 + 16), dW + 16);
+        tc_fence_before();
+        mbar_arrive(&mi->dw_empty[st]);
+        if (r < a.K0 && !a.w0_stopped) {
+          float A = a.P_scalar, Bm = a.R_scalar * (float)a.K0;
+          if (a.use_brd) {
+            const float tau = a.smp_tau[(long long)s * a.K0 + r], om = a.smp_om[(long long)s * a.K0 + r];
+            A = a.P_scalar / tau;
+            Bm = a.R_scalar * (float)a.K0 / (tau * om);
+          }
+          const uint32_t woff = L.w[st] + (uint32_t)(r >> 3) * W_RS + (uint32_t)(r & 7) * 16u;
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            const uint4 hv = *reinterpret_cast<const uint4*>(sm + woff + (uint32_t)(hc * 4 + c8) * 128u);
+            const uint4 lv = *reinterpret_cast<const uint4*>(sm + woff + L.w_plane + (uint32_t)(hc * 4 + c8) * 128u);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+#pragma unroll
+              for (int q2 = 0; q2 < 2; ++q2) {
+                const int i = c8 * 8 + p * 2 + q2;
+                const float W = q2 ? (bf16hi(hw[p]) + bf16hi(lw[p])) : (bf16lo(hw[p]) + bf16lo(lw[p]));
+                if (W > V_LO_M && W < V_HI_M) {
+                  const float t = a.scale * dW[i] * W + a.global_weight * (A - 1.f - Bm * W);
+                  acc_mu[i] += t;
+                  acc_lw[i] = fmaf(t, __logf(W), acc_lw[i]);
+                }
+              }
+            }
+          }
+        }
+        mbar_arrive(&mi->w_empty[st]);
+      }
+    }
+
+    if (GLOBAL) {
+      const int chunk = blockIdx.x / gm.n_tiles;
+      const int gq = tile_fixed * TG + hc * 32;
+      if (r < a.K0 && !a.w0_stopped) {
+        float* pm = ws.part + (((long long)chunk * 2 + 0) * a.K0 + r) * a.G + gq;
+        float* pr = ws.part + (((long long)chunk * 2 + 1) * a.K0 + r) * a.G + gq;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          if (gq + i < a.G) {
+            *reinterpret_cast<float4*>(pm + i) = make_float4(acc_mu[i], acc_mu[i + 1], acc_mu[i + 2], acc_mu[i + 3]);
+            *reinterpret_cast<float4*>(pr + i) = make_float4(acc_lw[i], acc_lw[i + 1], acc_lw[i + 2], acc_lw[i + 3]);
+          }
+        }
+      }
+    } else {
+      // ---- drain dz0[half] (this thread: cell row r, k0 columns of its half hc) ----
+      mbar_wait(&mi->dz_full, 0);
+      tc_fence_after();
+      const int range = blockIdx.x % gm.NG;
+      for (int h = 0; h < units_per_outer; ++h) {
+        const int j = j_block0 + h * UC + r;
+        float* dst = ws.part + (((long long)s_fixed * gm.NG + range) * a.B + j) * a.K0;
+        for (int cc = hc; cc < KP / 16; cc += 2) {
+          float v[16];
+          tmem_ld16(tmem_acc2 + (lane_base << 16) + (uint32_t)(h * KP + cc * 16), v);
+          if (j < a.B) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (cc * 16 + i < a.K0) dst[cc * 16 + i] = v[i];
+          }
+        }
+        if (j < a.B && esum[h] != 0.f) atomicAdd(&a.G_c[(long long)s_fixed * a.B + j], a.scale * esum[h] / a.smp_c[(long long)s_fixed * a.B + j]);
+      }
+    }
+    // loss: reduce over the 256 epilogue threads
+    double v = warp_sum_d((double)ll);
+    if (lane == 0) mi->red[e] = v;
+    named_bar_sync(2, E_THREADS);
+    if (e == 0 && lane == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < 8; ++i) tot += mi->red[i];
+      atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)a.S);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
