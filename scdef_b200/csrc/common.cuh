@@ -47,6 +47,12 @@ struct NoiseTag {
   uint32_t a, b;
 };
 
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // Four standard normals for the elements (4*quad .. 4*quad+3) of block `tag`, MC sample `s`:
 // one Philox call, two Box-Muller pairs.
 __device__ __forceinline__ float4 philox_normal4(PhiloxKey key, NoiseTag tag, uint32_t s, uint32_t quad) {
@@ -56,7 +62,7 @@ __device__ __forceinline__ float4 philox_normal4(PhiloxKey key, NoiseTag tag, ui
   float u2 = ((float)r.y + 0.5f) * k;
   float u3 = fminf(((float)r.z + 0.5f) * k, 0.99999994f);
   float u4 = ((float)r.w + 0.5f) * k;
-  float ra = sqrtf(-2.0f * __logf(u1)), rb = sqrtf(-2.0f * __logf(u3));
+  float ra = fast_sqrt(-2.0f * __logf(u1)), rb = fast_sqrt(-2.0f * __logf(u3));
   float sa, ca, sb, cb;
   __sincosf(6.283185307179586f * u2, &sa, &ca);
   __sincosf(6.283185307179586f * u4, &sb, &cb);

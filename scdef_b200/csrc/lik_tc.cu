@@ -18,6 +18,7 @@
 //   Q [cell][gene]: A of the LOCAL dz MMA (K-major) and B of the GLOBAL dW MMA (MN-major)
 // Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #include <cuda_bf16.h>
+#include <cstdio>
 #include <cstdlib>
 
 #include "lik_tc.cuh"
@@ -31,6 +32,7 @@ constexpr int CB = 256;   // cells per block: two M=128 halves
 constexpr int NT = 256;   // threads per CTA (8 warps)
 constexpr int MAX_NB = 8; // batches handled by the shared-memory column accumulators
 constexpr int SM_TARGET = 148;
+constexpr int UC = 128;   // cells per pipeline unit
 constexpr uint32_t W_RS = 1024, Q_RS = 1024;  // row-group strides of the W and Q tiles (8 col groups x 128 B)
 constexpr float V_LO_M = 1.0001e-15f, V_HI_M = 0.9999e15f;  // "inside the sample clip" with a margin for hi+lo rounding
 constexpr float LOG_V_LO = -34.538776394910684f, LOG_V_HI = 34.538776394910684f;
@@ -90,16 +92,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// split 8 floats into bf16 hi and lo = bf16(x - hi), packed as two 16-byte vectors
+// split 8 floats into bf16 hi and lo = bf16(x - hi), packed as two 16-byte vectors.
+// Packed conversions (F2FP.BF16.F32.PACK_AB, one instruction per pair, round-to-nearest).
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b (high half)
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-    __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-    __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+    const float r0 = x[2 * i] - __uint_as_float(h[i] << 16);
+    const float r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
+    l[i] = pack_bf16x2(r0, r1);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -327,6 +333,11 @@ struct TcScratch {
   float* ctilde;    // (S,nb,K0)
   float* colsumX;   // (nb,G)
   float* part;      // LOCAL: (S,NG,B,K0)   GLOBAL: (n_chunks,2,K0,G)
+  float* wmu;       // (K0,G) clip(mu) of W_0            } written once per pass by k_tc_wprep
+  float* wsig;      // (K0,G) exp(clip(rho)) of W_0      }
+  uint8_t* zimg;    // (S, ceil(B/128), 2 planes) z0 samples pre-split to bf16 hi/lo in the UMMA layout
+  int* brow;        // (B) batch of each minibatch row
+  long long* xoff;  // (B) element offset of each minibatch row in X
 };
 
 // =====================================================================================================
@@ -597,6 +608,52 @@ __global__ void __launch_bounds__(NT, 1) k_lik_tc_global(const LikTcArgs a, cons
 
 #include "lik_tc_pipe.cuh"
 
+// ---- pre-kernels of the pipelined path -----------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tc_wprep(const LikTcArgs a, float* wmu, float* wsig) {
+  const long long n = (long long)a.K0 * a.G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    wmu[i] = fminf(fmaxf(a.mu_W0[i], LOG_1E_10), LOG_1E6);
+    wsig[i] = expf(fminf(fmaxf(a.rho_W0[i], LOG_1E_10), LOG_1E10));
+  }
+}
+__global__ void __launch_bounds__(256) k_tc_rowprep(const LikTcArgs a, int* brow, long long* xoff) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.B) return;
+  brow[j] = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
+  xoff[j] = (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
+}
+// z0 samples (S,B,K0) fp32 -> per (s, 128-cell unit) image [hi plane | lo plane] in the canonical layout
+__global__ void __launch_bounds__(256) k_tc_zprep(const LikTcArgs a, uint8_t* zimg, int KP) {
+  const int nchunk = KP / 8, units = (a.B + UC - 1) / UC;
+  const uint32_t z_rs = (uint32_t)nchunk * 128u, z_plane = 16u * z_rs;
+  const long long per_unit = (long long)UC * nchunk, total = (long long)a.S * units * per_unit;
+  const bool vec = (a.K0 & 3) == 0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long su = t / per_unit;
+    const int i = (int)(t - su * per_unit);
+    const int s = (int)(su / units), un = (int)(su - (long long)s * units);
+    const int r = i % UC, c = i / UC, j = un * UC + r, k = c * 8;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = 0.f;
+    if (j < a.B) {
+      const float* row = a.smp_z0 + ((long long)s * a.B + j) * a.K0;
+      if (vec) {
+        if (k + 4 <= a.K0) { float4 v = *reinterpret_cast<const float4*>(row + k); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+        if (k + 8 <= a.K0) { float4 v = *reinterpret_cast<const float4*>(row + k + 4); x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (k + e < a.K0) x[e] = row[k + e];
+      }
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    uint8_t* dst = zimg + su * (2ll * z_plane) + (uint32_t)(r >> 3) * z_rs + (uint32_t)c * 128u + (uint32_t)(r & 7) * 16u;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + z_plane) = lo;
+  }
+}
+
 // ---- small companions ---------------------------------------------------------------------------------
 // ctilde[s][b][k] = sum_{n in batch b} c_n^s z_nk^s ;  grid = S, block = 128
 __global__ void __launch_bounds__(128) k_tc_ctilde(const LikTcArgs a, float* ctilde) {
@@ -740,8 +797,11 @@ size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb) {
   const Geom g = make_geom(B, S, K0, G);
   size_t part_local = (size_t)S * g.NG * (size_t)(B > 0 ? B : 1) * K0 * 4;
   size_t part_global = (size_t)g.n_chunks * 2 * K0 * G * 4;
+  const size_t Bp = (size_t)(B > 0 ? B : 1), units = (Bp + 127) / 128;
+  const size_t zimg = (size_t)S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
   return a256((size_t)S * K0 * 2 * 4) + a256((size_t)S * nb * K0 * 4) + a256((size_t)nb * G * 4) +
-         a256(part_local > part_global ? part_local : part_global) + 1024;
+         a256(part_local > part_global ? part_local : part_global) + 2 * a256((size_t)K0 * G * 4) + a256(zimg) +
+         a256(Bp * 4) + a256(Bp * 8) + 1024;
 }
 
 void lik_tc_set_debug(float* p) { cudaMemcpyToSymbol(g_dbg_R, &p, sizeof(p)); }
@@ -758,20 +818,37 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   ws.ctilde = (float*)w;   w += a256((size_t)a.S * a.nb * a.K0 * 4);
   ws.colsumX = (float*)w;  w += a256((size_t)a.nb * a.G * 4);
   ws.part = (float*)w;
+  {
+    size_t part_local = (size_t)a.S * g.NG * (size_t)(a.B > 0 ? a.B : 1) * a.K0 * 4;
+    size_t part_global = (size_t)g.n_chunks * 2 * a.K0 * a.G * 4;
+    w += a256(part_local > part_global ? part_local : part_global);
+  }
+  const size_t Bp = (size_t)(a.B > 0 ? a.B : 1), units = (Bp + 127) / 128;
+  const size_t zimg_bytes = (size_t)a.S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
+  ws.wmu = (float*)w;      w += a256((size_t)a.K0 * a.G * 4);
+  ws.wsig = (float*)w;     w += a256((size_t)a.K0 * a.G * 4);
+  ws.zimg = (uint8_t*)w;   w += a256(zimg_bytes);
+  ws.brow = (int*)w;       w += a256(Bp * 4);
+  ws.xoff = (long long*)w; w += a256(Bp * 8);
   if ((size_t)(w - (char*)a.ws) > a.ws_bytes) return SCDEF_EWORKSPACE;
   const Smem L = plan_smem(g.KP);
   const PipeSmem PL = plan_pipe_smem(g.KP);
   static const bool mono = getenv("SCDEF_TC_MONO") != nullptr;  // A/B switch: the monolithic v2a kernels
   const bool global_pass = a.pass == SCDEF_PASS_GLOBAL;
   cudaMemsetAsync(ws.rowstats, 0, (size_t)a.S * a.K0 * 2 * 4, st);
+  if (a.lik_on && !mono) {
+    k_tc_wprep<<<148 * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
+    k_tc_rowprep<<<(a.B + 255) / 256, 256, 0, st>>>(a, ws.brow, ws.xoff);
+    k_tc_zprep<<<148 * 4, 256, 0, st>>>(a, ws.zimg, g.KP);
+  }
   if (global_pass) {
     if (a.lik_on) {
       k_tc_ctilde<<<a.S, 128, 0, st>>>(a, ws.ctilde);
       k_tc_colsum<<<(a.G + 255) / 256, 256, 0, st>>>(a, ws.colsumX);
     }
     if (a.lik_on && !mono) {
-      cudaFuncSetAttribute(k_lik_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
-      k_lik_pipe<true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+      cudaFuncSetAttribute(k_lik_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+      k_lik_pipe<true, true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
     } else {
       cudaFuncSetAttribute(k_lik_tc_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
       k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(a, g, ws, loss_out);
@@ -779,8 +856,8 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   } else {
     if (a.lik_on) {
       if (!mono) {
-        cudaFuncSetAttribute(k_lik_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
-        k_lik_pipe<false><<<dim3(a.S * g.NG, g.n_cblocks), PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+        cudaFuncSetAttribute(k_lik_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+        k_lik_pipe<false, true><<<dim3(a.S * g.NG, g.n_cblocks), PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
       } else {
         cudaFuncSetAttribute(k_lik_tc_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
         k_lik_tc_local<<<dim3(a.S * g.NG, g.n_cblocks), NT, L.total, st>>>(a, g, ws, loss_out);
@@ -798,7 +875,12 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   }
   k_tc_w0_prior<<<(a.S * a.K0 + 127) / 128, 128, 0, st>>>(a, ws.rowstats, loss_out);
   k_tc_w0_final<<<148 * 4, 256, 0, st>>>(a, ws.part, g.n_chunks, loss_out);
-  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    fprintf(stderr, "scdef_b200: lik_tc_launch: %s (smem mono %u, pipe %u)\n", cudaGetErrorString(err), L.total, PL.total);
+    return SCDEF_ECUDA;
+  }
+  return SCDEF_OK;
 }
 
 }  // namespace scdef

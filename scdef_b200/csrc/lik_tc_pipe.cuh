@@ -6,6 +6,7 @@
 //                          in the GLOBAL pass, stage z0^s blocks; side sums for the W_0 prior / gene scale
 //   warps 4-11 EPILOGUE  : TMEM -> registers, Poisson terms, Q tile back to smem; GLOBAL: fold dW
 //   warp  12   MMA ISSUER: one thread issues every tcgen05.mma and tcgen05.commit
+//   warp  13   COPY      : one thread streams pre-split z0^s blocks into smem with cp.async.bulk (TMA)
 // Work is cut into UNITS of 128 cells x 64 genes.  W tiles, z blocks and the R accumulators are
 // double-buffered, so generating tile/sample n+1, the tensor-core work of unit u+1 and the
 // epilogue of unit u overlap.  All hand-offs are mbarriers (full/empty pairs).
@@ -16,9 +17,8 @@
 //          blocks of s; epilogue 2 folds W.dW into per-thread d mu / d rho accumulators over the chunk.
 #pragma once
 
-constexpr int PIPE_NT = 416;           // 13 warps
+constexpr int PIPE_NT = 448;           // 14 warps
 constexpr int P_THREADS = 128, E_THREADS = 256;
-constexpr int UC = 128;                // cells per unit
 
 struct PipeSmem {
   uint32_t z[2], w[2], q, misc, total;   // each z / w / q region = hi plane followed by lo plane
@@ -53,60 +53,28 @@ struct PipeMisc {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (1-D), completion signalled on an mbarrier (complete_tx::bytes)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // ---- producers -------------------------------------------------------------------------------------
-// 128 cells x KP of z0^s (rows j0..j0+127) -> bf16 hi/lo planes; `nthr` cooperating threads, id `tid`
-__device__ __forceinline__ void pipe_load_z(const LikTcArgs& a, uint8_t* zbuf, uint32_t z_rs, uint32_t z_plane, int KP, int s,
-                                            int j0, int tid, int nthr) {
-  const int nchunk = KP / 8;
-  const float* zs = a.smp_z0 + (long long)s * a.B * a.K0;
-  const bool vec = (a.K0 & 3) == 0;
-  for (int t0 = tid; t0 < UC * nchunk; t0 += 4 * nthr) {
-    float x[4][8];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = t0 + u * nthr;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[u][e] = 0.f;
-      if (t < UC * nchunk) {
-        const int r = t % UC, c = t / UC, j = j0 + r, k = c * 8;
-        if (j < a.B) {
-          const float* row = zs + (long long)j * a.K0;
-          if (vec) {
-            if (k + 4 <= a.K0) { float4 v = *reinterpret_cast<const float4*>(row + k); x[u][0] = v.x; x[u][1] = v.y; x[u][2] = v.z; x[u][3] = v.w; }
-            if (k + 8 <= a.K0) { float4 v = *reinterpret_cast<const float4*>(row + k + 4); x[u][4] = v.x; x[u][5] = v.y; x[u][6] = v.z; x[u][7] = v.w; }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) if (k + e < a.K0) x[u][e] = row[k + e];
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = t0 + u * nthr;
-      if (t < UC * nchunk) {
-        const int r = t % UC, c = t / UC;
-        uint4 hi, lo;
-        split8(x[u], hi, lo);
-        const uint32_t off = (uint32_t)(r >> 3) * z_rs + (uint32_t)c * 128u + (uint32_t)(r & 7) * 16u;
-        *reinterpret_cast<uint4*>(zbuf + off) = hi;
-        *reinterpret_cast<uint4*>(zbuf + z_plane + off) = lo;
-      }
-    }
-  }
-}
-
 // W^s tile -> wbuf (hi/lo planes); row sums of (log W, W) and, GLOBAL, ctilde^T W into the stage's accumulators.
 template <bool GLOBAL>
-__device__ __forceinline__ void pipe_gen_w(const LikTcArgs& a, uint8_t* wbuf, uint32_t w_plane, PipeMisc* mi, int stage, int KP,
-                                           int s, int g0, const float* ctilde_s, bool want_stats, int tid) {
+__device__ __forceinline__ void pipe_gen_w(const LikTcArgs& a, const TcScratch& ws, uint8_t* wbuf, uint32_t w_plane, PipeMisc* mi,
+                                           int stage, int KP, int s, int g0, const float* ctilde_s, bool want_stats, int tid) {
   const int nkg = KP / 8;
   const int kk = tid & 7, cg = (tid >> 3) & 7, lane = tid & 31;
   const int g = g0 + cg * 8;
+  const bool gok = g < a.G;
   float col[MAX_NB][8];
   if (GLOBAL) {
 #pragma unroll
@@ -114,32 +82,42 @@ __device__ __forceinline__ void pipe_gen_w(const LikTcArgs& a, uint8_t* wbuf, ui
 #pragma unroll
       for (int e = 0; e < 8; ++e) col[b][e] = 0.f;
   }
+  // software pipeline: the loads of item i+1 are in flight while item i is sampled
+  float4 nm0, nm1, ns0, ns1, ne0, ne1;
+  auto fetch = [&](int kg) {
+    const int k = kg * 8 + kk;
+    if (kg < nkg && k < a.K0 && gok) {
+      const long long base = (long long)k * a.G + g;
+      nm0 = *reinterpret_cast<const float4*>(ws.wmu + base); nm1 = *reinterpret_cast<const float4*>(ws.wmu + base + 4);
+      ns0 = *reinterpret_cast<const float4*>(ws.wsig + base); ns1 = *reinterpret_cast<const float4*>(ws.wsig + base + 4);
+      if (a.eps_W0) {
+        const float* ep = a.eps_W0 + (long long)s * a.K0 * a.G + base;
+        ne0 = *reinterpret_cast<const float4*>(ep); ne1 = *reinterpret_cast<const float4*>(ep + 4);
+      }
+    }
+  };
+  fetch(tid >> 6);
   for (int kg = tid >> 6; kg < nkg; kg += P_THREADS / 64) {
     const int k = kg * 8 + kk;
+    const float4 m0 = nm0, m1 = nm1, s0 = ns0, s1 = ns1;
+    float4 e0 = ne0, e1 = ne1;
+    fetch(kg + P_THREADS / 64);
     float w[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) w[e] = 0.f;
     float su = 0.f, sw = 0.f;
-    if (k < a.K0 && g < a.G) {
-      const long long base = (long long)k * a.G + g;
-      float4 m0 = *reinterpret_cast<const float4*>(a.mu_W0 + base), m1 = *reinterpret_cast<const float4*>(a.mu_W0 + base + 4);
-      float4 r0 = *reinterpret_cast<const float4*>(a.rho_W0 + base), r1 = *reinterpret_cast<const float4*>(a.rho_W0 + base + 4);
-      float4 e0, e1;
-      if (a.eps_W0) {
-        const float* ep = a.eps_W0 + (long long)s * a.K0 * a.G + base;
-        e0 = *reinterpret_cast<const float4*>(ep); e1 = *reinterpret_cast<const float4*>(ep + 4);
-      } else {
-        e0 = philox_normal4(a.key, a.tag, (uint32_t)s, (uint32_t)(base >> 2));
-        e1 = philox_normal4(a.key, a.tag, (uint32_t)s, (uint32_t)(base >> 2) + 1u);
+    if (k < a.K0 && gok) {
+      if (!a.eps_W0) {
+        const uint32_t quad = (uint32_t)(((long long)k * a.G + g) >> 2);
+        e0 = philox_normal4(a.key, a.tag, (uint32_t)s, quad);
+        e1 = philox_normal4(a.key, a.tag, (uint32_t)s, quad + 1u);
       }
       const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-      const float rho[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      const float sg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
       const float ep[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float mut = fminf(fmaxf(mu[e], LOG_1E_10), LOG_1E6);
-        float sig = __expf(fminf(fmaxf(rho[e], LOG_1E_10), LOG_1E10));
-        float u = fminf(fmaxf(fmaf(sig, ep[e], mut), LOG_V_LO), LOG_V_HI);
+        const float u = fminf(fmaxf(fmaf(sg[e], ep[e], mu[e]), LOG_V_LO), LOG_V_HI);
         w[e] = __expf(u);
         su += u;
         sw += w[e];
@@ -189,7 +167,7 @@ __device__ __forceinline__ void pipe_gen_w(const LikTcArgs& a, uint8_t* wbuf, ui
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------
-template <bool GLOBAL>
+template <bool GLOBAL, bool WANT_LL>
 __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, const Geom gm, const TcScratch ws, double* loss_out) {
   extern __shared__ __align__(1024) uint8_t sm[];
   const int KP = gm.KP;
@@ -222,7 +200,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
     for (int i = 0; i < 2; ++i) {
       mbar_init(&mi->w_full[i], P_THREADS);
       mbar_init(&mi->w_empty[i], GLOBAL ? E_THREADS : 1);
-      mbar_init(&mi->z_full[i], P_THREADS);
+      mbar_init(&mi->z_full[i], 1);
       mbar_init(&mi->z_empty[i], 1);
       mbar_init(&mi->r_full[i], 1);
       mbar_init(&mi->r_empty[i], E_THREADS);
@@ -240,14 +218,11 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&mi->tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (!GLOBAL) {  // z0^s of the 256-cell block is static: both halves staged once
-    for (int h = 0; h < units_per_outer; ++h)
-      pipe_load_z(a, sm + L.z[h], L.z_rs, L.z_plane, KP, s_fixed, j_block0 + h * UC, threadIdx.x, PIPE_NT);
-    fence_async_smem();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const int units_total_B = (a.B + UC - 1) / UC;  // z image: (S, units_total_B, 2 planes)
+  const uint32_t z_bytes = 2u * L.z_plane;
   const uint32_t tmem = mi->tmem_base;
   const uint32_t tmem_acc2 = tmem + 2 * TG;  // LOCAL: dz[half] (KP cols each); GLOBAL: dW[stage] (TG cols each)
 
@@ -261,7 +236,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
       const int s = GLOBAL ? outer_begin + oi : s_fixed;
       const int g0 = (GLOBAL ? tile_fixed : outer_begin + oi) * TG;
       mbar_wait(&mi->w_empty[st], ((oi >> 1) & 1) ^ 1);
-      pipe_gen_w<GLOBAL>(a, sm + L.w[st], L.w_plane, mi, st, KP, s, g0,
+      pipe_gen_w<GLOBAL>(a, ws, sm + L.w[st], L.w_plane, mi, st, KP, s, g0,
                          GLOBAL ? ws.ctilde + (long long)s * a.nb * a.K0 : nullptr, want_stats, tid);
       fence_async_smem();
       mbar_arrive(&mi->w_full[st]);
@@ -284,16 +259,31 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
           mi->colacc[st][b][tid] = 0.f;
         }
       }
+    }
+    (void)u;
+  } else if (warp == 13) {
+    // =========================================== COPY (TMA) ===========================================
+    if (lane == 0) {
       if (GLOBAL) {
-        for (int cb = 0; cb < units_per_outer; ++cb, ++u) {
-          const int zs = u & 1;
-          mbar_wait(&mi->z_empty[zs], ((u >> 1) & 1) ^ 1);
-          pipe_load_z(a, sm + L.z[zs], L.z_rs, L.z_plane, KP, s, cb * UC, tid, P_THREADS);
-          fence_async_smem();
-          mbar_arrive(&mi->z_full[zs]);
+        int u = 0;
+        for (int oi = 0; oi < n_outer; ++oi) {
+          const int s = outer_begin + oi;
+          for (int cb = 0; cb < units_per_outer; ++cb, ++u) {
+            const int zs = u & 1;
+            mbar_wait(&mi->z_empty[zs], ((u >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(&mi->z_full[zs], z_bytes);
+            bulk_g2s(sbase + L.z[zs], ws.zimg + ((long long)s * units_total_B + cb) * z_bytes, z_bytes, &mi->z_full[zs]);
+          }
         }
+      } else {
+        // z0^s of the 256-cell block is static: both halves land once, on z_full[0]
+        mbar_arrive_expect_tx(&mi->z_full[0], z_bytes * (uint32_t)units_per_outer);
+        for (int h = 0; h < units_per_outer; ++h)
+          bulk_g2s(sbase + L.z[h], ws.zimg + ((long long)s_fixed * units_total_B + (j_block0 / UC + h)) * z_bytes, z_bytes,
+                   &mi->z_full[0]);
       }
     }
+    __syncwarp();
   } else if (warp == 12) {
     // =========================================== MMA ISSUER ===========================================
     if (lane == 0) {
@@ -318,6 +308,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
         }
         umma_commit(&mi->r_full[rs]);
       };
+      if (!GLOBAL) mbar_wait(&mi->z_full[0], 0);
       if (U > 0) issue_mma1(0);
       for (int u = 0; u < U; ++u) {
         if (u + 1 < U) issue_mma1(u + 1);
@@ -375,29 +366,43 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
 #pragma unroll
       for (int i = 0; i < 32; ++i) { acc_mu[i] = 0.f; acc_lw[i] = 0.f; }
     }
+    // row context of a unit: (c, batch row of the gene-scale sample, row of X); the next unit's
+    // context is fetched while the current one is processed (no dependent-load chains in the loop)
+    struct Ctx { float c; int b; long long xoff; bool valid; };
+    auto fetch_ctx = [&](int u) {
+      Ctx cx; cx.c = 0.f; cx.b = 0; cx.xoff = 0; cx.valid = false;
+      if (u < U) {
+        const int oi = u / units_per_outer, cb = u - oi * units_per_outer;
+        const int s = GLOBAL ? outer_begin + oi : s_fixed;
+        const int j = (GLOBAL ? cb * UC : j_block0 + cb * UC) + r;
+        if (j < a.B) {
+          cx.valid = true;
+          cx.c = a.smp_c[(long long)s * a.B + j];
+          cx.b = ws.brow[j];
+          cx.xoff = ws.xoff[j];
+        }
+      }
+      return cx;
+    };
+    Ctx nxt = fetch_ctx(0);
     for (int u = 0; u < U; ++u) {
       const int oi = u / units_per_outer, cb = u - oi * units_per_outer;
       const int st = oi & 1, rs = u & 1;
       const int s = GLOBAL ? outer_begin + oi : s_fixed;
       const int g0 = (GLOBAL ? tile_fixed : outer_begin + oi) * TG + hc * 32;
       const int j = (GLOBAL ? cb * UC : j_block0 + cb * UC) + r;
-      const bool valid = j < a.B;
-      float c = 1.f;
-      const float* srow = a.smp_s;
-      const float* xrow = a.X;
-      if (valid) {
-        c = a.smp_c[(long long)s * a.B + j];
-        const int b = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
-        srow = a.smp_s + ((long long)s * a.nb + b) * a.G;
-        xrow = a.X + (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
-      }
+      const Ctx cx = nxt;
+      const bool valid = cx.valid;
+      const float c = cx.c;
+      const float* srow = a.smp_s + ((long long)s * a.nb + cx.b) * a.G;
+      const float* xrow = a.X + cx.xoff;
       float4 x4[4], s4[4];
       auto load_xs = [&](int cc) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const int g = g0 + cc * 16 + v * 4;
           x4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-          s4[v] = make_float4(1.f, 1.f, 1.f, 1.f);
+          s4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (valid && g < a.G) {
             x4[v] = *reinterpret_cast<const float4*>(xrow + g);
             s4[v] = *reinterpret_cast<const float4*>(srow + g);
@@ -405,6 +410,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
         }
       };
       load_xs(0);
+      nxt = fetch_ctx(u + 1);
       mbar_wait(&mi->r_full[rs], (u >> 1) & 1);
       tc_fence_after();
       mbar_wait(&mi->q_empty, (u & 1) ^ 1);
@@ -415,20 +421,21 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
         float q[16];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
+          // rows / genes outside the problem carry s = 0 (=> Lambda = 0, E = x = 0) and are masked by `ok`
           const bool ok = valid && (g0 + cc * 16 + v * 4 < a.G);
           const float xs[4] = {x4[v].x, x4[v].y, x4[v].z, x4[v].w}, ss[4] = {s4[v].x, s4[v].y, s4[v].z, s4[v].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float Rv = R[v * 4 + i];
-            float qq = 0.f;
-            if (ok) {
-              const float lam = c * ss[i] * Rv;
-              const float E = xs[i] - lam;
-              qq = __fdividef(E, Rv);
-              ll += (xs[i] > 0.f ? xs[i] * __logf(lam) : 0.f) - lam;
-              esum[cb & 1] += E;
+            const float lam = (c * ss[i]) * Rv;
+            const float E = xs[i] - lam;
+            const float qq = __fdividef(E, Rv);
+            q[v * 4 + i] = ok ? qq : 0.f;
+            if (WANT_LL) {
+              const float t = xs[i] * __logf(lam);
+              ll += (xs[i] > 0.f ? t : 0.f) - lam;
             }
-            q[v * 4 + i] = qq;
+            esum[cb & 1] += E;
           }
         }
         if (g_dbg_R && valid) {
