@@ -20,6 +20,17 @@
 constexpr int PIPE_NT = 448;           // 14 warps
 constexpr int P_THREADS = 128, E_THREADS = 256;
 
+struct PipeMisc {
+  uint64_t w_full[2], w_empty[2], z_full[2], z_empty[2], r_full[2], r_empty[2], q_full, q_empty, dw_full[2],
+      dw_empty[2], dz_full;
+  uint32_t tmem_base, pad;
+  double red[32];
+  float rowU[2][128], rowW[2][128];
+  float colacc[2][MAX_NB][TG];
+  float stile[2][MAX_NB][TG];   // gene-scale samples s_{b,g} of the stage's (sample, tile)
+  float ct_sm[MAX_NB][128];     // ctilde of the sample being generated (GLOBAL)
+};
+
 struct PipeSmem {
   uint32_t z[2], w[2], q, misc, total;   // each z / w / q region = hi plane followed by lo plane
   uint32_t z_rs, z_plane, w_plane, q_plane;
@@ -37,18 +48,10 @@ __host__ __device__ inline PipeSmem plan_pipe_smem(int KP) {
   s.w[1] = o; o += 2 * s.w_plane;
   s.q = o; o += 2 * s.q_plane;
   s.misc = o;
-  s.total = o + 8192;
+  s.total = o + (uint32_t)((sizeof(PipeMisc) + 1023) / 1024 * 1024);
   return s;
 }
 
-struct PipeMisc {
-  uint64_t w_full[2], w_empty[2], z_full[2], z_empty[2], r_full[2], r_empty[2], q_full, q_empty, dw_full[2],
-      dw_empty[2], dz_full;
-  uint32_t tmem_base, pad;
-  double red[32];
-  float rowU[2][128], rowW[2][128];
-  float colacc[2][MAX_NB][TG];
-};
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -61,6 +64,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -126,7 +138,7 @@ __device__ __forceinline__ void pipe_gen_w(const LikTcArgs& a, const TcScratch& 
 #pragma unroll
         for (int b = 0; b < MAX_NB; ++b) {
           if (b < a.nb) {
-            const float ct = ctilde_s[b * a.K0 + k];
+            const float ct = mi->ct_sm[b][k];
 #pragma unroll
             for (int e = 0; e < 8; ++e) col[b][e] = fmaf(ct, w[e], col[b][e]);
           }
@@ -236,6 +248,16 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
       const int s = GLOBAL ? outer_begin + oi : s_fixed;
       const int g0 = (GLOBAL ? tile_fixed : outer_begin + oi) * TG;
       mbar_wait(&mi->w_empty[st], ((oi >> 1) & 1) ^ 1);
+      // stage the gene-scale sample tile (and ctilde) of this (sample, tile) for the other roles
+      for (int i = tid; i < a.nb * TG; i += P_THREADS) {
+        const int b = i / TG, gl = i - b * TG;
+        mi->stile[st][b][gl] = (g0 + gl < a.G) ? a.smp_s[((long long)s * a.nb + b) * a.G + g0 + gl] : 0.f;
+      }
+      if (GLOBAL) {
+        const float* ct = ws.ctilde + (long long)s * a.nb * a.K0;
+        for (int i = tid; i < a.nb * a.K0; i += P_THREADS) mi->ct_sm[i / a.K0][i % a.K0] = ct[i];
+        named_bar_sync(1, P_THREADS);
+      }
       pipe_gen_w<GLOBAL>(a, ws, sm + L.w[st], L.w_plane, mi, st, KP, s, g0,
                          GLOBAL ? ws.ctilde + (long long)s * a.nb * a.K0 : nullptr, want_stats, tid);
       fence_async_smem();
@@ -253,7 +275,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
         const int g = g0 + tid;
         for (int b = 0; b < a.nb; ++b) {
           if (g < a.G && a.G_s) {
-            const float sv = a.smp_s[((long long)s * a.nb + b) * a.G + g];
+            const float sv = mi->stile[st][b][tid];
             a.G_s[((long long)s * a.nb + b) * a.G + g] += a.scale * (ws.colsumX[(long long)b * a.G + g] / sv - mi->colacc[st][b][tid]);
           }
           mi->colacc[st][b][tid] = 0.f;
@@ -361,6 +383,23 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
     const int hc = e >> 2;                // 32-gene half of the tile
     float ll = 0.f;
     float esum[2] = {0.f, 0.f};
+    const uint32_t tmem_x = tmem + 4 * TG;  // GLOBAL: the X tile of the first two 128-cell units (2 x TG columns)
+    if (GLOBAL) {
+      for (int cb = 0; cb < min(units_per_outer, 2); ++cb) {
+        const int j = cb * UC + r;
+        const int gq = tile_fixed * TG + hc * 32;
+        float xv[32];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < a.B && gq + v * 4 < a.G) t4 = *reinterpret_cast<const float4*>(a.X + ws.xoff[j] + gq + v * 4);
+          xv[v * 4] = t4.x; xv[v * 4 + 1] = t4.y; xv[v * 4 + 2] = t4.z; xv[v * 4 + 3] = t4.w;
+        }
+        tmem_st16(tmem_x + (lane_base << 16) + (uint32_t)(cb * TG + hc * 32), xv);
+        tmem_st16(tmem_x + (lane_base << 16) + (uint32_t)(cb * TG + hc * 32 + 16), xv + 16);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
     float acc_mu[32], acc_lw[32];
     if (GLOBAL) {
 #pragma unroll
@@ -394,46 +433,53 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
       const Ctx cx = nxt;
       const bool valid = cx.valid;
       const float c = cx.c;
-      const float* srow = a.smp_s + ((long long)s * a.nb + cx.b) * a.G;
       const float* xrow = a.X + cx.xoff;
-      float4 x4[4], s4[4];
-      auto load_xs = [&](int cc) {
+      const bool x_in_tmem = GLOBAL && cb < 2;
+      float4 x4[8];
+      if (!x_in_tmem) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int g = g0 + cc * 16 + v * 4;
+        for (int v = 0; v < 8; ++v) {
+          const int g = g0 + v * 4;
           x4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-          s4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid && g < a.G) {
-            x4[v] = *reinterpret_cast<const float4*>(xrow + g);
-            s4[v] = *reinterpret_cast<const float4*>(srow + g);
-          }
+          if (valid && g < a.G) x4[v] = *reinterpret_cast<const float4*>(xrow + g);
         }
-      };
-      load_xs(0);
+      }
       nxt = fetch_ctx(u + 1);
       mbar_wait(&mi->r_full[rs], (u >> 1) & 1);
       tc_fence_after();
       mbar_wait(&mi->q_empty, (u & 1) ^ 1);
-#pragma unroll 1
+#pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         float R[16];
         tmem_ld16(tmem + (lane_base << 16) + (uint32_t)(rs * TG + hc * 32 + cc * 16), R);
         float q[16];
+        float xs16[16];
+        if (x_in_tmem) {
+          tmem_ld16(tmem_x + (lane_base << 16) + (uint32_t)(cb * TG + hc * 32 + cc * 16), xs16);
+        } else {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            xs16[v * 4 + 0] = x4[cc * 4 + v].x; xs16[v * 4 + 1] = x4[cc * 4 + v].y;
+            xs16[v * 4 + 2] = x4[cc * 4 + v].z; xs16[v * 4 + 3] = x4[cc * 4 + v].w;
+          }
+        }
+        const float* srow_sm = &mi->stile[st][cx.b][hc * 32 + cc * 16];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-          // rows / genes outside the problem carry s = 0 (=> Lambda = 0, E = x = 0) and are masked by `ok`
+          // rows / genes outside the problem carry x = 0 and are masked by `ok`
           const bool ok = valid && (g0 + cc * 16 + v * 4 < a.G);
-          const float xs[4] = {x4[v].x, x4[v].y, x4[v].z, x4[v].w}, ss[4] = {s4[v].x, s4[v].y, s4[v].z, s4[v].w};
+          const float4 s4v = *reinterpret_cast<const float4*>(srow_sm + v * 4);
+          const float ss[4] = {s4v.x, s4v.y, s4v.z, s4v.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float Rv = R[v * 4 + i];
+            const float xv = xs16[v * 4 + i];
             const float lam = (c * ss[i]) * Rv;
-            const float E = xs[i] - lam;
-            const float qq = __fdividef(E, Rv);
-            q[v * 4 + i] = ok ? qq : 0.f;
+            const float E = ok ? xv - lam : 0.f;
+            q[v * 4 + i] = ok ? __fdividef(E, Rv) : 0.f;
             if (WANT_LL) {
-              const float t = xs[i] * __logf(lam);
-              ll += (xs[i] > 0.f ? t : 0.f) - lam;
+              const float t = xv * __logf(lam);
+              ll += ok ? ((xv > 0.f ? t : 0.f) - lam) : 0.f;
             }
             esum[cb & 1] += E;
           }
@@ -442,7 +488,6 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
           for (int i = 0; i < 16; ++i)
             if (g0 + cc * 16 + i < a.G) g_dbg_R[((long long)s * a.B + j) * a.G + g0 + cc * 16 + i] = R[i];
         }
-        if (cc == 0) load_xs(1);
         uint4 hi, lo;
         const uint32_t off = L.q + (uint32_t)(r >> 3) * Q_RS + (uint32_t)(r & 7) * 16u + (uint32_t)(hc * 4 + cc * 2) * 128u;
         split8(q, hi, lo);
