@@ -46,9 +46,13 @@ def _allreduce_np(a: np.ndarray, shard: ShardInfo, device=None) -> np.ndarray:
         return a
     import torch
 
+    import torch.distributed as td
+
     t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64))
     if device is not None:
         t = t.to(device)
+    elif td.get_backend(shard.group) == "nccl":  # NCCL only moves device tensors
+        t = t.cuda()
     all_reduce_sum(t, shard)
     return t.cpu().numpy()
 
