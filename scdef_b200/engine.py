@@ -299,14 +299,25 @@ class Engine:
         nz = self._noise_struct(noise, keep)
         if zero_loss:
             self.loss_buf.zero_()
-        params = _merge(self.local.blocks(self.L, True), self.glob.blocks(self.L, False), self.L)
-        grads = _merge(self.local_grad.blocks(self.L, True), self.glob_grad.blocks(self.L, False), self.L)
+        params, grads = self._cached_blocks()
         rc = self.lib.scdef_elbo_grad(self.ctx, C.byref(call), C.byref(params), C.byref(nz),
                                       _ptr(self.loss_buf), C.byref(grads), _ptr(self.workspace),
                                       self.workspace.numel(), self._stream())
         self._check(rc, "scdef_elbo_grad")
         self._keep = keep  # explicit-noise tensors must outlive the enqueued kernels
         return self.loss_buf
+
+    def _cached_blocks(self):
+        key = self.local_grad.flat.data_ptr()
+        if getattr(self, "_blk_key", None) != key:
+            self._blk_params = _merge(self.local.blocks(self.L, True), self.glob.blocks(self.L, False), self.L)
+            self._blk_grads = _merge(self.local_grad.blocks(self.L, True), self.glob_grad.blocks(self.L, False), self.L)
+            self._blk_lm = self.local_m.blocks(self.L, True)
+            self._blk_lv = self.local_v.blocks(self.L, True)
+            self._blk_gm = self.glob_m.blocks(self.L, False)
+            self._blk_gv = self.glob_v.blocks(self.L, False)
+            self._blk_key = key
+        return self._blk_params, self._blk_grads
 
     def local_grads(self, B: int) -> List[torch.Tensor]:
         """Views of the compact local gradient written by the last LOCAL pass: (2,B,1), (2,B,sumK)."""
@@ -324,17 +335,17 @@ class Engine:
         fz = (C.c_int32 * MAX_LAYERS)()
         for l in freeze_z_layers:
             fz[int(l)] = 1
+        params, grads = self._cached_blocks()
         rc = self.lib.scdef_adam_local(
-            self.ctx, C.byref(self.local.blocks(self.L, True)), C.byref(self.local_grad.blocks(self.L, True)),
-            C.byref(self.local_m.blocks(self.L, True)), C.byref(self.local_v.blocks(self.L, True)),
+            self.ctx, C.byref(params), C.byref(grads), C.byref(self._blk_lm), C.byref(self._blk_lv),
             C.c_void_p(indices.data_ptr()) if B > 0 else None, B, self.local_step, lr, b1, b2, eps, fz, self._stream())
         self._check(rc, "scdef_adam_local")
 
     def adam_global(self, lr: float, freeze_w=False, b1=0.9, b2=0.999, eps=1e-8):
         self.global_step += 1
+        params, grads = self._cached_blocks()
         rc = self.lib.scdef_adam_global(
-            self.ctx, C.byref(self.glob.blocks(self.L, False)), C.byref(self.glob_grad.blocks(self.L, False)),
-            C.byref(self.glob_m.blocks(self.L, False)), C.byref(self.glob_v.blocks(self.L, False)),
+            self.ctx, C.byref(params), C.byref(grads), C.byref(self._blk_gm), C.byref(self._blk_gv),
             self.global_step, lr, b1, b2, eps, int(bool(freeze_w)), self._stream())
         self._check(rc, "scdef_adam_global")
 

@@ -16,9 +16,11 @@ TOL = 1e-4
 
 
 def _run_case(N, G, Ks, nb, B, S, sg, scb=0.0, sgb=0.0, use_brd=True, marg=False, anneal=1.3,
-              resident=True, lik_impl=0, seed=0, couple=False, **hyper):
+              resident=True, lik_impl=0, seed=0, couple=False, mutate=None, **hyper):
     X, batch, model, lp, gp = small_problem(N, G, Ks, nb, seed=seed, use_brd=use_brd,
                                             marginalize_alpha=marg, **hyper)
+    if mutate is not None:
+        mutate(model, X)
     eng = make_engine(X, batch, model, lp, gp, resident=resident)
     idx = np.random.RandomState(seed).permutation(N)[:B]
     noise = Noise.draw(S, B, nb, G, Ks, seed=seed + 7, dtype=torch.float32, couple_like_reference=couple)
@@ -117,3 +119,32 @@ def test_tc_request_on_unsupported_shape_fails_loudly():
 
     with pytest.raises(ScdefError, match="tcgen05"):
         _run_case(96, 70, (9, 5, 2), 1, 40, 3, [0, 0, 0], lik_impl=2)   # G % 8 != 0
+
+
+def test_sscdef_pinned_layer():
+    """a8: supervised top layer (`_sscdef.py:484-531`): constant z = onehot(label) v 1e-3, no entropy for it,
+    alpha floor 1.0, zero gradient for its variational parameters."""
+    def pin(model, X):
+        rng = np.random.default_rng(3)
+        lab = rng.integers(0, 3, size=X.shape[0])
+        fz = np.full((X.shape[0], 3), 1e-3)
+        fz[np.arange(X.shape[0]), lab] = 1.0
+        model.supervised_layer = 2
+        model.fixed_top_z = fz
+        model.alpha_floor = 1.0
+    errs = _run_case(110, 64, (9, 5, 3), 1, 48, 3, [0, 0, 1], mutate=pin)
+    _run_case(110, 70, (9, 5, 3), 2, 48, 2, [0, 0, 1], mutate=pin)
+
+
+def test_iscdef_matrix_valued_w0_priors():
+    """iscDEF feeds (K0,G) matrices as w_priors[0] (`_iscdef.py:442-450`) and block priors for l>=1."""
+    def markers(model, X):
+        rng = np.random.default_rng(5)
+        K0, G = model.layer_sizes[0], X.shape[1]
+        strengths = np.where(rng.random((K0, G)) < 0.15, 20.0, 1.0)
+        gene_sets = np.where(strengths > 1.0, 1.0, 0.05)
+        model.w_priors[0] = [strengths, strengths / gene_sets]
+        conn = np.where(rng.random(np.asarray(model.w_priors[1][0]).shape) < 0.5, 1.0, 1e-2)
+        model.w_priors[1] = [np.asarray(model.w_priors[1][0]) * 5.0, np.asarray(model.w_priors[1][1]) * 5.0 / conn]
+    _run_case(90, 64, (12, 4, 1), 1, 40, 3, [0, 0, 0], mutate=markers)           # BRD: A = P/tau per element
+    _run_case(90, 70, (12, 4, 1), 1, 40, 2, [0, 0, 0], use_brd=False, mutate=markers)
