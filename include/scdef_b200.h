@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SCDEF_ABI_VERSION 3
+#define SCDEF_ABI_VERSION 4
 #define SCDEF_MAX_LAYERS 8
 
 #define SCDEF_OK 0
@@ -134,7 +134,17 @@ typedef struct scdef_call {
                             the all-reduce sum restores them */
   const int64_t* indices;/* device (B) rows of this rank's local tensors */
   const float* X_batch;  /* device (B,G) counts of the minibatch, or NULL -> gathered from desc.X */
+  int32_t flags;         /* SCDEF_FLAG_* */
+  int32_t reserved;
 } scdef_call;
+
+/* The previous scdef_elbo_grad on this ctx used the same workspace, noise, num_samples, lik_impl and
+   W_0 / gene-scale parameters (the LOCAL pass of the same hot-loop iteration, `_scdef.py:3238,3260`:
+   same rng_input, globals not yet updated): its sampled W_0 tile images may be reused. */
+#define SCDEF_FLAG_REUSE_W0_SAMPLES 1
+/* The caller ignores loss_out of this pass (the reference overwrites the local-pass loss with the
+   global-pass one, `_scdef.py:3235-3271`): kernels may skip value-only work. */
+#define SCDEF_FLAG_SKIP_LOSS 2
 
 int scdef_abi_version(void);
 int scdef_ctx_create(const scdef_model_desc* desc, scdef_ctx** out);

@@ -10,11 +10,12 @@ import ctypes as C
 import os
 
 MAX_LAYERS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 PASS_LOCAL, PASS_GLOBAL = 1, 2
 NOISE_PHILOX, NOISE_EXPLICIT = 0, 1
 LIK_AUTO, LIK_SIMT, LIK_TC = 0, 1, 2
+FLAG_REUSE_W0_SAMPLES, FLAG_SKIP_LOSS = 1, 2
 
 _f32p = C.c_void_p  # device pointers travel as integers
 
@@ -96,6 +97,8 @@ class Call(C.Structure):
         ("global_weight", C.c_float),
         ("indices", C.c_void_p),
         ("X_batch", _f32p),
+        ("flags", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

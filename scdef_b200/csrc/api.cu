@@ -436,6 +436,8 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       a.P_scalar = d.w_prior_shape_scalar[0]; a.R_scalar = d.w_prior_rate_scalar[0];
       a.use_brd = d.use_brd; a.B = B; a.G = G; a.K0 = K0; a.nb = nb; a.pass = pass; a.S = S;
       a.scale = scale; a.global_weight = gw; a.anneal = anneal; a.w0_stopped = st0; a.lik_on = lik_run;
+      a.reuse_w0 = (call->flags & SCDEF_FLAG_REUSE_W0_SAMPLES) ? 1 : 0;
+      a.want_loss = (call->flags & SCDEF_FLAG_SKIP_LOSS) ? 0 : 1;
       a.ws = ws + plan.tc_off; a.ws_bytes = plan.tc_bytes;
       {
         ProfScope ps(ctx, SCDEF_PROF_LIK, st);
@@ -625,6 +627,7 @@ int scdef_posterior(scdef_ctx* ctx, const scdef_blocks* params, const scdef_bloc
 
 /* bring-up hook (not part of the public header): dump the tcgen05 rate tile R as (S,B,G) */
 void scdef_debug_tc_dump(float* p) { lik_tc_set_debug(p); }
+void scdef_debug_tc_timing(unsigned long long* out) { cudaDeviceSynchronize(); lik_tc_read_timing(out); }
 
 int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam, void* cuda_stream) {
   if (!X || n_rows < 0 || n_genes < 1) return SCDEF_EINVAL;

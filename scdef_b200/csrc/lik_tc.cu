@@ -336,6 +336,7 @@ struct TcScratch {
   float* wmu;       // (K0,G) clip(mu) of W_0            } written once per pass by k_tc_wprep
   float* wsig;      // (K0,G) exp(clip(rho)) of W_0      }
   uint8_t* zimg;    // (S, ceil(B/128), 2 planes) z0 samples pre-split to bf16 hi/lo in the UMMA layout
+  uint8_t* wimg;    // (S, n_tiles) W_0 sample tiles: [hi plane | lo plane | gene-scale tile (MAX_NB x 64 f32)]
   int* brow;        // (B) batch of each minibatch row
   long long* xoff;  // (B) element offset of each minibatch row in X
 };
@@ -654,6 +655,83 @@ __global__ void __launch_bounds__(256) k_tc_zprep(const LikTcArgs a, uint8_t* zi
   }
 }
 
+// W_0 samples of every (MC sample, gene tile) -> tile images for the TMA-fed pipeline, at full occupancy.
+// grid = (ceil(G/256), S), block = 256: thread = (row lane kk, 8-gene chunk), loop over the k0 row groups.
+// Also: the per-row sums (sum_g log W, sum_g W) of the W_0 prior, and the gene-scale sample tile.
+__global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScratch ws, int KP, int n_tiles, uint32_t w_plane,
+                                                 uint32_t w_unit) {
+  __shared__ float rowacc[128][2];
+  const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int kk = tid & 7, cgl = tid >> 3;
+  const int g = blockIdx.x * 256 + cgl * 8;
+  const int tile = g / TG, cg = (g % TG) / 8;
+  const int nkg = KP / 8;
+  for (int i = tid; i < 256; i += 256) (&rowacc[0][0])[i] = 0.f;
+  __syncthreads();
+  if (tile < n_tiles) {
+    uint8_t* unit = ws.wimg + ((long long)s * n_tiles + tile) * w_unit;
+    const bool gok = g < a.G;
+    for (int kg = 0; kg < nkg; ++kg) {
+      const int k = kg * 8 + kk;
+      float w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = 0.f;
+      float su = 0.f, sw = 0.f;
+      if (k < a.K0 && gok) {
+        const long long base = (long long)k * a.G + g;
+        const float4 m0 = *reinterpret_cast<const float4*>(ws.wmu + base), m1 = *reinterpret_cast<const float4*>(ws.wmu + base + 4);
+        const float4 s0 = *reinterpret_cast<const float4*>(ws.wsig + base), s1 = *reinterpret_cast<const float4*>(ws.wsig + base + 4);
+        float4 e0, e1;
+        if (a.eps_W0) {
+          const float* ep = a.eps_W0 + (long long)s * a.K0 * a.G + base;
+          e0 = *reinterpret_cast<const float4*>(ep); e1 = *reinterpret_cast<const float4*>(ep + 4);
+        } else {
+          e0 = philox_normal4(a.key, a.tag, (uint32_t)s, (uint32_t)(base >> 2));
+          e1 = philox_normal4(a.key, a.tag, (uint32_t)s, (uint32_t)(base >> 2) + 1u);
+        }
+        const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        const float sg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float ep[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float u = fminf(fmaxf(fmaf(sg[e], ep[e], mu[e]), LOG_V_LO), LOG_V_HI);
+          w[e] = __expf(u);
+          su += u;
+          sw += w[e];
+        }
+      }
+      uint4 hi, lo;
+      split8(w, hi, lo);
+      const uint32_t off = (uint32_t)kg * W_RS + (uint32_t)cg * 128u + (uint32_t)kk * 16u;
+      *reinterpret_cast<uint4*>(unit + off) = hi;
+      *reinterpret_cast<uint4*>(unit + w_plane + off) = lo;
+      // lanes {kk, kk+8, kk+16, kk+24} hold 4 chunks of row k
+      su += __shfl_xor_sync(0xffffffffu, su, 8); sw += __shfl_xor_sync(0xffffffffu, sw, 8);
+      su += __shfl_xor_sync(0xffffffffu, su, 16); sw += __shfl_xor_sync(0xffffffffu, sw, 16);
+      if (lane < 8 && k < a.K0) {
+        atomicAdd(&rowacc[k][0], su);
+        atomicAdd(&rowacc[k][1], sw);
+      }
+    }
+  }
+  // gene-scale sample tile(s) of this block's 256 genes
+  for (int i = tid; i < a.nb * 256; i += 256) {
+    const int b = i / 256, gl = i - b * 256, gg = blockIdx.x * 256 + gl;
+    const int t2 = gg / TG;
+    if (t2 < n_tiles) {
+      float* st = reinterpret_cast<float*>(ws.wimg + ((long long)s * n_tiles + t2) * w_unit + 2 * w_plane);
+      st[b * TG + (gg % TG)] = gg < a.G ? a.smp_s[((long long)s * a.nb + b) * a.G + gg] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < a.K0; k += 256) {
+    if (rowacc[k][0] != 0.f || rowacc[k][1] != 0.f) {
+      atomicAdd(&ws.rowstats[((long long)s * a.K0 + k) * 2 + 0], rowacc[k][0]);
+      atomicAdd(&ws.rowstats[((long long)s * a.K0 + k) * 2 + 1], rowacc[k][1]);
+    }
+  }
+}
+
 // ---- small companions ---------------------------------------------------------------------------------
 // ctilde[s][b][k] = sum_{n in batch b} c_n^s z_nk^s ;  grid = S, block = 128
 __global__ void __launch_bounds__(128) k_tc_ctilde(const LikTcArgs a, float* ctilde) {
@@ -801,10 +879,18 @@ size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb) {
   const size_t zimg = (size_t)S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
   return a256((size_t)S * K0 * 2 * 4) + a256((size_t)S * nb * K0 * 4) + a256((size_t)nb * G * 4) +
          a256(part_local > part_global ? part_local : part_global) + 2 * a256((size_t)K0 * G * 4) + a256(zimg) +
-         a256(Bp * 4) + a256(Bp * 8) + 1024;
+         a256(Bp * 4) + a256(Bp * 8) + a256((size_t)S * g.n_tiles * plan_pipe_smem(g.KP).w_unit) + 1024;
 }
 
 void lik_tc_set_debug(float* p) { cudaMemcpyToSymbol(g_dbg_R, &p, sizeof(p)); }
+
+void lik_tc_read_timing(unsigned long long* out) {
+#ifdef SCDEF_TC_TIMING
+  cudaMemcpyFromSymbol(out, g_tc_timing, sizeof(unsigned long long) * 2 * 4 * 16);
+#else
+  for (int i = 0; i < 128; ++i) out[i] = 0;
+#endif
+}
 
 int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStream_t st) {
   (void)sm_count;
@@ -830,16 +916,22 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   ws.zimg = (uint8_t*)w;   w += a256(zimg_bytes);
   ws.brow = (int*)w;       w += a256(Bp * 4);
   ws.xoff = (long long*)w; w += a256(Bp * 8);
+  ws.wimg = (uint8_t*)w;   w += a256((size_t)a.S * g.n_tiles * plan_pipe_smem(g.KP).w_unit);
   if ((size_t)(w - (char*)a.ws) > a.ws_bytes) return SCDEF_EWORKSPACE;
   const Smem L = plan_smem(g.KP);
   const PipeSmem PL = plan_pipe_smem(g.KP);
   static const bool mono = getenv("SCDEF_TC_MONO") != nullptr;  // A/B switch: the monolithic v2a kernels
   const bool global_pass = a.pass == SCDEF_PASS_GLOBAL;
-  cudaMemsetAsync(ws.rowstats, 0, (size_t)a.S * a.K0 * 2 * 4, st);
-  if (a.lik_on && !mono) {
-    k_tc_wprep<<<148 * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
+  const bool pipe = a.lik_on && !mono;
+  const bool reuse = pipe && a.reuse_w0;  // W_0 image + row sums of the previous pass (same noise, same W_0) are still valid
+  if (!reuse) cudaMemsetAsync(ws.rowstats, 0, (size_t)a.S * a.K0 * 2 * 4, st);
+  if (pipe) {
     k_tc_rowprep<<<(a.B + 255) / 256, 256, 0, st>>>(a, ws.brow, ws.xoff);
     k_tc_zprep<<<148 * 4, 256, 0, st>>>(a, ws.zimg, g.KP);
+    if (!reuse) {
+      k_tc_wprep<<<148 * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
+      k_tc_wgen<<<dim3((a.G + 255) / 256, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
+    }
   }
   if (global_pass) {
     if (a.lik_on) {
@@ -856,8 +948,13 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   } else {
     if (a.lik_on) {
       if (!mono) {
-        cudaFuncSetAttribute(k_lik_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
-        k_lik_pipe<false, true><<<dim3(a.S * g.NG, g.n_cblocks), PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+        if (a.want_loss) {
+          cudaFuncSetAttribute(k_lik_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+          k_lik_pipe<false, true><<<dim3(a.S * g.NG, g.n_cblocks), PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+        } else {
+          cudaFuncSetAttribute(k_lik_pipe<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+          k_lik_pipe<false, false><<<dim3(a.S * g.NG, g.n_cblocks), PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+        }
       } else {
         cudaFuncSetAttribute(k_lik_tc_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
         k_lik_tc_local<<<dim3(a.S * g.NG, g.n_cblocks), NT, L.total, st>>>(a, g, ws, loss_out);

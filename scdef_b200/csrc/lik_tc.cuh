@@ -29,7 +29,7 @@ struct LikTcArgs {
   const float* P;  // W_0 prior matrices or nullptr
   const float* R;
   float P_scalar, R_scalar;
-  int use_brd, B, G, K0, nb, pass, S, w0_stopped, lik_on;
+  int use_brd, B, G, K0, nb, pass, S, w0_stopped, lik_on, reuse_w0, want_loss;
   float scale, global_weight, anneal;
   void* ws;
   size_t ws_bytes;
@@ -38,6 +38,7 @@ struct LikTcArgs {
 bool lik_tc_supported(int K0, int G, int nb);
 size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb);
 void lik_tc_set_debug(float* p);
+void lik_tc_read_timing(unsigned long long* out);
 int lik_tc_launch(const LikTcArgs& a, double* loss_out, int sm_count, cudaStream_t st);
 
 }  // namespace scdef

@@ -27,13 +27,20 @@ struct PipeMisc {
   double red[32];
   float rowU[2][128], rowW[2][128];
   float colacc[2][MAX_NB][TG];
-  float stile[2][MAX_NB][TG];   // gene-scale samples s_{b,g} of the stage's (sample, tile)
   float ct_sm[MAX_NB][128];     // ctilde of the sample being generated (GLOBAL)
 };
+
+#ifdef SCDEF_TC_TIMING
+__device__ unsigned long long g_tc_timing[2][4][16];  // [kernel variant][role P/MMA/E/COPY][slot]
+#define TWAIT(slot, bar, par) do { long long _t0 = clock64(); mbar_wait(bar, par); tacc[slot] += clock64() - _t0; } while (0)
+#else
+#define TWAIT(slot, bar, par) mbar_wait(bar, par)
+#endif
 
 struct PipeSmem {
   uint32_t z[2], w[2], q, misc, total;   // each z / w / q region = hi plane followed by lo plane
   uint32_t z_rs, z_plane, w_plane, q_plane;
+  uint32_t w_unit;                       // bytes of one W image unit: hi | lo | gene-scale tile (MAX_NB x TG floats)
 };
 __host__ __device__ inline PipeSmem plan_pipe_smem(int KP) {
   PipeSmem s;
@@ -44,8 +51,9 @@ __host__ __device__ inline PipeSmem plan_pipe_smem(int KP) {
   uint32_t o = 0;
   s.z[0] = o; o += 2 * s.z_plane;
   s.z[1] = o; o += 2 * s.z_plane;
-  s.w[0] = o; o += 2 * s.w_plane;
-  s.w[1] = o; o += 2 * s.w_plane;
+  s.w_unit = 2 * s.w_plane + (uint32_t)(MAX_NB * TG * 4);
+  s.w[0] = o; o += s.w_unit;
+  s.w[1] = o; o += s.w_unit;
   s.q = o; o += 2 * s.q_plane;
   s.misc = o;
   s.total = o + (uint32_t)((sizeof(PipeMisc) + 1023) / 1024 * 1024);
@@ -79,100 +87,47 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 }
 
 // ---- producers -------------------------------------------------------------------------------------
-// W^s tile -> wbuf (hi/lo planes); row sums of (log W, W) and, GLOBAL, ctilde^T W into the stage's accumulators.
-template <bool GLOBAL>
-__device__ __forceinline__ void pipe_gen_w(const LikTcArgs& a, const TcScratch& ws, uint8_t* wbuf, uint32_t w_plane, PipeMisc* mi,
-                                           int stage, int KP, int s, int g0, const float* ctilde_s, bool want_stats, int tid) {
+// GLOBAL side work on a landed W tile: colacc[b][g] = sum_k ctilde[b][k] W[k][g]  (W = hi + lo from smem)
+__device__ __forceinline__ void pipe_col_w(const LikTcArgs& a, const uint8_t* wbuf, uint32_t w_plane, PipeMisc* mi, int stage,
+                                           int KP, int tid) {
   const int nkg = KP / 8;
-  const int kk = tid & 7, cg = (tid >> 3) & 7, lane = tid & 31;
-  const int g = g0 + cg * 8;
-  const bool gok = g < a.G;
+  const int kk = tid & 7, cg = (tid >> 3) & 7;
   float col[MAX_NB][8];
-  if (GLOBAL) {
 #pragma unroll
-    for (int b = 0; b < MAX_NB; ++b)
+  for (int b = 0; b < MAX_NB; ++b)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) col[b][e] = 0.f;
-  }
-  // software pipeline: the loads of item i+1 are in flight while item i is sampled
-  float4 nm0, nm1, ns0, ns1, ne0, ne1;
-  auto fetch = [&](int kg) {
-    const int k = kg * 8 + kk;
-    if (kg < nkg && k < a.K0 && gok) {
-      const long long base = (long long)k * a.G + g;
-      nm0 = *reinterpret_cast<const float4*>(ws.wmu + base); nm1 = *reinterpret_cast<const float4*>(ws.wmu + base + 4);
-      ns0 = *reinterpret_cast<const float4*>(ws.wsig + base); ns1 = *reinterpret_cast<const float4*>(ws.wsig + base + 4);
-      if (a.eps_W0) {
-        const float* ep = a.eps_W0 + (long long)s * a.K0 * a.G + base;
-        ne0 = *reinterpret_cast<const float4*>(ep); ne1 = *reinterpret_cast<const float4*>(ep + 4);
-      }
-    }
-  };
-  fetch(tid >> 6);
+    for (int e = 0; e < 8; ++e) col[b][e] = 0.f;
   for (int kg = tid >> 6; kg < nkg; kg += P_THREADS / 64) {
     const int k = kg * 8 + kk;
-    const float4 m0 = nm0, m1 = nm1, s0 = ns0, s1 = ns1;
-    float4 e0 = ne0, e1 = ne1;
-    fetch(kg + P_THREADS / 64);
+    if (k >= a.K0) continue;
+    const uint32_t off = (uint32_t)kg * W_RS + (uint32_t)cg * 128u + (uint32_t)kk * 16u;
+    const uint4 hv = *reinterpret_cast<const uint4*>(wbuf + off), lv = *reinterpret_cast<const uint4*>(wbuf + w_plane + off);
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
     float w[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) w[e] = 0.f;
-    float su = 0.f, sw = 0.f;
-    if (k < a.K0 && gok) {
-      if (!a.eps_W0) {
-        const uint32_t quad = (uint32_t)(((long long)k * a.G + g) >> 2);
-        e0 = philox_normal4(a.key, a.tag, (uint32_t)s, quad);
-        e1 = philox_normal4(a.key, a.tag, (uint32_t)s, quad + 1u);
-      }
-      const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-      const float sg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-      const float ep[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float u = fminf(fmaxf(fmaf(sg[e], ep[e], mu[e]), LOG_V_LO), LOG_V_HI);
-        w[e] = __expf(u);
-        su += u;
-        sw += w[e];
-      }
-      if (GLOBAL) {
-#pragma unroll
-        for (int b = 0; b < MAX_NB; ++b) {
-          if (b < a.nb) {
-            const float ct = mi->ct_sm[b][k];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) col[b][e] = fmaf(ct, w[e], col[b][e]);
-          }
-        }
-      }
+    for (int p = 0; p < 4; ++p) {
+      w[2 * p] = bf16lo(hw[p]) + bf16lo(lw[p]);
+      w[2 * p + 1] = bf16hi(hw[p]) + bf16hi(lw[p]);
     }
-    uint4 hi, lo;
-    split8(w, hi, lo);
-    const uint32_t off = (uint32_t)kg * W_RS + (uint32_t)cg * 128u + (uint32_t)kk * 16u;
-    *reinterpret_cast<uint4*>(wbuf + off) = hi;
-    *reinterpret_cast<uint4*>(wbuf + w_plane + off) = lo;
-    if (want_stats) {
-      // the 4 lanes {kk, kk+8, kk+16, kk+24} of this warp hold 4 gene chunks of the same row k
-      su += __shfl_xor_sync(0xffffffffu, su, 8); sw += __shfl_xor_sync(0xffffffffu, sw, 8);
-      su += __shfl_xor_sync(0xffffffffu, su, 16); sw += __shfl_xor_sync(0xffffffffu, sw, 16);
-      if (lane < 8 && k < a.K0) {
-        atomicAdd(&mi->rowU[stage][k], su);
-        atomicAdd(&mi->rowW[stage][k], sw);
-      }
-    }
-  }
-  if (GLOBAL) {
-    // reduce over the 8 rows kk held by lanes (lane & 7), then one atomic per (b, gene)
 #pragma unroll
     for (int b = 0; b < MAX_NB; ++b) {
       if (b < a.nb) {
+        const float ct = mi->ct_sm[b][k];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float v = col[b][e];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          if (kk == 0) atomicAdd(&mi->colacc[stage][b][cg * 8 + e], v);
-        }
+        for (int e = 0; e < 8; ++e) col[b][e] = fmaf(ct, w[e], col[b][e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < MAX_NB; ++b) {
+    if (b < a.nb) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = col[b][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (kk == 0) atomicAdd(&mi->colacc[stage][b][cg * 8 + e], v);
       }
     }
   }
@@ -187,6 +142,11 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
   PipeMisc* mi = reinterpret_cast<PipeMisc*>(sm + L.misc);
   const uint32_t sbase = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef SCDEF_TC_TIMING
+  long long tacc[16];
+  for (int i = 0; i < 16; ++i) tacc[i] = 0;
+  const long long t_start = clock64();
+#endif
 
   // ---- work of this CTA ----
   int s_fixed = 0, tile_fixed = 0, outer_begin, outer_end, j_block0 = 0, units_per_outer;
@@ -210,8 +170,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
   // ---- prologue ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&mi->w_full[i], P_THREADS);
-      mbar_init(&mi->w_empty[i], GLOBAL ? E_THREADS : 1);
+      mbar_init(&mi->w_full[i], 1);
+      mbar_init(&mi->w_empty[i], GLOBAL ? E_THREADS + P_THREADS : 1);
       mbar_init(&mi->z_full[i], 1);
       mbar_init(&mi->z_empty[i], 1);
       mbar_init(&mi->r_full[i], 1);
@@ -239,70 +199,61 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
   const uint32_t tmem_acc2 = tmem + 2 * TG;  // LOCAL: dz[half] (KP cols each); GLOBAL: dW[stage] (TG cols each)
 
   if (warp < 4) {
-    // =========================================== PRODUCERS ===========================================
-    const int tid = threadIdx.x;
-    const bool want_stats = GLOBAL ? true : (blockIdx.y == 0);
-    int u = 0;
-    for (int oi = 0; oi < n_outer; ++oi) {
-      const int st = oi & 1;
-      const int s = GLOBAL ? outer_begin + oi : s_fixed;
-      const int g0 = (GLOBAL ? tile_fixed : outer_begin + oi) * TG;
-      mbar_wait(&mi->w_empty[st], ((oi >> 1) & 1) ^ 1);
-      // stage the gene-scale sample tile (and ctilde) of this (sample, tile) for the other roles
-      for (int i = tid; i < a.nb * TG; i += P_THREADS) {
-        const int b = i / TG, gl = i - b * TG;
-        mi->stile[st][b][gl] = (g0 + gl < a.G) ? a.smp_s[((long long)s * a.nb + b) * a.G + g0 + gl] : 0.f;
-      }
-      if (GLOBAL) {
+    // =========================================== SIDE WARPS ===========================================
+    // GLOBAL: gene-scale likelihood gradient  G_s += scale * (colsumX / s - ctilde^T W)  per (tile, sample)
+    if (GLOBAL) {
+      const int tid = threadIdx.x;
+      const int g0 = tile_fixed * TG;
+      for (int oi = 0; oi < n_outer; ++oi) {
+        const int st = oi & 1;
+        const int s = outer_begin + oi;
         const float* ct = ws.ctilde + (long long)s * a.nb * a.K0;
         for (int i = tid; i < a.nb * a.K0; i += P_THREADS) mi->ct_sm[i / a.K0][i % a.K0] = ct[i];
         named_bar_sync(1, P_THREADS);
-      }
-      pipe_gen_w<GLOBAL>(a, ws, sm + L.w[st], L.w_plane, mi, st, KP, s, g0,
-                         GLOBAL ? ws.ctilde + (long long)s * a.nb * a.K0 : nullptr, want_stats, tid);
-      fence_async_smem();
-      mbar_arrive(&mi->w_full[st]);
-      named_bar_sync(1, P_THREADS);
-      if (want_stats) {
-        for (int k = tid; k < a.K0; k += P_THREADS) {
-          atomicAdd(&ws.rowstats[((long long)s * a.K0 + k) * 2 + 0], mi->rowU[st][k]);
-          atomicAdd(&ws.rowstats[((long long)s * a.K0 + k) * 2 + 1], mi->rowW[st][k]);
-          mi->rowU[st][k] = 0.f;
-          mi->rowW[st][k] = 0.f;
-        }
-      }
-      if (GLOBAL && tid < TG) {
-        const int g = g0 + tid;
-        for (int b = 0; b < a.nb; ++b) {
-          if (g < a.G && a.G_s) {
-            const float sv = mi->stile[st][b][tid];
-            a.G_s[((long long)s * a.nb + b) * a.G + g] += a.scale * (ws.colsumX[(long long)b * a.G + g] / sv - mi->colacc[st][b][tid]);
+        TWAIT(0, &mi->w_full[st], (oi >> 1) & 1);
+        pipe_col_w(a, sm + L.w[st], L.w_plane, mi, st, KP, tid);
+        named_bar_sync(1, P_THREADS);
+        if (tid < TG) {
+          const int g = g0 + tid;
+          const float* stile = reinterpret_cast<const float*>(sm + L.w[st] + 2 * L.w_plane);
+          for (int b = 0; b < a.nb; ++b) {
+            if (g < a.G && a.G_s) {
+              const float sv = stile[b * TG + tid];
+              a.G_s[((long long)s * a.nb + b) * a.G + g] += a.scale * (ws.colsumX[(long long)b * a.G + g] / sv - mi->colacc[st][b][tid]);
+            }
+            mi->colacc[st][b][tid] = 0.f;
           }
-          mi->colacc[st][b][tid] = 0.f;
         }
+        mbar_arrive(&mi->w_empty[st]);
       }
     }
-    (void)u;
   } else if (warp == 13) {
     // =========================================== COPY (TMA) ===========================================
     if (lane == 0) {
-      if (GLOBAL) {
-        int u = 0;
-        for (int oi = 0; oi < n_outer; ++oi) {
-          const int s = outer_begin + oi;
-          for (int cb = 0; cb < units_per_outer; ++cb, ++u) {
-            const int zs = u & 1;
-            mbar_wait(&mi->z_empty[zs], ((u >> 1) & 1) ^ 1);
-            mbar_arrive_expect_tx(&mi->z_full[zs], z_bytes);
-            bulk_g2s(sbase + L.z[zs], ws.zimg + ((long long)s * units_total_B + cb) * z_bytes, z_bytes, &mi->z_full[zs]);
-          }
-        }
-      } else {
+      const uint32_t w_bytes = 2u * L.w_plane + (uint32_t)(a.nb * TG * 4);
+      if (!GLOBAL) {
         // z0^s of the 256-cell block is static: both halves land once, on z_full[0]
         mbar_arrive_expect_tx(&mi->z_full[0], z_bytes * (uint32_t)units_per_outer);
         for (int h = 0; h < units_per_outer; ++h)
           bulk_g2s(sbase + L.z[h], ws.zimg + ((long long)s_fixed * units_total_B + (j_block0 / UC + h)) * z_bytes, z_bytes,
                    &mi->z_full[0]);
+      }
+      int u = 0;
+      for (int oi = 0; oi < n_outer; ++oi) {
+        const int st = oi & 1;
+        const int s = GLOBAL ? outer_begin + oi : s_fixed;
+        const int tile = GLOBAL ? tile_fixed : outer_begin + oi;
+        TWAIT(1, &mi->w_empty[st], ((oi >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&mi->w_full[st], w_bytes);
+        bulk_g2s(sbase + L.w[st], ws.wimg + ((long long)s * gm.n_tiles + tile) * L.w_unit, w_bytes, &mi->w_full[st]);
+        if (GLOBAL) {
+          for (int cb = 0; cb < units_per_outer; ++cb, ++u) {
+            const int zs = u & 1;
+            TWAIT(0, &mi->z_empty[zs], ((u >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(&mi->z_full[zs], z_bytes);
+            bulk_g2s(sbase + L.z[zs], ws.zimg + ((long long)s * units_total_B + cb) * z_bytes, z_bytes, &mi->z_full[zs]);
+          }
+        }
       }
     }
     __syncwarp();
@@ -314,9 +265,9 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
       auto issue_mma1 = [&](int u) {
         const int oi = u / units_per_outer, cb = u - oi * units_per_outer;
         const int st = oi & 1, rs = u & 1, zb = GLOBAL ? (u & 1) : cb;
-        if (cb == 0) mbar_wait(&mi->w_full[st], (oi >> 1) & 1);
-        if (GLOBAL) mbar_wait(&mi->z_full[zb], (u >> 1) & 1);
-        mbar_wait(&mi->r_empty[rs], ((u >> 1) & 1) ^ 1);
+        if (cb == 0) TWAIT(0, &mi->w_full[st], (oi >> 1) & 1);
+        if (GLOBAL) TWAIT(1, &mi->z_full[zb], (u >> 1) & 1);
+        TWAIT(2, &mi->r_empty[rs], ((u >> 1) & 1) ^ 1);
         tc_fence_after();
         uint32_t acc = 0;
         for (int ks = 0; ks < KP / 16; ++ks) {
@@ -336,8 +287,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
         if (u + 1 < U) issue_mma1(u + 1);
         const int oi = u / units_per_outer, cb = u - oi * units_per_outer;
         const int st = oi & 1;
-        mbar_wait(&mi->q_full, u & 1);
-        if (GLOBAL && cb == 0) mbar_wait(&mi->dw_empty[st], ((oi >> 1) & 1) ^ 1);
+        TWAIT(3, &mi->q_full, u & 1);
+        if (GLOBAL && cb == 0) TWAIT(4, &mi->dw_empty[st], ((oi >> 1) & 1) ^ 1);
         tc_fence_after();
         if (GLOBAL) {
           // dW[st] (+)= z0^T Q : A = z (MN-major, M = k0), B = Q (MN-major, N = genes), K = cells of the unit
@@ -382,7 +333,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
     const int r = (int)lane_base + lane;  // row of the unit (cell) / k0 row in epilogue 2
     const int hc = e >> 2;                // 32-gene half of the tile
     float ll = 0.f;
-    float esum[2] = {0.f, 0.f};
+    float esum0 = 0.f, esum1 = 0.f;
     const uint32_t tmem_x = tmem + 4 * TG;  // GLOBAL: the X tile of the first two 128-cell units (2 x TG columns)
     if (GLOBAL) {
       for (int cb = 0; cb < min(units_per_outer, 2); ++cb) {
@@ -435,6 +386,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
       const float c = cx.c;
       const float* xrow = a.X + cx.xoff;
       const bool x_in_tmem = GLOBAL && cb < 2;
+      float es = 0.f;
       float4 x4[8];
       if (!x_in_tmem) {
 #pragma unroll
@@ -445,9 +397,10 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
         }
       }
       nxt = fetch_ctx(u + 1);
-      mbar_wait(&mi->r_full[rs], (u >> 1) & 1);
+      if (cb == 0) mbar_wait(&mi->w_full[st], (oi >> 1) & 1);  // the gene-scale tile rides with the W image
+      TWAIT(0, &mi->r_full[rs], (u >> 1) & 1);
       tc_fence_after();
-      mbar_wait(&mi->q_empty, (u & 1) ^ 1);
+      TWAIT(1, &mi->q_empty, (u & 1) ^ 1);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         float R[16];
@@ -463,11 +416,10 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
             xs16[v * 4 + 2] = x4[cc * 4 + v].z; xs16[v * 4 + 3] = x4[cc * 4 + v].w;
           }
         }
-        const float* srow_sm = &mi->stile[st][cx.b][hc * 32 + cc * 16];
+        const float* srow_sm = reinterpret_cast<const float*>(sm + L.w[st] + 2 * L.w_plane) + cx.b * TG + hc * 32 + cc * 16;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-          // rows / genes outside the problem carry x = 0 and are masked by `ok`
-          const bool ok = valid && (g0 + cc * 16 + v * 4 < a.G);
+          // rows / genes outside the problem carry c = 0 / s = 0 and x = 0: Lambda = E = Q = 0 without masks
           const float4 s4v = *reinterpret_cast<const float4*>(srow_sm + v * 4);
           const float ss[4] = {s4v.x, s4v.y, s4v.z, s4v.w};
 #pragma unroll
@@ -475,13 +427,13 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
             const float Rv = R[v * 4 + i];
             const float xv = xs16[v * 4 + i];
             const float lam = (c * ss[i]) * Rv;
-            const float E = ok ? xv - lam : 0.f;
-            q[v * 4 + i] = ok ? __fdividef(E, Rv) : 0.f;
+            const float E = xv - lam;
+            q[v * 4 + i] = __fdividef(E, fmaxf(Rv, 1e-37f));
             if (WANT_LL) {
-              const float t = xv * __logf(lam);
-              ll += ok ? ((xv > 0.f ? t : 0.f) - lam) : 0.f;
+              const float t = xv * __logf(lam);   // lam = 0 only where x = 0: the select discards -inf * 0
+              ll += (xv > 0.f ? t : 0.f) - lam;
             }
-            esum[cb & 1] += E;
+            es += E;
           }
         }
         if (g_dbg_R && valid) {
@@ -501,10 +453,11 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
       mbar_arrive(&mi->r_empty[rs]);
       fence_async_smem();
       mbar_arrive(&mi->q_full);
+      if (cb & 1) esum1 += es; else esum0 += es;
 
       if (GLOBAL && cb == units_per_outer - 1) {
         // ---- epilogue 2: fold dW^s (and the W_0 prior gradient) into d mu, sum t log W ----
-        mbar_wait(&mi->dw_full[st], (oi >> 1) & 1);
+        TWAIT(2, &mi->dw_full[st], (oi >> 1) & 1);
         tc_fence_after();
         float dW[32];
         tmem_ld16(tmem_acc2 + (lane_base << 16) + (uint32_t)(st * TG + hc * 32), dW);
@@ -574,7 +527,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
               if (cc * 16 + i < a.K0) dst[cc * 16 + i] = v[i];
           }
         }
-        if (j < a.B && esum[h] != 0.f) atomicAdd(&a.G_c[(long long)s_fixed * a.B + j], a.scale * esum[h] / a.smp_c[(long long)s_fixed * a.B + j]);
+        const float eh = h ? esum1 : esum0;
+        if (j < a.B && eh != 0.f) atomicAdd(&a.G_c[(long long)s_fixed * a.B + j], a.scale * eh / a.smp_c[(long long)s_fixed * a.B + j]);
       }
     }
     // loss: reduce over the 256 epilogue threads
@@ -588,6 +542,13 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
     }
   }
 
+#ifdef SCDEF_TC_TIMING
+  if (blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 12 || warp == 4 || warp == 13)) {
+    const int role = warp == 0 ? 0 : (warp == 12 ? 1 : (warp == 4 ? 2 : 3));
+    for (int i = 0; i < 15; ++i) g_tc_timing[GLOBAL ? 1 : 0][role][i] = (unsigned long long)tacc[i];
+    g_tc_timing[GLOBAL ? 1 : 0][role][15] = (unsigned long long)(clock64() - t_start);
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");

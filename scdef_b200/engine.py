@@ -270,7 +270,7 @@ class Engine:
     def elbo_grad(self, which: str, indices: torch.Tensor, noise: NoiseSpec, *, num_samples: int,
                   annealing=1.0, stop_gradients=None, stop_cell_budgets=0.0, stop_gene_budgets=0.0,
                   alpha=1.0, scale=None, global_weight=1.0, X_batch: Optional[torch.Tensor] = None,
-                  lik_impl=_lib.LIK_AUTO, zero_loss=True):
+                  lik_impl=_lib.LIK_AUTO, zero_loss=True, reuse_w0=False, want_loss=True):
         """Enqueue loss + gradient (`local_loss_grad` / `global_loss_grad`, `_scdef.py:2848-2849`).
         `indices`: int64 device tensor of this rank's rows.  Results: `self.loss_buf` (device
         double[2]: cell part, global part) and `self.local_grad` / `self.glob_grad`."""
@@ -288,6 +288,7 @@ class Engine:
         call.alpha = float(alpha)
         call.scale = float(scale) if scale is not None else (self.N / max(B, 1))
         call.global_weight = float(global_weight)
+        call.flags = (_lib.FLAG_REUSE_W0_SAMPLES if reuse_w0 else 0) | (0 if want_loss else _lib.FLAG_SKIP_LOSS)
         keep = []
         if B > 0:
             assert indices.dtype == torch.int64 and indices.is_cuda and indices.is_contiguous()

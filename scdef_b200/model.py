@@ -714,10 +714,12 @@ class scDEF:
                               stop_gene_budgets=stop_gene_budgets, alpha=alpha_f, scale=n_total / n_glob,
                               global_weight=gw, X_batch=Xb, lik_impl=self.lik_impl)
                     if update_locals:
-                        eng.elbo_grad("local", idx, noise, **kw)
+                        # the local-pass loss is overwritten by the global pass (3235-3271): skip it when unused
+                        eng.elbo_grad("local", idx, noise, want_loss=not update_globals, **kw)
                         eng.adam_local(idx, float(local_lr), freeze_z_layers)
                     if update_globals:
-                        eng.elbo_grad("global", idx, noise, **kw)
+                        # same rng_input, globals untouched since the local pass: its W_0 sample tiles are reusable
+                        eng.elbo_grad("global", idx, noise, reuse_w0=bool(update_locals), **kw)
                         if shard.world > 1:
                             _dist.all_reduce_sum(eng.glob_grad.flat, shard)
                         eng.adam_global(float(lr), freeze_w=bool(freeze_w))
