@@ -336,6 +336,7 @@ struct TcScratch {
   float* wmu;       // (K0,G) clip(mu) of W_0            } written once per pass by k_tc_wprep
   float* wsig;      // (K0,G) exp(clip(rho)) of W_0      }
   uint8_t* zimg;    // (S, ceil(B/128), 2 planes) z0 samples pre-split to bf16 hi/lo in the UMMA layout
+  float* ximg;      // (n_tiles, units, 4 lane quarters, 16 chunks, 32 lanes, 4) minibatch counts, lane-per-row coalesced
   uint8_t* wimg;    // (S, n_tiles) W_0 sample tiles: [hi plane | lo plane | gene-scale tile (MAX_NB x 64 f32)]
   int* brow;        // (B) batch of each minibatch row
   long long* xoff;  // (B) element offset of each minibatch row in X
@@ -623,6 +624,26 @@ __global__ void __launch_bounds__(256) k_tc_rowprep(const LikTcArgs a, int* brow
   brow[j] = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
   xoff[j] = (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
 }
+// minibatch counts -> image in which the epilogue's "lane = cell row, 16 B per lane" loads are contiguous:
+// element (row = unit*128 + q*32 + lane, gene = tile*64 + v*4 + i) at ((((tile*units + unit)*4 + q)*16 + v)*32 + lane)*4 + i
+__global__ void __launch_bounds__(256) k_tc_xprep(const LikTcArgs a, float* ximg, int n_tiles) {
+  const int units = (a.B + UC - 1) / UC;
+  const long long total = (long long)n_tiles * units * 4 * 16 * 32;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    // decode so that consecutive threads read consecutive genes of one row (coalesced reads)
+    const int v = (int)(t % 16);
+    long long rest = t / 16;
+    const int tile = (int)(rest % n_tiles); rest /= n_tiles;
+    const int lane = (int)(rest % 32); rest /= 32;
+    const int q = (int)(rest % 4);
+    const int unit = (int)(rest / 4);
+    const int j = unit * UC + q * 32 + lane, g = tile * TG + v * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < a.B && g < a.G) x = *reinterpret_cast<const float4*>(a.X + (a.idx_x ? a.idx_x[j] : (long long)j) * a.G + g);
+    *reinterpret_cast<float4*>(ximg + ((((((long long)tile * units + unit) * 4 + q) * 16 + v) * 32 + lane) * 4)) = x;
+  }
+}
+
 // z0 samples (S,B,K0) fp32 -> per (s, 128-cell unit) image [hi plane | lo plane] in the canonical layout
 __global__ void __launch_bounds__(256) k_tc_zprep(const LikTcArgs a, uint8_t* zimg, int KP) {
   const int nchunk = KP / 8, units = (a.B + UC - 1) / UC;
@@ -729,6 +750,68 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
       atomicAdd(&ws.rowstats[((long long)s * a.K0 + k) * 2 + 0], rowacc[k][0]);
       atomicAdd(&ws.rowstats[((long long)s * a.K0 + k) * 2 + 1], rowacc[k][1]);
     }
+  }
+}
+
+// GLOBAL pass: likelihood gradient of the gene scale from the W_0 tile images,
+//   G_s[s,b,g] += scale * ( colsumX[b][g] / s_{b,g} - sum_k ctilde[s][b][k] W^s[k][g] ).   grid = (n_tiles, S), block = 256
+__global__ void __launch_bounds__(256) k_tc_colw(const LikTcArgs a, const TcScratch ws, int KP, int n_tiles, uint32_t w_plane,
+                                                 uint32_t w_unit) {
+  __shared__ float colacc[MAX_NB][TG];
+  __shared__ float ct_sm[MAX_NB][128];
+  const int tile = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+  const int kk = tid & 7, cg = (tid >> 3) & 7, nkg = KP / 8;
+  const uint8_t* unit = ws.wimg + ((long long)s * n_tiles + tile) * w_unit;
+  for (int i = tid; i < MAX_NB * TG; i += 256) (&colacc[0][0])[i] = 0.f;
+  const float* ct = ws.ctilde + (long long)s * a.nb * a.K0;
+  for (int i = tid; i < a.nb * a.K0; i += 256) ct_sm[i / a.K0][i % a.K0] = ct[i];
+  __syncthreads();
+  float col[MAX_NB][8];
+#pragma unroll
+  for (int b = 0; b < MAX_NB; ++b)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) col[b][e] = 0.f;
+  for (int kg = tid >> 6; kg < nkg; kg += 4) {
+    const int k = kg * 8 + kk;
+    if (k >= a.K0) continue;
+    const uint32_t off = (uint32_t)kg * W_RS + (uint32_t)cg * 128u + (uint32_t)kk * 16u;
+    const uint4 hv = *reinterpret_cast<const uint4*>(unit + off), lv = *reinterpret_cast<const uint4*>(unit + w_plane + off);
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+    float w[8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      w[2 * p] = bf16lo(hw[p]) + bf16lo(lw[p]);
+      w[2 * p + 1] = bf16hi(hw[p]) + bf16hi(lw[p]);
+    }
+#pragma unroll
+    for (int b = 0; b < MAX_NB; ++b) {
+      if (b < a.nb) {
+        const float c1 = ct_sm[b][k];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) col[b][e] = fmaf(c1, w[e], col[b][e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < MAX_NB; ++b) {
+    if (b < a.nb) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = col[b][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (kk == 0) atomicAdd(&colacc[b][cg * 8 + e], v);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < TG) {
+    const int g = tile * TG + tid;
+    const float* stile = reinterpret_cast<const float*>(unit + 2 * w_plane);
+    if (g < a.G && a.G_s)
+      for (int b = 0; b < a.nb; ++b)
+        a.G_s[((long long)s * a.nb + b) * a.G + g] += a.scale * (ws.colsumX[(long long)b * a.G + g] / stile[b * TG + tid] - colacc[b][tid]);
   }
 }
 
@@ -879,7 +962,8 @@ size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb) {
   const size_t zimg = (size_t)S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
   return a256((size_t)S * K0 * 2 * 4) + a256((size_t)S * nb * K0 * 4) + a256((size_t)nb * G * 4) +
          a256(part_local > part_global ? part_local : part_global) + 2 * a256((size_t)K0 * G * 4) + a256(zimg) +
-         a256(Bp * 4) + a256(Bp * 8) + a256((size_t)S * g.n_tiles * plan_pipe_smem(g.KP).w_unit) + 1024;
+         a256(Bp * 4) + a256(Bp * 8) + a256((size_t)S * g.n_tiles * plan_pipe_smem(g.KP).w_unit) +
+         a256((size_t)g.n_tiles * units * 128 * 64 * 4) + 1024;
 }
 
 void lik_tc_set_debug(float* p) { cudaMemcpyToSymbol(g_dbg_R, &p, sizeof(p)); }
@@ -917,6 +1001,7 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   ws.brow = (int*)w;       w += a256(Bp * 4);
   ws.xoff = (long long*)w; w += a256(Bp * 8);
   ws.wimg = (uint8_t*)w;   w += a256((size_t)a.S * g.n_tiles * plan_pipe_smem(g.KP).w_unit);
+  ws.ximg = (float*)w;     w += a256((size_t)g.n_tiles * units * 128 * 64 * 4);
   if ((size_t)(w - (char*)a.ws) > a.ws_bytes) return SCDEF_EWORKSPACE;
   const Smem L = plan_smem(g.KP);
   const PipeSmem PL = plan_pipe_smem(g.KP);
@@ -928,6 +1013,7 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   if (pipe) {
     k_tc_rowprep<<<(a.B + 255) / 256, 256, 0, st>>>(a, ws.brow, ws.xoff);
     k_tc_zprep<<<148 * 4, 256, 0, st>>>(a, ws.zimg, g.KP);
+    k_tc_xprep<<<148 * 4, 256, 0, st>>>(a, ws.ximg, g.n_tiles);
     if (!reuse) {
       k_tc_wprep<<<148 * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
       k_tc_wgen<<<dim3((a.G + 255) / 256, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
@@ -939,6 +1025,7 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       k_tc_colsum<<<(a.G + 255) / 256, 256, 0, st>>>(a, ws.colsumX);
     }
     if (a.lik_on && !mono) {
+      k_tc_colw<<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
       cudaFuncSetAttribute(k_lik_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
       k_lik_pipe<true, true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
     } else {

@@ -14,7 +14,7 @@ lib = _lib.load()
 out = (ctypes.c_ulonglong * 128)()
 lib.scdef_debug_tc_timing(out)
 a = np.array(out[:]).reshape(2, 4, 16)
-names = {0: ["P: w_empty"], 1: ["MMA: w_full", "z_full", "r_empty", "q_full", "dw_empty"], 2: ["E: r_full", "q_empty", "dw_full"], 3: ["COPY: z_empty"]}
+names = {0: ["P: w_empty"], 1: ["MMA: w_full", "z_full", "r_empty", "q_full", "dw_empty"], 2: ["E: r_full", "q_empty", "dw_full", "t_tmem_ld", "t_math", "t_store+fence", "t_top(loads issue)", "t_wfull"], 3: ["COPY: z_empty"]}
 for v, vn in enumerate(["LOCAL", "GLOBAL"]):
     print(vn)
     for role in range(4):
