@@ -173,6 +173,28 @@ int scdef_adam_local(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blo
                      int B, int64_t step, float lr, float b1, float b2, float eps,
                      const int32_t* freeze_z_layers, void* cuda_stream);
 
+/* Exact lazy form of scdef_adam_local (bit-identical results, see adam.cuh): rows outside the minibatch are
+   not streamed every step; their zero-gradient Adam steps are replayed when the row is next needed.
+     phase SCDEF_LAZY_CATCHUP     : replay steps row_step[n]+1 .. step-1 for the rows `indices`
+                                    (call BEFORE the local pass of iteration `step`)
+     phase SCDEF_LAZY_UPDATE      : apply iteration `step` with `grads` to the rows `indices` (call after it)
+     phase SCDEF_LAZY_CATCHUP_ALL : replay up to and including `step` for every row (before the parameters are
+                                    read, the optimiser is reset, or lr / betas change)
+   `row_step` (device int32[n_cells], caller zero-fills when the optimiser state is reset) and `bc_table`
+   (device float2[bc_len]: (1/(1-b1^k), 1/(1-b2^k)) for k = 1..bc_len, the last entry is used beyond) are
+   caller-owned. */
+/* Fills host_out[2*(k-1)..] = (1/(1-b1^k), 1/(1-b2^k)) for k = 1.. until both are exactly 1 (or max_len);
+   returns the number of entries.  Same arithmetic as the dense kernel's per-step factors. */
+int scdef_adam_bias_table(float b1, float b2, float* host_out, int max_len);
+#define SCDEF_LAZY_CATCHUP 0
+#define SCDEF_LAZY_UPDATE 1
+#define SCDEF_LAZY_CATCHUP_ALL 2
+int scdef_adam_local_lazy(scdef_ctx* ctx, int phase, const scdef_blocks* params, const scdef_blocks* grads,
+                          const scdef_blocks* m, const scdef_blocks* v, const int64_t* indices, int B,
+                          int64_t step, float lr, float b1, float b2, float eps,
+                          const int32_t* freeze_z_layers, int32_t* row_step, const float* bc_table,
+                          int bc_len, void* cuda_stream);
+
 /* Adam over the global blocks, then freeze_w restore (W blocks keep their values, moments
    still update) and clip_params: mu <= 1e4, rho <= 10 on gene_scale, brd and every W
    (not ard, not alpha). */

@@ -106,7 +106,9 @@ EXPORTS = [
     "scdef_abi_version", "scdef_ctx_create", "scdef_ctx_destroy", "scdef_last_error",
     "scdef_workspace_bytes", "scdef_elbo_grad", "scdef_adam_local", "scdef_adam_global",
     "scdef_posterior", "scdef_row_stats", "scdef_noise_fill", "scdef_profile_enable", "scdef_profile_read",
+    "scdef_adam_local_lazy", "scdef_adam_bias_table",
 ]
+LAZY_CATCHUP, LAZY_UPDATE, LAZY_CATCHUP_ALL = 0, 1, 2
 PROF_KINDS = ["lik", "adam_local_z", "hier", "sample", "wprior", "finish", "adam_global", "priors", "adam_local_c"]
 
 _LIB = None
@@ -152,6 +154,14 @@ def load():
         C.POINTER(C.c_int32), C.c_void_p,
     ]
     lib.scdef_adam_local.restype = C.c_int
+    lib.scdef_adam_local_lazy.argtypes = [
+        C.c_void_p, C.c_int, C.POINTER(Blocks), C.POINTER(Blocks), C.POINTER(Blocks), C.POINTER(Blocks),
+        C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+        C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+    ]
+    lib.scdef_adam_local_lazy.restype = C.c_int
+    lib.scdef_adam_bias_table.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_int]
+    lib.scdef_adam_bias_table.restype = C.c_int
     lib.scdef_adam_global.argtypes = [
         C.c_void_p, C.POINTER(Blocks), C.POINTER(Blocks), C.POINTER(Blocks), C.POINTER(Blocks),
         C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p,

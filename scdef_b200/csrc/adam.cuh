@@ -11,12 +11,15 @@ struct AdamHyper {
   float inv_bc1, inv_bc2;           // reciprocals (the kernels multiply instead of dividing)
 };
 
+// One optax-Adam element update.  The operation sequence is pinned with explicit intrinsics (no compiler
+// FMA contraction) so that the dense kernel and the lazy replay are bit-identical.
 __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, const AdamHyper& h,
                                           bool write_p, float clip_hi) {
-  m = h.b1 * m + (1.f - h.b1) * g;
-  v = h.b2 * v + (1.f - h.b2) * g * g;
-  float mh = m * h.inv_bc1, vh = v * h.inv_bc2;
-  float pn = p - h.lr * __fdividef(mh, sqrtf(vh) + h.eps);
+  m = __fmaf_rn(__fsub_rn(1.f, h.b1), g, __fmul_rn(h.b1, m));
+  v = __fmaf_rn(__fmul_rn(__fsub_rn(1.f, h.b2), g), g, __fmul_rn(h.b2, v));
+  const float mh = __fmul_rn(m, h.inv_bc1), vh = __fmul_rn(v, h.inv_bc2);
+  const float upd = __fdividef(mh, __fadd_rn(__fsqrt_rn(vh), h.eps));
+  const float pn = __fmaf_rn(-h.lr, upd, p);
   if (write_p) p = fminf(pn, clip_hi);  // clip_params lower bounds (-1e10) can never bind after fminf of finite
 }
 
@@ -133,6 +136,73 @@ __global__ void __launch_bounds__(256) k_adam_local(const AdamLocalArgs a, const
       }
     }
   }
+}
+
+// ---- lazy (exact) variant of the dense local Adam ------------------------------------------------------
+// A row outside the minibatch sees g = 0: m <- b1 m, v <- b2 v, p <- p - lr * m^ / (sqrt(v^) + eps).  Those steps
+// depend only on the row's own state and the step number, so they can be replayed in registers when the row is
+// next needed instead of streaming all N rows through HBM every step.  The replay executes the SAME fp32
+// operations as k_adam_local (same adam_elem, same per-step bias-correction factors from `bc_tab`), so the
+// result is bit-identical to the dense kernel.
+struct AdamLazyArgs {
+  float *p, *m, *v;        // (2, N, C)
+  const float* g;          // (2, B, C) compact (UPDATE phase)
+  const int64_t* idx;      // (B) rows, or nullptr = all N rows (full catch-up)
+  int32_t* row_step;       // (N) last Adam step applied to the row
+  const float2* bc_tab;    // [k-1] = (1/(1-b1^k), 1/(1-b2^k)); entries beyond the table are the last one (= 1, 1)
+  long long N;
+  int C, B, tab_len;
+  int target;              // CATCHUP: replay steps row_step+1 .. target;  UPDATE: the step being applied
+  int n_frozen;
+  int frozen_lo[SCDEF_MAX_LAYERS], frozen_hi[SCDEF_MAX_LAYERS];
+};
+
+// one thread per element of the selected rows; grid = (blocks, 2 halves)
+__global__ void __launch_bounds__(256) k_adam_lazy_catchup(const AdamLazyArgs a, AdamHyper h) {
+  const long long rows = a.idx ? a.B : a.N;
+  const long long total = rows * a.C;
+  const long long hoff = (long long)blockIdx.y * a.N * a.C;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long j = t / a.C;
+    const int c = (int)(t - j * a.C);
+    const long long n = a.idx ? a.idx[j] : j;
+    const int t0 = a.row_step[n];
+    if (t0 >= a.target) continue;
+    const long long i = hoff + n * a.C + c;
+    float p = a.p[i], m = a.m[i], v = a.v[i];
+    if (m == 0.f && v == 0.f) continue;  // never touched since the optimiser was reset: every replayed step is a no-op
+    bool frozen = false;
+    for (int f = 0; f < a.n_frozen; ++f) frozen |= (c >= a.frozen_lo[f]) && (c < a.frozen_hi[f]);
+    for (int k = t0 + 1; k <= a.target; ++k) {
+      const float2 bc = a.bc_tab[min(k, a.tab_len) - 1];
+      h.inv_bc1 = bc.x;
+      h.inv_bc2 = bc.y;
+      adam_elem(p, m, v, 0.f, h, !frozen, INFINITY);
+    }
+    a.p[i] = p; a.m[i] = m; a.v[i] = v;
+  }
+}
+
+// applies step `target` with the minibatch gradient to the minibatch rows (already caught up to target-1)
+__global__ void __launch_bounds__(256) k_adam_lazy_update(const AdamLazyArgs a, const AdamHyper h) {
+  const long long total = (long long)a.B * a.C;
+  const long long hoff = (long long)blockIdx.y * a.N * a.C;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long j = t / a.C;
+    const int c = (int)(t - j * a.C);
+    const long long n = a.idx[j];
+    const long long i = hoff + n * a.C + c;
+    float p = a.p[i], m = a.m[i], v = a.v[i];
+    bool frozen = false;
+    for (int f = 0; f < a.n_frozen; ++f) frozen |= (c >= a.frozen_lo[f]) && (c < a.frozen_hi[f]);
+    adam_elem(p, m, v, a.g[((long long)blockIdx.y * a.B + j) * a.C + c], h, !frozen, INFINITY);
+    a.p[i] = p; a.m[i] = m; a.v[i] = v;
+  }
+}
+
+__global__ void k_set_row_step(int32_t* row_step, const int64_t* idx, long long n, int value) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) row_step[idx ? idx[j] : j] = value;
 }
 
 // ---- posterior summaries ----------------------------------------------------------------------

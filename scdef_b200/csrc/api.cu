@@ -555,6 +555,80 @@ int scdef_adam_local(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blo
   return SCDEF_OK;
 }
 
+int scdef_adam_bias_table(float b1, float b2, float* host_out, int max_len) {
+  // (1/(1-b1^k), 1/(1-b2^k)) for k = 1.., with exactly the arithmetic scdef_adam_local uses for its per-step factors
+  if (!host_out || max_len < 1) return SCDEF_EINVAL;
+  int k = 1;
+  for (; k <= max_len; ++k) {
+    const float i1 = (float)(1.0 / (1.0 - pow((double)b1, (double)k)));
+    const float i2 = (float)(1.0 / (1.0 - pow((double)b2, (double)k)));
+    host_out[2 * (k - 1)] = i1;
+    host_out[2 * (k - 1) + 1] = i2;
+    if (i1 == 1.f && i2 == 1.f) return k;
+  }
+  return max_len;
+}
+
+int scdef_adam_local_lazy(scdef_ctx* ctx, int phase, const scdef_blocks* params, const scdef_blocks* grads,
+                          const scdef_blocks* m, const scdef_blocks* v, const int64_t* indices, int B,
+                          int64_t step, float lr, float b1, float b2, float eps,
+                          const int32_t* freeze_z_layers, int32_t* row_step, const float* bc_table,
+                          int bc_len, void* cuda_stream) {
+  if (!ctx) return SCDEF_EINVAL;
+  if (!params || !m || !v || !row_step || !bc_table || bc_len < 1 || step < 0) return fail(ctx, SCDEF_EINVAL, "bad argument");
+  if (phase != SCDEF_LAZY_CATCHUP && phase != SCDEF_LAZY_UPDATE && phase != SCDEF_LAZY_CATCHUP_ALL)
+    return fail(ctx, SCDEF_EINVAL, "bad phase %d", phase);
+  if (phase != SCDEF_LAZY_CATCHUP_ALL && B > 0 && !indices) return fail(ctx, SCDEF_EINVAL, "indices is null");
+  if (phase == SCDEF_LAZY_UPDATE && (!grads || step < 1)) return fail(ctx, SCDEF_EINVAL, "UPDATE needs grads and step >= 1");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const long long N = ctx->d.n_cells;
+  if (N == 0) return SCDEF_OK;
+  if (phase != SCDEF_LAZY_CATCHUP_ALL && B == 0) return SCDEF_OK;
+  AdamHyper h;
+  h.lr = lr; h.b1 = b1; h.b2 = b2; h.eps = eps;
+  const double s1 = (double)(step < 1 ? 1 : step);
+  h.bc1 = (float)(1.0 - pow((double)b1, s1));
+  h.bc2 = (float)(1.0 - pow((double)b2, s1));
+  h.inv_bc1 = (float)(1.0 / (1.0 - pow((double)b1, s1)));
+  h.inv_bc2 = (float)(1.0 / (1.0 - pow((double)b2, s1)));
+  int rc;
+  for (int which = 0; which < 2; ++which) {
+    AdamLazyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = which ? params->z : params->cell_scale;
+    a.m = which ? m->z : m->cell_scale;
+    a.v = which ? v->z : v->cell_scale;
+    a.g = grads ? (which ? grads->z : grads->cell_scale) : nullptr;
+    a.idx = phase == SCDEF_LAZY_CATCHUP_ALL ? nullptr : indices;
+    a.row_step = row_step;
+    a.bc_tab = reinterpret_cast<const float2*>(bc_table);
+    a.N = N; a.C = which ? ctx->Kt : 1; a.B = B; a.tab_len = bc_len;
+    a.target = phase == SCDEF_LAZY_CATCHUP ? (int)step - 1 : (int)step;
+    if (which && freeze_z_layers)
+      for (int l = 0; l < ctx->L; ++l)
+        if (freeze_z_layers[l]) { a.frozen_lo[a.n_frozen] = ctx->off[l]; a.frozen_hi[a.n_frozen] = ctx->off[l + 1]; a.n_frozen++; }
+    const long long rows = a.idx ? B : N;
+    long long blocks = (rows * a.C + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    {
+      ProfScope ps(ctx, which ? SCDEF_PROF_ADAM_LOCAL : SCDEF_PROF_ADAM_LOCAL_C, st);
+      if (phase == SCDEF_LAZY_UPDATE) k_adam_lazy_update<<<dim3((unsigned)blocks, 2), 256, 0, st>>>(a, h);
+      else k_adam_lazy_catchup<<<dim3((unsigned)blocks, 2), 256, 0, st>>>(a, h);
+    }
+    if ((rc = check_launch(ctx, "k_adam_lazy"))) return rc;
+  }
+  // the rows are now current up to `target`
+  {
+    const long long rows = phase == SCDEF_LAZY_CATCHUP_ALL ? N : B;
+    const int target = phase == SCDEF_LAZY_CATCHUP ? (int)step - 1 : (int)step;
+    k_set_row_step<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(row_step, phase == SCDEF_LAZY_CATCHUP_ALL ? nullptr : indices, rows, target);
+    if ((rc = check_launch(ctx, "k_set_row_step"))) return rc;
+  }
+  return SCDEF_OK;
+}
+
 int scdef_adam_global(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blocks* grads,
                       const scdef_blocks* m, const scdef_blocks* v, int64_t step, float lr, float b1,
                       float b2, float eps, int freeze_w, void* cuda_stream) {

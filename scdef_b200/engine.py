@@ -100,7 +100,7 @@ class Engine:
                  use_brd=True, marginalize_alpha=False, top_alpha=1.0, brd=1.0, brd_mean=1.0,
                  shrinkage_shape=1.0, shrinkage_rate=1.0, cell_scale_shape=1.0, gene_scale_shape=1.0,
                  alpha_floor=0.1, supervised_layer=None, fixed_top_z=None, X=None,
-                 device="cuda:0", batch_max=256):
+                 device="cuda:0", batch_max=256, lazy_adam=True):
         if not torch.cuda.is_available():
             raise ScdefError("scdef_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
         self.lib = _lib.load()
@@ -185,6 +185,12 @@ class Engine:
         self._ws_key = None
         self.local_step = 0
         self.global_step = 0
+        # exact lazy local Adam (bit-identical to the dense kernel): per-row "last applied step"
+        self.lazy_adam = bool(lazy_adam)
+        self.row_step = torch.zeros(max(self.N, 1), dtype=torch.int32, device=dev)
+        self._lazy_pending = False   # some rows are behind local_step
+        self._lazy_hyper = None      # (lr, b1, b2, eps, freeze tuple) of the pending steps
+        self._bc_key, self._bc_tab = None, None
         self.launches = 0  # kernels enqueued through the ABI (for bench.py's gpu_launches)
 
     # ------------------------------------------------------------------------------------
@@ -233,6 +239,7 @@ class Engine:
 
     def set_params(self, local_params=None, global_params=None):
         if local_params is not None:
+            self.local_sync()
             for v, p in zip(self.local.views, local_params):
                 v.copy_(torch.as_tensor(np.asarray(p) if not isinstance(p, torch.Tensor) else p).to(self.device, torch.float32).reshape(v.shape))
         if global_params is not None:
@@ -240,11 +247,14 @@ class Engine:
                 v.copy_(torch.as_tensor(np.asarray(p) if not isinstance(p, torch.Tensor) else p).to(self.device, torch.float32).reshape(v.shape))
 
     def get_params(self):
+        self.local_sync()
         return ([v.detach().cpu().numpy().copy() for v in self.local.views],
                 [v.detach().cpu().numpy().copy() for v in self.glob.views])
 
     def reset_optimizer(self):
         """Fresh optax state (`_scdef.py:3081-3082, 3317-3319`)."""
+        self.local_sync()  # pending zero-gradient steps belong to the old state
+        self.row_step.zero_()
         for g in (self.local_m, self.local_v, self.glob_m, self.glob_v):
             g.flat.zero_()
         self.local_step = 0
@@ -329,10 +339,64 @@ class Engine:
         return float(self.loss_buf.sum().item())
 
     # ---- optimiser ----------------------------------------------------------------------------
+    def _bc_table(self, b1, b2):
+        """(1/(1-b1^k), 1/(1-b2^k)) for k = 1.., computed exactly as the C side does for the dense kernel
+        (double pow of the float32 betas, rounded to float32); stops once both are exactly 1."""
+        key = (float(b1), float(b2))
+        if self._bc_key != key:
+            cap = 1 << 20
+            host = np.empty((cap, 2), dtype=np.float32)
+            n = self.lib.scdef_adam_bias_table(float(b1), float(b2), host.ctypes.data_as(C.c_void_p), cap)
+            if n < 1:
+                raise ScdefError("scdef_adam_bias_table failed")
+            self._bc_tab = torch.from_numpy(host[:n].copy()).to(self.device).contiguous()
+            self._bc_key = key
+        return self._bc_tab
+
+    def _lazy_call(self, phase, indices, step, lr, b1, b2, eps, freeze):
+        tab = self._bc_table(b1, b2)
+        fz = (C.c_int32 * MAX_LAYERS)()
+        for l in freeze:
+            fz[int(l)] = 1
+        params, grads = self._cached_blocks()
+        B = 0 if indices is None else int(indices.numel())
+        rc = self.lib.scdef_adam_local_lazy(
+            self.ctx, phase, C.byref(params), C.byref(grads), C.byref(self._blk_lm), C.byref(self._blk_lv),
+            C.c_void_p(indices.data_ptr()) if B > 0 else None, B, int(step), lr, b1, b2, eps, fz,
+            _ptr(self.row_step), _ptr(tab), int(tab.shape[0]), self._stream())
+        self._check(rc, "scdef_adam_local_lazy")
+
+    def local_catchup(self, indices: torch.Tensor):
+        """Lazy mode: bring the minibatch rows up to date before the objective reads them."""
+        if self.lazy_adam and self._lazy_pending:
+            lr, b1, b2, eps, freeze = self._lazy_hyper
+            self._lazy_call(_lib.LAZY_CATCHUP, indices, self.local_step + 1, lr, b1, b2, eps, freeze)
+
+    def local_sync(self):
+        """Lazy mode: replay the pending zero-gradient steps of every row (before anything reads all rows)."""
+        if getattr(self, "lazy_adam", False) and self._lazy_pending:
+            lr, b1, b2, eps, freeze = self._lazy_hyper
+            self._lazy_call(_lib.LAZY_CATCHUP_ALL, None, self.local_step, lr, b1, b2, eps, freeze)
+            self._lazy_pending = False
+
     def adam_local(self, indices: torch.Tensor, lr: float, freeze_z_layers: Sequence[int] = (),
                    b1=0.9, b2=0.999, eps=1e-8):
-        self.local_step += 1
+        """optax.adam over the local blocks (`_scdef.py:3112-3116`).  Dense: one pass over all N rows.
+        Lazy (default): only the minibatch rows are written now; the other rows' zero-gradient steps are
+        replayed on demand — the same fp32 operations, bit-identical parameters."""
         B = int(indices.numel())
+        if self.lazy_adam:
+            hyper = (float(lr), float(b1), float(b2), float(eps), tuple(int(l) for l in freeze_z_layers))
+            if self._lazy_pending and self._lazy_hyper != hyper:
+                self.local_sync()
+            self._lazy_hyper = hyper
+            if self._lazy_pending:  # rows of this minibatch may still be behind (if local_catchup was not called)
+                self._lazy_call(_lib.LAZY_CATCHUP, indices, self.local_step + 1, *hyper)
+            self.local_step += 1
+            self._lazy_call(_lib.LAZY_UPDATE, indices, self.local_step, *hyper)
+            self._lazy_pending = True
+            return
+        self.local_step += 1
         fz = (C.c_int32 * MAX_LAYERS)()
         for l in freeze_z_layers:
             fz[int(l)] = 1
@@ -353,6 +417,7 @@ class Engine:
     # ---- summaries -----------------------------------------------------------------------------
     def posterior(self):
         """(means, variances) of every block as lists shaped like one half of the params."""
+        self.local_sync()
         lshapes, gshapes = _block_shapes(self.N, self.Ks, self.nb, self.G)
         half = lambda shapes: [(n, s[1:]) for n, s in shapes]
         lm, lv = _FlatGroup(half(lshapes), self.device), _FlatGroup(half(lshapes), self.device)

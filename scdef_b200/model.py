@@ -76,12 +76,14 @@ class scDEF:
         noise_coupling: bool = True,
         lik_impl: int = 0,
         process_group=None,
+        lazy_adam: bool = True,
     ):
         # --- extensions of this package (keyword-only, all optional) ---
         self.device = device
         self.x_placement = x_placement  # "device": counts resident in HBM; "host": streamed per step
         self.noise_coupling = bool(noise_coupling)
         self.lik_impl = int(lik_impl)
+        self.lazy_adam = bool(lazy_adam)  # exact lazy form of the dense local Adam (bit-identical)
         self._shard = _dist.ShardInfo.from_group(process_group)
         self.max_steps_per_learn = None  # benchmark hook: stop the hot loop after this many steps
         self._step_hook = None           # benchmark hook: called as hook(step_index, engine) around each step
@@ -450,7 +452,7 @@ class scDEF:
                 shrinkage_rate=self.shrinkage_rate, cell_scale_shape=self.cell_scale_shape,
                 gene_scale_shape=self.gene_scale_shape, alpha_floor=self.alpha_floor,
                 supervised_layer=self.supervised_layer, fixed_top_z=getattr(self, "_fixed_top_z", None),
-                X=self.X if self.x_placement == "device" else None, device=dev)
+                X=self.X if self.x_placement == "device" else None, device=dev, lazy_adam=self.lazy_adam)
             self._engine_key = self._engine_signature()
             self._engine_stale = True
         elif self._engine_key != self._engine_signature():
@@ -714,6 +716,7 @@ class scDEF:
                               stop_gene_budgets=stop_gene_budgets, alpha=alpha_f, scale=n_total / n_glob,
                               global_weight=gw, X_batch=Xb, lik_impl=self.lik_impl)
                     if update_locals:
+                        eng.local_catchup(idx)  # lazy Adam: the minibatch rows become current before they are read
                         # the local-pass loss is overwritten by the global pass (3235-3271): skip it when unused
                         eng.elbo_grad("local", idx, noise, want_loss=not update_globals, **kw)
                         eng.adam_local(idx, float(local_lr), freeze_z_layers)
