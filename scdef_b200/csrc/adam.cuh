@@ -152,13 +152,19 @@ struct AdamLazyArgs {
   const float2* bc_tab;    // [k-1] = (1/(1-b1^k), 1/(1-b2^k)); entries beyond the table are the last one (= 1, 1)
   long long N;
   int C, B, tab_len;
+  int monotone;            // 1: |update| is decreasing over zero-gradient steps (enables the constant-p shortcut)
   int target;              // CATCHUP: replay steps row_step+1 .. target;  UPDATE: the step being applied
   int n_frozen;
   int frozen_lo[SCDEF_MAX_LAYERS], frozen_hi[SCDEF_MAX_LAYERS];
 };
 
-// one thread per element of the selected rows; grid = (blocks, 2 halves)
-__global__ void __launch_bounds__(256) k_adam_lazy_catchup(const AdamLazyArgs a, AdamHyper h) {
+// one thread per element of the selected rows; grid = (blocks, 2 halves, 2 blocks {cell_scale, z})
+struct AdamLazyPair {
+  AdamLazyArgs a[2];
+};
+
+__global__ void __launch_bounds__(256) k_adam_lazy_catchup(const AdamLazyPair pr, AdamHyper h) {
+  const AdamLazyArgs& a = pr.a[blockIdx.z];
   const long long rows = a.idx ? a.B : a.N;
   const long long total = rows * a.C;
   const long long hoff = (long long)blockIdx.y * a.N * a.C;
@@ -173,18 +179,33 @@ __global__ void __launch_bounds__(256) k_adam_lazy_catchup(const AdamLazyArgs a,
     if (m == 0.f && v == 0.f) continue;  // never touched since the optimiser was reset: every replayed step is a no-op
     bool frozen = false;
     for (int f = 0; f < a.n_frozen; ++f) frozen |= (c >= a.frozen_lo[f]) && (c < a.frozen_hi[f]);
-    for (int k = t0 + 1; k <= a.target; ++k) {
+    int k = t0 + 1;
+    // phase 1: full steps, until the update no longer changes p in fp32.  |update| shrinks by >= ~10 % per
+    // zero-gradient step (a.monotone: verified on the host from the bias-correction table), so from then on p is
+    // constant and only the two moment decays have to be replayed (phase 2); once m is exactly 0 only v (phase 3).
+    for (; k <= a.target; ++k) {
+      if (m == 0.f) break;
       const float2 bc = a.bc_tab[min(k, a.tab_len) - 1];
       h.inv_bc1 = bc.x;
       h.inv_bc2 = bc.y;
+      const float p_before = p;
       adam_elem(p, m, v, 0.f, h, !frozen, INFINITY);
+      if (a.monotone && p == p_before) { ++k; break; }
     }
+    const float omb1 = __fsub_rn(1.f, h.b1), omb2 = __fsub_rn(1.f, h.b2);
+    for (; k <= a.target; ++k) {
+      if (m == 0.f) break;
+      m = __fmaf_rn(omb1, 0.f, __fmul_rn(h.b1, m));
+      v = __fmaf_rn(__fmul_rn(omb2, 0.f), 0.f, __fmul_rn(h.b2, v));
+    }
+    for (; k <= a.target; ++k) v = __fmaf_rn(__fmul_rn(omb2, 0.f), 0.f, __fmul_rn(h.b2, v));
     a.p[i] = p; a.m[i] = m; a.v[i] = v;
   }
 }
 
 // applies step `target` with the minibatch gradient to the minibatch rows (already caught up to target-1)
-__global__ void __launch_bounds__(256) k_adam_lazy_update(const AdamLazyArgs a, const AdamHyper h) {
+__global__ void __launch_bounds__(256) k_adam_lazy_update(const AdamLazyPair pr, const AdamHyper h) {
+  const AdamLazyArgs& a = pr.a[blockIdx.z];
   const long long total = (long long)a.B * a.C;
   const long long hoff = (long long)blockIdx.y * a.N * a.C;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {

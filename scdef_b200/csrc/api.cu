@@ -592,9 +592,11 @@ int scdef_adam_local_lazy(scdef_ctx* ctx, int phase, const scdef_blocks* params,
   h.inv_bc1 = (float)(1.0 / (1.0 - pow((double)b1, s1)));
   h.inv_bc2 = (float)(1.0 / (1.0 - pow((double)b2, s1)));
   int rc;
+  AdamLazyPair pr;
+  memset(&pr, 0, sizeof(pr));
+  long long max_elems = 1;
   for (int which = 0; which < 2; ++which) {
-    AdamLazyArgs a;
-    memset(&a, 0, sizeof(a));
+    AdamLazyArgs& a = pr.a[which];
     a.p = which ? params->z : params->cell_scale;
     a.m = which ? m->z : m->cell_scale;
     a.v = which ? v->z : v->cell_scale;
@@ -603,22 +605,25 @@ int scdef_adam_local_lazy(scdef_ctx* ctx, int phase, const scdef_blocks* params,
     a.row_step = row_step;
     a.bc_tab = reinterpret_cast<const float2*>(bc_table);
     a.N = N; a.C = which ? ctx->Kt : 1; a.B = B; a.tab_len = bc_len;
+    a.monotone = (b1 <= 0.95f && b2 >= 0.99f && b2 < 1.f && b1 > 0.f) ? 1 : 0;  // b1 (1-b1^k)/(1-b1^(k+1)) sqrt((1-b2^(k+1))/(b2 (1-b2^k))) < 1 for all k
     a.target = phase == SCDEF_LAZY_CATCHUP ? (int)step - 1 : (int)step;
     if (which && freeze_z_layers)
       for (int l = 0; l < ctx->L; ++l)
         if (freeze_z_layers[l]) { a.frozen_lo[a.n_frozen] = ctx->off[l]; a.frozen_hi[a.n_frozen] = ctx->off[l + 1]; a.n_frozen++; }
     const long long rows = a.idx ? B : N;
-    long long blocks = (rows * a.C + 255) / 256;
+    if (rows * a.C > max_elems) max_elems = rows * a.C;
+  }
+  {
+    // one launch for both local blocks: the short serial replay of the (C = 1) cell-scale block hides under z's
+    long long blocks = (max_elems + 255) / 256;
     const long long cap = (long long)ctx->sm_count * 32;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    {
-      ProfScope ps(ctx, which ? SCDEF_PROF_ADAM_LOCAL : SCDEF_PROF_ADAM_LOCAL_C, st);
-      if (phase == SCDEF_LAZY_UPDATE) k_adam_lazy_update<<<dim3((unsigned)blocks, 2), 256, 0, st>>>(a, h);
-      else k_adam_lazy_catchup<<<dim3((unsigned)blocks, 2), 256, 0, st>>>(a, h);
-    }
-    if ((rc = check_launch(ctx, "k_adam_lazy"))) return rc;
+    ProfScope ps(ctx, SCDEF_PROF_ADAM_LOCAL, st);
+    if (phase == SCDEF_LAZY_UPDATE) k_adam_lazy_update<<<dim3((unsigned)blocks, 2, 2), 256, 0, st>>>(pr, h);
+    else k_adam_lazy_catchup<<<dim3((unsigned)blocks, 2, 2), 256, 0, st>>>(pr, h);
   }
+  if ((rc = check_launch(ctx, "k_adam_lazy"))) return rc;
   // the rows are now current up to `target`
   {
     const long long rows = phase == SCDEF_LAZY_CATCHUP_ALL ? N : B;
