@@ -726,6 +726,8 @@ class scDEF:
                         if shard.world > 1:
                             _dist.all_reduce_sum(eng.glob_grad.flat, shard)
                         eng.adam_global(float(lr), freeze_w=bool(freeze_w))
+                    stream.release()
+                    stream.prefetch(it + 1)  # host placement: stage the next minibatch while this step runs
                     loss_dev[it] = eng.loss_buf.sum()
                     n_it += 1
                     steps_done += 1

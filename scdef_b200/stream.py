@@ -29,6 +29,8 @@ class MinibatchStream:
         self.host_X = host_X
         self.h2d_bytes = 0
         self._slots, self._events, self._slot_i = [], [], 0
+        self._staged = {}
+        self._copy_stream = None
         if host_X is not None:
             G = host_X.shape[1]
             cap = min(self.gb, self.n_total)
@@ -36,6 +38,7 @@ class MinibatchStream:
                 self._slots.append(torch.empty((cap, G), dtype=torch.float32).pin_memory())
                 self._events.append(None)
             self._dev_slots = [torch.empty((cap, G), dtype=torch.float32, device=device) for _ in range(pinned_slots)]
+            self._copy_stream = torch.cuda.Stream(device=device)
 
     def new_epoch(self):
         perm = self.rng.permutation(self.n_total)
@@ -51,26 +54,52 @@ class MinibatchStream:
         self.offs = offs
         self.perm_dev = torch.from_numpy(self.perm_host).to(self.device, non_blocking=False)
         self.h2d_bytes += self.perm_host.nbytes
+        self._staged = {}
 
     def indices_host(self, it: int) -> np.ndarray:
         return self.perm_host[self.offs[it] : self.offs[it + 1]]
+
+    def _stage(self, it: int):
+        """Host placement: gather X[batch] into a pinned slot and start its H2D copy on the copy stream."""
+        rows = self.indices_host(it)
+        k = self._slot_i
+        self._slot_i = (k + 1) % len(self._slots)
+        if self._events[k] is not None:
+            self._events[k].synchronize()  # the step that last read this slot's device buffer has finished
+        pin = self._slots[k][: len(rows)]
+        np.take(self.host_X, rows, axis=0, out=pin.numpy())
+        Xb = self._dev_slots[k][: len(rows)]
+        with torch.cuda.stream(self._copy_stream):
+            Xb.copy_(pin, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        self.h2d_bytes += pin.numel() * 4
+        self._staged[it] = (k, Xb, ready)
+
+    def prefetch(self, it: int):
+        """Start staging minibatch `it` of the current epoch (host placement only).  Called by the hot loop right
+        after step it-1 has been enqueued, so the host gather and the H2D copy overlap that step's kernels."""
+        if self.host_X is not None and 0 <= it < self.num_batches and it not in self._staged:
+            self._stage(it)
 
     def batch(self, it: int):
         """(device int64 indices of this rank, device X rows or None, global minibatch size)."""
         idx = self.perm_dev[self.offs[it] : self.offs[it + 1]]
         Xb = None
         if self.host_X is not None:
-            rows = self.indices_host(it)
-            k = self._slot_i
-            self._slot_i = (k + 1) % len(self._slots)
-            if self._events[k] is not None:
-                self._events[k].synchronize()  # the copy that last used this pinned slot is done
-            pin = self._slots[k][: len(rows)]
-            np.take(self.host_X, rows, axis=0, out=pin.numpy())
-            Xb = self._dev_slots[k][: len(rows)]
-            Xb.copy_(pin, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.device))
-            self._events[k] = ev
-            self.h2d_bytes += pin.numel() * 4
+            if it not in self._staged:
+                self._stage(it)
+            k, Xb, ready = self._staged.pop(it)
+            torch.cuda.current_stream(self.device).wait_event(ready)
+            done = torch.cuda.Event()   # recorded by release(): the compute stream is finished with this slot
+            self._pending_release = (k, done)
         return idx, Xb, int(self.n_glob[it])
+
+    def release(self):
+        """Marks the end of the step that consumed the last batch (its device slot may be overwritten afterwards)."""
+        pr = getattr(self, "_pending_release", None)
+        if pr is not None:
+            k, done = pr
+            done.record(torch.cuda.current_stream(self.device))
+            self._events[k] = done
+            self._pending_release = None
