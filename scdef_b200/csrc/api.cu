@@ -1,6 +1,7 @@
 // C ABI of scdef_b200 (include/scdef_b200.h): host-side orchestration of the kernels.
 // Every entry point only enqueues work on the caller's stream.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -393,6 +394,32 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     h.top_layer = root_frozen ? L - 2 : L - 1;
     h.alpha = call->alpha; h.alpha_floor = d.alpha_floor; h.top_alpha = d.top_alpha;
     h.lgam_top = lgammaf(d.top_alpha); h.scale = scale;
+    // register-tiled kernel when its shared-memory plan fits two CTAs per SM, else the warp-per-cell kernel
+    HierTArgs ht;
+    memset(&ht, 0, sizeof(ht));
+    int wtot4 = 0, kmax = 1;
+    for (int l = 0; l < L; ++l) {
+      if (ctx->K[l] > kmax) kmax = ctx->K[l];
+      if (l >= 1) {
+        ht.wld[l] = (ctx->K[l - 1] + 3) / 4 * 4;
+        ht.woff[l] = wtot4;
+        wtot4 += ctx->K[l] * ht.wld[l];
+      }
+    }
+    ht.wtot = wtot4; ht.kmax = kmax;
+    const size_t smem_t = ((size_t)wtot4 * (global_pass ? 2 : 1) + (size_t)ctx->Kt * HLD + (size_t)kmax * HLD * (global_pass ? 1 : 3)) * sizeof(float);
+    static const bool hier_old = getenv("SCDEF_HIER_OLD") != nullptr;
+    if (smem_t <= 110 * 1024 && kmax <= 128 && !hier_old) {
+      const int n_t32 = (B + HT - 1) / HT;
+      int tpc = (int)((long long)n_t32 * S / (2 * ctx->sm_count * 2));  // aim for >= ~2 waves of 2 CTAs/SM
+      if (tpc < 1) tpc = 1;
+      if (tpc > n_t32) tpc = n_t32;
+      ht.h = h;
+      ht.tiles_per_cta = tpc;
+      if (smem_t > 48 * 1024) cudaFuncSetAttribute(k_hier_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+      ProfScope ps(ctx, SCDEF_PROF_HIER, st);
+      k_hier_tiled<<<dim3((n_t32 + tpc - 1) / tpc, S), 256, smem_t, st>>>(ht, S, loss_out);
+    } else {
     // enough CTAs to fill the GPU, at least one round of 8 cells each
     int chunks = (ctx->sm_count * 2 + S - 1) / S;
     int max_chunks = (B + HIER_WARPS - 1) / HIER_WARPS;
@@ -406,6 +433,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     {
       ProfScope ps(ctx, SCDEF_PROF_HIER, st);
       k_hier<<<dim3(chunks, S), HIER_WARPS * 32, smem, st>>>(h, S, loss_out);
+    }
     }
     if ((rc = check_launch(ctx, "k_hier"))) return rc;
 

@@ -383,4 +383,211 @@ __global__ void __launch_bounds__(HIER_WARPS * 32) k_hier(const HierArgs a, int 
   if (tid == 0) atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)S);
 }
 
+// -----------------------------------------------------------------------------------------
+// K5, register-tiled version (used whenever its shared-memory plan fits).  Same math as k_hier.
+// CTA = (MC sample s, a run of 32-cell tiles); lane = cell, so every per-layer matrix product
+//   m_l = z_{l+1} W_{l+1},   d z_{l+1} += P_l W_{l+1}^T,   d W_{l+1} += z_{l+1}^T P_l
+// is a small GEMM on smem tiles stored [k][cell] (row stride 33: conflict-free with lanes on the
+// cells AND with lanes on k), with 4x register blocking and LDS.128 on the W rows.
+// Layers are processed top-down; only the gradient buffers of two adjacent layers are live.
+// -----------------------------------------------------------------------------------------
+struct HierTArgs {
+  HierArgs h;
+  int tiles_per_cta;
+  int wld[SCDEF_MAX_LAYERS];   // row stride of W_l in smem (multiple of 4)
+  int woff[SCDEF_MAX_LAYERS];
+  int wtot, kmax;
+};
+constexpr int HT = 32, HLD = 33;
+
+__global__ void __launch_bounds__(256, 2) k_hier_tiled(const HierTArgs t, int S, double* loss_out) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ double red[32];
+  const HierArgs& a = t.h;
+  const int L = a.L, Kt = a.off[L];
+  const bool global_pass = (a.pass == SCDEF_PASS_GLOBAL);
+  float* Wsm = sm;                                   // [wtot]
+  float* GWsm = Wsm + t.wtot;                        // [wtot]           GLOBAL only
+  float* zt = GWsm + (global_pass ? t.wtot : 0);     // [Kt][HLD]
+  float* Pm = zt + Kt * HLD;                         // [kmax][HLD]      m_l, then P_l in place
+  float* gzA = Pm + t.kmax * HLD;                    // [kmax][HLD]      LOCAL only: layer l+1
+  float* gzB = gzA + t.kmax * HLD;                   // [kmax][HLD]      LOCAL only: layer l
+  const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int l = 1; l < L; ++l) {
+    const int rows = a.K[l], cols = a.K[l - 1], ld = t.wld[l];
+    const float* src = a.smp_W[l] + (long long)s * rows * cols;
+    for (int e = tid; e < rows * ld; e += 256) {
+      const int u = e / ld, k = e - u * ld;
+      Wsm[t.woff[l] + e] = k < cols ? src[u * cols + k] : 0.f;
+      if (global_pass) GWsm[t.woff[l] + e] = 0.f;
+    }
+  }
+  const float alpha_value = a.smp_a ? a.smp_a[s] : a.alpha;
+  double val = 0.0;
+  float dal_acc = 0.f;
+
+  for (int tile = blockIdx.x * t.tiles_per_cta; tile < (blockIdx.x + 1) * t.tiles_per_cta; ++tile) {
+    const int j0 = tile * HT;
+    if (j0 >= a.B) break;
+    __syncthreads();
+    // z samples of the tile, all layers: coalesced over k, stored [k][cell]
+    for (int l = 0; l < L; ++l) {
+      const int Kl = a.K[l];
+      for (int e = tid; e < HT * Kl; e += 256) {
+        const int c = e / Kl, k = e - c * Kl;
+        const int j = j0 + c;
+        zt[(a.off[l] + k) * HLD + c] = j < a.B ? a.smp_z[l][((long long)s * a.B + j) * Kl + k] : 1.f;
+      }
+    }
+    const int jl = j0 + lane;
+    const bool cvalid = jl < a.B;
+    const float caf = cvalid ? a.caf[a.idx[jl]] : 1.f;
+    const float araw = alpha_value * caf;
+    const float al = fmaxf(araw, a.alpha_floor);
+    const float lgam_al = lgammaf(al), log_al = logf(al);
+    const float psi_al = a.G_a ? digammaf(al) : 0.f;
+    float dal = 0.f;
+    __syncthreads();
+
+    for (int l = L - 1; l >= 0; --l) {
+      const int Kl = a.K[l];
+      const bool top = (l == a.top_layer);
+      const bool has_parent = (l < L - 1) && !top;
+      // (1) m_l = z_{l+1} W_{l+1}  -> Pm[k][cell]
+      if (has_parent) {
+        const int Ku = a.K[l + 1], ld = t.wld[l + 1];
+        const float* Wl = Wsm + t.woff[l + 1];
+        const float* zu = zt + a.off[l + 1] * HLD + lane;
+        for (int k0 = warp * 4; k0 < Kl; k0 += 32) {
+          float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 4
+          for (int u = 0; u < Ku; ++u) {
+            const float z = zu[u * HLD];
+            const float4 w = *reinterpret_cast<const float4*>(Wl + u * ld + k0);
+            acc0 = fmaf(z, w.x, acc0); acc1 = fmaf(z, w.y, acc1); acc2 = fmaf(z, w.z, acc2); acc3 = fmaf(z, w.w, acc3);
+          }
+          Pm[(k0 + 0) * HLD + lane] = acc0;
+          if (k0 + 1 < Kl) Pm[(k0 + 1) * HLD + lane] = acc1;
+          if (k0 + 2 < Kl) Pm[(k0 + 2) * HLD + lane] = acc2;
+          if (k0 + 3 < Kl) Pm[(k0 + 3) * HLD + lane] = acc3;
+        }
+        __syncthreads();
+      }
+      // (2) prior value, own gradient, P_l (in place over m_l)
+      float* gz_cur = (l & 1) ? gzA : gzB;   // LOCAL: layers alternate between the two buffers
+      for (int k = warp; k < Kl; k += 8) {
+        const float zz = zt[(a.off[l] + k) * HLD + lane];
+        const float lz = logf(zz);
+        float g;
+        if (top) {
+          if (cvalid) val += (double)gamma_lp(zz, lz, a.top_alpha, a.top_alpha, a.lgam_top, logf(a.top_alpha));
+          g = (a.top_alpha - 1.f) / zz - a.top_alpha;
+        } else {
+          const float m = has_parent ? Pm[k * HLD + lane] : 1.f;
+          const float rate = al / m, lrate = log_al - logf(m);
+          if (cvalid) val += (double)gamma_lp(zz, lz, al, rate, lgam_al, lrate);
+          g = (al - 1.f) / zz - rate;
+          if (has_parent) Pm[k * HLD + lane] = cvalid ? rate * (zz / m - 1.f) : 0.f;
+          if (cvalid) dal += lz - psi_al + lrate + 1.f - zz / m;
+        }
+        if (!global_pass) gz_cur[k * HLD + lane] = g;
+      }
+      __syncthreads();
+      // (3) children -> parents
+      if (has_parent) {
+        const int Ku = a.K[l + 1], ld = t.wld[l + 1];
+        if (!global_pass) {
+          // gz_{l+1}[u][cell] += sum_k P_l[k][cell] W_{l+1}[u][k]
+          float* gz_par = ((l + 1) & 1) ? gzA : gzB;
+          const float* Wl = Wsm + t.woff[l + 1];
+          for (int u0 = warp * 4; u0 < Ku; u0 += 32) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k0 = 0; k0 < Kl; k0 += 4) {
+              float p[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) p[i] = (k0 + i < Kl) ? Pm[(k0 + i) * HLD + lane] : 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (u0 + q < Ku) {
+                  const float4 w = *reinterpret_cast<const float4*>(Wl + (u0 + q) * ld + k0);
+                  acc[q] = fmaf(p[0], w.x, fmaf(p[1], w.y, fmaf(p[2], w.z, fmaf(p[3], w.w, acc[q]))));
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (u0 + q < Ku) gz_par[(u0 + q) * HLD + lane] += acc[q];
+          }
+        } else {
+          // GW_{l+1}[u][k] += sum_cell z_{l+1}[u][cell] P_l[k][cell]   (lanes on k)
+          float* GWl = GWsm + t.woff[l + 1];
+          const float* zu = zt + a.off[l + 1] * HLD;
+          for (int u0 = warp * 4; u0 < Ku; u0 += 32) {
+            float acc[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
+            const int nkb = (Kl + 31) / 32;
+            for (int c = 0; c < HT; ++c) {
+              float z4[4], p4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) z4[q] = (u0 + q < Ku) ? zu[(u0 + q) * HLD + c] : 0.f;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) p4[i] = (i < nkb && lane + 32 * i < Kl) ? Pm[(lane + 32 * i) * HLD + c] : 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[q][i] = fmaf(z4[q], p4[i], acc[q][i]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (u0 + q < Ku && lane + 32 * i < Kl) GWl[(u0 + q) * ld + lane + 32 * i] += acc[q][i];
+          }
+        }
+        __syncthreads();
+      }
+      // (4) LOCAL: the gradient of layer l+1 is complete -> global (coalesced over k); layer 0 / childless layers at once
+      if (!global_pass) {
+        for (int which = 0; which < 2; ++which) {
+          int lw;
+          if (which == 0) { if (l == L - 1) continue; lw = l + 1; }     // parent layer: complete after this iteration
+          else { if (l != 0) continue; lw = 0; }                          // bottom layer: no children
+          const float* gsrc = (lw & 1) ? gzA : gzB;
+          const int Kw = a.K[lw];
+          for (int e = tid; e < HT * Kw; e += 256) {
+            const int c = e / Kw, k = e - c * Kw;
+            const int j = j0 + c;
+            if (j < a.B) a.G_z[lw][((long long)s * a.B + j) * Kw + k] = a.scale * gsrc[k * HLD + c];
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (a.G_a && cvalid && araw > a.alpha_floor) dal_acc += dal * caf;
+  }
+
+  if (global_pass) {
+    __syncthreads();
+    for (int l = 1; l < L; ++l) {
+      if (l - 1 == a.top_layer) continue;
+      const int rows = a.K[l], cols = a.K[l - 1], ld = t.wld[l];
+      float* dst = a.G_W[l] + (long long)s * rows * cols;
+      for (int e = tid; e < rows * cols; e += 256) {
+        const int u = e / cols, k = e - u * cols;
+        atomicAdd(&dst[e], a.scale * GWsm[t.woff[l] + u * ld + k]);
+      }
+    }
+    if (a.G_a) {
+      dal_acc = warp_sum(dal_acc);
+      if (lane == 0 && dal_acc != 0.f) atomicAdd(&a.G_a[s], a.scale * dal_acc);
+    }
+  }
+  double tot = block_sum_d(val, red);
+  if (tid == 0) atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)S);
+}
+
 }  // namespace scdef
