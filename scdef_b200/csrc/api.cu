@@ -313,8 +313,9 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     if (B > 0) add(BLK_C);
     add(BLK_S); add(BLK_TAU); add(BLK_OM); add(BLK_A);
     for (int l = 0; l < L; ++l) { add(BLK_W + l); if (B > 0) add(BLK_Z + l); }
-    size_t gx = (max_el + 255) / 256;
+    size_t gx = (max_el / 4 + 255) / 256;
     if (gx > (size_t)ctx->sm_count * 16) gx = (size_t)ctx->sm_count * 16;
+    if (gx < 1) gx = 1;
     ProfScope ps(ctx, SCDEF_PROF_SAMPLE, st);
     k_sample<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key, loss_out, gw);
     if ((rc = check_launch(ctx, "k_sample"))) return rc;

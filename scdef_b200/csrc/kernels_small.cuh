@@ -16,28 +16,36 @@ __global__ void __launch_bounds__(256) k_sample(const BlockTable tab, int S, Phi
   __shared__ double red[32];
   const BlockDesc& b = tab.b[blockIdx.y];
   const int per = b.rows * b.cols;
-  const long long total = (long long)S * per;
+  const int nquad = (per + 3) >> 2;                 // one Philox call yields the normals of 4 flat elements
+  const long long total = (long long)S * nquad;
   double ent = 0.0;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
-    int s = (int)(e / per);
-    int i = (int)(e - (long long)s * per);
-    int r = i / b.cols, c = i - r * b.cols;
-    long long row = b.gather ? b.gather[r] : r;
-    float v;
-    if (b.fixed) {
-      v = b.fixed[row * b.cols + c];
-    } else {
-      float mu = b.mu[row * b.ld + b.col0 + c];
-      float rho = b.rho[row * b.ld + b.col0 + c];
-      float mut = fminf(fmaxf(mu, LOG_1E_10), b.mu_hi);
-      float rhot = fminf(fmaxf(rho, LOG_1E_10), LOG_1E10);
-      float eps = b.eps ? b.eps[((long long)s * b.rows + r) * b.eps_ld + b.eps_col0 + c]
-                        : philox_normal(key, b.tag, (uint32_t)s, (uint32_t)i);
-      v = fminf(fmaxf(expf(mut + expf(rhot) * eps), V_LO), V_HI);
-      if (s == 0) ent += (double)(mut + rhot + HALF_LOG_2PI_PLUS_HALF);
+    const int s = (int)(e / nquad);
+    const int qd = (int)(e - (long long)s * nquad);
+    float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!b.eps && !b.fixed) n4 = philox_normal4(key, b.tag, (uint32_t)s, (uint32_t)qd);
+    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = qd * 4 + q;
+      if (i >= per) break;
+      const int r = i / b.cols, c = i - r * b.cols;
+      const long long row = b.gather ? b.gather[r] : r;
+      float v;
+      if (b.fixed) {
+        v = b.fixed[row * b.cols + c];
+      } else {
+        const float mu = b.mu[row * b.ld + b.col0 + c];
+        const float rho = b.rho[row * b.ld + b.col0 + c];
+        const float mut = fminf(fmaxf(mu, LOG_1E_10), b.mu_hi);
+        const float rhot = fminf(fmaxf(rho, LOG_1E_10), LOG_1E10);
+        const float eps = b.eps ? b.eps[((long long)s * b.rows + r) * b.eps_ld + b.eps_col0 + c] : nn[q];
+        v = fminf(fmaxf(expf(mut + expf(rhot) * eps), V_LO), V_HI);
+        if (s == 0) ent += (double)(mut + rhot + HALF_LOG_2PI_PLUS_HALF);
+      }
+      b.smp[(long long)s * per + i] = v;
     }
-    b.smp[e] = v;
   }
   // entropy value: ent_weight already holds w_H * scale_H (* global_weight for global blocks)
   double tot = block_sum_d(ent, red);
@@ -65,21 +73,20 @@ __global__ void __launch_bounds__(256) k_finish(const BlockTable tab, int S, Phi
       float rho = b.rho[row * b.ld + b.col0 + c];
       bool in_mu = (mu >= LOG_1E_10) && (mu <= b.mu_hi);
       bool in_rho = (rho >= LOG_1E_10) && (rho <= LOG_1E10);
-      float sigma = expf(fminf(fmaxf(rho, LOG_1E_10), LOG_1E10));
+      const float mut = fminf(fmaxf(mu, LOG_1E_10), b.mu_hi);
       float gv = 0.f, gve = 0.f;
       for (int s = 0; s < S; ++s) {
         long long e = (long long)s * per + i;
         float v = b.smp[e];
         if (v > V_LO && v < V_HI) {
-          float eps = b.eps ? b.eps[((long long)s * b.rows + r) * b.eps_ld + b.eps_col0 + c]
-                            : philox_normal(key, b.tag, (uint32_t)s, (uint32_t)i);
+          // inside the sample clip v = exp(mu~ + sigma eps)  =>  sigma eps = log v - mu~ : no noise needed here
           float t = b.G[e] * v;
           gv += t;
-          gve += t * eps;
+          gve = fmaf(t, logf(v) - mut, gve);
         }
       }
       dmu = in_mu ? -(gv * invS * b.g_weight + b.ent_weight) : 0.f;
-      drho = in_rho ? -(gve * sigma * invS * b.g_weight + b.ent_weight) : 0.f;
+      drho = in_rho ? -(gve * invS * b.g_weight + b.ent_weight) : 0.f;
     }
     b.gmu[(long long)r * b.g_ld + b.g_col0 + c] = dmu;
     b.grho[(long long)r * b.g_ld + b.g_col0 + c] = drho;
