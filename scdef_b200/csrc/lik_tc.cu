@@ -755,20 +755,21 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
 
 // GLOBAL pass: likelihood gradient of the gene scale from the W_0 tile images,
 //   G_s[s,b,g] += scale * ( colsumX[b][g] / s_{b,g} - sum_k ctilde[s][b][k] W^s[k][g] ).   grid = (n_tiles, S), block = 256
+template <int NBT>
 __global__ void __launch_bounds__(256) k_tc_colw(const LikTcArgs a, const TcScratch ws, int KP, int n_tiles, uint32_t w_plane,
                                                  uint32_t w_unit) {
-  __shared__ float colacc[MAX_NB][TG];
-  __shared__ float ct_sm[MAX_NB][128];
+  __shared__ float colacc[NBT][TG];
+  __shared__ float ct_sm[NBT][128];
   const int tile = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
   const int kk = tid & 7, cg = (tid >> 3) & 7, nkg = KP / 8;
   const uint8_t* unit = ws.wimg + ((long long)s * n_tiles + tile) * w_unit;
-  for (int i = tid; i < MAX_NB * TG; i += 256) (&colacc[0][0])[i] = 0.f;
+  for (int i = tid; i < NBT * TG; i += 256) (&colacc[0][0])[i] = 0.f;
   const float* ct = ws.ctilde + (long long)s * a.nb * a.K0;
   for (int i = tid; i < a.nb * a.K0; i += 256) ct_sm[i / a.K0][i % a.K0] = ct[i];
   __syncthreads();
-  float col[MAX_NB][8];
+  float col[NBT][8];
 #pragma unroll
-  for (int b = 0; b < MAX_NB; ++b)
+  for (int b = 0; b < NBT; ++b)
 #pragma unroll
     for (int e = 0; e < 8; ++e) col[b][e] = 0.f;
   for (int kg = tid >> 6; kg < nkg; kg += 4) {
@@ -784,7 +785,7 @@ __global__ void __launch_bounds__(256) k_tc_colw(const LikTcArgs a, const TcScra
       w[2 * p + 1] = bf16hi(hw[p]) + bf16hi(lw[p]);
     }
 #pragma unroll
-    for (int b = 0; b < MAX_NB; ++b) {
+    for (int b = 0; b < NBT; ++b) {
       if (b < a.nb) {
         const float c1 = ct_sm[b][k];
 #pragma unroll
@@ -793,7 +794,7 @@ __global__ void __launch_bounds__(256) k_tc_colw(const LikTcArgs a, const TcScra
     }
   }
 #pragma unroll
-  for (int b = 0; b < MAX_NB; ++b) {
+  for (int b = 0; b < NBT; ++b) {
     if (b < a.nb) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -816,36 +817,61 @@ __global__ void __launch_bounds__(256) k_tc_colw(const LikTcArgs a, const TcScra
 }
 
 // ---- small companions ---------------------------------------------------------------------------------
-// ctilde[s][b][k] = sum_{n in batch b} c_n^s z_nk^s ;  grid = S, block = 128
-__global__ void __launch_bounds__(128) k_tc_ctilde(const LikTcArgs a, float* ctilde) {
-  const int s = blockIdx.x, k = threadIdx.x;
-  if (k >= a.K0) return;
+// ctilde[s][b][k] = sum_{n in batch b} c_n^s z_nk^s ;  grid = S, block = 1024 (k = tid & 127, 8 row groups)
+__global__ void __launch_bounds__(1024) k_tc_ctilde(const LikTcArgs a, float* ctilde) {
+  __shared__ float part[8][MAX_NB][128];
+  const int s = blockIdx.x, k = threadIdx.x & 127, rg = threadIdx.x >> 7;
   float acc[MAX_NB];
 #pragma unroll
   for (int b = 0; b < MAX_NB; ++b) acc[b] = 0.f;
-  for (int j = 0; j < a.B; ++j) {
-    const float v = a.smp_c[(long long)s * a.B + j] * a.smp_z0[((long long)s * a.B + j) * a.K0 + k];
-    const int bj = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
+  if (k < a.K0) {
+    for (int j = rg; j < a.B; j += 8) {
+      const float v = a.smp_c[(long long)s * a.B + j] * a.smp_z0[((long long)s * a.B + j) * a.K0 + k];
+      const int bj = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
 #pragma unroll
-    for (int b = 0; b < MAX_NB; ++b) acc[b] += (b == bj) ? v : 0.f;
+      for (int b = 0; b < MAX_NB; ++b) acc[b] += (b == bj) ? v : 0.f;
+    }
   }
-  for (int b = 0; b < a.nb; ++b) ctilde[((long long)s * a.nb + b) * a.K0 + k] = acc[b];
+#pragma unroll
+  for (int b = 0; b < MAX_NB; ++b) part[rg][b][k] = acc[b];
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.nb * a.K0; i += 1024) {
+    const int b = i / a.K0, kk = i - b * a.K0;
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += part[r][b][kk];
+    ctilde[((long long)s * a.nb + b) * a.K0 + kk] = t;
+  }
 }
 
-// colsumX[b][g] = sum_{n in batch b} x_ng ;  grid over genes
-__global__ void __launch_bounds__(256) k_tc_colsum(const LikTcArgs a, float* colsumX) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.G) return;
+// colsumX[b][g] = sum_{n in batch b} x_ng ;  grid = ceil(G/64), block = 1024 (gene = tid & 63, 16 row groups)
+__global__ void __launch_bounds__(1024) k_tc_colsum(const LikTcArgs a, float* colsumX) {
+  __shared__ float part[16][MAX_NB][64];
+  const int gl = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int g = blockIdx.x * 64 + gl;
   float acc[MAX_NB];
 #pragma unroll
   for (int b = 0; b < MAX_NB; ++b) acc[b] = 0.f;
-  for (int j = 0; j < a.B; ++j) {
-    const float x = a.X[(a.idx_x ? a.idx_x[j] : (long long)j) * a.G + g];
-    const int bj = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
+  if (g < a.G) {
+    for (int j = rg; j < a.B; j += 16) {
+      const float x = a.X[(a.idx_x ? a.idx_x[j] : (long long)j) * a.G + g];
+      const int bj = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
 #pragma unroll
-    for (int b = 0; b < MAX_NB; ++b) acc[b] += (b == bj) ? x : 0.f;
+      for (int b = 0; b < MAX_NB; ++b) acc[b] += (b == bj) ? x : 0.f;
+    }
   }
-  for (int b = 0; b < a.nb; ++b) colsumX[(long long)b * a.G + g] = acc[b];
+#pragma unroll
+  for (int b = 0; b < MAX_NB; ++b) part[rg][b][gl] = acc[b];
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.nb * 64; i += 1024) {
+    const int b = i / 64, c = i - b * 64;
+    if (blockIdx.x * 64 + c < a.G) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) t += part[r][b][c];
+      colsumX[(long long)b * a.G + blockIdx.x * 64 + c] = t;
+    }
+  }
 }
 
 // G_z0[s][j][k] += scale * sum_r part[s][r][j][k]
@@ -1021,11 +1047,12 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   }
   if (global_pass) {
     if (a.lik_on) {
-      k_tc_ctilde<<<a.S, 128, 0, st>>>(a, ws.ctilde);
-      k_tc_colsum<<<(a.G + 255) / 256, 256, 0, st>>>(a, ws.colsumX);
+      k_tc_ctilde<<<a.S, 1024, 0, st>>>(a, ws.ctilde);
+      k_tc_colsum<<<(a.G + 63) / 64, 1024, 0, st>>>(a, ws.colsumX);
     }
     if (a.lik_on && !mono) {
-      k_tc_colw<<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
+      if (a.nb == 1) k_tc_colw<1><<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
+      else k_tc_colw<MAX_NB><<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
       cudaFuncSetAttribute(k_lik_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
       k_lik_pipe<true, true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
     } else {
