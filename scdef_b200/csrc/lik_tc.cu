@@ -1005,6 +1005,8 @@ void lik_tc_read_timing(unsigned long long* out) {
 int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStream_t st) {
   (void)sm_count;
   LikTcArgs a = a_in;
+  static const int dbg_nsplit = getenv("SCDEF_TC_NSPLIT") ? atoi(getenv("SCDEF_TC_NSPLIT")) : 3;  // timing experiments only
+  a.dbg_nsplit = dbg_nsplit;
   if (!lik_tc_supported(a.K0, a.G, a.nb) || a.P || a.R) return SCDEF_EUNSUPPORTED;
   if (a.B <= 0) a.lik_on = 0;
   const Geom g = make_geom(a.B, a.S, a.K0, a.G);

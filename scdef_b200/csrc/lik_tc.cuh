@@ -29,7 +29,7 @@ struct LikTcArgs {
   const float* P;  // W_0 prior matrices or nullptr
   const float* R;
   float P_scalar, R_scalar;
-  int use_brd, B, G, K0, nb, pass, S, w0_stopped, lik_on, reuse_w0, want_loss;
+  int use_brd, B, G, K0, nb, pass, S, w0_stopped, lik_on, reuse_w0, want_loss, dbg_nsplit;
   float scale, global_weight, anneal;
   void* ws;
   size_t ws_bytes;

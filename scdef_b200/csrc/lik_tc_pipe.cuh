@@ -207,14 +207,13 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
         tc_fence_after();
         uint64_t da = dz_k[zb], db = dw_m[st];
         const uint32_t d = tmem + rs * TG;
-        umma_bf16(d, da + zpl, db, idesc1, 0u);
-        umma_bf16(d, da, db + wpl, idesc1, 1u);
-        umma_bf16(d, da, db, idesc1, 1u);
+        const bool full = a.dbg_nsplit != 1;
+        if (full) { umma_bf16(d, da + zpl, db, idesc1, 0u); umma_bf16(d, da, db + wpl, idesc1, 1u); }
+        umma_bf16(d, da, db, idesc1, full ? 1u : 0u);
         for (int ks = 1; ks < nk1; ++ks) {
           da += 16;              // 256 B along K
           db += 2 * (W_RS >> 4); // two k0 row groups
-          umma_bf16(d, da + zpl, db, idesc1, 1u);
-          umma_bf16(d, da, db + wpl, idesc1, 1u);
+          if (full) { umma_bf16(d, da + zpl, db, idesc1, 1u); umma_bf16(d, da, db + wpl, idesc1, 1u); }
           umma_bf16(d, da, db, idesc1, 1u);
         }
         umma_commit(&mi->r_full[rs]);
@@ -238,14 +237,13 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
           const int zb = u & 1;
           uint64_t da = dz_m[zb], db = dq_m;
           const uint32_t d = tmem_acc2 + st * TG;
-          umma_bf16(d, da + zpl, db, idesc2, cb > 0 ? 1u : 0u);
-          umma_bf16(d, da, db + qpl, idesc2, 1u);
-          umma_bf16(d, da, db, idesc2, 1u);
+          const bool full = a.dbg_nsplit != 1;
+          if (full) { umma_bf16(d, da + zpl, db, idesc2, cb > 0 ? 1u : 0u); umma_bf16(d, da, db + qpl, idesc2, 1u); }
+          umma_bf16(d, da, db, idesc2, (full || cb > 0) ? 1u : 0u);
           for (int ks = 1; ks < nks; ++ks) {
             da += 2 * (L.z_rs >> 4);
             db += 2 * (Q_RS >> 4);
-            umma_bf16(d, da + zpl, db, idesc2, 1u);
-            umma_bf16(d, da, db + qpl, idesc2, 1u);
+            if (full) { umma_bf16(d, da + zpl, db, idesc2, 1u); umma_bf16(d, da, db + qpl, idesc2, 1u); }
             umma_bf16(d, da, db, idesc2, 1u);
           }
           umma_commit(&mi->q_empty);
@@ -255,15 +253,14 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
           // dz[cb] (+)= Q W^T : A = Q (K-major), B = W (K-major, N = k0), K = genes of the tile
           uint64_t da = dq_k, db = dw_k[st];
           const uint32_t d = tmem_acc2 + cb * KP;
-          umma_bf16(d, da + qpl, db, idesc2, oi > 0 ? 1u : 0u);
-          umma_bf16(d, da, db + wpl, idesc2, 1u);
-          umma_bf16(d, da, db, idesc2, 1u);
+          const bool full = a.dbg_nsplit != 1;
+          if (full) { umma_bf16(d, da + qpl, db, idesc2, oi > 0 ? 1u : 0u); umma_bf16(d, da, db + wpl, idesc2, 1u); }
+          umma_bf16(d, da, db, idesc2, (full || oi > 0) ? 1u : 0u);
 #pragma unroll
           for (int ks = 1; ks < TG / 16; ++ks) {
             da += 16;
             db += 16;
-            umma_bf16(d, da + qpl, db, idesc2, 1u);
-            umma_bf16(d, da, db + wpl, idesc2, 1u);
+            if (full) { umma_bf16(d, da + qpl, db, idesc2, 1u); umma_bf16(d, da, db + wpl, idesc2, 1u); }
             umma_bf16(d, da, db, idesc2, 1u);
           }
           umma_commit(&mi->q_empty);
@@ -323,6 +320,46 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
       return cx;
     };
     Ctx nxt = fetch_ctx(0);
+    auto epilogue2 = [&](int oi2) {
+      // ---- fold dW^s (and the W_0 prior gradient) into d mu, sum t log W ----
+      const int st2 = oi2 & 1;
+      const int s2 = outer_begin + oi2;
+        TWAIT(2, &mi->dw_full[st2], (oi2 >> 1) & 1);
+        tc_fence_after();
+        float dW[16];
+        tmem_ld16(tmem_acc2 + (lane_base << 16) + (uint32_t)(st2 * TG + cq * 16), dW);
+        tc_fence_before();
+        mbar_arrive(&mi->dw_empty[st2]);
+        if (r < a.K0 && !a.w0_stopped) {
+          float A = a.P_scalar, Bm = a.R_scalar * (float)a.K0;
+          if (a.use_brd) {
+            const float tau = a.smp_tau[(long long)s2 * a.K0 + r], om = a.smp_om[(long long)s2 * a.K0 + r];
+            A = a.P_scalar / tau;
+            Bm = a.R_scalar * (float)a.K0 / (tau * om);
+          }
+          const uint32_t woff = L.w[st2] + (uint32_t)(r >> 3) * W_RS + (uint32_t)(r & 7) * 16u;
+#pragma unroll
+          for (int c8 = 0; c8 < 2; ++c8) {
+            const uint4 hv = *reinterpret_cast<const uint4*>(sm + woff + (uint32_t)(cq * 2 + c8) * 128u);
+            const uint4 lv = *reinterpret_cast<const uint4*>(sm + woff + L.w_plane + (uint32_t)(cq * 2 + c8) * 128u);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+#pragma unroll
+              for (int q2 = 0; q2 < 2; ++q2) {
+                const int i = c8 * 8 + p * 2 + q2;
+                const float W = q2 ? (bf16hi(hw[p]) + bf16hi(lw[p])) : (bf16lo(hw[p]) + bf16lo(lw[p]));
+                if (W > V_LO_M && W < V_HI_M) {
+                  const float t = a.scale * dW[i] * W + a.global_weight * (A - 1.f - Bm * W);
+                  acc_mu[i] += t;
+                  acc_lw[i] = fmaf(t, __logf(W), acc_lw[i]);
+                }
+              }
+            }
+          }
+        }
+        mbar_arrive(&mi->w_empty[st2]);
+    };
     for (int u = 0; u < U; ++u) {
 #ifdef SCDEF_TC_TIMING
       long long tq0 = clock64();
@@ -419,45 +456,11 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
 #endif
       if (cb & 1) esum1 += es; else esum0 += es;
 
-      if (GLOBAL && cb == units_per_outer - 1) {
-        // ---- epilogue 2: fold dW^s (and the W_0 prior gradient) into d mu, sum t log W ----
-        TWAIT(2, &mi->dw_full[st], (oi >> 1) & 1);
-        tc_fence_after();
-        float dW[16];
-        tmem_ld16(tmem_acc2 + (lane_base << 16) + (uint32_t)(st * TG + cq * 16), dW);
-        tc_fence_before();
-        mbar_arrive(&mi->dw_empty[st]);
-        if (r < a.K0 && !a.w0_stopped) {
-          float A = a.P_scalar, Bm = a.R_scalar * (float)a.K0;
-          if (a.use_brd) {
-            const float tau = a.smp_tau[(long long)s * a.K0 + r], om = a.smp_om[(long long)s * a.K0 + r];
-            A = a.P_scalar / tau;
-            Bm = a.R_scalar * (float)a.K0 / (tau * om);
-          }
-          const uint32_t woff = L.w[st] + (uint32_t)(r >> 3) * W_RS + (uint32_t)(r & 7) * 16u;
-#pragma unroll
-          for (int c8 = 0; c8 < 2; ++c8) {
-            const uint4 hv = *reinterpret_cast<const uint4*>(sm + woff + (uint32_t)(cq * 2 + c8) * 128u);
-            const uint4 lv = *reinterpret_cast<const uint4*>(sm + woff + L.w_plane + (uint32_t)(cq * 2 + c8) * 128u);
-            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-#pragma unroll
-              for (int q2 = 0; q2 < 2; ++q2) {
-                const int i = c8 * 8 + p * 2 + q2;
-                const float W = q2 ? (bf16hi(hw[p]) + bf16hi(lw[p])) : (bf16lo(hw[p]) + bf16lo(lw[p]));
-                if (W > V_LO_M && W < V_HI_M) {
-                  const float t = a.scale * dW[i] * W + a.global_weight * (A - 1.f - Bm * W);
-                  acc_mu[i] += t;
-                  acc_lw[i] = fmaf(t, __logf(W), acc_lw[i]);
-                }
-              }
-            }
-          }
-        }
-        mbar_arrive(&mi->w_empty[st]);
-      }
+      // epilogue 2 of sample oi-1 runs one unit late: its dW MMA has certainly drained by then (dW is double-buffered),
+      // so the epilogue warps never idle on dw_full
+      if (GLOBAL && cb == 0 && oi > 0) epilogue2(oi - 1);
     }
+    if (GLOBAL && n_outer > 0) epilogue2(n_outer - 1);
 
     if (GLOBAL) {
       const int chunk = blockIdx.x / gm.n_tiles;
