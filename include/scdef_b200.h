@@ -228,7 +228,8 @@ int scdef_noise_fill(scdef_ctx* ctx, const scdef_noise* noise, int block_kind, i
 #define SCDEF_PROF_ADAM_GLOBAL 6
 #define SCDEF_PROF_PRIORS 7
 #define SCDEF_PROF_ADAM_LOCAL_C 8 /* dense Adam over the cell-scale block */
-#define SCDEF_PROF_KINDS 9
+#define SCDEF_PROF_LIK_MAIN 9     /* the fused likelihood kernel alone (without its pre-/post-kernels) */
+#define SCDEF_PROF_KINDS 10
 int scdef_profile_enable(scdef_ctx* ctx, int on);
 /* Sums the elapsed ms of the (up to 256 most recent) timed launches of each kind; syncs on them. */
 int scdef_profile_read(scdef_ctx* ctx, double* ms_sum, int64_t* n_timed, int64_t* n_launched,

@@ -109,7 +109,7 @@ EXPORTS = [
     "scdef_adam_local_lazy", "scdef_adam_bias_table",
 ]
 LAZY_CATCHUP, LAZY_UPDATE, LAZY_CATCHUP_ALL = 0, 1, 2
-PROF_KINDS = ["lik", "adam_local_z", "hier", "sample", "wprior", "finish", "adam_global", "priors", "adam_local_c"]
+PROF_KINDS = ["lik", "adam_local_z", "hier", "sample", "wprior", "finish", "adam_global", "priors", "adam_local_c", "lik_main"]
 
 _LIB = None
 

@@ -470,7 +470,11 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       a.ws = ws + plan.tc_off; a.ws_bytes = plan.tc_bytes;
       {
         ProfScope ps(ctx, SCDEF_PROF_LIK, st);
+        const bool pm = ctx->prof_on && ctx->prof_ready && lik_run;
+        const int slot = (int)(ctx->prof_count[SCDEF_PROF_LIK_MAIN] % PROF_RING);
+        if (pm) { a.ev0 = ctx->prof_ev[SCDEF_PROF_LIK_MAIN][slot][0]; a.ev1 = ctx->prof_ev[SCDEF_PROF_LIK_MAIN][slot][1]; }
         rc = lik_tc_launch(a, loss_out, ctx->sm_count, st);
+        if (pm && rc == 0) ctx->prof_count[SCDEF_PROF_LIK_MAIN]++;
       }
       ctx->launches += 4;
       if (rc) return fail(ctx, rc, "lik_tc_launch failed (%d)", rc);
@@ -487,6 +491,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       dim3 grid((G + LT - 1) / LT, (B + LT - 1) / LT, S);
       {
         ProfScope ps(ctx, SCDEF_PROF_LIK, st);
+        ProfScope pm(ctx, SCDEF_PROF_LIK_MAIN, st);
         k_lik_simt<<<grid, 256, smem, st>>>(a, S, loss_out);
       }
       if ((rc = check_launch(ctx, "k_lik_simt"))) return rc;
@@ -514,7 +519,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       for (int l = 0; l < L; ++l) add(BLK_Z + l);
     }
     if (t.n > 0) {
-      size_t gx = (max_el + 255) / 256;
+      size_t gx = (max_el * FIN_SPLIT + 255) / 256;
       if (gx > (size_t)ctx->sm_count * 16) gx = (size_t)ctx->sm_count * 16;
       ProfScope ps(ctx, SCDEF_PROF_FINISH, st);
       k_finish<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key);

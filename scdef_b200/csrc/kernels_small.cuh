@@ -60,36 +60,52 @@ __global__ void __launch_bounds__(256) k_sample(const BlockTable tab, int S, Phi
 //                       d loss/d rho = -1[rho in clip]( (1/S) sum_s 1[..] G v eps sigma + w_H ).
 // grid = (ceil(max_elems/256), n_blocks); only blocks of the requested pass are in `tab`.
 // -----------------------------------------------------------------------------------------
+constexpr int FIN_SPLIT = 8;  // lanes that share one element and split its loop over the MC samples
+
 __global__ void __launch_bounds__(256) k_finish(const BlockTable tab, int S, PhiloxKey key) {
+  (void)key;
   const BlockDesc& b = tab.b[blockIdx.y];
   const int per = b.rows * b.cols;
   const float invS = 1.f / (float)S;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
-    int r = i / b.cols, c = i - r * b.cols;
+  const int sub = threadIdx.x & (FIN_SPLIT - 1);
+  const int per_pad = (per + 31) & ~31;  // keep whole warps in the loop for the shuffles
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) / FIN_SPLIT; i < per_pad; i += gridDim.x * blockDim.x / FIN_SPLIT) {
+    const bool live = i < per;
+    const int r = live ? i / b.cols : 0, c = live ? i - r * b.cols : 0;
     float dmu = 0.f, drho = 0.f;
-    if (b.active && !b.stopped) {
-      long long row = b.gather ? b.gather[r] : r;
-      float mu = b.mu[row * b.ld + b.col0 + c];
-      float rho = b.rho[row * b.ld + b.col0 + c];
-      bool in_mu = (mu >= LOG_1E_10) && (mu <= b.mu_hi);
-      bool in_rho = (rho >= LOG_1E_10) && (rho <= LOG_1E10);
+    const bool on = live && b.active && !b.stopped;
+    float mu = 0.f, rho = 0.f, gv = 0.f, gve = 0.f;
+    if (on) {
+      const long long row = b.gather ? b.gather[r] : r;
+      mu = b.mu[row * b.ld + b.col0 + c];
+      rho = b.rho[row * b.ld + b.col0 + c];
       const float mut = fminf(fmaxf(mu, LOG_1E_10), b.mu_hi);
-      float gv = 0.f, gve = 0.f;
-      for (int s = 0; s < S; ++s) {
-        long long e = (long long)s * per + i;
-        float v = b.smp[e];
+      for (int s = sub; s < S; s += FIN_SPLIT) {
+        const long long e = (long long)s * per + i;
+        const float v = b.smp[e];
         if (v > V_LO && v < V_HI) {
           // inside the sample clip v = exp(mu~ + sigma eps)  =>  sigma eps = log v - mu~ : no noise needed here
-          float t = b.G[e] * v;
+          const float t = b.G[e] * v;
           gv += t;
           gve = fmaf(t, logf(v) - mut, gve);
         }
       }
+    }
+#pragma unroll
+    for (int o = FIN_SPLIT / 2; o > 0; o >>= 1) {
+      gv += __shfl_xor_sync(0xffffffffu, gv, o);
+      gve += __shfl_xor_sync(0xffffffffu, gve, o);
+    }
+    if (on) {
+      const bool in_mu = (mu >= LOG_1E_10) && (mu <= b.mu_hi);
+      const bool in_rho = (rho >= LOG_1E_10) && (rho <= LOG_1E10);
       dmu = in_mu ? -(gv * invS * b.g_weight + b.ent_weight) : 0.f;
       drho = in_rho ? -(gve * invS * b.g_weight + b.ent_weight) : 0.f;
     }
-    b.gmu[(long long)r * b.g_ld + b.g_col0 + c] = dmu;
-    b.grho[(long long)r * b.g_ld + b.g_col0 + c] = drho;
+    if (live && sub == 0) {
+      b.gmu[(long long)r * b.g_ld + b.g_col0 + c] = dmu;
+      b.grho[(long long)r * b.g_ld + b.g_col0 + c] = drho;
+    }
   }
 }
 

@@ -1036,6 +1036,8 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   static const bool mono = getenv("SCDEF_TC_MONO") != nullptr;  // A/B switch: the monolithic v2a kernels
   const bool global_pass = a.pass == SCDEF_PASS_GLOBAL;
   const bool pipe = a.lik_on && !mono;
+  cudaEvent_t ev0 = a.ev0, ev1 = a.ev1;
+  a.ev0 = a.ev1 = nullptr;
   const bool reuse = pipe && a.reuse_w0;  // W_0 image + row sums of the previous pass (same noise, same W_0) are still valid
   if (!reuse) cudaMemsetAsync(ws.rowstats, 0, (size_t)a.S * a.K0 * 2 * 4, st);
   if (pipe) {
@@ -1047,6 +1049,9 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       k_tc_wgen<<<dim3((a.G + 255) / 256, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
     }
   }
+  bool ev_started = false;
+  auto main_begin = [&]() { if (ev0) { cudaEventRecord(ev0, st); ev_started = true; } };
+  auto main_end = [&]() { if (ev1 && ev_started) cudaEventRecord(ev1, st); };
   if (global_pass) {
     if (a.lik_on) {
       k_tc_ctilde<<<a.S, 1024, 0, st>>>(a, ws.ctilde);
@@ -1056,7 +1061,9 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       if (a.nb == 1) k_tc_colw<1><<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
       else k_tc_colw<MAX_NB><<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
       cudaFuncSetAttribute(k_lik_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+      main_begin();
       k_lik_pipe<true, true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+      main_end();
     } else {
       cudaFuncSetAttribute(k_lik_tc_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
       k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(a, g, ws, loss_out);
@@ -1066,10 +1073,14 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       if (!mono) {
         if (a.want_loss) {
           cudaFuncSetAttribute(k_lik_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+          main_begin();
           k_lik_pipe<false, true><<<dim3(a.S * g.NG, g.n_cblocks), PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+          main_end();
         } else {
           cudaFuncSetAttribute(k_lik_pipe<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+          main_begin();
           k_lik_pipe<false, false><<<dim3(a.S * g.NG, g.n_cblocks), PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+          main_end();
         }
       } else {
         cudaFuncSetAttribute(k_lik_tc_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);

@@ -33,6 +33,7 @@ struct LikTcArgs {
   float scale, global_weight, anneal;
   void* ws;
   size_t ws_bytes;
+  cudaEvent_t ev0, ev1;  // optional: recorded around the main fused kernel (measurement)
 };
 
 bool lik_tc_supported(int K0, int G, int nb);
