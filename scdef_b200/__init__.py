@@ -1,6 +1,7 @@
 """scdef_b200 — B200-native training hot path of scDEF."""
 from .anndata_compat import MiniAnnData
 from .model import scDEF
+from .sscdef import sscDEF
 
-__all__ = ["scDEF", "MiniAnnData"]
+__all__ = ["scDEF", "sscDEF", "MiniAnnData"]
 __version__ = "0.1.0"

@@ -465,7 +465,7 @@ class scDEF:
 
     def _engine_signature(self):
         return (tuple(self.layer_sizes), bool(self.marginalize_alpha), bool(self.use_brd), float(self.top_alpha),
-                self.x_placement)
+                self.x_placement, self.supervised_layer, float(self.alpha_floor))
 
     def _pull_params(self):
         lp, gp = self._engine.get_params()

@@ -171,3 +171,30 @@ def test_struct_layout_matches_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [ctypes.sizeof(_lib.ModelDesc), ctypes.sizeof(_lib.Blocks), ctypes.sizeof(_lib.Noise), ctypes.sizeof(_lib.Call)]
+
+
+def test_sscdef_constructor_matches_reference_test():
+    """/root/reference/tests/test_sscdef.py:8-35 and :55-83 (layer sizes, names, pinned z)."""
+    from scdef_b200 import sscDEF
+
+    X, _ = synth_counts_numpy(80, 120, seed=0)
+    rng = np.random.RandomState(0)
+    types = rng.choice(["A", "B"], size=80)
+    m = sscDEF(MiniAnnData(X, obs={"cell_type": types}), top_key="cell_type", n_layers=2, n_factors=4, seed=1)
+    assert m.n_layers == 3 and m.layer_sizes == [4, 2, 1]
+    assert m.layer_names[m.supervised_top_layer_idx] == "cell_type"
+    assert len(m.w_priors) == 3 and np.asarray(m.w_priors[1][0]).shape == (2, 4)
+    top = m._supervised_top_z
+    assert top.shape == (80, 2)
+    np.testing.assert_allclose(top.sum(1), 1.0 + m._Z_OFF_TYPE, rtol=1e-5)
+    np.testing.assert_allclose(top.max(1), m._Z_ON)
+    np.testing.assert_allclose(m.pmeans["cell_typez"], top, rtol=1e-5, atol=1e-5)
+    start, end = m._layer_column_range(m.supervised_top_layer_idx)
+    zs, zr = m.local_params[1]
+    np.testing.assert_allclose(np.exp(zs[:, start:end] + 0.5 * np.exp(zr[:, start:end]) ** 2), top, rtol=1e-3, atol=1e-3)
+    assert m.factor_names[m.supervised_top_layer_idx] == ["A", "B"]
+    m2 = sscDEF(MiniAnnData(np.ones((10, 5), dtype=np.float32) + np.arange(5), obs={"t": np.array(list("aabbccddee"))}),
+                top_key="t", n_factors=20, n_layers=3)
+    assert m2.layer_sizes == sscDEF._geometric_layer_sizes_no_root(20, 5, 3) + [1] == [20, 10, 5, 1]
+    with pytest.raises(KeyError):
+        sscDEF(MiniAnnData(X), top_key="nope")

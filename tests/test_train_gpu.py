@@ -303,3 +303,22 @@ def test_lazy_adam_is_bit_identical_to_dense(freeze_z):
     dense.reset_optimizer(); lazy.reset_optimizer()           # a reset with pending steps flushes them first
     same_state()
     assert int(lazy.row_step.max().item()) == 0
+
+
+def test_sscdef_fit_keeps_the_top_layer_pinned():
+    """/root/reference/tests/test_sscdef.py:36-49: after fit, the top layer's posterior mean is the label one-hot."""
+    from scdef_b200 import MiniAnnData, sscDEF
+    from scdef_b200.synth import synth_counts_numpy
+
+    X, _ = synth_counts_numpy(80, 120, seed=0)
+    types = np.random.RandomState(0).choice(["A", "B"], size=80)
+    m = sscDEF(MiniAnnData(X, obs={"cell_type": types}), top_key="cell_type", n_layers=2, n_factors=4, seed=1, logginglevel=30)
+    before = [p.copy() for p in m.local_params]
+    m.fit(n_epoch=2, n_rounds=1, num_samples=5)
+    top = m._supervised_top_z
+    np.testing.assert_allclose(m.pmeans["cell_typez"], top, rtol=1e-5, atol=1e-5)
+    start, end = m._layer_column_range(m.supervised_top_layer_idx)
+    zs, zr = m.local_params[1]
+    np.testing.assert_allclose(np.exp(zs[:, start:end] + 0.5 * np.exp(zr[:, start:end]) ** 2), top, rtol=1e-3, atol=1e-3)
+    assert len(m.elbos) == 2 and all(np.all(np.isfinite(e)) for e in m.elbos)   # main fit + root phase (root_epochs=10)
+    assert np.any(m.local_params[1][0][:, :start] != before[1][0][:, :start])   # the other layers did learn
