@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SCDEF_ABI_VERSION 4
+#define SCDEF_ABI_VERSION 5
 #define SCDEF_MAX_LAYERS 8
 
 #define SCDEF_OK 0
@@ -115,6 +115,11 @@ typedef struct scdef_noise {
   const float* eps_W[SCDEF_MAX_LAYERS]; /* (S,K_l,K_{l-1}) */
   const float* eps_ard;        /* (S,K0,1)   */
   const float* eps_alpha;      /* (S,1,1)    */
+  /* Data parallelism with position-based ownership (philox mode, per-cell blocks only): this rank's
+     B rows are rows [local_row_offset, local_row_offset+B) of a global minibatch of local_rows_total
+     rows, and draw exactly the normals the single-rank run draws for those rows.  0/0: B rows at 0. */
+  int64_t local_row_offset;
+  int64_t local_rows_total;
 } scdef_noise;
 
 /* Per-call arguments of the objective (the non-array arguments of `objective`). */
@@ -230,6 +235,8 @@ int scdef_noise_fill(scdef_ctx* ctx, const scdef_noise* noise, int block_kind, i
 #define SCDEF_PROF_ADAM_LOCAL_C 8 /* dense Adam over the cell-scale block */
 #define SCDEF_PROF_LIK_MAIN 9     /* the fused likelihood kernel alone (without its pre-/post-kernels) */
 #define SCDEF_PROF_KINDS 10
+/* on: 0 = off, 1 = every kind, otherwise a mask (bit k+1 = kind k) so that a timed region can carry the
+   event pairs of its dominant kernel only (two records per launch are not free on a ~30-launch step). */
 int scdef_profile_enable(scdef_ctx* ctx, int on);
 /* Sums the elapsed ms of the (up to 256 most recent) timed launches of each kind; syncs on them. */
 int scdef_profile_read(scdef_ctx* ctx, double* ms_sum, int64_t* n_timed, int64_t* n_launched,

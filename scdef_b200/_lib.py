@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 MAX_LAYERS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 PASS_LOCAL, PASS_GLOBAL = 1, 2
 NOISE_PHILOX, NOISE_EXPLICIT = 0, 1
@@ -79,6 +79,8 @@ class Noise(C.Structure):
         ("eps_W", _f32p * MAX_LAYERS),
         ("eps_ard", _f32p),
         ("eps_alpha", _f32p),
+        ("local_row_offset", C.c_int64),
+        ("local_rows_total", C.c_int64),
     ]
 
 

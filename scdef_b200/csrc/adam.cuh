@@ -270,13 +270,13 @@ __global__ void __launch_bounds__(256) k_row_stats(const float* X, long long n_r
   }
 }
 
-__global__ void __launch_bounds__(256) k_noise_fill(float* out, int S, int per, PhiloxKey key, NoiseTag tag) {
+__global__ void __launch_bounds__(256) k_noise_fill(float* out, int S, int per, PhiloxKey key, NoiseTag tag, long long e0) {
   const long long total = (long long)S * per;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     int s = (int)(e / per);
     int i = (int)(e - (long long)s * per);
-    out[e] = philox_normal(key, tag, (uint32_t)s, (uint32_t)i);
+    out[e] = philox_normal(key, tag, (uint32_t)s, (uint32_t)(e0 + i));
   }
 }
 

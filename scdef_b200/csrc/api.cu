@@ -25,6 +25,7 @@ struct scdef_ctx {
   char err[512];
   // profiling: CUDA-event pairs around every launch of each kernel family, on the launch stream
   bool prof_on, prof_ready;
+  unsigned prof_mask;  // bit k: kind k is timed
   cudaEvent_t prof_ev[SCDEF_PROF_KINDS][PROF_RING][2];
   long long prof_count[SCDEF_PROF_KINDS];
   long long launches;
@@ -54,7 +55,7 @@ int check_launch(scdef_ctx* ctx, const char* what) {
 struct ProfScope {
   scdef_ctx* c; int kind; cudaStream_t st; int slot;
   ProfScope(scdef_ctx* c_, int kind_, cudaStream_t st_) : c(c_), kind(kind_), st(st_), slot(-1) {
-    if (c->prof_on && c->prof_ready) {
+    if (c->prof_on && c->prof_ready && ((c->prof_mask >> kind) & 1u)) {
       slot = (int)(c->prof_count[kind] % PROF_RING);
       cudaEventRecord(c->prof_ev[kind][slot][0], st);
     }
@@ -182,6 +183,7 @@ int scdef_profile_enable(scdef_ctx* ctx, int on) {
     ctx->prof_ready = true;
   }
   ctx->prof_on = on != 0;
+  ctx->prof_mask = on == 1 ? 0xffffffffu : ((unsigned)on >> 1);
   return SCDEF_OK;
 }
 
@@ -256,6 +258,11 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
   auto Gb = [&](int b) { return (float*)(ws + plan.G[b]); };
 
   // ---- block table ----------------------------------------------------------------------
+  // data-parallel row window of the per-cell noise (scdef_noise.local_row_offset / local_rows_total)
+  const long long noise_rows_total = noise->local_rows_total > 0 ? noise->local_rows_total : B;
+  const long long noise_row0 = noise->local_rows_total > 0 ? noise->local_row_offset : 0;
+  if (noise_row0 < 0 || noise_row0 + B > noise_rows_total || noise_rows_total > 0x7fffffffLL)
+    return fail(ctx, SCDEF_EINVAL, "noise row window out of range");
   BlockTable all;
   memset(&all, 0, sizeof(all));
   auto fill = [&](int blk, const float* base, int rows, int cols, int ld, int col0, bool local,
@@ -271,7 +278,8 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     b.gmu = gbase; b.grho = gbase ? gbase + (long long)g_rows * g_ld : nullptr;
     b.rows = rows; b.cols = cols; b.ld = ld; b.col0 = col0;
     b.eps_ld = eps_ld; b.eps_col0 = eps_col0; b.g_ld = g_ld; b.g_col0 = g_col0;
-    b.tag = make_tag(noise, blk, rows, cols);
+    b.tag = make_tag(noise, blk, local ? (int)noise_rows_total : rows, cols);
+    b.noise_e0 = local ? noise_row0 * cols : 0;
     b.mu_hi = mu_hi; b.ent_weight = ent_w; b.g_weight = 1.f;
     b.stopped = stopped; b.active = active;
   };
@@ -470,7 +478,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       a.ws = ws + plan.tc_off; a.ws_bytes = plan.tc_bytes;
       {
         ProfScope ps(ctx, SCDEF_PROF_LIK, st);
-        const bool pm = ctx->prof_on && ctx->prof_ready && lik_run;
+        const bool pm = ctx->prof_on && ctx->prof_ready && lik_run && ((ctx->prof_mask >> SCDEF_PROF_LIK_MAIN) & 1u);
         const int slot = (int)(ctx->prof_count[SCDEF_PROF_LIK_MAIN] % PROF_RING);
         if (pm) { a.ev0 = ctx->prof_ev[SCDEF_PROF_LIK_MAIN][slot][0]; a.ev1 = ctx->prof_ev[SCDEF_PROF_LIK_MAIN][slot][1]; }
         rc = lik_tc_launch(a, loss_out, ctx->sm_count, st);
@@ -769,11 +777,19 @@ int scdef_noise_fill(scdef_ctx* ctx, const scdef_noise* noise, int block_kind, i
     default: return fail(ctx, SCDEF_EINVAL, "bad block kind");
   }
   if (rows * cols == 0) return SCDEF_OK;
+  long long e0 = 0;
+  int tag_rows = rows;
+  if (block_kind <= 1 && noise->local_rows_total > 0) {
+    if (noise->local_row_offset < 0 || noise->local_row_offset + B > noise->local_rows_total)
+      return fail(ctx, SCDEF_EINVAL, "noise row window out of range");
+    e0 = noise->local_row_offset * cols;
+    tag_rows = (int)noise->local_rows_total;
+  }
   long long total = (long long)S * rows * cols;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
   k_noise_fill<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(out, S, rows * cols, make_key(noise),
-                                                                          make_tag(noise, blk, rows, cols));
+                                                                          make_tag(noise, blk, tag_rows, cols), e0);
   return check_launch(ctx, "k_noise_fill");
 }
 

@@ -140,6 +140,7 @@ struct BlockDesc {
   float* grho;
   int rows, cols, ld, col0, eps_ld, eps_col0, g_ld, g_col0;
   NoiseTag tag;
+  long long noise_e0;  // flat element offset of row 0 in the philox stream of this block (data-parallel row offset)
   float mu_hi;      // LOG_1E6, or +inf for the gene scale (_scdef.py:1872)
   float ent_weight; // w_H * scale_H * (block weight), 0 for the pinned sscDEF layer
   float g_weight;   // multiplies the sample-gradient part (1; global_weight handled upstream)

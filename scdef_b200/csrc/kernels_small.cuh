@@ -16,7 +16,10 @@ __global__ void __launch_bounds__(256) k_sample(const BlockTable tab, int S, Phi
   __shared__ double red[32];
   const BlockDesc& b = tab.b[blockIdx.y];
   const int per = b.rows * b.cols;
-  const int nquad = (per + 3) >> 2;                 // one Philox call yields the normals of 4 flat elements
+  // one Philox call yields the normals of 4 flat elements; the block's elements are [e0, e0+per) of the stream
+  const long long e0 = b.noise_e0;
+  const long long q0 = e0 >> 2;
+  const int nquad = (int)(((e0 + per + 3) >> 2) - q0);
   const long long total = (long long)S * nquad;
   double ent = 0.0;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -24,12 +27,13 @@ __global__ void __launch_bounds__(256) k_sample(const BlockTable tab, int S, Phi
     const int s = (int)(e / nquad);
     const int qd = (int)(e - (long long)s * nquad);
     float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!b.eps && !b.fixed) n4 = philox_normal4(key, b.tag, (uint32_t)s, (uint32_t)qd);
+    if (!b.eps && !b.fixed) n4 = philox_normal4(key, b.tag, (uint32_t)s, (uint32_t)(q0 + qd));
     const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int i = qd * 4 + q;
-      if (i >= per) break;
+      const long long gi = (q0 + qd) * 4 + q - e0;
+      if (gi < 0 || gi >= per) continue;
+      const int i = (int)gi;
       const int r = i / b.cols, c = i - r * b.cols;
       const long long row = b.gather ? b.gather[r] : r;
       float v;

@@ -37,6 +37,11 @@ class ShardInfo:
 def all_reduce_sum(t, shard: ShardInfo):
     import torch.distributed as td
 
+    if t.is_cuda and td.get_backend(shard.group) != "nccl":  # gloo (tests): stage through the host
+        h = t.cpu()
+        td.all_reduce(h, op=td.ReduceOp.SUM, group=shard.group)
+        t.copy_(h)
+        return t
     td.all_reduce(t, op=td.ReduceOp.SUM, group=shard.group)
     return t
 
@@ -150,3 +155,146 @@ def local_members(perm_slice: np.ndarray, start: int, n_local: int) -> np.ndarra
     in the order they appear in it."""
     m = (perm_slice >= start) & (perm_slice < start + n_local)
     return perm_slice[m] - start
+
+
+# ---------------------------------------------------------------------------------------------
+# Position-based ownership ("epoch resharding").
+#
+# With cells owned statically, the number of members of a global minibatch that fall into one
+# rank's block is binomial (b ± sqrt(b)); the slowest rank sets the step time and the likelihood
+# kernel works in units of 128 cells, so b = 256 costs 3 units instead of 2 on about half the ranks.
+# Instead, at the start of every epoch the cells MOVE: rank r owns positions [r*b, (r+1)*b) of every
+# global slice perm[i*R*b : (i+1)*R*b] of that epoch's permutation, stored so that its minibatch i is
+# the contiguous row range [i*b, (i+1)*b).  Every rank then has exactly b rows per step, the global
+# minibatch is the reference's bit for bit, and the per-cell Philox rows line up with the single-rank
+# run (scdef_noise.local_row_offset).  The move is one all-to-all of the per-cell rows per epoch
+# (counts, variational parameters, Adam moments, per-cell constants) over NVLink.
+# ---------------------------------------------------------------------------------------------
+def epoch_layout(perm: np.ndarray, global_batch: int, counts):
+    """(rank_of, row_of, offs, row0) for one epoch, or None when the ranks' row counts cannot be kept.
+
+    rank_of[g], row_of[g]: where global cell g lives during this epoch.  Rank r keeps exactly counts[r]
+    rows: the full global minibatches give every rank b = global_batch/R rows, the short last one gives
+    rank r its remaining counts[r] - n_full*b rows.  offs[r]: row boundaries of rank r's minibatches;
+    row0[r][i]: position of rank r's first row inside global minibatch i (the noise row offset)."""
+    perm = np.asarray(perm)
+    N, R, gb = len(perm), len(counts), int(global_batch)
+    if gb % R != 0:
+        return None
+    b = gb // R
+    n_full, rem = divmod(N, gb)
+    tail = np.asarray(counts, dtype=np.int64) - n_full * b
+    if np.any(tail < 0) or int(tail.sum()) != rem:
+        return None
+    cum = np.concatenate([[0], np.cumsum(tail)])
+    pos = np.arange(N, dtype=np.int64)
+    i = pos // gb
+    t = pos - i * gb
+    rank = np.minimum(t // b, R - 1)
+    row = i * b + (t - rank * b)
+    if rem:
+        tl = slice(n_full * gb, N)
+        rr = np.searchsorted(cum, t[tl], side="right") - 1
+        rank[tl] = rr
+        row[tl] = n_full * b + t[tl] - cum[rr]
+    rank_of = np.empty(N, dtype=np.int32)
+    row_of = np.empty(N, dtype=np.int64)
+    rank_of[perm] = rank
+    row_of[perm] = row
+    offs, row0 = [], []
+    for r in range(R):
+        o = np.arange(n_full + 1, dtype=np.int64) * b
+        z = np.full(n_full, r * b, dtype=np.int64)
+        if rem:
+            o = np.concatenate([o, [n_full * b + tail[r]]])
+            z = np.concatenate([z, [cum[r]]])
+        offs.append(o)
+        row0.append(z)
+    return rank_of, row_of, offs, row0
+
+
+class RowMigrator:
+    """Moves per-cell rows between ranks so that cell g ends up at (rank_of[g], row_of[g]).
+
+    Every rank tracks the placement of ALL cells on the host (two integer arrays of n_total), so the
+    send and receive orders are computed locally and the only communication is the payload itself:
+    one `all_to_all_single` per tensor (column-chunked so the staging buffers stay below `chunk_bytes`)."""
+
+    def __init__(self, shard: ShardInfo, counts, chunk_bytes: int = 1 << 30):
+        self.shard = shard
+        self.counts = np.asarray(counts, dtype=np.int64)
+        starts = np.concatenate([[0], np.cumsum(self.counts)])
+        self.n_total = int(starts[-1])
+        self.home_rank = np.repeat(np.arange(len(self.counts), dtype=np.int32), self.counts)
+        self.home_row = np.arange(self.n_total, dtype=np.int64) - starts[self.home_rank]
+        self.cur_rank, self.cur_row = self.home_rank, self.home_row
+        self.chunk_bytes = int(chunk_bytes)
+        self.moved_bytes = 0
+        self.n_moves = 0
+
+    @property
+    def at_home(self) -> bool:
+        return self.cur_rank is self.home_rank and self.cur_row is self.home_row
+
+    def plan(self, rank_of, row_of):
+        """(send_rows, in_splits, place_rows, out_splits) of this rank for the move to (rank_of, row_of)."""
+        me, R = self.shard.rank, self.shard.world
+        starts = np.concatenate([[0], np.cumsum(self.counts)])
+        # destination slot (rank-major, then row) of every cell: a permutation of 0..n_total-1, so "sorted by
+        # (destination rank, destination row)" is a scatter, not a sort
+        slot = starts[rank_of] + row_of
+        src_rank = np.empty(self.n_total, dtype=np.int16)
+        src_row = np.empty(self.n_total, dtype=np.int64)
+        src_rank[slot] = self.cur_rank
+        src_row[slot] = self.cur_row
+        from_me = np.nonzero(src_rank == me)[0]                       # ascending destination slot
+        send_rows = src_row[from_me]
+        in_splits = np.diff(np.searchsorted(from_me, starts)).astype(np.int64)
+        mine = src_rank[starts[me] : starts[me + 1]]                  # source rank of each of my future rows
+        place_rows = np.argsort(mine, kind="stable").astype(np.int64)  # received order: by source rank, then row
+        out_splits = np.bincount(mine, minlength=R).astype(np.int64)
+        if len(send_rows) != self.counts[me]:
+            raise ValueError("row migration must keep every rank's row count")
+        return send_rows, in_splits, place_rows, out_splits
+
+    def _exchange(self, send, in_splits, out_splits):
+        import torch
+        import torch.distributed as td
+
+        n_out = int(out_splits.sum())
+        staged = send.is_cuda and td.get_backend(self.shard.group) != "nccl"  # gloo moves host tensors
+        s = send.cpu() if staged else send
+        recv = s.new_empty((n_out,) + tuple(s.shape[1:]))
+        td.all_to_all_single(recv, s, [int(x) for x in out_splits], [int(x) for x in in_splits], group=self.shard.group)
+        self.moved_bytes += int(send.numel() * send.element_size())
+        return recv.to(send.device) if staged else recv
+
+    def move(self, tensors, rank_of, row_of, plan=None):
+        """In place: every tensor's row for cell g goes from its current placement to (rank_of[g], row_of[g]).
+        `tensors`: 2-D views (rows, width) whose row count is this rank's counts[rank].  `plan`: the result of
+        `self.plan(rank_of, row_of)` when it was computed ahead of time."""
+        import torch
+
+        send_rows, in_splits, place_rows, out_splits = plan if plan is not None else self.plan(rank_of, row_of)
+        if self.shard.world > 1 or not np.array_equal(send_rows, place_rows):
+            dev = tensors[0].device if tensors else None
+            sr = torch.from_numpy(np.ascontiguousarray(send_rows)).to(dev)
+            inv = np.empty_like(place_rows)
+            inv[place_rows] = np.arange(len(place_rows))             # row j of the result = received row inv[j]
+            pr = torch.from_numpy(inv).to(dev)
+            for t in tensors:
+                n, w = int(t.shape[0]), int(t.shape[1])
+                # the chunk width must be the same on every rank: size it by the largest shard
+                step = max(1, min(w, self.chunk_bytes // max(1, int(self.counts.max()) * t.element_size())))
+                for c0 in range(0, w, step):
+                    blk = t[:, c0 : c0 + step]
+                    send = blk.index_select(0, sr).contiguous()
+                    recv = self._exchange(send, in_splits, out_splits) if self.shard.world > 1 else send
+                    blk.copy_(recv.index_select(0, pr))
+        self.cur_rank, self.cur_row = rank_of, row_of
+        self.n_moves += 1
+
+    def go_home(self, tensors):
+        if not self.at_home:
+            self.move(tensors, self.home_rank, self.home_row)
+        self.cur_rank, self.cur_row = self.home_rank, self.home_row

@@ -35,10 +35,12 @@ class NoiseSpec:
     step: int = 0
     coupling: bool = True  # reference behaviour: same-shape blocks share draws
     eps: Optional[Dict[str, object]] = None  # explicit: c, z, s, tau, omega, a, W (list)
+    row_offset: int = 0  # data parallelism: this rank's rows are [row_offset, row_offset+B) of rows_total
+    rows_total: int = 0  # (0: no window) — per-cell philox draws then equal the single-rank run's
 
     @staticmethod
-    def philox(seed: int, step: int, coupling: bool = True) -> "NoiseSpec":
-        return NoiseSpec(_lib.NOISE_PHILOX, int(seed), int(step), bool(coupling), None)
+    def philox(seed: int, step: int, coupling: bool = True, row_offset: int = 0, rows_total: int = 0) -> "NoiseSpec":
+        return NoiseSpec(_lib.NOISE_PHILOX, int(seed), int(step), bool(coupling), None, int(row_offset), int(rows_total))
 
     @staticmethod
     def explicit(c, z, s, tau, omega, a, W) -> "NoiseSpec":
@@ -251,6 +253,20 @@ class Engine:
         return ([v.detach().cpu().numpy().copy() for v in self.local.views],
                 [v.detach().cpu().numpy().copy() for v in self.glob.views])
 
+    def per_cell_tensors(self) -> List[torch.Tensor]:
+        """Every per-cell array of this rank as an in-place 2-D (rows, width) view: the counts, the per-cell
+        constants, the local blocks and their Adam moments (mu and rho planes), the lazy-Adam row clock.
+        This is what `dist.RowMigrator` moves when the cells change ranks at an epoch boundary."""
+        out = []
+        for t in (self.X, self.batch_id, self.batch_lib_ratio, self.cell_alpha_factor, self.x_lgamma,
+                  self.row_step, self.fixed_top_z):
+            if t is not None and t.numel() > 0:
+                out.append(t.view(self.N, -1))
+        for grp in (self.local, self.local_m, self.local_v):
+            for v in grp.views:          # (2, N, width): the two planes are separate row-major matrices
+                out.extend([v[0], v[1]])
+        return out
+
     def reset_optimizer(self):
         """Fresh optax state (`_scdef.py:3081-3082, 3317-3319`)."""
         self.local_sync()  # pending zero-gradient steps belong to the old state
@@ -264,6 +280,7 @@ class Engine:
     def _noise_struct(self, noise: NoiseSpec, keep):
         n = Noise()
         n.mode, n.coupling, n.seed, n.step = noise.mode, int(noise.coupling), noise.seed, noise.step
+        n.local_row_offset, n.local_rows_total = int(noise.row_offset), int(noise.rows_total)
         if noise.mode == _lib.NOISE_EXPLICIT:
             dev = self.device
             conv = lambda t: torch.as_tensor(np.asarray(t) if not isinstance(t, torch.Tensor) else t).to(dev, torch.float32).contiguous()
@@ -429,8 +446,12 @@ class Engine:
         self._check(rc, "scdef_posterior")
         return (lm.views, gm.views), (lv.views, gv.views)
 
-    def profile(self, on: bool):
-        self._check(self.lib.scdef_profile_enable(self.ctx, int(on)), "scdef_profile_enable")
+    def profile(self, on: bool, kinds: Optional[Sequence[str]] = None):
+        """Time every kernel family (kinds=None) or only the named ones (e.g. ["lik_main"])."""
+        flag = int(bool(on))
+        if on and kinds is not None:
+            flag = sum(1 << (_lib.PROF_KINDS.index(k) + 1) for k in kinds)
+        self._check(self.lib.scdef_profile_enable(self.ctx, flag), "scdef_profile_enable")
 
     def profile_read(self, reset=True):
         """{kind: (ms_sum, n_timed, n_launched)}, total kernel launches through the ABI."""

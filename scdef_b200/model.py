@@ -77,6 +77,7 @@ class scDEF:
         lik_impl: int = 0,
         process_group=None,
         lazy_adam: bool = True,
+        epoch_reshard: bool = True,
     ):
         # --- extensions of this package (keyword-only, all optional) ---
         self.device = device
@@ -84,6 +85,7 @@ class scDEF:
         self.noise_coupling = bool(noise_coupling)
         self.lik_impl = int(lik_impl)
         self.lazy_adam = bool(lazy_adam)  # exact lazy form of the dense local Adam (bit-identical)
+        self.epoch_reshard = bool(epoch_reshard)  # data parallel: position-based ownership (dist.epoch_layout)
         self._shard = _dist.ShardInfo.from_group(process_group)
         self.max_steps_per_learn = None  # benchmark hook: stop the hot loop after this many steps
         self._step_hook = None           # benchmark hook: called as hook(step_index, engine) around each step
@@ -677,10 +679,18 @@ class scDEF:
 
         eng = self._get_engine()
         eng.reset_optimizer()  # fresh optax state per _learn call (3079-3082)
-        start, _, _ = _dist.shard_bounds(self.n_cells, shard)
+        start, _, counts = _dist.shard_bounds(self.n_cells, shard)
+        # data parallel with resident counts: position-based ownership, the cells move once per epoch so that
+        # every rank has exactly batch_size rows per step (dist.epoch_layout); static ownership otherwise
+        migrator = None
+        if (shard.world > 1 and self.epoch_reshard and self.x_placement != "host" and num_batches > 1
+                and _dist.epoch_layout(np.arange(n_total), global_batch, counts) is not None):
+            migrator = _dist.RowMigrator(shard, counts)
         stream = MinibatchStream(n_total, global_batch, shard, eng.device,
                                  host_X=self.X if self.x_placement == "host" else None,
-                                 n_local=self.n_cells, start=start)
+                                 n_local=self.n_cells, start=start, migrator=migrator,
+                                 tensors_fn=eng.per_cell_tensors)
+        self._last_stream = stream
         annealing_parameter = float(annealing)
         alpha_f = float(self.alpha)
         scale_den = None  # set per step: global minibatch size
@@ -709,7 +719,7 @@ class scDEF:
                     if self._step_hook is not None:
                         self._step_hook(steps_done, eng, stream)
                     step_counter += 1
-                    noise = NoiseSpec.philox(self.seed or 0, step_counter, self.noise_coupling)
+                    noise = NoiseSpec.philox(self.seed or 0, step_counter, self.noise_coupling, *stream.noise_window(it))
                     idx, Xb, n_glob = stream.batch(it)
                     kw = dict(num_samples=int(num_samples), annealing=annealing_parameter,
                               stop_gradients=stop_gradients, stop_cell_budgets=stop_cell_budgets,
@@ -786,14 +796,15 @@ class scDEF:
         finally:
             if pbar is not None:
                 pbar.close()
+            if self._step_hook is not None:
+                self._step_hook(steps_done, eng, stream)
+            stream.finish()  # position-based ownership: the rows go back to block order before anything reads them
 
         if stop_message is None and not interrupted:
             stop_message = f"Stopping learning: reached max epochs (n_epoch={int(n_epoch)})."
         if stop_message is not None:
             self.logger.info(stop_message)
         self._noise_step = step_counter
-        if self._step_hook is not None:
-            self._step_hook(steps_done, eng, stream)
 
         self._device_summaries = eng.posterior()
         self._pull_params()

@@ -6,6 +6,11 @@ permutation is drawn on the host (it IS NumPy's algorithm) and uploaded once per
 are device views of it.  With the counts resident in HBM nothing else moves per step; in
 "host" placement the rows `X[batch_idx]` are gathered into pinned memory and copied each step,
 as the reference does (`jnp.array(self.X[batch_idx])`).
+
+Data parallel, counts resident (`migrator` given): position-based ownership, see `dist.epoch_layout` — at
+every epoch boundary the per-cell rows move so that this rank's minibatch i is its contiguous row range
+[i*b, (i+1)*b); every rank gets exactly b rows per step.  Otherwise (host placement, or row counts that
+cannot be kept) ownership is static and a rank takes the members of each global slice that it owns.
 """
 from __future__ import annotations
 
@@ -17,8 +22,8 @@ from . import dist as _dist
 
 class MinibatchStream:
     def __init__(self, n_total: int, global_batch: int, shard: _dist.ShardInfo, device,
-                 host_X=None, n_local=None, start=None, pinned_slots: int = 3):
-        self.n_total, self.gb, self.shard, self.device = int(n_total), int(global_batch), shard, device
+                 host_X=None, n_local=None, start=None, pinned_slots: int = 3, migrator=None, tensors_fn=None):
+        self.n_total, self.gb, self.shard, self.device = int(n_total), int(global_batch), shard, torch.device(device)
         self.rng = np.random.RandomState(0)
         num_complete, leftover = divmod(self.n_total, self.gb)
         self.num_batches = num_complete + bool(leftover)
@@ -27,6 +32,11 @@ class MinibatchStream:
         self.n_local = self.n_total if n_local is None else int(n_local)
         self.start = 0 if start is None else int(start)
         self.host_X = host_X
+        self.migrator, self.tensors_fn = migrator, tensors_fn
+        if migrator is not None and host_X is not None:
+            raise ValueError("epoch resharding needs the counts resident on the device")
+        self.row0 = None
+        self._move_events = []
         self.h2d_bytes = 0
         self._slots, self._events, self._slot_i = [], [], 0
         self._staged = {}
@@ -40,10 +50,39 @@ class MinibatchStream:
             self._dev_slots = [torch.empty((cap, G), dtype=torch.float32, device=device) for _ in range(pinned_slots)]
             self._copy_stream = torch.cuda.Stream(device=device)
 
+    # Position-based ownership: the next epoch's permutation, layout and send/receive plan are pure host work on
+    # n_total integers (~0.1 s per million cells); a helper thread does it while the current epoch runs.
+    def _layout_job(self, box):
+        perm = self.rng.permutation(self.n_total)
+        lay = _dist.epoch_layout(perm, self.gb, self.migrator.counts)
+        box.append(lay + (self.migrator.plan(lay[0], lay[1]),))
+
+    def _prepare_ahead(self):
+        import threading
+
+        box = []
+        th = threading.Thread(target=self._layout_job, args=(box,), daemon=True)
+        th.start()
+        self._ahead = (th, box)
+
+    def _next_layout(self, perm):
+        lay = _dist.epoch_layout(perm, self.gb, self.migrator.counts)
+        return lay + (self.migrator.plan(lay[0], lay[1]),)
+
     def new_epoch(self):
+        ahead = getattr(self, "_ahead", None)
+        if ahead is not None:   # the helper thread drew this epoch's permutation and planned its move
+            ahead[0].join()
+            self._ahead = None
+            rank_of, row_of, offs_all, row0_all, plan = ahead[1][0]
+            self._apply_layout(rank_of, row_of, offs_all, row0_all, plan)
+            return
         perm = self.rng.permutation(self.n_total)
         bounds = np.minimum(np.arange(self.num_batches + 1, dtype=np.int64) * self.gb, self.n_total)
         self.n_glob = np.diff(bounds)
+        if self.migrator is not None:
+            self._apply_layout(*self._next_layout(perm))
+            return
         if self.shard.world == 1:
             local, offs = perm, bounds
         else:
@@ -55,6 +94,49 @@ class MinibatchStream:
         self.perm_dev = torch.from_numpy(self.perm_host).to(self.device, non_blocking=False)
         self.h2d_bytes += self.perm_host.nbytes
         self._staged = {}
+
+    def _apply_layout(self, rank_of, row_of, offs_all, row0_all, plan):
+        bounds = np.minimum(np.arange(self.num_batches + 1, dtype=np.int64) * self.gb, self.n_total)
+        self.n_glob = np.diff(bounds)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if self.device.type == "cuda" else None
+        if ev:
+            ev[0].record()
+        self.migrator.move(self.tensors_fn(), rank_of, row_of, plan)
+        self._prepare_ahead()
+        if ev:
+            ev[1].record()
+            self._move_events.append(ev)
+        offs, self.row0 = offs_all[self.shard.rank], row0_all[self.shard.rank]
+        if getattr(self, "_arange_dev", None) is None:
+            self._arange_host = np.arange(self.n_local, dtype=np.int64)
+            self._arange_dev = torch.from_numpy(self._arange_host).to(self.device)
+            self.h2d_bytes += self._arange_host.nbytes
+        self.perm_host, self.perm_dev, self.offs = self._arange_host, self._arange_dev, offs
+        self._staged = {}
+
+    def noise_window(self, it: int):
+        """(row offset, total rows) of this rank's rows inside global minibatch `it` for the per-cell Philox
+        draws; (0, 0) under static ownership, where a rank's members are not a contiguous range of the slice."""
+        if self.row0 is None or self.shard.world == 1:
+            return 0, 0
+        return int(self.row0[it]), int(self.n_glob[it])
+
+    def finish(self):
+        """Return every per-cell row to its home rank and row (block order) after the last epoch."""
+        ahead = getattr(self, "_ahead", None)
+        if ahead is not None:
+            ahead[0].join()
+            self._ahead = None
+        if self.migrator is not None and not self.migrator.at_home:
+            self.migrator.go_home(self.tensors_fn())
+
+    def reshard_ms(self):
+        """Device time of each epoch-boundary move so far (synchronises)."""
+        out = []
+        for a, b in self._move_events:
+            b.synchronize()
+            out.append(a.elapsed_time(b))
+        return out
 
     def indices_host(self, it: int) -> np.ndarray:
         return self.perm_host[self.offs[it] : self.offs[it + 1]]

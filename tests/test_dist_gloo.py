@@ -73,3 +73,89 @@ def test_two_rank_statistics_and_stream_equal_single_rank(tmp_path):
         expect = next(ref)
         assert sorted(np.concatenate([a, c]).tolist()) == sorted(expect.tolist())
     np.testing.assert_array_equal(r0["gsum"], np.full(5, 3.0))
+
+
+# ---- position-based ownership (dist.epoch_layout / RowMigrator) ----------------------------------
+@pytest.mark.parametrize("n,gb,counts", [(121, 32, (70, 51)), (1000, 64, (250, 250, 250, 250)), (96, 32, (48, 48)),
+                                         (77, 24, (26, 26, 25))])
+def test_epoch_layout_is_balanced_and_keeps_the_reference_minibatches(n, gb, counts):
+    from oracle import host_ref
+    from scdef_b200.dist import epoch_layout
+
+    R, b = len(counts), gb // len(counts)
+    rng = np.random.RandomState(0)
+    ref = host_ref.data_stream_indices(n, gb)
+    for _ in range(2):
+        perm = rng.permutation(n)
+        rank_of, row_of, offs, row0 = epoch_layout(perm, gb, counts)
+        for r in range(R):  # every rank keeps its row count and every row is used exactly once
+            assert sorted(row_of[rank_of == r].tolist()) == list(range(counts[r]))
+        inv = {(int(rank_of[g]), int(row_of[g])): g for g in range(n)}
+        nb = (n + gb - 1) // gb
+        for i in range(nb):
+            expect = next(ref)
+            got = []
+            for r in range(R):
+                rows = range(int(offs[r][i]), int(offs[r][i + 1]))
+                if i < n // gb:
+                    assert len(rows) == b           # exactly b rows per rank on every full minibatch
+                got.append([inv[(r, j)] for j in rows])
+                # rank r's rows are the contiguous window [row0, row0+len) of the reference's slice, in order
+                assert got[-1] == expect[int(row0[r][i]) : int(row0[r][i]) + len(rows)].tolist()
+            assert np.concatenate(got).astype(np.int64).tolist() == expect.tolist()   # bit-exact, in order
+
+
+def test_epoch_layout_refuses_counts_it_cannot_keep():
+    from scdef_b200.dist import epoch_layout
+
+    assert epoch_layout(np.arange(100), 32, (90, 10)) is None     # rank 1 owns fewer rows than 3 full minibatches need
+    assert epoch_layout(np.arange(100), 33, (50, 50)) is None     # global batch not divisible by the world size
+
+
+def _migrate_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from scdef_b200.dist import RowMigrator, ShardInfo, epoch_layout
+
+    counts = (70, 51)
+    start = sum(counts[:rank])
+    gid = np.arange(start, start + counts[rank])
+    # three per-cell arrays of different widths/dtypes, each row tagged with its global cell id
+    A = torch.from_numpy(np.stack([gid * 10.0 + c for c in range(7)], 1).astype(np.float32))
+    Bt = torch.from_numpy(gid.astype(np.int32)).view(-1, 1)
+    P = torch.zeros(2, counts[rank], 3)
+    P[0] = torch.from_numpy(gid[:, None] + np.zeros((1, 3))).float()
+    P[1] = -P[0]
+    tensors = [A, Bt, P[0], P[1]]
+    mig = RowMigrator(ShardInfo.from_group("world"), counts, chunk_bytes=4 * 70 * 3)   # forces column chunking
+    rng = np.random.RandomState(0)
+    seen = []
+    for _ in range(3):
+        perm = rng.permutation(121)
+        rank_of, row_of, offs, row0 = epoch_layout(perm, 32, counts)
+        mig.move(tensors, rank_of, row_of)
+        here = np.nonzero(rank_of == rank)[0]
+        want = np.empty(counts[rank], dtype=np.int64)
+        want[row_of[here]] = here
+        assert np.array_equal(Bt[:, 0].numpy(), want)
+        assert np.array_equal(A.numpy(), np.stack([want * 10.0 + c for c in range(7)], 1).astype(np.float32))
+        assert np.array_equal(P[0, :, 1].numpy(), want.astype(np.float32)) and np.array_equal(P[1].numpy(), -P[0].numpy())
+        seen.append([Bt[int(offs[rank][i]) : int(offs[rank][i + 1]), 0].numpy().copy() for i in range(len(offs[rank]) - 1)])
+    mig.go_home(tensors)
+    assert mig.at_home and np.array_equal(Bt[:, 0].numpy(), gid) and np.array_equal(P[0, :, 0].numpy(), gid.astype(np.float32))
+    torch.save(seen, out + f".{rank}")
+    td.destroy_process_group()
+
+
+def test_row_migration_two_ranks_round_trip(tmp_path):
+    port = _free_port()
+    out = str(tmp_path / "mig")
+    mp.spawn(_migrate_worker, args=(2, port, out), nprocs=2, join=True)
+    s0 = torch.load(out + ".0", weights_only=False)
+    s1 = torch.load(out + ".1", weights_only=False)
+    from oracle import host_ref
+
+    ref = host_ref.data_stream_indices(121, 32)
+    for e in range(3):
+        for a, c in zip(s0[e], s1[e]):
+            np.testing.assert_array_equal(np.concatenate([a, c]), next(ref))   # rank 0's rows then rank 1's = the slice

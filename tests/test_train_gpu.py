@@ -322,3 +322,66 @@ def test_sscdef_fit_keeps_the_top_layer_pinned():
     np.testing.assert_allclose(np.exp(zs[:, start:end] + 0.5 * np.exp(zr[:, start:end]) ** 2), top, rtol=1e-3, atol=1e-3)
     assert len(m.elbos) == 2 and all(np.all(np.isfinite(e)) for e in m.elbos)   # main fit + root phase (root_epochs=10)
     assert np.any(m.local_params[1][0][:, :start] != before[1][0][:, :start])   # the other layers did learn
+
+
+# ---- data parallel with position-based ownership: two ranks == one rank with twice the batch ---------------------
+def _dp_problem():
+    from scdef_b200.synth import synth_counts_numpy
+
+    X, _ = synth_counts_numpy(600, 64, seed=3)
+    return X, [10, 5, 2], dict(n_epoch=3, batch_size=64, num_samples=5, lr=0.05, local_lr=0.02)
+
+
+def _dp_worker(rank, world, port, out, reshard):
+    import torch.distributed as td
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    td.init_process_group("gloo", rank=rank, world_size=world)   # one GPU here: gloo, payloads staged through the host
+    from scdef_b200 import MiniAnnData, scDEF
+
+    X, Ks, kw = _dp_problem()
+    sl = slice(0, 300) if rank == 0 else slice(300, 600)
+    init = torch.load(out + ".init", weights_only=False)
+    m = scDEF(MiniAnnData(X[sl]), layer_sizes=Ks, seed=1, logginglevel=30, process_group="world", epoch_reshard=reshard)
+    m.local_params = [p[:, sl] for p in init["lp"]]
+    m.global_params = init["gp"]
+    Xdev_before = m._get_engine().X.clone()
+    m._learn(**kw)
+    st = m._last_stream
+    torch.save(dict(elbos=m.elbos[-1], lp=m.local_params, gp=m.global_params, moves=0 if st.migrator is None else st.migrator.n_moves,
+                    x_restored=bool(torch.equal(m._get_engine().X, Xdev_before))), out + f".{rank}")
+    td.destroy_process_group()
+
+
+@pytest.mark.parametrize("reshard", [True, False])
+def test_two_ranks_equal_one_rank_with_twice_the_batch(tmp_path, reshard):
+    """SURVEY.md §8e end to end: `_learn` on 2 ranks (batch b each) against `_learn` on 1 rank with batch 2b.
+    With position-based ownership the per-cell Philox rows line up too, so the trajectories agree up to
+    floating-point summation order; with static ownership only the global minibatches are the same."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    from scdef_b200 import MiniAnnData, scDEF
+
+    X, Ks, kw = _dp_problem()
+    one = scDEF(MiniAnnData(X), layer_sizes=Ks, seed=1, logginglevel=30)
+    out = str(tmp_path / "dp")
+    torch.save(dict(lp=[np.array(p) for p in one.local_params], gp=[np.array(p) for p in one.global_params]), out + ".init")
+    one._learn(**dict(kw, batch_size=128))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_dp_worker, args=(2, port, out, reshard), nprocs=2, join=True)
+    r0, r1 = (torch.load(out + f".{r}", weights_only=False) for r in (0, 1))
+    assert r0["x_restored"] and r1["x_restored"]
+    assert r0["moves"] == (3 + 1 if reshard else 0)          # one move per epoch + the way home
+    np.testing.assert_allclose(r0["elbos"], r1["elbos"], rtol=1e-12)
+    if reshard:
+        np.testing.assert_allclose(r0["elbos"], one.elbos[-1], rtol=2e-5)
+        for i, p in enumerate(one.local_params):
+            got = np.concatenate([r0["lp"][i], r1["lp"][i]], axis=1)
+            np.testing.assert_allclose(got, p, rtol=2e-3, atol=2e-4)
+        for a, b_, p in zip(r0["gp"], r1["gp"], one.global_params):
+            np.testing.assert_array_equal(a, b_)              # replicated blocks stay bit-identical across ranks
+            np.testing.assert_allclose(a, p, rtol=2e-3, atol=2e-4)
+    else:
+        np.testing.assert_allclose(r0["elbos"], one.elbos[-1], rtol=5e-2)   # same minibatches, other per-cell noise
