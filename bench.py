@@ -249,7 +249,7 @@ def run_ours(args):
             t = torch.tensor([rms[-1] if rms else 0.0], dtype=torch.float64, device=dev)
             td.all_reduce(t, op=td.ReduceOp.MAX)
             st["reshard"] = {"moves": len(rms), "ms_per_move_rank0": [round(x, 2) for x in rms],
-                             "ms_per_epoch_steady": float(t.item()),
+                             "ms_per_epoch_steady": float(t.item()), "host_rank0": stream.host_stats,
                              "amortised_ms_per_step": float(t.item()) / steps_per_epoch,
                              "bytes_per_rank_per_epoch": stream.migrator.moved_bytes // max(1, stream.migrator.n_moves)}
         return st

@@ -170,15 +170,15 @@ def local_members(perm_slice: np.ndarray, start: int, n_local: int) -> np.ndarra
 # run (scdef_noise.local_row_offset).  The move is one all-to-all of the per-cell rows per epoch
 # (counts, variational parameters, Adam moments, per-cell constants) over NVLink.
 # ---------------------------------------------------------------------------------------------
-def epoch_layout(perm: np.ndarray, global_batch: int, counts):
-    """(rank_of, row_of, offs, row0) for one epoch, or None when the ranks' row counts cannot be kept.
+_POS_CACHE = {}
 
-    rank_of[g], row_of[g]: where global cell g lives during this epoch.  Rank r keeps exactly counts[r]
-    rows: the full global minibatches give every rank b = global_batch/R rows, the short last one gives
-    rank r its remaining counts[r] - n_full*b rows.  offs[r]: row boundaries of rank r's minibatches;
-    row0[r][i]: position of rank r's first row inside global minibatch i (the noise row offset)."""
-    perm = np.asarray(perm)
-    N, R, gb = len(perm), len(counts), int(global_batch)
+
+def _position_layout(N: int, gb: int, counts: tuple):
+    """The permutation-independent part of `epoch_layout`: owner rank and row of every POSITION of an epoch."""
+    key = (N, gb, counts)
+    if key in _POS_CACHE:
+        return _POS_CACHE[key]
+    R = len(counts)
     if gb % R != 0:
         return None
     b = gb // R
@@ -197,10 +197,6 @@ def epoch_layout(perm: np.ndarray, global_batch: int, counts):
         rr = np.searchsorted(cum, t[tl], side="right") - 1
         rank[tl] = rr
         row[tl] = n_full * b + t[tl] - cum[rr]
-    rank_of = np.empty(N, dtype=np.int32)
-    row_of = np.empty(N, dtype=np.int64)
-    rank_of[perm] = rank
-    row_of[perm] = row
     offs, row0 = [], []
     for r in range(R):
         o = np.arange(n_full + 1, dtype=np.int64) * b
@@ -210,6 +206,27 @@ def epoch_layout(perm: np.ndarray, global_batch: int, counts):
             z = np.concatenate([z, [cum[r]]])
         offs.append(o)
         row0.append(z)
+    _POS_CACHE.clear()   # one layout at a time is enough (a `_learn` call uses one)
+    _POS_CACHE[key] = (rank.astype(np.int32), row, offs, row0)
+    return _POS_CACHE[key]
+
+
+def epoch_layout(perm: np.ndarray, global_batch: int, counts):
+    """(rank_of, row_of, offs, row0) for one epoch, or None when the ranks' row counts cannot be kept.
+
+    rank_of[g], row_of[g]: where global cell g lives during this epoch.  Rank r keeps exactly counts[r]
+    rows: the full global minibatches give every rank b = global_batch/R rows, the short last one gives
+    rank r its remaining counts[r] - n_full*b rows.  offs[r]: row boundaries of rank r's minibatches;
+    row0[r][i]: position of rank r's first row inside global minibatch i (the noise row offset)."""
+    perm = np.asarray(perm)
+    lay = _position_layout(len(perm), int(global_batch), tuple(int(c) for c in counts))
+    if lay is None:
+        return None
+    rank_pos, row_pos, offs, row0 = lay
+    rank_of = np.empty(len(perm), dtype=np.int32)
+    row_of = np.empty(len(perm), dtype=np.int64)
+    rank_of[perm] = rank_pos
+    row_of[perm] = row_pos
     return rank_of, row_of, offs, row0
 
 

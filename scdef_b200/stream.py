@@ -14,6 +14,8 @@ cannot be kept) ownership is static and a rank takes the members of each global 
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 import torch
 
@@ -37,6 +39,7 @@ class MinibatchStream:
             raise ValueError("epoch resharding needs the counts resident on the device")
         self.row0 = None
         self._move_events = []
+        self.host_stats = {"plan_s": [], "join_wait_s": [], "move_enqueue_s": []}
         self.h2d_bytes = 0
         self._slots, self._events, self._slot_i = [], [], 0
         self._staged = {}
@@ -53,9 +56,11 @@ class MinibatchStream:
     # Position-based ownership: the next epoch's permutation, layout and send/receive plan are pure host work on
     # n_total integers (~0.1 s per million cells); a helper thread does it while the current epoch runs.
     def _layout_job(self, box):
+        t0 = time.perf_counter()
         perm = self.rng.permutation(self.n_total)
         lay = _dist.epoch_layout(perm, self.gb, self.migrator.counts)
         box.append(lay + (self.migrator.plan(lay[0], lay[1]),))
+        self.host_stats["plan_s"].append(round(time.perf_counter() - t0, 4))
 
     def _prepare_ahead(self):
         import threading
@@ -72,7 +77,9 @@ class MinibatchStream:
     def new_epoch(self):
         ahead = getattr(self, "_ahead", None)
         if ahead is not None:   # the helper thread drew this epoch's permutation and planned its move
+            t0 = time.perf_counter()
             ahead[0].join()
+            self.host_stats["join_wait_s"].append(round(time.perf_counter() - t0, 4))
             self._ahead = None
             rank_of, row_of, offs_all, row0_all, plan = ahead[1][0]
             self._apply_layout(rank_of, row_of, offs_all, row0_all, plan)
@@ -101,7 +108,9 @@ class MinibatchStream:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if self.device.type == "cuda" else None
         if ev:
             ev[0].record()
+        t0 = time.perf_counter()
         self.migrator.move(self.tensors_fn(), rank_of, row_of, plan)
+        self.host_stats["move_enqueue_s"].append(round(time.perf_counter() - t0, 4))
         self._prepare_ahead()
         if ev:
             ev[1].record()
