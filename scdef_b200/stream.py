@@ -44,6 +44,7 @@ class MinibatchStream:
         self._slots, self._events, self._slot_i = [], [], 0
         self._staged = {}
         self._copy_stream = None
+        self._pool = None
         if host_X is not None:
             G = host_X.shape[1]
             cap = min(self.gb, self.n_total)
@@ -150,28 +151,40 @@ class MinibatchStream:
     def indices_host(self, it: int) -> np.ndarray:
         return self.perm_host[self.offs[it] : self.offs[it + 1]]
 
-    def _stage(self, it: int):
-        """Host placement: gather X[batch] into a pinned slot and start its H2D copy on the copy stream."""
-        rows = self.indices_host(it)
-        k = self._slot_i
-        self._slot_i = (k + 1) % len(self._slots)
+    def _stage_job(self, rows, k):
+        """Worker thread: gather X[rows] into pinned slot k and start its H2D copy on the copy stream."""
+        torch.cuda.set_device(self.device)
         if self._events[k] is not None:
             self._events[k].synchronize()  # the step that last read this slot's device buffer has finished
         pin = self._slots[k][: len(rows)]
-        np.take(self.host_X, rows, axis=0, out=pin.numpy())
+        np.take(self.host_X, rows, axis=0, out=pin.numpy(), mode="clip")   # unbuffered; releases the GIL: overlaps the main thread's launches
         Xb = self._dev_slots[k][: len(rows)]
         with torch.cuda.stream(self._copy_stream):
             Xb.copy_(pin, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self._copy_stream)
         self.h2d_bytes += pin.numel() * 4
-        self._staged[it] = (k, Xb, ready)
+        return k, Xb, ready
+
+    def _stage(self, it: int):
+        """Host placement: hand minibatch `it` to the staging thread (FIFO, one slot per job)."""
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="scdef-stage")
+        k = self._slot_i
+        self._slot_i = (k + 1) % len(self._slots)
+        self._staged[it] = self._pool.submit(self._stage_job, self.indices_host(it), k)
 
     def prefetch(self, it: int):
-        """Start staging minibatch `it` of the current epoch (host placement only).  Called by the hot loop right
-        after step it-1 has been enqueued, so the host gather and the H2D copy overlap that step's kernels."""
-        if self.host_X is not None and 0 <= it < self.num_batches and it not in self._staged:
-            self._stage(it)
+        """Start staging minibatches `it` and `it+1` of the current epoch (host placement only).  Called by the hot loop
+        right after step it-1 has been enqueued: the host gather (a helper thread) and the H2D copy (a copy stream)
+        overlap that step's kernels and the main thread's launches."""
+        if self.host_X is None:
+            return
+        for j in (it, it + 1):
+            if 0 <= j < self.num_batches and j not in self._staged and len(self._staged) < len(self._slots) - 1:
+                self._stage(j)
 
     def batch(self, it: int):
         """(device int64 indices of this rank, device X rows or None, global minibatch size)."""
@@ -180,7 +193,7 @@ class MinibatchStream:
         if self.host_X is not None:
             if it not in self._staged:
                 self._stage(it)
-            k, Xb, ready = self._staged.pop(it)
+            k, Xb, ready = self._staged.pop(it).result()
             torch.cuda.current_stream(self.device).wait_event(ready)
             done = torch.cuda.Event()   # recorded by release(): the compute stream is finished with this slot
             self._pending_release = (k, done)
