@@ -212,6 +212,12 @@ int scdef_adam_global(scdef_ctx* ctx, const scdef_blocks* params, const scdef_bl
 int scdef_posterior(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blocks* means,
                     const scdef_blocks* vars, void* cuda_stream);
 
+/* Hard assignment counts per factor (`filter_factors`, _scdef.py:3540-3549, and `get_effective_factors`,
+   1378-1385): for every layer l, counts[off_l + k] = #{cells n : argmax_j E[z_l][n, j] = k} with
+   E[z] = exp(mu + sigma^2/2) evaluated exactly as scdef_posterior does (first maximum on ties, like
+   np.argmax).  counts: device int64[sum K], overwritten.  Reads the z block of `params` only. */
+int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t* counts, void* cuda_stream);
+
 /* Per-cell constants from a resident count matrix: lib[n] = sum_g x, lgam[n] = sum_g lgamma(x+1). */
 int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam,
                     void* cuda_stream);

@@ -235,3 +235,29 @@ def lognormal_mean(mu, log_sigma):
 def lognormal_var(mu, log_sigma):
     s2 = np.exp(log_sigma) ** 2
     return (np.exp(s2) - 1.0) * np.exp(2.0 * mu + s2)
+
+
+def filter_factors_upper_only(pmeans_z, pmeans_W, layer_sizes, n_cells, min_cells_upper=0.001, filter_up=True):
+    """`filter_factors(upper_only=True)` as `_learn` calls it (`_scdef.py:3386-3387, 3518-3568`): layer 0 is kept
+    whole; an upper layer keeps the factors that at least `min_cells_upper` cells are hard-assigned to
+    (argmax of the posterior mean z, `3540-3549`), intersected — `filter_up` — with the factors that the kept
+    factors of the layer below attach to most strongly (argmax over the kept rows of W, `3550-3558`); an empty
+    result keeps the whole layer (`3560-3566`).  pmeans_z[l]: (N, K_l); pmeans_W[l]: (K_l, K_{l-1})."""
+    if min_cells_upper != 0 and min_cells_upper < 1.0:
+        min_cells_upper = max(min_cells_upper * n_cells, 10)
+    out = []
+    for i, K in enumerate(layer_sizes):
+        if i == 0:
+            keep = np.arange(K)
+        else:
+            assignments = np.argmax(pmeans_z[i], axis=1)
+            counts = np.array([np.count_nonzero(assignments == a) for a in range(K)])
+            keep = np.arange(K)[np.where(counts >= min_cells_upper)[0]]
+            if filter_up and len(keep) > 0 and len(out[i - 1]) > 0:
+                mat = pmeans_W[i][keep]
+                att = [keep[np.argmax(mat[:, f])] for f in out[i - 1]]
+                keep = np.unique(list(set(np.unique(att)).intersection(keep)))
+        if len(keep) == 0:
+            keep = np.arange(K)
+        out.append(np.asarray(keep, dtype=int))
+    return out

@@ -250,6 +250,48 @@ __global__ void __launch_bounds__(256) k_posterior(const PostSegTable tab) {
   }
 }
 
+// ---- hard assignment counts per factor (one warp per cell, shared-memory histogram per CTA) -------
+struct AssignArgs {
+  const float* mu;    // (N, Kt)
+  const float* rho;   // (N, Kt)
+  long long N;
+  int L, Kt;
+  int K[SCDEF_MAX_LAYERS], off[SCDEF_MAX_LAYERS];
+};
+
+__global__ void __launch_bounds__(256) k_assignment_counts(const AssignArgs a, unsigned long long* counts) {
+  extern __shared__ unsigned int hist[];
+  for (int i = threadIdx.x; i < a.Kt; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp0; row < a.N; row += nwarps) {
+    const float* mu = a.mu + row * a.Kt;
+    const float* rho = a.rho + row * a.Kt;
+    for (int l = 0; l < a.L; ++l) {
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int k = lane; k < a.K[l]; k += 32) {
+        float s2 = expf(rho[a.off[l] + k]);
+        s2 *= s2;
+        const float v = expf(mu[a.off[l] + k] + 0.5f * s2);   // same expression as k_posterior
+        if (v > best || bi == 0x7fffffff) { best = v; bi = k; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+      }
+      if (lane == 0 && bi != 0x7fffffff) atomicAdd(&hist[a.off[l] + bi], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.Kt; i += blockDim.x)
+    if (hist[i]) atomicAdd(&counts[i], (unsigned long long)hist[i]);
+}
+
 // ---- per-cell constants of a resident count matrix ---------------------------------------------
 __global__ void __launch_bounds__(256) k_row_stats(const float* X, long long n_rows, int G, float* lib,
                                                    float* lgam) {

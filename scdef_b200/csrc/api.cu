@@ -746,6 +746,24 @@ int scdef_posterior(scdef_ctx* ctx, const scdef_blocks* params, const scdef_bloc
   return check_launch(ctx, "k_posterior");
 }
 
+int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t* counts, void* cuda_stream) {
+  if (!ctx) return SCDEF_EINVAL;
+  if (!params || !params->z || !counts) return fail(ctx, SCDEF_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cudaMemsetAsync(counts, 0, sizeof(int64_t) * ctx->Kt, st);
+  const long long N = ctx->d.n_cells;
+  if (N == 0) return SCDEF_OK;
+  AssignArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mu = params->z; a.rho = params->z + N * ctx->Kt;
+  a.N = N; a.L = ctx->L; a.Kt = ctx->Kt;
+  for (int l = 0; l < ctx->L; ++l) { a.K[l] = ctx->K[l]; a.off[l] = ctx->off[l]; }
+  long long blocks = (N + 7) / 8;
+  if (blocks > (long long)ctx->sm_count * 8) blocks = (long long)ctx->sm_count * 8;
+  k_assignment_counts<<<(unsigned)blocks, 256, sizeof(unsigned int) * ctx->Kt, st>>>(a, reinterpret_cast<unsigned long long*>(counts));
+  return check_launch(ctx, "k_assignment_counts");
+}
+
 /* bring-up hook (not part of the public header): dump the tcgen05 rate tile R as (S,B,G) */
 void scdef_debug_tc_dump(float* p) { lik_tc_set_debug(p); }
 void scdef_debug_tc_timing(unsigned long long* out) { cudaDeviceSynchronize(); lik_tc_read_timing(out); }

@@ -446,6 +446,17 @@ class Engine:
         self._check(rc, "scdef_posterior")
         return (lm.views, gm.views), (lv.views, gv.views)
 
+    def assignment_counts(self) -> List[torch.Tensor]:
+        """Per layer, the number of this rank's cells whose posterior-mean z is largest at each factor
+        (`filter_factors` / `get_effective_factors`, `_scdef.py:3540-3549, 1378-1385`): int64 device tensors (K_l,)."""
+        self.local_sync()
+        counts = torch.empty(self.Kt, dtype=torch.int64, device=self.device)
+        params, _ = self._cached_blocks()
+        rc = self.lib.scdef_assignment_counts(self.ctx, C.byref(params), _ptr(counts), self._stream())
+        self._check(rc, "scdef_assignment_counts")
+        offs = np.concatenate([[0], np.cumsum(self.Ks)])
+        return [counts[offs[l] : offs[l + 1]] for l in range(self.L)]
+
     def profile(self, on: bool, kinds: Optional[Sequence[str]] = None):
         """Time every kernel family (kinds=None) or only the named ones (e.g. ["lik_main"])."""
         flag = int(bool(on))

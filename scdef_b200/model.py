@@ -807,6 +807,7 @@ class scDEF:
         self._noise_step = step_counter
 
         self._device_summaries = eng.posterior()
+        self._assignment_counts = self._device_assignment_counts(eng)
         self._pull_params()
         self.elbos.append(all_losses)
         self.step_sizes.append(lr)
@@ -821,7 +822,64 @@ class scDEF:
         self.set_posterior_means()
         self.set_posterior_variances()
         self._device_summaries = None
-        # factor filtering / annotation (`_scdef.py:3386-3392`) are unchanged library code that
-        # consumes `pmeans`; they are outside this package's scope and are skipped here.
+        if self.use_brd and filter:
+            self.filter_factors(upper_only=True, annotate=annotate)   # `_scdef.py:3386-3387`
+        self._assignment_counts = None
+        # annotation (`annotate_adata`, `make_layercolors`, `3388-3392`) is unchanged library code that
+        # consumes `pmeans` / `factor_lists`; it is outside this package's scope and is skipped here.
+
+    # ------------------------------------------------------------------------------------------
+    # factor filtering — `filter_factors`, `_scdef.py:3478-3582`
+    # ------------------------------------------------------------------------------------------
+    def _device_assignment_counts(self, eng=None):
+        """Per layer, how many cells (over all ranks) have their largest posterior-mean z at each factor:
+        computed on the device from the local blocks (`scdef_assignment_counts`), summed over the ranks."""
+        import torch
+
+        eng = eng if eng is not None else self._get_engine()
+        counts = eng.assignment_counts()
+        if self._shard.world > 1:
+            flat = torch.cat(counts)
+            _dist.all_reduce_sum(flat, self._shard)
+            offs = np.concatenate([[0], np.cumsum(self.layer_sizes)])
+            counts = [flat[offs[l]: offs[l + 1]] for l in range(self.n_layers)]
+        return [c.cpu().numpy().astype(np.int64) for c in counts]
+
+    def filter_factors(self, brd_min=1.0, ard_min=0.001, clarity_min=0.5, n_eff_parents_max=1.5,
+                       local_l0_scores=False, batch_purity_max=None, batch_purity_soft_max=None,
+                       min_cells_upper=0.001, min_cells_lower=0.0, filter_up=True, annotate=True,
+                       upper_only=False):
+        """The reference's `filter_factors` for `upper_only=True` — the call `_learn` makes (`_scdef.py:3386-3387`).
+        Layer 0 is left whole; upper layers keep the factors with enough hard-assigned cells (counts from the
+        device, all ranks) and, with `filter_up`, only those the kept factors below attach to (`3540-3568`).
+        Filtering layer 0 (`upper_only=False`) needs `tools.factor_diagnostics` (BRD/ARD/clarity table), which is
+        host-side library code outside this package."""
+        if not upper_only:
+            raise NotImplementedError("filter_factors(upper_only=False) needs scdef.tools.factor_diagnostics "
+                                      "(out of scope here); `_learn` itself only uses upper_only=True")
+        n_all = int(self.n_cells_total)
+        if min_cells_upper != 0 and min_cells_upper < 1.0:
+            min_cells_upper = max(min_cells_upper * n_all, 10)
+        counts_all = getattr(self, "_assignment_counts", None)
+        if counts_all is None:
+            counts_all = self._device_assignment_counts()
+        new_factor_lists = []
+        for i, layer_name in enumerate(self.layer_names):
+            if i == 0:
+                keep = np.arange(self.layer_sizes[i])
+            else:
+                counts = np.asarray(counts_all[i])
+                keep = np.arange(self.layer_sizes[i])[np.where(counts >= min_cells_upper)[0]]
+                if filter_up and len(keep) > 0 and len(new_factor_lists[i - 1]) > 0:
+                    mat = np.asarray(self.pmeans[f"{layer_name}W"])[keep]
+                    att = [keep[np.argmax(mat[:, f])] for f in new_factor_lists[i - 1]]
+                    keep = np.unique(list(set(np.unique(att)).intersection(keep)))
+            if len(keep) == 0:
+                self.logger.info(f"No factors in layer {i} satisfy the filtering criterion. Please adjust the filtering "
+                                 f"parameters.Keeping all factors for layer {i} for now.")
+                keep = np.arange(self.layer_sizes[i])
+            new_factor_lists.append(np.asarray(keep, dtype=int))
+        self.factor_lists = new_factor_lists
+        self.set_factor_names()
 
     learn = _learn  # legacy name used by the docs notebook / benchmarks (SURVEY.md §2)

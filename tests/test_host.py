@@ -198,3 +198,25 @@ def test_sscdef_constructor_matches_reference_test():
     assert m2.layer_sizes == sscDEF._geometric_layer_sizes_no_root(20, 5, 3) + [1] == [20, 10, 5, 1]
     with pytest.raises(KeyError):
         sscDEF(MiniAnnData(X), top_key="nope")
+
+
+def test_filter_factors_upper_only_restatement_known_answer():
+    """oracle/host_ref.filter_factors_upper_only on a hand-made case (`_scdef.py:3518-3568`)."""
+    # 12 cells; layer 1 (3 factors): cells assigned 10 / 2 / 0 -> with min 2 cells keep {0, 1}; factor 2 is empty
+    z1 = np.zeros((12, 3)); z1[:10, 0] = 1.0; z1[10:, 1] = 1.0
+    z0 = np.ones((12, 4))
+    # layer-0 factors attach (argmax over the kept rows of W_1) to: f0->0, f1->0, f2->0, f3->0  => filter_up drops 1
+    W1 = np.array([[5.0, 4.0, 3.0, 2.0], [1.0, 1.0, 1.0, 1.0], [9.0, 9.0, 9.0, 9.0]])
+    # layer 2 (2 factors): all cells on factor 1; W_2's kept row attaches layer-1 factor 0 to factor 1
+    z2 = np.zeros((12, 2)); z2[:, 1] = 1.0
+    W2 = np.array([[3.0, 0.0, 0.0], [1.0, 2.0, 0.0]])
+    out = host_ref.filter_factors_upper_only([z0, z1, z2], [None, W1, W2], [4, 3, 2], 12, min_cells_upper=2)
+    assert [o.tolist() for o in out] == [[0, 1, 2, 3], [0], [1]]
+    out = host_ref.filter_factors_upper_only([z0, z1, z2], [None, W1, W2], [4, 3, 2], 12, min_cells_upper=2, filter_up=False)
+    assert [o.tolist() for o in out] == [[0, 1, 2, 3], [0, 1], [1]]
+    # fraction -> max(frac * n, 10): nothing reaches 10 cells in layer 2's factor 0, factor 1 has 12
+    out = host_ref.filter_factors_upper_only([z0, z1, z2], [None, W1, W2], [4, 3, 2], 12, min_cells_upper=0.5, filter_up=False)
+    assert [o.tolist() for o in out] == [[0, 1, 2, 3], [0], [1]]
+    # an empty layer falls back to all of its factors
+    out = host_ref.filter_factors_upper_only([z0, z1, z2], [None, W1, W2], [4, 3, 2], 12, min_cells_upper=11, filter_up=False)
+    assert [o.tolist() for o in out] == [[0, 1, 2, 3], [0, 1, 2], [1]]

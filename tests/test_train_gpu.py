@@ -348,7 +348,7 @@ def _dp_worker(rank, world, port, out, reshard):
     Xdev_before = m._get_engine().X.clone()
     m._learn(**kw)
     st = m._last_stream
-    torch.save(dict(elbos=m.elbos[-1], lp=m.local_params, gp=m.global_params, moves=0 if st.migrator is None else st.migrator.n_moves,
+    torch.save(dict(elbos=m.elbos[-1], lp=m.local_params, gp=m.global_params, factor_lists=[f.tolist() for f in m.factor_lists], moves=0 if st.migrator is None else st.migrator.n_moves,
                     x_restored=bool(torch.equal(m._get_engine().X, Xdev_before))), out + f".{rank}")
     td.destroy_process_group()
 
@@ -383,5 +383,44 @@ def test_two_ranks_equal_one_rank_with_twice_the_batch(tmp_path, reshard):
         for a, b_, p in zip(r0["gp"], r1["gp"], one.global_params):
             np.testing.assert_array_equal(a, b_)              # replicated blocks stay bit-identical across ranks
             np.testing.assert_allclose(a, p, rtol=2e-3, atol=2e-4)
+        # the hard-assignment counts behind filter_factors are summed over the ranks
+        assert r0["factor_lists"] == r1["factor_lists"] == [f.tolist() for f in one.factor_lists]
     else:
         np.testing.assert_allclose(r0["elbos"], one.elbos[-1], rtol=5e-2)   # same minibatches, other per-cell noise
+
+
+def test_assignment_counts_match_numpy_argmax_including_ties():
+    """`scdef_assignment_counts` against np.argmax / count_nonzero on the pulled posterior means (`_scdef.py:3540-3549`)."""
+    N, G, Ks, nb = 777, 40, (33, 7, 3), 1
+    X, batch, model, lp, gp = small_problem(N, G, Ks, nb, seed=4)
+    lp = [np.array(p) for p in lp]
+    lp[1][:, :50, :] = lp[1][:, :1, :]          # 50 identical rows
+    lp[1][0, 100:140, 33:40] = 0.25             # exact ties inside layer 1 -> the first maximum wins
+    lp[1][1, 100:140, 33:40] = -1.0
+    eng = make_engine(X, batch, model, lp, gp)
+    counts = [c.cpu().numpy() for c in eng.assignment_counts()]
+    (means_l, _), _ = eng.posterior()
+    zm = means_l[1].cpu().numpy()
+    off = 0
+    for l, K in enumerate(Ks):
+        a = np.argmax(zm[:, off:off + K], axis=1)
+        np.testing.assert_array_equal(counts[l], np.bincount(a, minlength=K))
+        assert counts[l].sum() == N
+        off += K
+    assert counts[1][0] >= 40
+
+
+def test_learn_filters_upper_layers_like_the_reference():
+    X, m = _fit_model()
+    m._learn(n_epoch=3, num_samples=5, batch_size=64)
+    Ks = m.layer_sizes
+    pz = [np.asarray(m.pmeans[f"{n}z"]) for n in m.layer_names]
+    pW = [np.asarray(m.pmeans[f"{n}W"]) for n in m.layer_names]
+    want = host_ref.filter_factors_upper_only(pz, pW, Ks, X.shape[0])
+    assert [f.tolist() for f in m.factor_lists] == [w.tolist() for w in want]
+    assert [len(n) for n in m.factor_names] == [len(w) for w in want]
+    m.filter_factors(upper_only=True, min_cells_upper=1, filter_up=False)     # recomputed from the engine's parameters
+    want = host_ref.filter_factors_upper_only(pz, pW, Ks, X.shape[0], min_cells_upper=1, filter_up=False)
+    assert [f.tolist() for f in m.factor_lists] == [w.tolist() for w in want]
+    with pytest.raises(NotImplementedError):
+        m.filter_factors()
