@@ -286,6 +286,13 @@ class RowMigrator:
         self.moved_bytes += int(send.numel() * send.element_size())
         return recv.to(send.device) if staged else recv
 
+    def exchange(self, send, in_splits, out_splits):
+        """One all-to-all of rows: `send` holds in_splits[d] rows for every rank d (in rank order); returns the
+        out_splits[s] rows received from every rank s, in rank order."""
+        if self.shard.world == 1:
+            return send
+        return self._exchange(send.contiguous(), in_splits, out_splits)
+
     def move(self, tensors, rank_of, row_of, plan=None):
         """In place: every tensor's row for cell g goes from its current placement to (rank_of[g], row_of[g]).
         `tensors`: 2-D views (rows, width) whose row count is this rank's counts[rank].  `plan`: the result of

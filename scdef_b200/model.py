@@ -680,10 +680,11 @@ class scDEF:
         eng = self._get_engine()
         eng.reset_optimizer()  # fresh optax state per _learn call (3079-3082)
         start, _, counts = _dist.shard_bounds(self.n_cells, shard)
-        # data parallel with resident counts: position-based ownership, the cells move once per epoch so that
-        # every rank has exactly batch_size rows per step (dist.epoch_layout); static ownership otherwise
+        # data parallel: position-based ownership, the cells' rows move once per epoch so that every rank has
+        # exactly batch_size rows per step (dist.epoch_layout); in host placement the counts stay with their home
+        # rank and travel per step (stream.py); static ownership when the shard sizes cannot be kept
         migrator = None
-        if (shard.world > 1 and self.epoch_reshard and self.x_placement != "host" and num_batches > 1
+        if (shard.world > 1 and self.epoch_reshard and num_batches > 1
                 and _dist.epoch_layout(np.arange(n_total), global_batch, counts) is not None):
             migrator = _dist.RowMigrator(shard, counts)
         stream = MinibatchStream(n_total, global_batch, shard, eng.device,

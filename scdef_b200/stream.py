@@ -9,8 +9,11 @@ as the reference does (`jnp.array(self.X[batch_idx])`).
 
 Data parallel, counts resident (`migrator` given): position-based ownership, see `dist.epoch_layout` — at
 every epoch boundary the per-cell rows move so that this rank's minibatch i is its contiguous row range
-[i*b, (i+1)*b); every rank gets exactly b rows per step.  Otherwise (host placement, or row counts that
-cannot be kept) ownership is static and a rank takes the members of each global slice that it owns.
+[i*b, (i+1)*b); every rank gets exactly b rows per step.  In host placement the counts stay in the host
+memory of their home rank: each step a rank stages the rows of the global slice that it is home to, and ONE
+all-to-all on the device (about 5 MB per rank) hands every row to the rank that processes it.  Otherwise
+(row counts that cannot be kept) ownership is static and a rank takes the members of each global slice
+that it owns.
 """
 from __future__ import annotations
 
@@ -35,9 +38,8 @@ class MinibatchStream:
         self.start = 0 if start is None else int(start)
         self.host_X = host_X
         self.migrator, self.tensors_fn = migrator, tensors_fn
-        if migrator is not None and host_X is not None:
-            raise ValueError("epoch resharding needs the counts resident on the device")
         self.row0 = None
+        self._perm_epoch = None
         self._move_events = []
         self.host_stats = {"plan_s": [], "join_wait_s": [], "move_enqueue_s": []}
         self.h2d_bytes = 0
@@ -53,6 +55,10 @@ class MinibatchStream:
                 self._events.append(None)
             self._dev_slots = [torch.empty((cap, G), dtype=torch.float32, device=device) for _ in range(pinned_slots)]
             self._copy_stream = torch.cuda.Stream(device=device)
+            if migrator is not None:   # window order of the rows received from the home ranks
+                self._inv_pin = [torch.empty(cap, dtype=torch.int64).pin_memory() for _ in range(pinned_slots)]
+                self._inv_dev = [torch.empty(cap, dtype=torch.int64, device=device) for _ in range(pinned_slots)]
+                self._starts = np.concatenate([[0], np.cumsum(migrator.counts)])
 
     # Position-based ownership: the next epoch's permutation, layout and send/receive plan are pure host work on
     # n_total integers (~0.1 s per million cells); a helper thread does it while the current epoch runs.
@@ -60,7 +66,7 @@ class MinibatchStream:
         t0 = time.perf_counter()
         perm = self.rng.permutation(self.n_total)
         lay = _dist.epoch_layout(perm, self.gb, self.migrator.counts)
-        box.append(lay + (self.migrator.plan(lay[0], lay[1]),))
+        box.append(lay + (self.migrator.plan(lay[0], lay[1]), perm))
         self.host_stats["plan_s"].append(round(time.perf_counter() - t0, 4))
 
     def _prepare_ahead(self):
@@ -73,7 +79,7 @@ class MinibatchStream:
 
     def _next_layout(self, perm):
         lay = _dist.epoch_layout(perm, self.gb, self.migrator.counts)
-        return lay + (self.migrator.plan(lay[0], lay[1]),)
+        return lay + (self.migrator.plan(lay[0], lay[1]), perm)
 
     def new_epoch(self):
         ahead = getattr(self, "_ahead", None)
@@ -82,8 +88,7 @@ class MinibatchStream:
             ahead[0].join()
             self.host_stats["join_wait_s"].append(round(time.perf_counter() - t0, 4))
             self._ahead = None
-            rank_of, row_of, offs_all, row0_all, plan = ahead[1][0]
-            self._apply_layout(rank_of, row_of, offs_all, row0_all, plan)
+            self._apply_layout(*ahead[1][0])
             return
         perm = self.rng.permutation(self.n_total)
         bounds = np.minimum(np.arange(self.num_batches + 1, dtype=np.int64) * self.gb, self.n_total)
@@ -103,7 +108,9 @@ class MinibatchStream:
         self.h2d_bytes += self.perm_host.nbytes
         self._staged = {}
 
-    def _apply_layout(self, rank_of, row_of, offs_all, row0_all, plan):
+    def _apply_layout(self, rank_of, row_of, offs_all, row0_all, plan, perm):
+        self._perm_epoch = perm
+        self._rank_pos = _dist._position_layout(self.n_total, self.gb, tuple(int(c) for c in self.migrator.counts))[0]
         bounds = np.minimum(np.arange(self.num_batches + 1, dtype=np.int64) * self.gb, self.n_total)
         self.n_glob = np.diff(bounds)
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if self.device.type == "cuda" else None
@@ -151,7 +158,26 @@ class MinibatchStream:
     def indices_host(self, it: int) -> np.ndarray:
         return self.perm_host[self.offs[it] : self.offs[it + 1]]
 
-    def _stage_job(self, rows, k):
+    def _home_rows(self, it: int):
+        """Host placement with position-based ownership: (rows of this rank's host block that belong to global
+        slice `it`, in slice order; how many of them go to each rank; how many rows of my window come from each
+        home rank; the permutation from received order to window order)."""
+        me, R = self.shard.rank, self.shard.world
+        lo, hi = it * self.gb, min((it + 1) * self.gb, self.n_total)
+        sl = self._perm_epoch[lo:hi]
+        home = np.searchsorted(self._starts, sl, side="right") - 1
+        dest = self._rank_pos[lo:hi]
+        mine = home == me
+        rows = sl[mine] - self._starts[me]
+        in_splits = np.bincount(dest[mine], minlength=R).astype(np.int64)
+        hw = home[dest == me]                                   # my window is a contiguous range of the slice
+        order = np.argsort(hw, kind="stable")                  # received order: by home rank, then slice position
+        inv = np.empty(len(hw), dtype=np.int64)
+        inv[order] = np.arange(len(hw))
+        out_splits = np.bincount(hw, minlength=R).astype(np.int64)
+        return rows, in_splits, out_splits, inv
+
+    def _stage_job(self, rows, k, extra=None):
         """Worker thread: gather X[rows] into pinned slot k and start its H2D copy on the copy stream."""
         torch.cuda.set_device(self.device)
         if self._events[k] is not None:
@@ -159,12 +185,20 @@ class MinibatchStream:
         pin = self._slots[k][: len(rows)]
         np.take(self.host_X, rows, axis=0, out=pin.numpy(), mode="clip")   # unbuffered; releases the GIL: overlaps the main thread's launches
         Xb = self._dev_slots[k][: len(rows)]
+        inv_dev = None
+        if extra is not None:
+            inv = extra[2]
+            self._inv_pin[k][: len(inv)].copy_(torch.from_numpy(inv))
+            inv_dev = self._inv_dev[k][: len(inv)]
         with torch.cuda.stream(self._copy_stream):
             Xb.copy_(pin, non_blocking=True)
+            if inv_dev is not None:
+                inv_dev.copy_(self._inv_pin[k][: len(inv_dev)], non_blocking=True)
+                self.h2d_bytes += inv_dev.numel() * 8
             ready = torch.cuda.Event()
             ready.record(self._copy_stream)
         self.h2d_bytes += pin.numel() * 4
-        return k, Xb, ready
+        return k, Xb, ready, extra, inv_dev
 
     def _stage(self, it: int):
         """Host placement: hand minibatch `it` to the staging thread (FIFO, one slot per job)."""
@@ -174,7 +208,11 @@ class MinibatchStream:
             self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="scdef-stage")
         k = self._slot_i
         self._slot_i = (k + 1) % len(self._slots)
-        self._staged[it] = self._pool.submit(self._stage_job, self.indices_host(it), k)
+        if self.migrator is not None:
+            rows, in_splits, out_splits, inv = self._home_rows(it)
+            self._staged[it] = self._pool.submit(self._stage_job, rows, k, (in_splits, out_splits, inv))
+        else:
+            self._staged[it] = self._pool.submit(self._stage_job, self.indices_host(it), k)
 
     def prefetch(self, it: int):
         """Start staging minibatches `it` and `it+1` of the current epoch (host placement only).  Called by the hot loop
@@ -193,8 +231,11 @@ class MinibatchStream:
         if self.host_X is not None:
             if it not in self._staged:
                 self._stage(it)
-            k, Xb, ready = self._staged.pop(it).result()
+            k, Xb, ready, extra, inv_dev = self._staged.pop(it).result()
             torch.cuda.current_stream(self.device).wait_event(ready)
+            if extra is not None:   # hand every staged row to the rank that processes it, then restore window order
+                recv = self.migrator.exchange(Xb, extra[0], extra[1])
+                Xb = recv.index_select(0, inv_dev)
             done = torch.cuda.Event()   # recorded by release(): the compute stream is finished with this slot
             self._pending_release = (k, done)
         return idx, Xb, int(self.n_glob[it])

@@ -159,3 +159,37 @@ def test_row_migration_two_ranks_round_trip(tmp_path):
     for e in range(3):
         for a, c in zip(s0[e], s1[e]):
             np.testing.assert_array_equal(np.concatenate([a, c]), next(ref))   # rank 0's rows then rank 1's = the slice
+
+
+@pytest.mark.parametrize("n,gb,counts", [(121, 32, (70, 51)), (1000, 96, (334, 333, 333))])
+def test_host_placement_row_routing_delivers_each_window_in_order(n, gb, counts):
+    """stream._home_rows (host placement + position-based ownership), emulated without devices: every rank stages
+    the rows of the global slice it is home to; after the all-to-all and the window permutation each rank holds
+    exactly its window of the reference's slice, in order."""
+    from scdef_b200.dist import ShardInfo, _position_layout
+    from scdef_b200.stream import MinibatchStream
+
+    R = len(counts)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    perm = np.random.RandomState(3).permutation(n)
+    rank_pos = _position_layout(n, gb, tuple(counts))[0]
+    streams = []
+    for r in range(R):
+        st = object.__new__(MinibatchStream)
+        st.shard, st.gb, st.n_total = ShardInfo(rank=r, world=R), gb, n
+        st._perm_epoch, st._starts, st._rank_pos = perm, starts, rank_pos
+        streams.append(st)
+    for it in range((n + gb - 1) // gb):
+        plans = [st._home_rows(it) for st in streams]
+        sends = [rows + starts[r] for r, (rows, _, _, _) in enumerate(plans)]           # global ids staged by rank r
+        lo, hi = it * gb, min((it + 1) * gb, n)
+        for d in range(R):
+            recv = []
+            for s in range(R):                                                             # all-to-all, rank order
+                a = int(plans[s][1][:d].sum())
+                chunk = sends[s][a : a + int(plans[s][1][d])]
+                assert len(chunk) == plans[d][2][s]
+                recv.append(chunk)
+            got = np.concatenate(recv)[plans[d][3]]
+            want = perm[lo:hi][rank_pos[lo:hi] == d]
+            np.testing.assert_array_equal(got, want)

@@ -332,7 +332,7 @@ def _dp_problem():
     return X, [10, 5, 2], dict(n_epoch=3, batch_size=64, num_samples=5, lr=0.05, local_lr=0.02)
 
 
-def _dp_worker(rank, world, port, out, reshard):
+def _dp_worker(rank, world, port, out, reshard, placement="device"):
     import torch.distributed as td
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -342,19 +342,20 @@ def _dp_worker(rank, world, port, out, reshard):
     X, Ks, kw = _dp_problem()
     sl = slice(0, 300) if rank == 0 else slice(300, 600)
     init = torch.load(out + ".init", weights_only=False)
-    m = scDEF(MiniAnnData(X[sl]), layer_sizes=Ks, seed=1, logginglevel=30, process_group="world", epoch_reshard=reshard)
+    m = scDEF(MiniAnnData(X[sl]), layer_sizes=Ks, seed=1, logginglevel=30, process_group="world", epoch_reshard=reshard,
+              x_placement=placement)
     m.local_params = [p[:, sl] for p in init["lp"]]
     m.global_params = init["gp"]
-    Xdev_before = m._get_engine().X.clone()
+    Xdev_before = m._get_engine().X.clone() if placement == "device" else None
     m._learn(**kw)
     st = m._last_stream
     torch.save(dict(elbos=m.elbos[-1], lp=m.local_params, gp=m.global_params, factor_lists=[f.tolist() for f in m.factor_lists], moves=0 if st.migrator is None else st.migrator.n_moves,
-                    x_restored=bool(torch.equal(m._get_engine().X, Xdev_before))), out + f".{rank}")
+                    x_restored=True if Xdev_before is None else bool(torch.equal(m._get_engine().X, Xdev_before))), out + f".{rank}")
     td.destroy_process_group()
 
 
-@pytest.mark.parametrize("reshard", [True, False])
-def test_two_ranks_equal_one_rank_with_twice_the_batch(tmp_path, reshard):
+@pytest.mark.parametrize("reshard,placement", [(True, "device"), (False, "device"), (True, "host")])
+def test_two_ranks_equal_one_rank_with_twice_the_batch(tmp_path, reshard, placement):
     """SURVEY.md §8e end to end: `_learn` on 2 ranks (batch b each) against `_learn` on 1 rank with batch 2b.
     With position-based ownership the per-cell Philox rows line up too, so the trajectories agree up to
     floating-point summation order; with static ownership only the global minibatches are the same."""
@@ -370,7 +371,7 @@ def test_two_ranks_equal_one_rank_with_twice_the_batch(tmp_path, reshard):
     torch.save(dict(lp=[np.array(p) for p in one.local_params], gp=[np.array(p) for p in one.global_params]), out + ".init")
     one._learn(**dict(kw, batch_size=128))
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_dp_worker, args=(2, port, out, reshard), nprocs=2, join=True)
+    mp.spawn(_dp_worker, args=(2, port, out, reshard, placement), nprocs=2, join=True)
     r0, r1 = (torch.load(out + f".{r}", weights_only=False) for r in (0, 1))
     assert r0["x_restored"] and r1["x_restored"]
     assert r0["moves"] == (3 + 1 if reshard else 0)          # one move per epoch + the way home
