@@ -427,7 +427,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       ht.tiles_per_cta = tpc;
       if (smem_t > 48 * 1024) cudaFuncSetAttribute(k_hier_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
       ProfScope ps(ctx, SCDEF_PROF_HIER, st);
-      k_hier_tiled<<<dim3((n_t32 + tpc - 1) / tpc, S), 256, smem_t, st>>>(ht, S, loss_out);
+      k_hier_tiled<<<dim3((n_t32 + tpc - 1) / tpc, S), HNT, smem_t, st>>>(ht, S, loss_out);
     } else {
     // enough CTAs to fill the GPU, at least one round of 8 cells each
     int chunks = (ctx->sm_count * 2 + S - 1) / S;

@@ -426,8 +426,9 @@ struct HierTArgs {
   int wtot, kmax;
 };
 constexpr int HT = 32, HLD = 33;
+constexpr int HNW = 16, HNT = HNW * 32;   // warps / threads per CTA of k_hier_tiled (2 CTAs per SM: 32 warps)
 
-__global__ void __launch_bounds__(256, 2) k_hier_tiled(const HierTArgs t, int S, double* loss_out) {
+__global__ void __launch_bounds__(HNT, 2) k_hier_tiled(const HierTArgs t, int S, double* loss_out) {
   extern __shared__ __align__(16) float sm[];
   __shared__ double red[32];
   const HierArgs& a = t.h;
@@ -444,10 +445,13 @@ __global__ void __launch_bounds__(256, 2) k_hier_tiled(const HierTArgs t, int S,
   for (int l = 1; l < L; ++l) {
     const int rows = a.K[l], cols = a.K[l - 1], ld = t.wld[l];
     const float* src = a.smp_W[l] + (long long)s * rows * cols;
-    for (int e = tid; e < rows * ld; e += 256) {
-      const int u = e / ld, k = e - u * ld;
-      Wsm[t.woff[l] + e] = k < cols ? src[u * cols + k] : 0.f;
-      if (global_pass) GWsm[t.woff[l] + e] = 0.f;
+    // one warp per row, lanes along the row: coalesced, no index divisions, several loads in flight
+#pragma unroll 4
+    for (int u = warp; u < rows; u += HNW) {
+      for (int k = lane; k < ld; k += 32) {
+        Wsm[t.woff[l] + u * ld + k] = k < cols ? __ldg(src + u * cols + k) : 0.f;
+        if (global_pass) GWsm[t.woff[l] + u * ld + k] = 0.f;
+      }
     }
   }
   const float alpha_value = a.smp_a ? a.smp_a[s] : a.alpha;
@@ -461,10 +465,14 @@ __global__ void __launch_bounds__(256, 2) k_hier_tiled(const HierTArgs t, int S,
     // z samples of the tile, all layers: coalesced over k, stored [k][cell]
     for (int l = 0; l < L; ++l) {
       const int Kl = a.K[l];
-      for (int e = tid; e < HT * Kl; e += 256) {
-        const int c = e / Kl, k = e - c * Kl;
-        const int j = j0 + c;
-        zt[(a.off[l] + k) * HLD + c] = j < a.B ? a.smp_z[l][((long long)s * a.B + j) * Kl + k] : 1.f;
+      const float* zsrc = a.smp_z[l] + ((long long)s * a.B + j0) * Kl;
+      float* zdst = zt + a.off[l] * HLD;
+      // one warp per cell, lanes along k: coalesced reads; smem bank = (k + c) % 32, conflict-free
+#pragma unroll
+      for (int ci = 0; ci < HT / HNW; ++ci) {
+        const int c = warp + HNW * ci;
+        const bool ok = j0 + c < a.B;
+        for (int k = lane; k < Kl; k += 32) zdst[k * HLD + c] = ok ? __ldg(zsrc + c * Kl + k) : 1.f;
       }
     }
     const int jl = j0 + lane;
@@ -486,7 +494,7 @@ __global__ void __launch_bounds__(256, 2) k_hier_tiled(const HierTArgs t, int S,
         const int Ku = a.K[l + 1], ld = t.wld[l + 1];
         const float* Wl = Wsm + t.woff[l + 1];
         const float* zu = zt + a.off[l + 1] * HLD + lane;
-        for (int k0 = warp * 4; k0 < Kl; k0 += 32) {
+        for (int k0 = warp * 4; k0 < Kl; k0 += 4 * HNW) {
           float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll 4
           for (int u = 0; u < Ku; ++u) {
@@ -503,20 +511,22 @@ __global__ void __launch_bounds__(256, 2) k_hier_tiled(const HierTArgs t, int S,
       }
       // (2) prior value, own gradient, P_l (in place over m_l)
       float* gz_cur = (l & 1) ? gzA : gzB;   // LOCAL: layers alternate between the two buffers
-      for (int k = warp; k < Kl; k += 8) {
+      for (int k = warp; k < Kl; k += HNW) {
         const float zz = zt[(a.off[l] + k) * HLD + lane];
-        const float lz = logf(zz);
+        const float lz = __logf(zz);   // MUFU path (as in the likelihood epilogue): <= 2 ulp, far inside the 1e-4 bar
         float g;
         if (top) {
           if (cvalid) val += (double)gamma_lp(zz, lz, a.top_alpha, a.top_alpha, a.lgam_top, logf(a.top_alpha));
           g = (a.top_alpha - 1.f) / zz - a.top_alpha;
         } else {
           const float m = has_parent ? Pm[k * HLD + lane] : 1.f;
-          const float rate = al / m, lrate = log_al - logf(m);
+          const float inv_m = __frcp_rn(m);                // one reciprocal serves rate and z/m
+          const float rate = al * inv_m, lrate = log_al - __logf(m);
+          const float zm = zz * inv_m;
           if (cvalid) val += (double)gamma_lp(zz, lz, al, rate, lgam_al, lrate);
-          g = (al - 1.f) / zz - rate;
-          if (has_parent) Pm[k * HLD + lane] = cvalid ? rate * (zz / m - 1.f) : 0.f;
-          if (cvalid) dal += lz - psi_al + lrate + 1.f - zz / m;
+          g = __fdividef(al - 1.f, zz) - rate;
+          if (has_parent) Pm[k * HLD + lane] = cvalid ? rate * (zm - 1.f) : 0.f;
+          if (cvalid) dal += lz - psi_al + lrate + 1.f - zm;
         }
         if (!global_pass) gz_cur[k * HLD + lane] = g;
       }
@@ -528,7 +538,7 @@ __global__ void __launch_bounds__(256, 2) k_hier_tiled(const HierTArgs t, int S,
           // gz_{l+1}[u][cell] += sum_k P_l[k][cell] W_{l+1}[u][k]
           float* gz_par = ((l + 1) & 1) ? gzA : gzB;
           const float* Wl = Wsm + t.woff[l + 1];
-          for (int u0 = warp * 4; u0 < Ku; u0 += 32) {
+          for (int u0 = warp * 4; u0 < Ku; u0 += 4 * HNW) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int k0 = 0; k0 < Kl; k0 += 4) {
               float p[4];
@@ -550,7 +560,7 @@ __global__ void __launch_bounds__(256, 2) k_hier_tiled(const HierTArgs t, int S,
           // GW_{l+1}[u][k] += sum_cell z_{l+1}[u][cell] P_l[k][cell]   (lanes on k)
           float* GWl = GWsm + t.woff[l + 1];
           const float* zu = zt + a.off[l + 1] * HLD;
-          for (int u0 = warp * 4; u0 < Ku; u0 += 32) {
+          for (int u0 = warp * 4; u0 < Ku; u0 += 4 * HNW) {
             float acc[4][4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -585,10 +595,12 @@ __global__ void __launch_bounds__(256, 2) k_hier_tiled(const HierTArgs t, int S,
           else { if (l != 0) continue; lw = 0; }                          // bottom layer: no children
           const float* gsrc = (lw & 1) ? gzA : gzB;
           const int Kw = a.K[lw];
-          for (int e = tid; e < HT * Kw; e += 256) {
-            const int c = e / Kw, k = e - c * Kw;
-            const int j = j0 + c;
-            if (j < a.B) a.G_z[lw][((long long)s * a.B + j) * Kw + k] = a.scale * gsrc[k * HLD + c];
+          float* gdst = a.G_z[lw] + ((long long)s * a.B + j0) * Kw;
+#pragma unroll
+          for (int ci = 0; ci < HT / HNW; ++ci) {
+            const int c = warp + HNW * ci;
+            if (j0 + c < a.B)
+              for (int k = lane; k < Kw; k += 32) gdst[c * Kw + k] = a.scale * gsrc[k * HLD + c];
           }
         }
         __syncthreads();
@@ -603,10 +615,8 @@ __global__ void __launch_bounds__(256, 2) k_hier_tiled(const HierTArgs t, int S,
       if (l - 1 == a.top_layer) continue;
       const int rows = a.K[l], cols = a.K[l - 1], ld = t.wld[l];
       float* dst = a.G_W[l] + (long long)s * rows * cols;
-      for (int e = tid; e < rows * cols; e += 256) {
-        const int u = e / cols, k = e - u * cols;
-        atomicAdd(&dst[e], a.scale * GWsm[t.woff[l] + u * ld + k]);
-      }
+      for (int u = warp; u < rows; u += HNW)
+        for (int k = lane; k < cols; k += 32) atomicAdd(&dst[u * cols + k], a.scale * GWsm[t.woff[l] + u * ld + k]);
     }
     if (a.G_a) {
       dal_acc = warp_sum(dal_acc);
