@@ -222,6 +222,16 @@ int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t*
 int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam,
                     void* cuda_stream);
 
+/* Counts kept as CSR on the device (float32 data, int32 column indices, int64 row pointers; the reference
+   densifies `adata.X`, _scdef.py:491-496 — 40 GB of host memory at 1M x 5k — this keeps ~10 % of that in HBM).
+   scdef_csr_row_stats: the per-cell constants of scdef_row_stats from the CSR rows.
+   scdef_csr_gather_rows: out[j, :] = dense row `rows[j]` (out: n_rows x n_genes floats, overwritten); the
+   result is passed to scdef_elbo_grad as `X_batch`, so every kernel downstream is the dense path. */
+int scdef_csr_row_stats(const int64_t* indptr, const float* data, int64_t n_rows, float* lib, float* lgam,
+                        void* cuda_stream);
+int scdef_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* rows,
+                          int32_t n_rows, int32_t n_genes, float* out, void* cuda_stream);
+
 /* Writes the N(0,1) draws the kernels would use for one block in PHILOX mode (debug / parity):
    block_kind 0 cell_scale, 1 z layer `layer`, 2 gene_scale, 3 brd, 4 W layer `layer`, 5 ard,
    6 alpha; out is (S, rows, cols). */

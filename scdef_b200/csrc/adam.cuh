@@ -250,6 +250,36 @@ __global__ void __launch_bounds__(256) k_posterior(const PostSegTable tab) {
   }
 }
 
+// ---- CSR-resident counts: per-cell constants and minibatch densification (one warp per row) ------
+__global__ void __launch_bounds__(256) k_csr_row_stats(const long long* indptr, const float* data, long long n_rows,
+                                                       float* lib, float* lgam) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  float sl = 0.f, sg = 0.f;
+  for (long long p = indptr[row] + lane; p < indptr[row + 1]; p += 32) {
+    const float x = data[p];
+    sl += x;
+    if (x > 1.5f) sg += lgammaf(x + 1.f);
+  }
+  sl = warp_sum(sl);
+  sg = warp_sum(sg);
+  if (lane == 0) {
+    if (lib) lib[row] = sl;
+    if (lgam) lgam[row] = sg;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_csr_gather_rows(const long long* indptr, const int* indices, const float* data,
+                                                         const long long* rows, int n_rows, int G, float* out) {
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= n_rows) return;
+  const long long row = rows[j];
+  float* dst = out + (long long)j * G;
+  for (long long p = indptr[row] + lane; p < indptr[row + 1]; p += 32) dst[indices[p]] = data[p];
+}
+
 // ---- hard assignment counts per factor (one warp per cell, shared-memory histogram per CTA) -------
 struct AssignArgs {
   const float* mu;    // (N, Kt)

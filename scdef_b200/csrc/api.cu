@@ -746,6 +746,26 @@ int scdef_posterior(scdef_ctx* ctx, const scdef_blocks* params, const scdef_bloc
   return check_launch(ctx, "k_posterior");
 }
 
+int scdef_csr_row_stats(const int64_t* indptr, const float* data, int64_t n_rows, float* lib, float* lgam, void* cuda_stream) {
+  if (!indptr || !data || n_rows < 0) return SCDEF_EINVAL;
+  if (n_rows == 0) return SCDEF_OK;
+  k_csr_row_stats<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)cuda_stream>>>(
+      reinterpret_cast<const long long*>(indptr), data, n_rows, lib, lgam);
+  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+}
+
+int scdef_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* rows,
+                          int32_t n_rows, int32_t n_genes, float* out, void* cuda_stream) {
+  if (!indptr || !indices || !data || !out || n_rows < 0 || n_genes < 1) return SCDEF_EINVAL;
+  if (n_rows == 0) return SCDEF_OK;
+  if (!rows) return SCDEF_EINVAL;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_rows * n_genes, st);
+  k_csr_gather_rows<<<(n_rows + 7) / 8, 256, 0, st>>>(reinterpret_cast<const long long*>(indptr), indices, data,
+                                                      reinterpret_cast<const long long*>(rows), n_rows, n_genes, out);
+  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+}
+
 int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t* counts, void* cuda_stream) {
   if (!ctx) return SCDEF_EINVAL;
   if (!params || !params->z || !counts) return fail(ctx, SCDEF_EINVAL, "null argument");

@@ -83,9 +83,12 @@ def count_statistics(X, batch_labels, shard: ShardInfo, eps=1e-12):
     """The constants `load_adata` / `update_model_priors` derive from the counts
     (`_scdef.py:498-573, 1279-1287`), computed over ALL ranks' cells.  float64 throughout."""
     is_torch = hasattr(X, "is_cuda")
+    is_sparse = hasattr(X, "tocsr")
     dev = X.device if (is_torch and X.is_cuda and shard.world > 1) else None
     n_local, G = int(X.shape[0]), int(X.shape[1])
-    if is_torch:
+    if is_sparse:
+        lib = np.asarray(X.sum(axis=1, dtype=np.float64)).ravel()
+    elif is_torch:
         import torch
 
         lib = X.sum(dim=1, dtype=torch.float64).cpu().numpy()
@@ -102,6 +105,9 @@ def count_statistics(X, batch_labels, shard: ShardInfo, eps=1e-12):
     nb = len(batches)
 
     def gene_sums(mask=None):
+        if is_sparse:
+            rows = X if mask is None else X[mask]
+            return np.asarray(rows.sum(axis=0, dtype=np.float64)).ravel()
         if is_torch:
             import torch
 

@@ -101,7 +101,7 @@ class Engine:
                  batch_id, batch_lib_ratio, cell_alpha_factor, gene_ratio, w_priors,
                  use_brd=True, marginalize_alpha=False, top_alpha=1.0, brd=1.0, brd_mean=1.0,
                  shrinkage_shape=1.0, shrinkage_rate=1.0, cell_scale_shape=1.0, gene_scale_shape=1.0,
-                 alpha_floor=0.1, supervised_layer=None, fixed_top_z=None, X=None,
+                 alpha_floor=0.1, supervised_layer=None, fixed_top_z=None, X=None, X_csr=None,
                  device="cuda:0", batch_max=256, lazy_adam=True):
         if not torch.cuda.is_available():
             raise ScdefError("scdef_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
@@ -126,6 +126,22 @@ class Engine:
         self.gene_ratio = f32(np.ascontiguousarray(gr))
         self.row_slot = torch.full((max(self.N, 1),), -1, dtype=torch.int32, device=dev)
         self.x_lgamma = None
+        # counts kept as CSR on the device: (indptr int64, indices int32, data float32); a minibatch is densified
+        # per call (`scdef_csr_gather_rows`) and handed to the kernels as X_batch
+        self.X_csr = None
+        if X_csr is not None:
+            if self.X is not None:
+                raise ScdefError("give either X or X_csr")
+            ip, ix, dv = X_csr
+            as_t = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dev, dt).contiguous()
+            self.X_csr = (as_t(ip, torch.int64), as_t(ix, torch.int32), as_t(dv, torch.float32))
+            if int(self.X_csr[0].numel()) != self.N + 1:
+                raise ScdefError("X_csr row pointers must have n_cells + 1 entries")
+            self.x_lgamma = torch.empty(max(self.N, 1), dtype=torch.float32, device=dev)
+            rc = self.lib.scdef_csr_row_stats(_ptr(self.X_csr[0]), _ptr(self.X_csr[2]), self.N, None, _ptr(self.x_lgamma), self._stream())
+            if rc != 0:
+                raise ScdefError(f"scdef_csr_row_stats failed ({rc})")
+            self._xb_scratch = None
         if self.X is not None and self.N > 0:
             self.x_lgamma = torch.empty(self.N, dtype=torch.float32, device=dev)
             rc = self.lib.scdef_row_stats(_ptr(self.X), self.N, self.G, None, _ptr(self.x_lgamma), self._stream())
@@ -304,6 +320,8 @@ class Engine:
         B = int(indices.numel())
         self._ensure_batch(B)
         self._ensure_workspace(B, int(num_samples), lik_impl)
+        if X_batch is None and self.X_csr is not None and B > 0:
+            X_batch = self.gather_rows(indices)
         call = Call()
         call.pass_ = _lib.PASS_LOCAL if which == "local" else _lib.PASS_GLOBAL
         call.num_samples, call.batch, call.lik_impl = int(num_samples), B, int(lik_impl)
@@ -334,6 +352,18 @@ class Engine:
         self._check(rc, "scdef_elbo_grad")
         self._keep = keep  # explicit-noise tensors must outlive the enqueued kernels
         return self.loss_buf
+
+    def gather_rows(self, indices: torch.Tensor) -> torch.Tensor:
+        """CSR-resident counts: the dense (B, G) rows of this rank's cells `indices` (a view of a reused scratch)."""
+        B = int(indices.numel())
+        if self._xb_scratch is None or self._xb_scratch.shape[0] < B:
+            self._xb_scratch = torch.empty((max(B, self.batch_max), self.G), dtype=torch.float32, device=self.device)
+        out = self._xb_scratch[:B]
+        ip, ix, dv = self.X_csr
+        rc = self.lib.scdef_csr_gather_rows(_ptr(ip), _ptr(ix), _ptr(dv), _ptr(indices), B, self.G, _ptr(out), self._stream())
+        if rc != 0:
+            raise ScdefError(f"scdef_csr_gather_rows failed ({rc})")
+        return out
 
     def _cached_blocks(self):
         key = self.local_grad.flat.data_ptr()

@@ -81,7 +81,11 @@ class scDEF:
     ):
         # --- extensions of this package (keyword-only, all optional) ---
         self.device = device
-        self.x_placement = x_placement  # "device": counts resident in HBM; "host": streamed per step
+        # "device": dense counts resident in HBM; "csr": CSR counts resident in HBM (a minibatch is densified per
+        # step); "host": dense counts in host memory, streamed per step
+        if x_placement not in ("device", "csr", "host"):
+            raise ValueError("x_placement must be 'device', 'csr' or 'host'")
+        self.x_placement = x_placement
         self.noise_coupling = bool(noise_coupling)
         self.lik_impl = int(lik_impl)
         self.lazy_adam = bool(lazy_adam)  # exact lazy form of the dense local Adam (bit-identical)
@@ -172,16 +176,19 @@ class scDEF:
             raise TypeError("adata must be an instance of AnnData.")
         self.adata = adata.copy()
         X = self.adata.X if layer is None else self.adata.layers[layer]
-        try:
-            import scipy.sparse as sp
+        import scipy.sparse as sp
 
+        self._X_is_torch = hasattr(X, "is_cuda")
+        if self.x_placement == "csr":   # keep the counts sparse (the reference densifies, `_scdef.py:491-496`)
+            if self._X_is_torch:
+                raise TypeError("x_placement='csr' takes a scipy sparse or NumPy count matrix")
+            X = sp.csr_matrix(X, dtype=np.float32)
+            X.sort_indices()
+        else:
             if sp.issparse(X):
                 X = X.toarray()
-        except ImportError:  # pragma: no cover
-            pass
-        self._X_is_torch = hasattr(X, "is_cuda")
-        if not self._X_is_torch:
-            X = np.ascontiguousarray(np.asarray(X), dtype=np.float32)
+            if not self._X_is_torch:
+                X = np.ascontiguousarray(np.asarray(X), dtype=np.float32)
         self.X = X  # float32 (the reference keeps float64 on the host; counts are exact in f32)
         stats = _dist.count_statistics(X, self._batch_labels(batch_key), self._shard)
         self.n_cells_total = stats["n_cells_total"]
@@ -454,7 +461,9 @@ class scDEF:
                 shrinkage_rate=self.shrinkage_rate, cell_scale_shape=self.cell_scale_shape,
                 gene_scale_shape=self.gene_scale_shape, alpha_floor=self.alpha_floor,
                 supervised_layer=self.supervised_layer, fixed_top_z=getattr(self, "_fixed_top_z", None),
-                X=self.X if self.x_placement == "device" else None, device=dev, lazy_adam=self.lazy_adam)
+                X=self.X if self.x_placement == "device" else None,
+                X_csr=(self.X.indptr.astype(np.int64), self.X.indices.astype(np.int32), self.X.data.astype(np.float32))
+                if self.x_placement == "csr" else None, device=dev, lazy_adam=self.lazy_adam)
             self._engine_key = self._engine_signature()
             self._engine_stale = True
         elif self._engine_key != self._engine_signature():
@@ -684,7 +693,7 @@ class scDEF:
         # exactly batch_size rows per step (dist.epoch_layout); in host placement the counts stay with their home
         # rank and travel per step (stream.py); static ownership when the shard sizes cannot be kept
         migrator = None
-        if (shard.world > 1 and self.epoch_reshard and num_batches > 1
+        if (shard.world > 1 and self.epoch_reshard and num_batches > 1 and self.x_placement != "csr"  # CSR rows: static
                 and _dist.epoch_layout(np.arange(n_total), global_batch, counts) is not None):
             migrator = _dist.RowMigrator(shard, counts)
         stream = MinibatchStream(n_total, global_batch, shard, eng.device,

@@ -220,3 +220,28 @@ def test_filter_factors_upper_only_restatement_known_answer():
     # an empty layer falls back to all of its factors
     out = host_ref.filter_factors_upper_only([z0, z1, z2], [None, W1, W2], [4, 3, 2], 12, min_cells_upper=11, filter_up=False)
     assert [o.tolist() for o in out] == [[0, 1, 2, 3], [0, 1, 2], [1]]
+
+
+def test_count_statistics_of_sparse_counts_equal_dense():
+    import scipy.sparse as sp
+
+    from scdef_b200 import dist
+
+    X, b = synth_counts_numpy(150, 60, n_batches=3, seed=5)
+    labels = np.array(["p", "q", "r"])[b]
+    d = dist.count_statistics(X, labels, dist.ShardInfo())
+    s = dist.count_statistics(sp.csr_matrix(X), labels, dist.ShardInfo())
+    for k in d:
+        if isinstance(d[k], np.ndarray) and d[k].dtype.kind == "f":
+            np.testing.assert_allclose(s[k], d[k], rtol=1e-12)
+        elif isinstance(d[k], np.ndarray):
+            np.testing.assert_array_equal(s[k], d[k])
+        elif isinstance(d[k], float):
+            assert s[k] == pytest.approx(d[k], rel=1e-12)
+        else:
+            assert s[k] == d[k] or list(s[k]) == list(d[k])
+    m = scDEF(MiniAnnData(sp.csr_matrix(X), obs={"batch": labels}), batch_key="batch", layer_sizes=[6, 3], x_placement="csr")
+    m2 = scDEF(MiniAnnData(X, obs={"batch": labels}), batch_key="batch", layer_sizes=[6, 3])
+    assert m.alpha == pytest.approx(m2.alpha, rel=1e-12) and m.X.nnz == np.count_nonzero(X)
+    for a, c in zip(m.global_params, m2.global_params):
+        np.testing.assert_allclose(a, c, rtol=1e-6)

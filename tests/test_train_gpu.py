@@ -425,3 +425,26 @@ def test_learn_filters_upper_layers_like_the_reference():
     assert [f.tolist() for f in m.factor_lists] == [w.tolist() for w in want]
     with pytest.raises(NotImplementedError):
         m.filter_factors()
+
+
+def test_csr_resident_counts_equal_dense():
+    """x_placement='csr' (north star: "count matrix (dense or CSR)"): the minibatch densified from the CSR rows is the
+    dense minibatch bit for bit, so training follows the dense path exactly (up to the order of float atomics)."""
+    import scipy.sparse as sp
+
+    from scdef_b200 import MiniAnnData, scDEF
+    from scdef_b200.synth import synth_counts_numpy
+
+    X, _ = synth_counts_numpy(300, 120, seed=2)
+    md = scDEF(MiniAnnData(X), layer_sizes=[10, 5, 2], seed=1, logginglevel=30)
+    ms = scDEF(MiniAnnData(sp.csr_matrix(X)), layer_sizes=[10, 5, 2], seed=1, logginglevel=30, x_placement="csr")
+    eng_d, eng_s = md._get_engine(), ms._get_engine()
+    idx = torch.as_tensor(np.random.RandomState(1).permutation(300)[:77], dtype=torch.int64, device="cuda")
+    assert torch.equal(eng_s.gather_rows(idx), eng_d.X[idx])
+    np.testing.assert_allclose(eng_s.x_lgamma.cpu().numpy(), eng_d.x_lgamma.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    kw = dict(n_epoch=3, num_samples=5, batch_size=64)
+    md._learn(**kw)
+    ms._learn(**kw)
+    np.testing.assert_allclose(ms.elbos[-1], md.elbos[-1], rtol=1e-6)
+    for a, c in zip(ms.local_params + ms.global_params, md.local_params + md.global_params):
+        np.testing.assert_allclose(a, c, rtol=1e-4, atol=1e-5)
