@@ -245,3 +245,60 @@ def test_count_statistics_of_sparse_counts_equal_dense():
     assert m.alpha == pytest.approx(m2.alpha, rel=1e-12) and m.X.nnz == np.count_nonzero(X)
     for a, c in zip(m.global_params, m2.global_params):
         np.testing.assert_allclose(a, c, rtol=1e-6)
+
+
+def test_iscdef_hierarchical_ladder_names_and_priors():
+    """/root/reference/tests/test_integration.py:441-470 (block layout of the marker hierarchy) + the prior matrices
+    of `_iscdef.py:272-450`."""
+    from scdef_b200 import iscDEF
+
+    X, _ = synth_counts_numpy(60, 80, seed=0)
+    genes = [f"g{i}" for i in range(80)]
+    markers = {"T": genes[:3], "B": genes[3:6]}
+    m = iscDEF(MiniAnnData(X, var_names=genes), markers_dict=markers, markers_layer=2, add_other=0, decay_factor=2, seed=1)
+    assert m.layer_sizes == [8, 4, 2, 1] and m.layer_names == ["L0", "L1", "marker", "root"]
+    assert m.n_factors_per_marker == 4 and m.use_brd
+    assert all(m.factor_names[0][s].startswith("T_L0_") for s in range(4))
+    assert all(m.factor_names[0][s].startswith("B_L0_") for s in range(4, 8))
+    assert m.factor_names[2] == ["T", "B"] and m.factor_names[3] == ["root_0"]
+    shape0, rate0 = (np.asarray(a) for a in m.w_priors[0])
+    assert shape0.shape == rate0.shape == (8, 80)
+    scale0 = shape0 / rate0
+    np.testing.assert_allclose(scale0[:4, :3], 10.0, rtol=1e-6)       # T block x T markers: gs_big_scale
+    np.testing.assert_allclose(scale0[:4, 3:6], 1e-6, rtol=1e-5)      # T block x B markers: penalised
+    np.testing.assert_allclose(scale0[4:, 3:6], 10.0, rtol=1e-6)
+    np.testing.assert_allclose(scale0[:, 6:], 1.0, rtol=1e-6)         # everything else: gs_small_scale
+    np.testing.assert_allclose(shape0[:4, :3], 1.0)                   # marker_strength
+    np.testing.assert_allclose(shape0[:4, 3:6], 0.1, rtol=1e-6)       # other_strength
+    np.testing.assert_allclose(shape0[:, 6:], 1.0)                    # nonmarker_strength -> 1.0 under BRD
+    # connectivity prior of W_1 (4 x 8): factor u of L1 owns L0 factors {2u, 2u+1}
+    s1, r1 = (np.asarray(a) for a in m.w_priors[1])
+    own = np.zeros((4, 8), dtype=bool)
+    for u in range(4):
+        own[u, 2 * u: 2 * u + 2] = True
+    base = float(m.factor_shapes[1])
+    np.testing.assert_allclose(s1[own], base * 1.0, rtol=1e-6)        # cn_big_strength
+    np.testing.assert_allclose(s1[~own], base * 0.1, rtol=1e-6)       # cn_small_strength
+    np.testing.assert_allclose((s1 / r1)[own], 10.0, rtol=1e-5)       # mean = cn_big_mean
+    np.testing.assert_allclose((s1 / r1)[~own], 1.0, rtol=1e-5)       # mean = cn_small_mean
+    # the root's W keeps the plain scDEF prior
+    np.testing.assert_allclose(np.asarray(m.w_priors[3][0]), base, rtol=1e-6)
+    with pytest.raises(ValueError):
+        iscDEF(MiniAnnData(X, var_names=genes), markers_dict=markers, markers_layer=0, add_root=True)
+
+
+def test_iscdef_flat_markers_layer():
+    """`markers_layer=0`: one factor per marker set plus `other`, halving ladder above (`_iscdef.py:169-177`)."""
+    from scdef_b200 import iscDEF
+
+    X, _ = synth_counts_numpy(60, 40, seed=0)
+    genes = [f"g{i}" for i in range(40)]
+    m = iscDEF(MiniAnnData(X, var_names=genes), markers_dict={"B": genes[:2], "Mono": genes[2:4]}, markers_layer=0,
+               add_other=1, n_layers=2, seed=1)
+    assert m.layer_sizes == [3, 1] and m.layer_names == ["marker", "L1"] and not m.add_root
+    assert m.factor_names[0] == ["B", "Mono", "other0"]
+    scale0 = np.asarray(m.w_priors[0][0]) / np.asarray(m.w_priors[0][1])
+    np.testing.assert_allclose(scale0[0, :2], 10.0, rtol=1e-6)
+    np.testing.assert_allclose(scale0[2, :4], 1e-6, rtol=1e-5)        # `other` factors are pushed off every typed marker
+    m6 = iscDEF(MiniAnnData(X, var_names=genes), markers_dict={f"m{i}": [genes[i]] for i in range(9)}, markers_layer=0)
+    assert m6.layer_sizes == [9, 4, 2, 1]

@@ -448,3 +448,26 @@ def test_csr_resident_counts_equal_dense():
     np.testing.assert_allclose(ms.elbos[-1], md.elbos[-1], rtol=1e-6)
     for a, c in zip(ms.local_params + ms.global_params, md.local_params + md.global_params):
         np.testing.assert_allclose(a, c, rtol=1e-4, atol=1e-5)
+
+
+def test_iscdef_fit_runs_with_matrix_priors():
+    """iscDEF end to end (matrix-valued W_0 prior -> fp32 likelihood path; frozen-root second phase)."""
+    from scdef_b200 import MiniAnnData, iscDEF
+    from scdef_b200.synth import synth_counts_numpy
+
+    X, _ = synth_counts_numpy(120, 80, seed=0)
+    genes = [f"g{i}" for i in range(80)]
+    m = iscDEF(MiniAnnData(X, var_names=genes), markers_dict={"T": genes[:3], "B": genes[3:6]}, markers_layer=1,
+               add_other=1, seed=1, logginglevel=30)
+    assert m.layer_sizes == [6, 3, 1]
+    m.fit(n_epoch=3, num_samples=5, batch_size=64)
+    assert len(m.elbos) == 2 and len(m.elbos[1]) == 10          # main phase + 10 root epochs
+    assert all(np.all(np.isfinite(e)) for e in m.elbos)
+    assert m.pmeans["markerW"].shape == (3, 6) and np.all(np.isfinite(m.pmeans["L0W"]))
+    # the informed prior does its job: the T block loads its markers more than the B markers
+    W = np.asarray(m.pmeans["L0W"])
+    assert W[:2, :3].mean() > W[:2, 3:6].mean()
+    flat = iscDEF(MiniAnnData(X, var_names=genes), markers_dict={"T": genes[:3], "B": genes[3:6]}, markers_layer=0,
+                  add_other=1, n_layers=2, seed=1, logginglevel=30)
+    flat.fit(n_epoch=2, num_samples=5)
+    assert len(flat.elbos) == 1 and np.all(np.isfinite(flat.elbos[0]))
