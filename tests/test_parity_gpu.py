@@ -148,3 +148,34 @@ def test_iscdef_matrix_valued_w0_priors():
         model.w_priors[1] = [np.asarray(model.w_priors[1][0]) * 5.0, np.asarray(model.w_priors[1][1]) * 5.0 / conn]
     _run_case(90, 64, (12, 4, 1), 1, 40, 3, [0, 0, 0], mutate=markers)           # BRD: A = P/tau per element
     _run_case(90, 70, (12, 4, 1), 1, 40, 2, [0, 0, 0], use_brd=False, mutate=markers)
+
+
+@pytest.mark.parametrize("nb,S", [(1, 100), (8, 10)])
+def test_full_step_shape_tensor_core_path_equals_cuda_core_path(nb, S):
+    """BASELINE full per-step shapes (C5: 5000 genes, layers [100,60,30,10], 256 cells, 100 MC samples; C4: 8 batches):
+    the oracle cannot run these in seconds, so the size-independent property is that the two independent likelihood
+    implementations (tcgen05 split-bf16 vs fp32 CUDA cores), fed the same Philox draws, agree on the loss and on every
+    gradient tensor.  (The kernels' work does not depend on the number of cells beyond the minibatch.)"""
+    from scdef_b200.engine import NoiseSpec
+
+    N, G, Ks, B = 1536, 5000, (100, 60, 30, 10), 256
+    X, batch, model, lp, gp = small_problem(N, G, Ks, nb, seed=11)
+    eng = make_engine(X, batch, model, lp, gp)
+    idx = torch.as_tensor(np.random.RandomState(5).permutation(N)[:B], dtype=torch.int64, device="cuda")
+    spec = NoiseSpec.philox(seed=3, step=17, coupling=True)
+    kw = dict(num_samples=S, annealing=1.2, stop_gradients=[0, 0, 0, 0], alpha=model.alpha)
+    res = {}
+    for impl in (1, 2):
+        eng.elbo_grad("local", idx, spec, lik_impl=impl, **kw)
+        loss_l = eng.loss_value()
+        gl = [g.cpu().numpy().copy() for g in eng.local_grads(B)]
+        eng.elbo_grad("global", idx, spec, lik_impl=impl, **kw)
+        res[impl] = (loss_l, eng.loss_value(), gl, [g.cpu().numpy().copy() for g in eng.glob_grad.views])
+    a, b = res[1], res[2]
+    assert abs(a[0] - b[0]) / abs(a[0]) < 1e-5 and abs(a[1] - b[1]) / abs(a[1]) < 1e-5
+    assert abs(a[0] - a[1]) / abs(a[0]) < 1e-6          # both passes evaluate the same objective
+    for x, y in zip(a[2] + a[3], b[2] + b[3]):
+        if np.abs(x).max() > 0:
+            assert rel_err(y, x) < TOL
+        else:
+            assert np.abs(y).max() == 0
