@@ -51,7 +51,7 @@ extern "C" {
 
 #define SCDEF_LIK_AUTO 0
 #define SCDEF_LIK_SIMT 1 /* fp32 CUDA-core likelihood kernel (any shape)               */
-#define SCDEF_LIK_TC 2   /* tcgen05 / TMEM split-bf16 likelihood kernel (K0 <= 112, G % 8 == 0, nb <= 8, scalar W_0 prior) */
+#define SCDEF_LIK_TC 2   /* tcgen05 / TMEM split-bf16 likelihood kernel (K0 <= 112, G % 8 == 0, nb <= 8) */
 
 typedef struct scdef_ctx scdef_ctx;
 

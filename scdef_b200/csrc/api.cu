@@ -120,7 +120,7 @@ PhiloxKey make_key(const scdef_noise* nz) {
 }
 
 bool tc_ok(const scdef_ctx* c) {
-  return lik_tc_supported(c->K0, c->d.n_genes, c->d.n_batches) && !c->d.w_prior_shape[0] && !c->d.w_prior_rate[0];
+  return lik_tc_supported(c->K0, c->d.n_genes, c->d.n_batches);
 }
 
 int resolve_lik_impl(const scdef_ctx* c, int requested) {

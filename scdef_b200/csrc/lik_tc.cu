@@ -913,6 +913,60 @@ __global__ void __launch_bounds__(128) k_tc_w0_prior(const LikTcArgs a, const fl
   if (threadIdx.x == 0) atomicAdd(&loss_out[1], -tot * (double)a.global_weight / (double)a.S);
 }
 
+// W_0 prior with matrix-valued shape / rate (iscDEF gene-set priors, `_iscdef.py:442-450`): the Gamma parameters differ
+// per (k, g), so the row sums are not enough.  One CTA per (64-gene tile, MC sample) walks the tile image
+// (W = hi + lo, log W from it) and accumulates the prior value and, in the GLOBAL pass, the brd / ard gradients
+// (same arithmetic as k_wprior mode 0/1).  The per-element W gradient of the prior is folded by the main kernel.
+// fold_grad (GLOBAL pass of a rank without minibatch rows, W_0 not frozen): the main kernel does not run, so the
+// prior's W gradient  t = gw (A - 1 - B W)  is accumulated here into chunk 0 of the partials k_tc_w0_final reduces.
+__global__ void __launch_bounds__(256) k_tc_w0_prior_mat(const LikTcArgs a, const TcScratch ws, int KP, int n_tiles,
+                                                         uint32_t w_plane, uint32_t w_unit, double* loss_out, int fold_grad) {
+  __shared__ double red[32];
+  __shared__ float acc_t[128], acc_o[128];
+  const int tile = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < 128; i += 256) { acc_t[i] = 0.f; acc_o[i] = 0.f; }
+  __syncthreads();
+  const uint8_t* unit = ws.wimg + ((long long)s * n_tiles + tile) * w_unit;
+  const bool want_g = a.use_brd && a.pass == SCDEF_PASS_GLOBAL;
+  double val = 0.0;
+  // element e of the tile: k = e / 64 (row), gl = e % 64 (gene in tile); image offset (k/8)*W_RS + (gl/8)*128 + (k%8)*16 + (gl%8)*2
+  for (int e = tid; e < a.K0 * TG; e += 256) {
+    const int k = e >> 6, gl = e & 63, g = tile * TG + gl;
+    if (g >= a.G) continue;
+    const uint32_t off = (uint32_t)(k >> 3) * W_RS + (uint32_t)(gl >> 3) * 128u + (uint32_t)(k & 7) * 16u + (uint32_t)(gl & 7) * 2u;
+    const float W = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(unit + off)) +
+                    __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(unit + w_plane + off));
+    const float lw = logf(W);
+    const float P = a.P ? a.P[(long long)k * a.G + g] : a.P_scalar;
+    const float R = a.R ? a.R[(long long)k * a.G + g] : a.R_scalar;
+    float tau = 1.f, om = 1.f;
+    if (a.use_brd) { tau = a.smp_tau[(long long)s * a.K0 + k]; om = a.smp_om[(long long)s * a.K0 + k]; }
+    const float A = a.use_brd ? P / tau : P;
+    const float Bm = R * (float)a.K0 / (tau * om);
+    const float lB = logf(Bm);
+    val += (double)((A - 1.f) * lw - Bm * W - lgammaf(A) + A * lB);
+    if (want_g) {
+      const float dA = lw - digammaf(A) + lB;
+      const float dB = -W + A / Bm;
+      atomicAdd(&acc_t[k], dA * (-A / tau) + dB * (-Bm / tau));
+      atomicAdd(&acc_o[k], dB * (-Bm / om));
+    }
+    if (fold_grad && W > V_LO_M && W < V_HI_M) {
+      const float t = a.global_weight * (A - 1.f - Bm * W);
+      atomicAdd(&ws.part[(long long)k * a.G + g], t);
+      atomicAdd(&ws.part[(long long)a.K0 * a.G + (long long)k * a.G + g], t * lw);
+    }
+  }
+  __syncthreads();
+  if (want_g)
+    for (int k = tid; k < a.K0; k += 256) {
+      atomicAdd(&a.G_tau[(long long)s * a.K0 + k], a.global_weight * acc_t[k]);
+      atomicAdd(&a.G_om[(long long)s * a.K0 + k], a.global_weight * acc_o[k]);
+    }
+  double tot = block_sum_d(val, red);
+  if (tid == 0) atomicAdd(&loss_out[1], -tot * (double)a.global_weight / (double)a.S);
+}
+
 // W_0: entropy value (both passes) and, in the GLOBAL pass, the final (mu, rho) gradients from the
 // chunk partials.
 __global__ void __launch_bounds__(256) k_tc_w0_final(const LikTcArgs a, const float* part, int n_chunks, double* loss_out) {
@@ -1007,7 +1061,8 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   LikTcArgs a = a_in;
   static const int dbg_nsplit = getenv("SCDEF_TC_NSPLIT") ? atoi(getenv("SCDEF_TC_NSPLIT")) : 3;  // timing experiments only
   a.dbg_nsplit = dbg_nsplit;
-  if (!lik_tc_supported(a.K0, a.G, a.nb) || a.P || a.R) return SCDEF_EUNSUPPORTED;
+  if (!lik_tc_supported(a.K0, a.G, a.nb)) return SCDEF_EUNSUPPORTED;
+  const bool matrix_prior = a.P || a.R;   // iscDEF: Gamma shape / rate of W_0 per (k, g)
   if (a.B <= 0) a.lik_on = 0;
   const Geom g = make_geom(a.B, a.S, a.K0, a.G);
   char* w = (char*)a.ws;
@@ -1036,10 +1091,19 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   static const bool mono = getenv("SCDEF_TC_MONO") != nullptr;  // A/B switch: the monolithic v2a kernels
   const bool global_pass = a.pass == SCDEF_PASS_GLOBAL;
   const bool pipe = a.lik_on && !mono;
+  if (matrix_prior && mono) return SCDEF_EUNSUPPORTED;   // the monolithic kernels only know scalar W_0 priors
   cudaEvent_t ev0 = a.ev0, ev1 = a.ev1;
   a.ev0 = a.ev1 = nullptr;
   const bool reuse = pipe && a.reuse_w0;  // W_0 image + row sums of the previous pass (same noise, same W_0) are still valid
   if (!reuse) cudaMemsetAsync(ws.rowstats, 0, (size_t)a.S * a.K0 * 2 * 4, st);
+  // matrix prior without the main kernel (likelihood off = W_0 frozen, or a rank without minibatch rows): the tile
+  // images are still needed for the prior value and the brd / ard gradients
+  const bool fold_prior_grad = matrix_prior && !pipe && global_pass && !a.w0_stopped;
+  if (!pipe && matrix_prior) {
+    k_tc_wprep<<<148 * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
+    k_tc_wgen<<<dim3((a.G + 255) / 256, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
+    if (fold_prior_grad) cudaMemsetAsync(ws.part, 0, (size_t)g.n_chunks * 2 * a.K0 * a.G * 4, st);
+  }
   if (pipe) {
     k_tc_rowprep<<<(a.B + 255) / 256, 256, 0, st>>>(a, ws.brow, ws.xoff);
     k_tc_zprep<<<148 * 4, 256, 0, st>>>(a, ws.zimg, g.KP);
@@ -1060,11 +1124,16 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
     if (a.lik_on && !mono) {
       if (a.nb == 1) k_tc_colw<1><<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
       else k_tc_colw<MAX_NB><<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
-      cudaFuncSetAttribute(k_lik_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
       main_begin();
-      k_lik_pipe<true, true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+      if (matrix_prior) {
+        cudaFuncSetAttribute(k_lik_pipe<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+        k_lik_pipe<true, true, true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+      } else {
+        cudaFuncSetAttribute(k_lik_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
+        k_lik_pipe<true, true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
+      }
       main_end();
-    } else {
+    } else if (!matrix_prior) {
       cudaFuncSetAttribute(k_lik_tc_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
       k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(a, g, ws, loss_out);
     }
@@ -1089,7 +1158,7 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       long long total = (long long)a.S * a.B * a.K0;
       int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
       k_tc_dz_reduce<<<blocks, 256, 0, st>>>(a, ws.part, g.NG);
-    } else {
+    } else if (!matrix_prior) {
       // value only: the GLOBAL kernel without likelihood produces the W_0 row sums
       LikTcArgs v = a;
       v.w0_stopped = 1;
@@ -1097,7 +1166,9 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(v, g, ws, loss_out);
     }
   }
-  k_tc_w0_prior<<<(a.S * a.K0 + 127) / 128, 128, 0, st>>>(a, ws.rowstats, loss_out);
+  if (matrix_prior)
+    k_tc_w0_prior_mat<<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit, loss_out, fold_prior_grad ? 1 : 0);
+  else k_tc_w0_prior<<<(a.S * a.K0 + 127) / 128, 128, 0, st>>>(a, ws.rowstats, loss_out);
   k_tc_w0_final<<<148 * 4, 256, 0, st>>>(a, ws.part, g.n_chunks, loss_out);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {

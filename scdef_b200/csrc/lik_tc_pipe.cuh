@@ -93,7 +93,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 
 // ---- producers -------------------------------------------------------------------------------------
 // ---- the kernel ----------------------------------------------------------------------------------------
-template <bool GLOBAL, bool WANT_LL>
+template <bool GLOBAL, bool WANT_LL, bool MAT = false>   // MAT: matrix-valued W_0 prior (iscDEF), GLOBAL only
 __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, const Geom gm, const TcScratch ws, double* loss_out) {
   extern __shared__ __align__(1024) uint8_t sm[];
   const int KP = gm.KP;
@@ -332,11 +332,18 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
         mbar_arrive(&mi->dw_empty[st2]);
         if (r < a.K0 && !a.w0_stopped) {
           float A = a.P_scalar, Bm = a.R_scalar * (float)a.K0;
+          float inv_tau = 1.f, inv_tau_om = 1.f;
           if (a.use_brd) {
             const float tau = a.smp_tau[(long long)s2 * a.K0 + r], om = a.smp_om[(long long)s2 * a.K0 + r];
-            A = a.P_scalar / tau;
-            Bm = a.R_scalar * (float)a.K0 / (tau * om);
+            inv_tau = 1.f / tau;
+            inv_tau_om = 1.f / (tau * om);
+            A = a.P_scalar * inv_tau;
+            Bm = a.R_scalar * (float)a.K0 * inv_tau_om;
           }
+          // iscDEF: matrix-valued Gamma shape / rate of W_0, one (k, g) entry per element of this thread's 16 genes
+          const int gbase = tile_fixed * TG + cq * 16;
+          const float* Prow = (MAT && a.P) ? a.P + (long long)r * a.G + gbase : nullptr;
+          const float* Rrow = (MAT && a.R) ? a.R + (long long)r * a.G + gbase : nullptr;
           const uint32_t woff = L.w[st2] + (uint32_t)(r >> 3) * W_RS + (uint32_t)(r & 7) * 16u;
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
@@ -349,6 +356,10 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
               for (int q2 = 0; q2 < 2; ++q2) {
                 const int i = c8 * 8 + p * 2 + q2;
                 const float W = q2 ? (bf16hi(hw[p]) + bf16hi(lw[p])) : (bf16lo(hw[p]) + bf16lo(lw[p]));
+                if (MAT && gbase + i < a.G) {
+                  A = (Prow ? __ldg(Prow + i) : a.P_scalar) * inv_tau;
+                  Bm = (Rrow ? __ldg(Rrow + i) : a.R_scalar) * (float)a.K0 * inv_tau_om;
+                }
                 if (W > V_LO_M && W < V_HI_M) {
                   const float t = a.scale * dW[i] * W + a.global_weight * (A - 1.f - Bm * W);
                   acc_mu[i] += t;

@@ -1,8 +1,8 @@
 """`iscDEF` — marker-informed scDEF on the B200 training path.
 
 Mirrors the model-definition part of `/root/reference/src/scdef/models/_iscdef.py`: the layer ladder built from
-the marker sets (`167-212`), the gene-set prior on W_0 (`368-450`: a `(K0, G)` matrix of Gamma shapes/rates — the
-kernels take matrix-valued W_0 priors on the fp32 CUDA-core likelihood path), the block-diagonal connectivity prior
+the marker sets (`167-212`), the gene-set prior on W_0 (`368-450`: a `(K0, G)` matrix of Gamma shapes/rates — both
+likelihood paths take matrix-valued W_0 priors), the block-diagonal connectivity prior
 on the upper W_l (`272-366`), the marker-aware factor names (`452-526`) and `fit` with the frozen-root second
 phase (`936-1134`).  Not built: the Scanpy `score_genes` initialisation of z (`588-934`; Scanpy is not part of
 this image — `fit` then uses the ordinary initialisation and says so), the refit warm start and the

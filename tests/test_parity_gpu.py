@@ -136,8 +136,10 @@ def test_sscdef_pinned_layer():
     _run_case(110, 70, (9, 5, 3), 2, 48, 2, [0, 0, 1], mutate=pin)
 
 
-def test_iscdef_matrix_valued_w0_priors():
-    """iscDEF feeds (K0,G) matrices as w_priors[0] (`_iscdef.py:442-450`) and block priors for l>=1."""
+@pytest.mark.parametrize("lik_impl", [1, 2])
+def test_iscdef_matrix_valued_w0_priors(lik_impl):
+    """iscDEF feeds (K0,G) matrices as w_priors[0] (`_iscdef.py:442-450`) and block priors for l>=1; both likelihood
+    paths take them (the tensor-core path folds the per-element prior gradient in its W epilogue)."""
     def markers(model, X):
         rng = np.random.default_rng(5)
         K0, G = model.layer_sizes[0], X.shape[1]
@@ -146,8 +148,12 @@ def test_iscdef_matrix_valued_w0_priors():
         model.w_priors[0] = [strengths, strengths / gene_sets]
         conn = np.where(rng.random(np.asarray(model.w_priors[1][0]).shape) < 0.5, 1.0, 1e-2)
         model.w_priors[1] = [np.asarray(model.w_priors[1][0]) * 5.0, np.asarray(model.w_priors[1][1]) * 5.0 / conn]
-    _run_case(90, 64, (12, 4, 1), 1, 40, 3, [0, 0, 0], mutate=markers)           # BRD: A = P/tau per element
-    _run_case(90, 70, (12, 4, 1), 1, 40, 2, [0, 0, 0], use_brd=False, mutate=markers)
+    _run_case(90, 64, (12, 4, 1), 1, 40, 3, [0, 0, 0], mutate=markers, lik_impl=lik_impl)     # BRD: A = P/tau per element
+    _run_case(90, 72, (12, 4, 1), 1, 40, 2, [0, 0, 0], use_brd=False, mutate=markers, lik_impl=lik_impl)
+    _run_case(300, 136, (24, 6, 1), 2, 200, 2, [0, 0, 0], mutate=markers, lik_impl=lik_impl)  # 3 gene tiles, 2 cell units
+    _run_case(90, 64, (12, 4, 1), 1, 40, 2, [1, 0, 0], mutate=markers, lik_impl=lik_impl)     # layer 0 frozen: value + ard only
+    if lik_impl == 1:
+        _run_case(90, 70, (12, 4, 1), 1, 40, 2, [0, 0, 0], use_brd=False, mutate=markers)     # odd G: auto -> CUDA cores
 
 
 @pytest.mark.parametrize("nb,S", [(1, 100), (8, 10)])
@@ -179,3 +185,31 @@ def test_full_step_shape_tensor_core_path_equals_cuda_core_path(nb, S):
             assert rel_err(y, x) < TOL
         else:
             assert np.abs(y).max() == 0
+
+
+def test_rank_without_minibatch_rows_scalar_and_matrix_priors():
+    """Data parallel, static ownership: a rank may own no member of a global minibatch (B = 0).  Its global pass still
+    carries the cell-independent terms (priors / entropies x global_weight); both likelihood paths must agree on them,
+    with scalar and with matrix-valued W_0 priors (the latter folds the prior's W gradient outside the main kernel)."""
+    from scdef_b200.engine import NoiseSpec
+
+    for matrix in (False, True):
+        X, batch, model, lp, gp = small_problem(90, 64, (12, 4, 1), 1, seed=2)
+        if matrix:
+            rng = np.random.default_rng(5)
+            strengths = np.where(rng.random((12, 64)) < 0.15, 20.0, 1.0)
+            model.w_priors[0] = [strengths, strengths / np.where(strengths > 1.0, 1.0, 0.05)]
+        eng = make_engine(X, batch, model, lp, gp)
+        idx = torch.empty(0, dtype=torch.int64, device="cuda")
+        spec = NoiseSpec.philox(seed=3, step=5, coupling=True)
+        kw = dict(num_samples=3, annealing=1.1, stop_gradients=[0, 0, 0], alpha=model.alpha, scale=90 / 40, global_weight=0.5)
+        res = {}
+        for impl in (1, 2):
+            eng.elbo_grad("global", idx, spec, lik_impl=impl, **kw)
+            res[impl] = (eng.loss_value(), [g.cpu().numpy().copy() for g in eng.glob_grad.views])
+        assert abs(res[1][0] - res[2][0]) / abs(res[1][0]) < 1e-5
+        for x, y in zip(res[1][1], res[2][1]):
+            if np.abs(x).max() > 0:
+                assert rel_err(y, x) < TOL
+            else:
+                assert np.abs(y).max() == 0
