@@ -144,6 +144,11 @@ class MinibatchStream:
         if ahead is not None:
             ahead[0].join()
             self._ahead = None
+        if self._pool is not None:          # staging thread of the host placement
+            for f in self._staged.values():
+                f.cancel()
+            self._pool.shutdown(wait=True)
+            self._pool, self._staged = None, {}
         if self.migrator is not None and not self.migrator.at_home:
             self.migrator.go_home(self.tensors_fn())
 
