@@ -193,3 +193,51 @@ def test_host_placement_row_routing_delivers_each_window_in_order(n, gb, counts)
             got = np.concatenate(recv)[plans[d][3]]
             want = perm[lo:hi][rank_pos[lo:hi] == d]
             np.testing.assert_array_equal(got, want)
+
+
+def test_epoch_layout_properties_random_shapes():
+    """Property test over random shard sizes / batch sizes: every rank keeps its row count, every full global minibatch
+    gives each rank exactly b rows, and concatenating the ranks' windows reproduces the reference's slice in order."""
+    from hypothesis import given, settings, strategies as st
+
+    from scdef_b200.dist import RowMigrator, ShardInfo, epoch_layout
+
+    @settings(max_examples=60, deadline=None)
+    @given(R=st.integers(1, 5), b=st.integers(1, 9), n_full=st.integers(0, 6), data=st.data())
+    def check(R, b, n_full, data):
+        tail = [data.draw(st.integers(0, b)) for _ in range(R)]
+        if sum(tail) == R * b:          # that would be one more full minibatch
+            tail[0] -= 1
+        counts = [n_full * b + t for t in tail]
+        n = sum(counts)
+        if n == 0:
+            return
+        gb = R * b
+        perm = np.random.RandomState(data.draw(st.integers(0, 1000))).permutation(n)
+        lay = epoch_layout(perm, gb, counts)
+        assert lay is not None
+        rank_of, row_of, offs, row0 = lay
+        for r in range(R):
+            assert sorted(row_of[rank_of == r].tolist()) == list(range(counts[r]))
+        where = {(int(rank_of[g]), int(row_of[g])): g for g in range(n)}
+        for i in range((n + gb - 1) // gb):
+            want = perm[i * gb:(i + 1) * gb]
+            got = []
+            for r in range(R):
+                rows = list(range(int(offs[r][i]), int(offs[r][i + 1])))
+                if i < n_full:
+                    assert len(rows) == b
+                assert int(row0[r][i]) == len(got)
+                got += [where[(r, j)] for j in rows]
+            assert got == want.tolist()
+        # the send / receive plans of all ranks are mutually consistent
+        plans = []
+        for r in range(R):
+            m = RowMigrator(ShardInfo(rank=r, world=R), counts)
+            plans.append(m.plan(rank_of, row_of))
+        for s in range(R):
+            for d in range(R):
+                assert plans[s][1][d] == plans[d][3][s]          # what s sends to d is what d expects from s
+            assert sorted(plans[s][2].tolist()) == list(range(counts[s]))   # every row of a rank is written exactly once
+
+    check()
