@@ -123,7 +123,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["cells_per_s"], "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config} {N}x{G} layers {Ks}", "batch_per_gpu": args.batch, "num_samples": args.samples},
+        "config": {"workload": f"{args.config}: {N} cells x {G} genes, layers {Ks}, {nb} batch(es)", "batch_per_gpu": args.batch,
+                   "num_samples": args.samples, "step": "train (local pass + local Adam, global pass + global Adam + clip)",
+                   "sample": sample},
         "cpu_baseline": {"value": r["cells_per_s"], "unit": "cells/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["cells_per_s"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_per_s": r["steps_per_s"],
@@ -382,7 +384,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.config}: {N} cells x {G} genes, layers {Ks}, {nb} batch(es), cells block-sharded over {world} GPU(s)",
+            "config": {"workload": f"{args.config}: {N} cells x {G} genes, layers {Ks}, {nb} batch(es)",
+                       "sharding": f"cells sharded over {world} GPU(s)",
                        "batch_per_gpu": B, "num_samples": S, "step": "train (local pass + local Adam, global pass + global Adam + clip)",
                        "l2": ("inputs larger than L2: every step gathers B random rows of the %.1f GB count matrix and of the %.1f GB "
                               "local parameter/moment arrays, and regenerates %.0f MB of sampled-W_0 tile images (L2 = 126 MB)"
