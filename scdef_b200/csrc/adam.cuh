@@ -192,13 +192,25 @@ __global__ void __launch_bounds__(256) k_adam_lazy_catchup(const AdamLazyPair pr
       adam_elem(p, m, v, 0.f, h, !frozen, INFINITY);
       if (a.monotone && p == p_before) { ++k; break; }
     }
-    const float omb1 = __fsub_rn(1.f, h.b1), omb2 = __fsub_rn(1.f, h.b2);
-    for (; k <= a.target; ++k) {
-      if (m == 0.f) break;
-      m = __fmaf_rn(omb1, 0.f, __fmul_rn(h.b1, m));
-      v = __fmaf_rn(__fmul_rn(omb2, 0.f), 0.f, __fmul_rn(h.b2, v));
+    // phases 2 and 3: with g = 0 the dense kernel's  m = fma(1-b1, 0, b1*m)  and  v = fma((1-b2)*0, 0, b2*v)  are exactly
+    // b1*m and b2*v (adding +0 changes nothing but the sign of a zero, fixed below), so a replayed step is two, then one,
+    // multiplications.  m stops changing when it is 0 or a denormal that b1*m rounds back to itself: checked every 8 steps.
+    int remaining = a.target - k + 1;
+    while (remaining > 0) {
+      const float m_prev = m;
+      const int n = remaining < 8 ? remaining : 8;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (u < n) { m = __fmul_rn(h.b1, m); v = __fmul_rn(h.b2, v); }
+      remaining -= n;
+      if (m == m_prev) break;
     }
-    for (; k <= a.target; ++k) v = __fmaf_rn(__fmul_rn(omb2, 0.f), 0.f, __fmul_rn(h.b2, v));
+    for (; remaining >= 8; remaining -= 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v = __fmul_rn(h.b2, v);
+    }
+    for (; remaining > 0; --remaining) v = __fmul_rn(h.b2, v);
+    if (m == 0.f) m = 0.f;   // -0 -> +0, as the dense kernel's fma leaves it
     a.p[i] = p; a.m[i] = m; a.v[i] = v;
   }
 }
