@@ -357,8 +357,11 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
   }
 
   // ---- W priors ----------------------------------------------------------------------------
+  // In the LOCAL pass the W priors only contribute to the loss value: nothing to do when the caller discards it.
+  const bool value_only_skipped = !global_pass && (call->flags & SCDEF_FLAG_SKIP_LOSS);
   for (int l = 0; l < L; ++l) {
     if (tc && l == 0) continue;  // fused into the tcgen05 kernel
+    if (value_only_skipped) continue;
     WPriorArgs a;
     memset(&a, 0, sizeof(a));
     a.smp_W = smp(BLK_W + l);

@@ -1166,6 +1166,15 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(v, g, ws, loss_out);
     }
   }
+  // LOCAL pass with the loss discarded: the W_0 prior and entropy VALUES are all these two kernels would produce
+  if (!global_pass && !a.want_loss) {
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) {
+      fprintf(stderr, "scdef_b200: lik_tc_launch: %s\n", cudaGetErrorString(e0));
+      return SCDEF_ECUDA;
+    }
+    return SCDEF_OK;
+  }
   if (matrix_prior)
     k_tc_w0_prior_mat<<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit, loss_out, fold_prior_grad ? 1 : 0);
   else k_tc_w0_prior<<<(a.S * a.K0 + 127) / 128, 128, 0, st>>>(a, ws.rowstats, loss_out);

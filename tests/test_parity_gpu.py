@@ -213,3 +213,26 @@ def test_rank_without_minibatch_rows_scalar_and_matrix_priors():
                 assert rel_err(y, x) < TOL
             else:
                 assert np.abs(y).max() == 0
+
+
+@pytest.mark.parametrize("lik_impl", [1, 2])
+def test_skip_loss_and_reuse_flags_do_not_change_the_gradients(lik_impl):
+    """SCDEF_FLAG_SKIP_LOSS (LOCAL pass whose loss the caller discards) and SCDEF_FLAG_REUSE_W0_SAMPLES (GLOBAL pass right
+    after a LOCAL pass with the same noise) are pure work-saving hints: gradients and the global-pass loss are unchanged."""
+    from scdef_b200.engine import NoiseSpec
+
+    X, batch, model, lp, gp = small_problem(300, 136, (24, 6, 1), 2, seed=6)
+    eng = make_engine(X, batch, model, lp, gp)
+    idx = torch.as_tensor(np.random.RandomState(2).permutation(300)[:200], dtype=torch.int64, device="cuda")
+    spec = NoiseSpec.philox(seed=9, step=4, coupling=True)
+    kw = dict(num_samples=3, annealing=1.2, stop_gradients=[0, 0, 0], alpha=model.alpha, lik_impl=lik_impl)
+    eng.elbo_grad("local", idx, spec, **kw)
+    ref_l = [g.clone() for g in eng.local_grads(200)]
+    eng.elbo_grad("global", idx, spec, **kw)
+    ref_loss, ref_g = eng.loss_value(), eng.glob_grad.flat.clone()
+    eng.elbo_grad("local", idx, spec, want_loss=False, **kw)
+    for a, b in zip(ref_l, eng.local_grads(200)):
+        assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-6
+    eng.elbo_grad("global", idx, spec, reuse_w0=True, **kw)
+    assert abs(eng.loss_value() - ref_loss) / abs(ref_loss) < 1e-6
+    assert rel_err(eng.glob_grad.flat.cpu().numpy(), ref_g.cpu().numpy()) < 1e-6
