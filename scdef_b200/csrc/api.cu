@@ -329,6 +329,10 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     if ((rc = check_launch(ctx, "k_sample"))) return rc;
   }
 
+  // In the LOCAL pass the priors of the global blocks only contribute to the loss value: nothing to do when the caller
+  // discards it (SCDEF_FLAG_SKIP_LOSS).
+  const bool value_only_skipped = !global_pass && (call->flags & SCDEF_FLAG_SKIP_LOSS);
+
   // ---- scale priors ------------------------------------------------------------------------
   {
     SimplePriorTable t;
@@ -343,11 +347,12 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       p.is_cell = is_cell; p.active = active && p.rows * p.cols > 0;
     };
     set(0, BLK_C, d.cell_scale_shape, d.batch_lib_ratio, call->indices, d.cell_scale_shape, scale, 1, B > 0, !global_pass);
-    set(1, BLK_S, d.gene_scale_shape, d.gene_ratio, nullptr, d.gene_scale_shape, gw, 0, true, global_pass);
-    set(2, BLK_TAU, d.brd, nullptr, nullptr, d.brd / d.brd_mean, gw, 0, d.use_brd != 0, global_pass);
-    set(3, BLK_OM, d.shrinkage_shape, nullptr, nullptr, d.shrinkage_rate, gw, 0, d.use_brd != 0, global_pass);
-    set(4, BLK_A, 2.f, nullptr, nullptr, 2.f / fmaxf(call->alpha, 1e-8f), gw, 0, d.marginalize_alpha != 0, global_pass);
-    size_t max_el = (size_t)S * (size_t)((size_t)nb * G > (size_t)B ? (size_t)nb * G : (size_t)B);
+    const bool glob_on = !value_only_skipped;
+    set(1, BLK_S, d.gene_scale_shape, d.gene_ratio, nullptr, d.gene_scale_shape, gw, 0, glob_on, global_pass);
+    set(2, BLK_TAU, d.brd, nullptr, nullptr, d.brd / d.brd_mean, gw, 0, glob_on && d.use_brd != 0, global_pass);
+    set(3, BLK_OM, d.shrinkage_shape, nullptr, nullptr, d.shrinkage_rate, gw, 0, glob_on && d.use_brd != 0, global_pass);
+    set(4, BLK_A, 2.f, nullptr, nullptr, 2.f / fmaxf(call->alpha, 1e-8f), gw, 0, glob_on && d.marginalize_alpha != 0, global_pass);
+    size_t max_el = (size_t)S * (size_t)((glob_on && (size_t)nb * G > (size_t)B) ? (size_t)nb * G : (size_t)B);
     size_t gx = (max_el + 255) / 256;
     if (gx > (size_t)ctx->sm_count * 8) gx = (size_t)ctx->sm_count * 8;
     if (gx < 1) gx = 1;
@@ -356,9 +361,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     if ((rc = check_launch(ctx, "k_scale_priors"))) return rc;
   }
 
-  // ---- W priors ----------------------------------------------------------------------------
-  // In the LOCAL pass the W priors only contribute to the loss value: nothing to do when the caller discards it.
-  const bool value_only_skipped = !global_pass && (call->flags & SCDEF_FLAG_SKIP_LOSS);
+  // ---- W priors (value only in the LOCAL pass) ----------------------------------------------------
   for (int l = 0; l < L; ++l) {
     if (tc && l == 0) continue;  // fused into the tcgen05 kernel
     if (value_only_skipped) continue;
