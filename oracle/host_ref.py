@@ -261,3 +261,117 @@ def filter_factors_upper_only(pmeans_z, pmeans_W, layer_sizes, n_cells, min_cell
             keep = np.arange(K)
         out.append(np.asarray(keep, dtype=int))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# iscDEF prior construction (`/root/reference/src/scdef/models/_iscdef.py`), restated loop by loop
+# ---------------------------------------------------------------------------------------------
+def iscdef_layer_sizes(n_markers, markers_layer, add_root, decay_factor=2, n_layers_schedule=6):
+    """`set_layer_sizes` (`_iscdef.py:167-212`) + the decay schedule of `update_model_size` (`_scdef.py:1206-1234`).
+    Returns (layer_sizes, layer_names, n_factors_per_marker or None)."""
+    if markers_layer == 0:
+        n = int(n_markers)
+        sizes = [n]
+        if int(n_layers_schedule) > 1:
+            while len(sizes) < int(n_layers_schedule):
+                n = int(np.floor(n / float(decay_factor)))
+                sizes.append(n)
+                if n == 1:
+                    break
+            if sizes[-1] > 1:
+                sizes[-1] = 1
+        names = [f"L{i}" for i in range(len(sizes))]
+        names[0] = "marker"
+        return sizes, names, None
+    n_layers = markers_layer + 1
+    if n_layers_schedule == 1:
+        n_layers = 1
+    sizes, names = [], []
+    if n_layers == 1:
+        per = int(decay_factor)
+        sizes.append(n_markers * per)
+        names.append("marker")
+    else:
+        for layer in range(n_layers):
+            rev = (n_layers - 1) - layer
+            sizes.append(n_markers * int(decay_factor) ** rev)
+            names.append("marker" if layer == n_layers - 1 else f"L{layer}")
+        per = int(decay_factor) ** (n_layers - 1)
+    if add_root:
+        sizes.append(1)
+        names.append("root")
+    return sizes, names, per
+
+
+def iscdef_geneset_prior(var_names, markers_dict, marker_names, layer_sizes, markers_layer, n_factors_per_marker,
+                         gs_small_scale, gs_big_scale, marker_strength, nonmarker_strength, other_strength,
+                         penalize_other=True):
+    """`set_geneset_prior` (`_iscdef.py:368-450`) with all layer-0 factors kept: returns (strengths, strengths / gene_sets),
+    the Gamma shape and rate matrices of W_0."""
+    var_names = np.asarray(var_names)
+    K0, G = layer_sizes[0], len(var_names)
+    gene_sets = np.ones((K0, G)) * gs_small_scale
+    strengths = np.ones((K0, G)) * nonmarker_strength
+    kept = np.arange(K0)
+    for i, cellgroup in enumerate(marker_names):
+        if markers_layer == 0:
+            rows = np.where(kept == i)[0]
+        else:
+            rows = np.where((kept >= i * n_factors_per_marker) & (kept < (i + 1) * n_factors_per_marker))[0]
+        if len(rows) == 0:
+            continue
+        if "other" not in cellgroup:
+            for gene in markers_dict[cellgroup]:
+                loc = np.where(var_names == gene)[0]
+                if len(loc) == 0:
+                    continue
+                gene_sets[np.ix_(rows, loc)] = gs_big_scale
+                strengths[np.ix_(rows, loc)] = marker_strength
+        if penalize_other:
+            for group in markers_dict:
+                if group != cellgroup:
+                    for gene in markers_dict[group]:
+                        if "other" not in cellgroup:
+                            if gene not in markers_dict[cellgroup]:
+                                loc = np.where(var_names == gene)[0]
+                                if len(loc) == 0:
+                                    continue
+                                gene_sets[np.ix_(rows, loc)] = 1e-6
+                                strengths[np.ix_(rows, loc)] = other_strength
+                        else:
+                            loc = np.where(var_names == gene)[0]
+                            if len(loc) == 0:
+                                continue
+                            gene_sets[np.ix_(rows, loc)] = 1e-6
+                            strengths[np.ix_(rows, loc)] = other_strength
+    return strengths, strengths / gene_sets
+
+
+def iscdef_connectivity_prior(layer_sizes, n_markers, markers_layer, add_root, decay_factor, cn_small_mean, cn_big_mean,
+                              cn_small_strength, cn_big_strength):
+    """`set_connectivity_prior` (`_iscdef.py:272-366`) with all factors kept: per layer l >= 1 the factors
+    (strength_matrix, strength_matrix / max(connectivity_matrix, 1e-12)) that multiply the scDEF W_l shape / rate."""
+    n_layers = len(layer_sizes)
+    content = n_layers - 1 if (add_root and markers_layer > 0) else n_layers
+    connectivity_layers = markers_layer + 1 if (add_root and markers_layer > 0) else n_layers
+    out = {}
+    for layer_idx in range(1, connectivity_layers):
+        n_upper, n_lower = layer_sizes[layer_idx], layer_sizes[layer_idx - 1]
+        conn = cn_small_mean * np.ones((n_upper, n_lower))
+        stren = cn_small_strength * np.ones((n_upper, n_lower))
+        rev = content - 1 - layer_idx
+        upper_per, lower_per = int(decay_factor) ** rev, int(decay_factor) ** (rev + 1)
+        for i in range(n_markers):
+            upper_start, lower_start = i * upper_per, i * lower_per
+            for upper_factor in range(upper_start, (i + 1) * upper_per):
+                if upper_factor >= n_upper:
+                    continue
+                block = lower_per // upper_per
+                child_start = lower_start + (upper_factor - upper_start) * block
+                children = [c for c in range(child_start, child_start + block) if c < n_lower]
+                if not children:
+                    continue
+                conn[upper_factor, children] = cn_big_mean
+                stren[upper_factor, children] = cn_big_strength
+        out[layer_idx] = (stren, stren / np.maximum(conn, 1e-12))
+    return out

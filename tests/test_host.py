@@ -302,3 +302,36 @@ def test_iscdef_flat_markers_layer():
     np.testing.assert_allclose(scale0[2, :4], 1e-6, rtol=1e-5)        # `other` factors are pushed off every typed marker
     m6 = iscDEF(MiniAnnData(X, var_names=genes), markers_dict={f"m{i}": [genes[i]] for i in range(9)}, markers_layer=0)
     assert m6.layer_sizes == [9, 4, 2, 1]
+
+
+@pytest.mark.parametrize("markers_layer,add_other,penalize,use_brd", [(0, 0, True, True), (0, 2, True, False), (1, 1, True, True),
+                                                                      (2, 0, False, True), (2, 1, True, True), (3, 0, True, True)])
+def test_iscdef_priors_match_the_loop_restatement(markers_layer, add_other, penalize, use_brd):
+    """The vectorised prior construction of scdef_b200.iscDEF against oracle/host_ref's loop-by-loop restatement of
+    `_iscdef.py:167-450`, with overlapping marker lists, a marker missing from the data and `other` groups."""
+    from scdef_b200 import iscDEF
+
+    X, _ = synth_counts_numpy(40, 50, seed=1)
+    genes = [f"g{i}" for i in range(50)]
+    markers = {"T": genes[:4], "B": genes[3:8] + ["not_in_data"], "NK": genes[10:12]}
+    kw = dict(gs_small_scale=0.7, gs_big_scale=12.0, marker_strength=3.0, nonmarker_strength=0.2, other_strength=0.05,
+              cn_small_mean=0.5, cn_big_mean=7.0, cn_small_strength=0.3, cn_big_strength=1.5)
+    m = iscDEF(MiniAnnData(X, var_names=genes), markers_dict=markers, markers_layer=markers_layer, add_other=add_other,
+               penalize_other=penalize, use_brd=use_brd, seed=1, logginglevel=40, **kw)
+    names = list(markers) + [f"other{i}" for i in range(add_other)]
+    sizes, lnames, per = host_ref.iscdef_layer_sizes(len(names), markers_layer, m.add_root)
+    assert m.layer_sizes == sizes and m.layer_names == lnames
+    nonmarker = 1.0 if use_brd else kw["nonmarker_strength"]
+    shape0, rate0 = host_ref.iscdef_geneset_prior(genes, markers, names, sizes, markers_layer, per, kw["gs_small_scale"],
+                                                  kw["gs_big_scale"], kw["marker_strength"], nonmarker, kw["other_strength"],
+                                                  penalize_other=penalize)
+    np.testing.assert_allclose(np.asarray(m.w_priors[0][0]), shape0, rtol=1e-6)
+    np.testing.assert_allclose(np.asarray(m.w_priors[0][1]), rate0, rtol=1e-6)
+    if markers_layer > 0:
+        mult = host_ref.iscdef_connectivity_prior(sizes, len(names), markers_layer, m.add_root, 2, kw["cn_small_mean"],
+                                                  kw["cn_big_mean"], kw["cn_small_strength"], kw["cn_big_strength"])
+        for l in range(1, len(sizes)):
+            base = float(m.factor_shapes[l])
+            want = mult.get(l, (1.0, 1.0))
+            np.testing.assert_allclose(np.asarray(m.w_priors[l][0]), base * np.asarray(want[0]) * np.ones((sizes[l], sizes[l - 1])), rtol=1e-5)
+            np.testing.assert_allclose(np.asarray(m.w_priors[l][1]), base * np.asarray(want[1]) * np.ones((sizes[l], sizes[l - 1])), rtol=1e-5)
