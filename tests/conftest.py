@@ -10,3 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_sessionstart(session):
+    """A fresh checkout has no libscdef_b200.so (it is git-ignored): build it once if nvcc is here, so that the
+    ABI tests (`-m "not gpu"`) and the GPU tests do not depend on the order in which the driver runs things."""
+    import shutil
+    import subprocess
+
+    lib = os.path.join(ROOT, "scdef_b200", "libscdef_b200.so")
+    if not os.path.exists(lib) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        subprocess.call(["bash", os.path.join(ROOT, "scdef_b200", "csrc", "build.sh")])
