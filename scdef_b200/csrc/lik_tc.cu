@@ -137,6 +137,7 @@ struct Misc {                  // lives at Smem.misc
 
 struct Geom {
   int KP, n_tiles, n_chunks, NG, tiles_per_range, n_cblocks;
+  int NGp, ptiles_per_range;   // CTA-pair LOCAL kernel: ranges of 128-gene pair-tiles (0 when pair mode is off)
 };
 
 // ---- (a) z0^s block -> bf16 hi/lo planes --------------------------------------------------------
@@ -609,6 +610,7 @@ __global__ void __launch_bounds__(NT, 1) k_lik_tc_global(const LikTcArgs a, cons
 }
 
 #include "lik_tc_pipe.cuh"
+#include "lik_tc_pair.cuh"
 
 // ---- pre-kernels of the pipelined path -----------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_tc_wprep(const LikTcArgs a, float* wmu, float* wsig) {
@@ -1001,11 +1003,18 @@ __global__ void __launch_bounds__(256) k_tc_w0_final(const LikTcArgs a, const fl
 
 int round_up16(int k) { return (k + 15) / 16 * 16; }
 
+// SCDEF_TC_PAIR=1: the LOCAL pass runs on CTA pairs (lik_tc_pair.cuh).  Read once per process.
+bool pair_mode() {
+  static const bool on = getenv("SCDEF_TC_PAIR") != nullptr && atoi(getenv("SCDEF_TC_PAIR")) != 0;
+  return on;
+}
+
 // work decomposition: balance (items / 148 SMs rounded up) x (work per item)
 Geom make_geom(int B, int S, int K0, int G) {
   Geom g;
   g.KP = round_up16(K0);
   g.n_tiles = (G + TG - 1) / TG;
+  if (pair_mode()) g.n_tiles = (g.n_tiles + 1) / 2 * 2;   // a pair-tile is two tile images; the phantom one is all zeros
   g.n_cblocks = B > 0 ? (B + CB - 1) / CB : 1;
   double best = 1e30;
   g.n_chunks = 1;
@@ -1025,6 +1034,22 @@ Geom make_geom(int B, int S, int K0, int G) {
   }
   g.tiles_per_range = (g.n_tiles + g.NG - 1) / g.NG;
   g.NG = (g.n_tiles + g.tiles_per_range - 1) / g.tiles_per_range;
+  g.NGp = 0;
+  g.ptiles_per_range = 0;
+  if (pair_mode()) {
+    // pairs of CTAs: 74 pair slots; item = (s, range of pair-tiles, 256-cell block)
+    const int n_pt = g.n_tiles / 2;
+    best = 1e30;
+    g.NGp = 1;
+    for (int ng = 1; ng <= n_pt; ++ng) {
+      const long long items = (long long)S * ng * g.n_cblocks;
+      const double waves = (double)((items + SM_TARGET / 2 - 1) / (SM_TARGET / 2));
+      const double cost = waves * ((double)((n_pt + ng - 1) / ng) + 1.0) + 0.01 * ng;   // +1: per-item z load / dz drain
+      if (cost < best - 1e-9) { best = cost; g.NGp = ng; }
+    }
+    g.ptiles_per_range = (n_pt + g.NGp - 1) / g.NGp;
+    g.NGp = (n_pt + g.ptiles_per_range - 1) / g.ptiles_per_range;
+  }
   return g;
 }
 
@@ -1036,7 +1061,7 @@ bool lik_tc_supported(int K0, int G, int nb) { return K0 >= 1 && K0 <= 112 && (G
 
 size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb) {
   const Geom g = make_geom(B, S, K0, G);
-  size_t part_local = (size_t)S * g.NG * (size_t)(B > 0 ? B : 1) * K0 * 4;
+  size_t part_local = (size_t)S * (g.NG > g.NGp ? g.NG : g.NGp) * (size_t)(B > 0 ? B : 1) * K0 * 4;
   size_t part_global = (size_t)g.n_chunks * 2 * K0 * G * 4;
   const size_t Bp = (size_t)(B > 0 ? B : 1), units = (Bp + 127) / 128;
   const size_t zimg = (size_t)S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
@@ -1047,6 +1072,18 @@ size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb) {
 }
 
 void lik_tc_set_debug(float* p) { cudaMemcpyToSymbol(g_dbg_R, &p, sizeof(p)); }
+
+// after a trapped launch of the pair kernel: {code of the wait that timed out, blockIdx.x, warp / sub-unit, parity}
+static int* g_pair_stuck_host = nullptr;
+static void pair_stuck_init() {
+  if (g_pair_stuck_host) return;
+  int* dev = nullptr;
+  if (cudaHostAlloc((void**)&g_pair_stuck_host, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) { g_pair_stuck_host = nullptr; return; }
+  for (int i = 0; i < 4; ++i) g_pair_stuck_host[i] = 0;
+  cudaHostGetDevicePointer((void**)&dev, g_pair_stuck_host, 0);
+  cudaMemcpyToSymbol(g_pair_stuck, &dev, sizeof(dev));
+}
+void lik_tc_pair_stuck(int* out) { for (int i = 0; i < 4; ++i) out[i] = g_pair_stuck_host ? g_pair_stuck_host[i] : 0; }
 
 void lik_tc_read_timing(unsigned long long* out) {
 #ifdef SCDEF_TC_TIMING
@@ -1072,7 +1109,7 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   ws.colsumX = (float*)w;  w += a256((size_t)a.nb * a.G * 4);
   ws.part = (float*)w;
   {
-    size_t part_local = (size_t)a.S * g.NG * (size_t)(a.B > 0 ? a.B : 1) * a.K0 * 4;
+    size_t part_local = (size_t)a.S * (g.NG > g.NGp ? g.NG : g.NGp) * (size_t)(a.B > 0 ? a.B : 1) * a.K0 * 4;
     size_t part_global = (size_t)g.n_chunks * 2 * a.K0 * a.G * 4;
     w += a256(part_local > part_global ? part_local : part_global);
   }
@@ -1138,8 +1175,24 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(a, g, ws, loss_out);
     }
   } else {
+    // CTA-pair LOCAL kernel (opt-in): whole 256-cell blocks only; anything else takes the single-CTA pipeline
+    const bool pair = pipe && pair_mode() && a.B > 0 && (a.B % CB) == 0 && g.NGp > 0 && a.dbg_nsplit != 1;
+    int ng_used = g.NG;
     if (a.lik_on) {
-      if (!mono) {
+      if (pair) {
+        const PairSmem QL = plan_pair_smem(g.KP);
+        pair_stuck_init();
+        ng_used = g.NGp;
+        main_begin();
+        if (a.want_loss) {
+          cudaFuncSetAttribute(k_lik_pair_local<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
+          k_lik_pair_local<true><<<dim3(2 * a.S * g.NGp, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
+        } else {
+          cudaFuncSetAttribute(k_lik_pair_local<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
+          k_lik_pair_local<false><<<dim3(2 * a.S * g.NGp, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
+        }
+        main_end();
+      } else if (!mono) {
         if (a.want_loss) {
           cudaFuncSetAttribute(k_lik_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
           main_begin();
@@ -1157,7 +1210,7 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       }
       long long total = (long long)a.S * a.B * a.K0;
       int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-      k_tc_dz_reduce<<<blocks, 256, 0, st>>>(a, ws.part, g.NG);
+      k_tc_dz_reduce<<<blocks, 256, 0, st>>>(a, ws.part, ng_used);
     } else if (!matrix_prior) {
       // value only: the GLOBAL kernel without likelihood produces the W_0 row sums
       LikTcArgs v = a;

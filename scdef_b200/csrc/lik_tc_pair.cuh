@@ -1,0 +1,464 @@
+// CTA-PAIR version of the LOCAL likelihood kernel (included by lik_tc.cu inside its anonymous namespace, after
+// lik_tc_pipe.cuh; uses its PTX wrappers, layouts and the pre-kernels' images).
+//
+// STATUS: compiled for sm_100a and SASS-checked, NOT YET RUN ON A GPU (written when the round's GPU minutes were
+// spent).  Opt-in: SCDEF_TC_PAIR=1.  Every barrier wait in this file is bounded (trap after ~1 s) so that a protocol
+// error ends in a CUDA error, not a hung device.  Bring-up: tests/tc_bringup.py with SCDEF_TC_PAIR=1.
+//
+// Why (profiles/r01_mma_probe.txt): a cta_group::1 tcgen05.mma occupies the tensor pipe for ~86 cycles whatever
+// N <= 128 is; the pair's 256 x 128 x 16 MMA costs 64.  k_lik_pipe<LOCAL> issues 33 MMAs per 128-cell x 64-gene
+// unit (2.8k cycles); here the same work is 45 pair MMAs per FOUR units (0.72k cycles per unit).
+//
+// Work of one pair = (MC sample s, range of 128-gene pair-tiles, 256-cell block); CTA `rank` of the pair owns the
+// cells [j0 + 128 rank, j0 + 128 rank + 128).  Per pair-tile pt (W_0 tile images 2pt and 2pt+1 of k_tc_wgen):
+//   MMA1  R[256 cells, 128 genes] = z0 W           M = 256 (128 rows per CTA), N = 128, K = KP; 3 split products
+//         A = the CTA's own z unit (K-major); B = N split over the pair: CTA `rank` supplies genes
+//         [64 rank, 64 rank + 64) = ALL k0 rows of image 2pt+rank (MN-major) -> region WA of the stage
+//   epilogue (both CTAs, 16 warps each), two sub-units h = 0, 1 of 64 genes: R -> Q = (x - Lambda) / R, split to
+//         bf16 hi/lo into the CTA's single Q buffer (128 cells x 64 genes), exactly as k_lik_pipe does
+//   MMA2  dz0[256 cells, KP] += Q_h W_h^T          M = 256, N = KP, K = 64 genes (4 k-steps); per sub-unit
+//         A = the CTA's own Q (K-major); B = N split over the pair: CTA `rank` supplies the k0 rows
+//         [KP/2 rank, KP/2 rank + KP/2) of image 2pt+h (K-major) -> region B2[h] of the stage
+//   So a stage holds: [WA hi | WA lo | gene-scale tile of image 2pt | of image 2pt+1 | B2[0] hi | B2[0] lo |
+//   B2[1] hi | B2[1] lo]; the same smem offsets in both CTAs (one descriptor serves both: the issuing thread's
+//   descriptors are CTA-relative).  7 bulk copies per stage and CTA, all contiguous pieces of the tile images.
+//
+// Barrier protocol.  Only the leader (rank 0) issues MMAs.  tcgen05.commit is multicast to both CTAs, so
+// "tensor core is done with ..." barriers (r_full, q_empty, w_empty, dz_full) are waited locally in each CTA.
+// "... is ready for the tensor core" barriers live in the LEADER's shared memory and are arrived on remotely
+// (mapa + mbarrier.arrive on the shared::cluster address) by one elected lane per epilogue warp of both CTAs (r_empty, q_full:
+// 32 arrivals) or by the peer's relay thread (the peer's otherwise idle MMA warp forwards "my TMA landed":
+// pz_full, pw_full).
+#pragma once
+
+constexpr int PAIR_TMEM_DZ = 256;            // TMEM columns: R[2] at 0 / 128, dz at 256
+constexpr long long PAIR_DEADLINE = 2000000000ll;  // cycles (~1 s) before a stuck wait traps
+
+struct PairMisc {
+  uint64_t z_full, pz_full, w_full[2], pw_full[2], w_empty[2], r_full[2], r_empty[2], q_full, q_empty, dz_full;
+  uint32_t tmem_base, pad;
+  double red[32];
+};
+
+struct PairSmem {
+  uint32_t z, w[2], q, misc, total;
+  uint32_t z_rs, z_plane, w_plane, q_plane;
+  uint32_t sg_off, b2_off, b2_piece, w_stage;   // offsets inside a W stage
+};
+__host__ __device__ inline PairSmem plan_pair_smem(int KP) {
+  PairSmem s;
+  s.z_rs = (uint32_t)(KP / 8) * 128u;
+  s.z_plane = 16u * s.z_rs;                  // 128 cells
+  s.w_plane = (uint32_t)(KP / 8) * W_RS;     // KP rows x 64 genes
+  s.q_plane = 16u * Q_RS;                    // 128 cells x 64 genes
+  s.b2_piece = (uint32_t)(KP / 16) * W_RS;   // KP/2 rows x 64 genes
+  s.sg_off = 2u * s.w_plane;
+  s.b2_off = s.sg_off + 2u * (uint32_t)(MAX_NB * TG * 4);
+  s.w_stage = s.b2_off + 4u * s.b2_piece;
+  uint32_t o = 0;
+  s.z = o; o += 2u * s.z_plane;
+  s.w[0] = o; o += s.w_stage;
+  s.w[1] = o; o += s.w_stage;
+  s.q = o; o += 2u * s.q_plane;
+  s.misc = o;
+  s.total = o + (uint32_t)((sizeof(PairMisc) + 1023) / 1024 * 1024);
+  return s;
+}
+
+// ---- cluster-scope PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `bar` in the shared memory of CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+// Scope of the cross-CTA hand-offs.  Default: the PTX defaults (.release / .acquire at .cta scope), which is what the
+// CUTLASS 2-SM kernels use for the same hand-offs (ClusterBarrier::arrive(cta_id) / ::wait) -- the data they guard is
+// ordered by its own fences (fence.proxy.async for the Q tile, tcgen05.fence for tensor memory).  -DSCDEF_PAIR_STRICT
+// makes them cluster-scoped; ptxas then brackets every such wait with CCTL.IVALL and every arrive with
+// MEMBAR.ALL.GPU (seen in the SASS), so it is a debugging aid, not the production setting.
+#ifdef SCDEF_PAIR_STRICT
+#define PAIR_REL ".release.cluster"
+#define PAIR_ACQ ".acquire.cluster"
+#else
+#define PAIR_REL ""
+#define PAIR_ACQ ""
+#endif
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive" PAIR_REL ".shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// try_wait with a short suspend hint; REMOTE: the barrier is arrived on from the peer CTA
+template <bool REMOTE>
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  if (REMOTE)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity" PAIR_ACQ ".shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x10000u)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x10000u)
+        : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_remote(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity" PAIR_ACQ ".shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// {code of the wait that timed out, blockIdx.x, warp, parity}: points into mapped host memory (lik_tc_launch sets it
+// before the first pair launch), so the record survives the trap that follows it
+__device__ volatile int* g_pair_stuck = nullptr;
+__device__ __noinline__ void pair_stuck(int code, int x, int y, int z) {
+  volatile int* p = g_pair_stuck;
+  if (p) { p[0] = code; p[1] = x; p[2] = y; p[3] = z; }
+  __threadfence_system();
+  __trap();
+}
+// bounded waits: a protocol error ends in a trap (and a record of which wait it was), not in a hung device
+template <bool REMOTE>
+__device__ __forceinline__ void pair_wait_t(uint64_t* bar, uint32_t parity, int code) {
+  if (mbar_try<REMOTE>(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try<REMOTE>(bar, parity)) {
+    if (clock64() - t0 > PAIR_DEADLINE) pair_stuck(code, (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)parity);
+  }
+}
+__device__ __forceinline__ void pair_wait(uint64_t* bar, uint32_t parity, int code) { pair_wait_t<false>(bar, parity, code); }
+__device__ __forceinline__ void pair_wait_remote(uint64_t* bar, uint32_t parity, int code) { pair_wait_t<true>(bar, parity, code); }
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// completion of all MMAs issued so far by this thread -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// generic-proxy stores of the Q tile -> visible to the tensor core's (async proxy) operand reads.  The unqualified
+// fence costs MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC in SASS; the shared::cta form is the last one only.
+__device__ __forceinline__ void fence_async_q() {
+#ifdef SCDEF_PAIR_STRICT
+  asm volatile("fence.proxy.async;" ::: "memory");
+#else
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------
+// grid = (2 * S * NGp, B / 256), cluster (2,1,1): blockIdx.x >> 1 = (s, range); requires B % 256 == 0 and an even
+// number of tile images per MC sample (make_geom pads n_tiles in pair mode; the phantom image is all zeros:
+// R = 0, x = s = 0 -> Q = 0).
+template <bool WANT_LL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
+    k_lik_pair_local(const LikTcArgs a, const Geom gm, const TcScratch ws, double* loss_out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const int KP = gm.KP;
+  const PairSmem L = plan_pair_smem(KP);
+  PairMisc* mi = reinterpret_cast<PairMisc*>(sm + L.misc);
+  const uint32_t sbase = smem_u32(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  // ---- work of this pair ----
+  const int item = blockIdx.x >> 1;
+  const int s_fixed = item / gm.NGp, range = item % gm.NGp;
+  const int pt_begin = range * gm.ptiles_per_range;
+  const int pt_end = min(gm.n_tiles / 2, pt_begin + gm.ptiles_per_range);
+  const int n_outer = pt_end - pt_begin;          // pair-tiles of this range
+  const int U = 2 * n_outer;                      // sub-units (pair-tile, gene half)
+  const int j_block0 = blockIdx.y * CB;
+  const int units_total_B = (a.B + UC - 1) / UC;
+  const int unit_u = j_block0 / UC + (int)rank;   // this CTA's 128-cell unit in the z / x images
+
+  // ---- prologue ----
+  if (threadIdx.x == 0) {
+    mbar_init(&mi->z_full, 1);
+    mbar_init(&mi->pz_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&mi->w_full[i], 1);
+      mbar_init(&mi->pw_full[i], 1);
+      mbar_init(&mi->w_empty[i], 1);
+      mbar_init(&mi->r_full[i], 1);
+      mbar_init(&mi->r_empty[i], 2 * 2 * E_WARPS);   // (2 sub-units) x (16 warps) x (2 CTAs) elected arrivals
+    }
+    mbar_init(&mi->q_full, 2 * E_WARPS);             // 16 warps x 2 CTAs
+    mbar_init(&mi->q_empty, 1);
+    mbar_init(&mi->dz_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();                                // the peer's barriers exist before anything arrives on them
+  if (warp == MMA_WARP) {                            // same warp in both CTAs (Allocator2Sm contract)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&mi->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = mi->tmem_base;
+  const uint32_t tmem_dz = tmem + PAIR_TMEM_DZ;
+  const uint32_t z_bytes = 2u * L.z_plane;
+  const uint32_t sg_bytes = (uint32_t)(a.nb * TG * 4);
+  const uint32_t w_bytes = 2u * L.w_plane + 2u * sg_bytes + 4u * L.b2_piece;
+  const PipeSmem IL = plan_pipe_smem(KP);            // layout of one tile image in global memory (k_tc_wgen)
+
+  if (warp == COPY_WARP) {
+    // =========================================== COPY (TMA), each CTA for itself ===========================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&mi->z_full, z_bytes);
+      bulk_g2s(sbase + L.z, ws.zimg + ((long long)s_fixed * units_total_B + unit_u) * z_bytes, z_bytes, &mi->z_full);
+      for (int oi = 0; oi < n_outer; ++oi) {
+        const int st = oi & 1;
+        const int pt = pt_begin + oi;
+        const uint8_t* img0 = ws.wimg + ((long long)s_fixed * gm.n_tiles + 2 * pt) * IL.w_unit;
+        const uint8_t* img1 = img0 + IL.w_unit;
+        const uint8_t* own = rank ? img1 : img0;
+        pair_wait(&mi->w_empty[st], ((oi >> 1) & 1) ^ 1, 1);
+        mbar_arrive_expect_tx(&mi->w_full[st], w_bytes);
+        const uint32_t dst = sbase + L.w[st];
+        bulk_g2s(dst, own, 2u * L.w_plane, &mi->w_full[st]);                                        // WA: hi | lo
+        bulk_g2s(dst + L.sg_off, img0 + 2u * IL.w_plane, sg_bytes, &mi->w_full[st]);                // gene scale, half 0
+        bulk_g2s(dst + L.sg_off + (uint32_t)(MAX_NB * TG * 4), img1 + 2u * IL.w_plane, sg_bytes, &mi->w_full[st]);
+        const uint32_t row_off = rank * L.b2_piece;                                                 // k0 rows [KP/2 rank, +KP/2)
+        bulk_g2s(dst + L.b2_off + 0u * L.b2_piece, img0 + row_off, L.b2_piece, &mi->w_full[st]);             // B2[0] hi
+        bulk_g2s(dst + L.b2_off + 1u * L.b2_piece, img0 + IL.w_plane + row_off, L.b2_piece, &mi->w_full[st]); // B2[0] lo
+        bulk_g2s(dst + L.b2_off + 2u * L.b2_piece, img1 + row_off, L.b2_piece, &mi->w_full[st]);             // B2[1] hi
+        bulk_g2s(dst + L.b2_off + 3u * L.b2_piece, img1 + IL.w_plane + row_off, L.b2_piece, &mi->w_full[st]); // B2[1] lo
+      }
+      // the multicast commits of the last two pair-tiles are waited for by nobody else: see them land before this
+      // CTA can exit (a late arrival would hit the shared memory of whatever CTA runs here next)
+      for (int st = 0; st < 2; ++st) {
+        const int uses = (n_outer + 1 - st) / 2;   // pair-tiles that went through stage st
+        if (uses > 0) pair_wait(&mi->w_empty[st], (uint32_t)(uses - 1) & 1u, 15);
+      }
+      if (U > 0) pair_wait(&mi->q_empty, (uint32_t)(U - 1) & 1u, 16);
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    if (lane == 0 && !leader) {
+      // =========================================== RELAY (peer) ==========================================
+      // forwards "my TMA landed" to the leader, whose MMAs read this CTA's shared memory as well
+      const uint32_t r_pz = mapa_rank(&mi->pz_full, 0), r_pw0 = mapa_rank(&mi->pw_full[0], 0), r_pw1 = mapa_rank(&mi->pw_full[1], 0);
+      pair_wait(&mi->z_full, 0, 2);
+      mbar_arrive_remote(r_pz);
+      for (int oi = 0; oi < n_outer; ++oi) {
+        pair_wait(&mi->w_full[oi & 1], (oi >> 1) & 1, 3);
+        mbar_arrive_remote((oi & 1) ? r_pw1 : r_pw0);
+      }
+    } else if (lane == 0) {
+      // =========================================== MMA ISSUER (leader) ===================================
+      const uint32_t idesc1 = umma_idesc(256, 2 * TG, 0, 1);   // R : A K-major, B MN-major
+      const uint32_t idesc2 = umma_idesc(256, KP, 0, 0);       // dz: A K-major, B K-major
+      const uint64_t dz_k = umma_desc(sbase + L.z, 128u, L.z_rs);
+      const uint64_t dwa_m[2] = {umma_desc(sbase + L.w[0], W_RS, 128u), umma_desc(sbase + L.w[1], W_RS, 128u)};
+      const uint64_t db2_k[2] = {umma_desc(sbase + L.w[0] + L.b2_off, 128u, W_RS), umma_desc(sbase + L.w[1] + L.b2_off, 128u, W_RS)};
+      const uint64_t dq_k = umma_desc(sbase + L.q, 128u, Q_RS);
+      const uint64_t zpl = L.z_plane >> 4, wpl = L.w_plane >> 4, qpl = L.q_plane >> 4, b2pl = L.b2_piece >> 4;
+      const int nk1 = KP / 16;
+      auto ready1 = [&](int oi) {
+        const int st = oi & 1;
+        const uint32_t par = (uint32_t)(oi >> 1) & 1u;
+        return mbar_test(&mi->w_full[st], par) && mbar_test_remote(&mi->pw_full[st], par) &&
+               mbar_test_remote(&mi->r_empty[st], par ^ 1u);
+      };
+      auto issue_mma1 = [&](int oi) {
+        const int st = oi & 1;
+        const uint32_t par = (uint32_t)(oi >> 1) & 1u;
+        pair_wait(&mi->w_full[st], par, 4);
+        pair_wait_remote(&mi->pw_full[st], par, 5);
+        pair_wait_remote(&mi->r_empty[st], par ^ 1u, 6);
+        tc_fence_after();
+        uint64_t da = dz_k, db = dwa_m[st];
+        const uint32_t d = tmem + (uint32_t)st * (2 * TG);
+        umma2_bf16(d, da + zpl, db, idesc1, 0u);
+        umma2_bf16(d, da, db + wpl, idesc1, 1u);
+        umma2_bf16(d, da, db, idesc1, 1u);
+        for (int ks = 1; ks < nk1; ++ks) {
+          da += 16;                // 256 B along K (two k0 column groups of the z unit)
+          db += 2 * (W_RS >> 4);   // two k0 row groups of the W image
+          umma2_bf16(d, da + zpl, db, idesc1, 1u);
+          umma2_bf16(d, da, db + wpl, idesc1, 1u);
+          umma2_bf16(d, da, db, idesc1, 1u);
+        }
+        umma2_commit(&mi->r_full[st]);
+      };
+      pair_wait(&mi->z_full, 0, 7);
+      pair_wait_remote(&mi->pz_full, 0, 8);
+      int next1 = 0;
+      for (int u = 0; u < U; ++u) {
+        const int oi = u >> 1, h = u & 1, st = oi & 1;
+        // the rate GEMM of the next pair-tile is slipped in as soon as its operands and its R buffer are ready; the
+        // one of THIS pair-tile must have been issued before its Q can ever arrive
+        long long t_poll = 0;
+        for (;;) {
+          if (next1 < n_outer && next1 <= oi + 1 && (next1 == oi || ready1(next1))) { issue_mma1(next1); ++next1; continue; }
+          if (mbar_test_remote(&mi->q_full, (uint32_t)u & 1u)) break;
+          if (next1 > oi + 1 || next1 >= n_outer) { pair_wait_remote(&mi->q_full, (uint32_t)u & 1u, 9); break; }
+          if (t_poll == 0) t_poll = clock64();
+          else if (clock64() - t_poll > PAIR_DEADLINE) pair_stuck(14, (int)blockIdx.x, u, next1);
+        }
+        tc_fence_after();
+        // dz (+)= Q_h W_h^T : A = Q (K-major), B = B2[h] (K-major, N = k0), K = the 64 genes of the half
+        uint64_t da = dq_k, db = db2_k[st] + (uint64_t)(2 * h) * b2pl;
+        umma2_bf16(tmem_dz, da + qpl, db, idesc2, u > 0 ? 1u : 0u);
+        umma2_bf16(tmem_dz, da, db + b2pl, idesc2, 1u);
+        umma2_bf16(tmem_dz, da, db, idesc2, 1u);
+#pragma unroll
+        for (int ks = 1; ks < TG / 16; ++ks) {
+          da += 16;
+          db += 16;
+          umma2_bf16(tmem_dz, da + qpl, db, idesc2, 1u);
+          umma2_bf16(tmem_dz, da, db + b2pl, idesc2, 1u);
+          umma2_bf16(tmem_dz, da, db, idesc2, 1u);
+        }
+        umma2_commit(&mi->q_empty);
+        if (h == 1) umma2_commit(&mi->w_empty[st]);
+      }
+      umma2_commit(&mi->dz_full);
+    }
+    __syncwarp();
+  } else {
+    // =========================================== EPILOGUE (both CTAs) ====================================
+    const int e = warp;                   // 0..15
+    const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+    const int r = (int)lane_base + lane;  // cell row of this CTA's unit
+    const int cq = e >> 2;                // 16-gene quarter of the 64-gene half
+    const int j = j_block0 + (int)rank * UC + r;
+    const bool valid = j < a.B;
+    const float c = valid ? a.smp_c[(long long)s_fixed * a.B + j] : 0.f;
+    const int brow = valid ? ws.brow[j] : 0;
+    const uint32_t r_rempty[2] = {mapa_rank(&mi->r_empty[0], 0), mapa_rank(&mi->r_empty[1], 0)};
+    const uint32_t r_qfull = mapa_rank(&mi->q_full, 0);
+    float ll = 0.f, esum = 0.f;
+    auto x_ptr = [&](int u) {
+      const int tile_u = 2 * (pt_begin + (u >> 1)) + (u & 1);
+      return ws.ximg + ((((long long)tile_u * units_total_B + unit_u) * 4 + (warp & 3)) * 16 + cq * 4) * 128 + lane * 4;
+    };
+    float4 x4[4];
+    if (U > 0) {
+      const float* xi = x_ptr(0);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) x4[v] = *reinterpret_cast<const float4*>(xi + v * 128);
+    }
+    for (int u = 0; u < U; ++u) {
+      const int oi = u >> 1, h = u & 1, st = oi & 1;
+      const uint32_t par = (uint32_t)(oi >> 1) & 1u;
+      float xs16[16];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { xs16[v * 4] = x4[v].x; xs16[v * 4 + 1] = x4[v].y; xs16[v * 4 + 2] = x4[v].z; xs16[v * 4 + 3] = x4[v].w; }
+      if (u + 1 < U) {   // the next sub-unit's counts are in flight while this one is processed
+        const float* xi = x_ptr(u + 1);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) x4[v] = *reinterpret_cast<const float4*>(xi + v * 128);
+      }
+      if (h == 0) pair_wait(&mi->w_full[st], par, 10);   // the gene-scale tiles ride with the W stage
+      pair_wait(&mi->r_full[st], par, 11);
+      tc_fence_after();
+      float R[16], q[16];
+      tmem_ld16(tmem + (lane_base << 16) + (uint32_t)(st * (2 * TG) + h * TG + cq * 16), R);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(r_rempty[st]);   // this warp has read its part of R[st] for sub-unit h
+      const float* srow_sm =
+          reinterpret_cast<const float*>(sm + L.w[st] + L.sg_off + (uint32_t)h * (uint32_t)(MAX_NB * TG * 4)) + brow * TG + cq * 16;
+      float es = 0.f;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        // rows / genes outside the problem carry c = 0 / s = 0 and x = 0: Lambda = E = Q = 0 without masks
+        const float4 s4v = *reinterpret_cast<const float4*>(srow_sm + v * 4);
+        const float ss[4] = {s4v.x, s4v.y, s4v.z, s4v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float Rv = R[v * 4 + i];
+          const float xv = xs16[v * 4 + i];
+          const float lam = (c * ss[i]) * Rv;
+          const float E = xv - lam;
+          q[v * 4 + i] = __fdividef(E, fmaxf(Rv, 1e-37f));
+          if (WANT_LL) {
+            const float t = xv * __logf(lam);  // lam = 0 only where x = 0: the select discards -inf * 0
+            ll += (xv > 0.f ? t : 0.f) - lam;
+          }
+          es += E;
+        }
+      }
+      if (g_dbg_R && valid) {
+        const int g0 = (2 * (pt_begin + oi) + h) * TG + cq * 16;
+        for (int i = 0; i < 16; ++i)
+          if (g0 + i < a.G) g_dbg_R[((long long)s_fixed * a.B + j) * a.G + g0 + i] = R[i];
+      }
+      pair_wait(&mi->q_empty, ((uint32_t)u & 1u) ^ 1u, 12);
+      {
+        uint4 hi, lo;
+        const uint32_t off = L.q + (uint32_t)(r >> 3) * Q_RS + (uint32_t)(r & 7) * 16u + (uint32_t)(cq * 2) * 128u;
+        split8(q, hi, lo);
+        *reinterpret_cast<uint4*>(sm + off) = hi;
+        *reinterpret_cast<uint4*>(sm + off + L.q_plane) = lo;
+        split8(q + 8, hi, lo);
+        *reinterpret_cast<uint4*>(sm + off + 128u) = hi;
+        *reinterpret_cast<uint4*>(sm + off + 128u + L.q_plane) = lo;
+      }
+      fence_async_q();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(r_qfull);
+      esum += es;
+    }
+
+    // ---- drain dz0 (this thread: cell row r, every 4th 16-column chunk of k0) ----
+    pair_wait(&mi->dz_full, 0, 13);
+    tc_fence_after();
+    if (U > 0) {
+      float* dst = ws.part + (((long long)s_fixed * gm.NGp + range) * a.B + j) * a.K0;
+      for (int cc = cq; cc < KP / 16; cc += 4) {
+        float v[16];
+        tmem_ld16(tmem_dz + (lane_base << 16) + (uint32_t)(cc * 16), v);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (cc * 16 + i < a.K0) dst[cc * 16 + i] = v[i];
+        }
+      }
+      if (valid && esum != 0.f) atomicAdd(&a.G_c[(long long)s_fixed * a.B + j], a.scale * esum / c);
+    }
+    // loss: reduce over the epilogue threads
+    double v = warp_sum_d((double)ll);
+    if (lane == 0) mi->red[e] = v;
+    named_bar_sync(2, E_THREADS);
+    if (WANT_LL && e == 0 && lane == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < E_WARPS; ++i) tot += mi->red[i];
+      atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)a.S);
+    }
+  }
+
+  // nobody leaves while the peer may still signal into this CTA's shared memory or read its tensor memory
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}

@@ -1,0 +1,36 @@
+"""Per-launch time of the fused likelihood kernel, LOCAL and GLOBAL pass separately, at C5 shapes (256 cells x 5000
+genes, layers [100,60,30,10], 100 MC samples).  Run twice to compare the single-CTA pipeline with the CTA-pair LOCAL
+kernel:   python tests/pair_timing.py ;  SCDEF_TC_PAIR=1 python tests/pair_timing.py"""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from scdef_b200 import MiniAnnData, scDEF
+from scdef_b200.engine import NoiseSpec
+from scdef_b200.synth import synth_counts_torch
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+X, _ = synth_counts_torch(N, 5000, lib=3000.0, device="cuda")
+m = scDEF(MiniAnnData(X), layer_sizes=[100, 60, 30, 10], logginglevel=30)
+m.max_steps_per_learn = 3
+m._learn(n_epoch=1, num_samples=S, batch_size=256, filter=False, annotate=False)
+eng = m._get_engine()
+idx = torch.arange(256, dtype=torch.int64, device="cuda")
+kw = dict(num_samples=S, annealing=1.0, alpha=float(m.alpha), scale=N / 256.0)
+out = {}
+for which in ("local", "global"):
+    for rep in range(2):   # first round = warm-up
+        eng.profile(True, ["lik_main"])
+        eng.profile_read(reset=True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(20):
+            eng.elbo_grad(which, idx, NoiseSpec.philox(0, 100 + i), want_loss=(which == "global"), **kw)
+        ev1.record()
+        torch.cuda.synchronize()
+        prof, _ = eng.profile_read(reset=True)
+        out[which] = (prof["lik_main"][0] / max(prof["lik_main"][1], 1), ev0.elapsed_time(ev1) / 20)
+    eng.profile(False)
+mode = "pair" if os.environ.get("SCDEF_TC_PAIR") == "1" else "single"
+print(f"[{mode}] S={S}  main kernel ms/launch: LOCAL {out['local'][0]:.4f}  GLOBAL {out['global'][0]:.4f}   "
+      f"whole pass ms: LOCAL {out['local'][1]:.4f}  GLOBAL {out['global'][1]:.4f}", flush=True)

@@ -63,7 +63,27 @@ def run(N, G, Ks, nb, B, S, sg=None, dump=True, **kw):
     return out
 
 
+def pair_cases():
+    """CTA-pair LOCAL kernel (SCDEF_TC_PAIR=1; engaged only for B % 256 == 0).  On a trapped launch the record of the
+    wait that timed out is printed: (code, blockIdx.x, warp or sub-unit, parity) -- codes in lik_tc_pair.cuh."""
+    assert os.environ.get("SCDEF_TC_PAIR") == "1", "run with SCDEF_TC_PAIR=1"
+    try:
+        print("pair 1: one pair-tile, KP=16", flush=True); run(300, 128, (16, 4), 1, 256, 1)
+        print("pair 2: C5-like layers, phantom tile", flush=True); run(600, 312, (100, 60, 30, 10), 1, 256, 2)
+        print("pair 3: batches, two cell blocks", flush=True); run(700, 200, (24, 6, 1), 3, 512, 3)
+    finally:
+        lib = _lib.load()
+        rec = (ctypes.c_int * 4)()
+        lib.scdef_debug_pair_stuck.argtypes = [ctypes.c_void_p]
+        lib.scdef_debug_pair_stuck.restype = None
+        lib.scdef_debug_pair_stuck(rec)
+        print("pair stuck record (code, block, warp/sub-unit, parity):", list(rec), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pair":
+        pair_cases()
+        sys.exit(0)
     print("case 1: tiny", flush=True); run(64, 64, (16, 4), 1, 32, 1)
     print("case 2: C1-like", flush=True); run(200, 120, (10, 5, 2), 1, 200, 3)
     print("case 3: ragged", flush=True); run(300, 200, (100, 60, 30, 10), 1, 257, 2)
