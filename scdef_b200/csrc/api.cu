@@ -794,6 +794,7 @@ int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t*
 void scdef_debug_tc_dump(float* p) { lik_tc_set_debug(p); }
 void scdef_debug_tc_timing(unsigned long long* out) { cudaDeviceSynchronize(); lik_tc_read_timing(out); }
 void scdef_debug_pair_stuck(int* out) { lik_tc_pair_stuck(out); }
+void scdef_debug_pair_timing(unsigned long long* out) { cudaDeviceSynchronize(); lik_tc_read_pair_timing(out); }
 
 int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam, void* cuda_stream) {
   if (!X || n_rows < 0 || n_genes < 1) return SCDEF_EINVAL;

@@ -138,6 +138,7 @@ struct Misc {                  // lives at Smem.misc
 struct Geom {
   int KP, n_tiles, n_chunks, NG, tiles_per_range, n_cblocks;
   int NGp, ptiles_per_range;   // CTA-pair LOCAL kernel: ranges of 128-gene pair-tiles (0 when pair mode is off)
+  int Pflat;                   // persistent variant: CTA pairs per cell block (NGp = partial slots per sample then)
 };
 
 // ---- (a) z0^s block -> bf16 hi/lo planes --------------------------------------------------------
@@ -1003,10 +1004,11 @@ __global__ void __launch_bounds__(256) k_tc_w0_final(const LikTcArgs a, const fl
 
 int round_up16(int k) { return (k + 15) / 16 * 16; }
 
-// SCDEF_TC_PAIR=1: the LOCAL pass runs on CTA pairs (lik_tc_pair.cuh).  Read once per process.
-bool pair_mode() {
-  static const bool on = getenv("SCDEF_TC_PAIR") != nullptr && atoi(getenv("SCDEF_TC_PAIR")) != 0;
-  return on;
+// SCDEF_TC_PAIR=1: the LOCAL pass runs on CTA pairs (lik_tc_pair.cuh), one item per pair; =2: the persistent
+// (flattened) variant.  Read once per process.
+int pair_mode() {
+  static const int mode = getenv("SCDEF_TC_PAIR") != nullptr ? atoi(getenv("SCDEF_TC_PAIR")) : 0;
+  return mode;
 }
 
 // work decomposition: balance (items / 148 SMs rounded up) x (work per item)
@@ -1036,7 +1038,20 @@ Geom make_geom(int B, int S, int K0, int G) {
   g.NG = (g.n_tiles + g.tiles_per_range - 1) / g.tiles_per_range;
   g.NGp = 0;
   g.ptiles_per_range = 0;
-  if (pair_mode()) {
+  g.Pflat = 0;
+  if (pair_mode() == 2) {
+    const int n_pt = g.n_tiles / 2;
+    const long long T = (long long)S * n_pt;
+    g.Pflat = SM_TARGET / 2 / g.n_cblocks;
+    if (g.Pflat < 1) g.Pflat = 1;
+    if ((long long)g.Pflat > T) g.Pflat = (int)(T > 0 ? T : 1);
+    int slots = 1;
+    for (int s2 = 0; s2 < S; ++s2) {
+      const int n = flat_chunk_of((long long)(s2 + 1) * n_pt - 1, T, g.Pflat) - flat_chunk_of((long long)s2 * n_pt, T, g.Pflat) + 1;
+      if (n > slots) slots = n;
+    }
+    g.NGp = slots;
+  } else if (pair_mode()) {
     // pairs of CTAs: 74 pair slots; item = (s, range of pair-tiles, 256-cell block)
     const int n_pt = g.n_tiles / 2;
     best = 1e30;
@@ -1084,6 +1099,14 @@ static void pair_stuck_init() {
   cudaMemcpyToSymbol(g_pair_stuck, &dev, sizeof(dev));
 }
 void lik_tc_pair_stuck(int* out) { for (int i = 0; i < 4; ++i) out[i] = g_pair_stuck_host ? g_pair_stuck_host[i] : 0; }
+
+void lik_tc_read_pair_timing(unsigned long long* out) {
+#ifdef SCDEF_TC_TIMING
+  cudaMemcpyFromSymbol(out, g_pair_timing, sizeof(unsigned long long) * 2 * 4 * 16);
+#else
+  for (int i = 0; i < 128; ++i) out[i] = 0;
+#endif
+}
 
 void lik_tc_read_timing(unsigned long long* out) {
 #ifdef SCDEF_TC_TIMING
@@ -1184,7 +1207,15 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
         pair_stuck_init();
         ng_used = g.NGp;
         main_begin();
-        if (a.want_loss) {
+        if (g.Pflat > 0) {
+          if (a.want_loss) {
+            cudaFuncSetAttribute(k_lik_pair_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
+            k_lik_pair_flat<true><<<dim3(2 * g.Pflat, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
+          } else {
+            cudaFuncSetAttribute(k_lik_pair_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
+            k_lik_pair_flat<false><<<dim3(2 * g.Pflat, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
+          }
+        } else if (a.want_loss) {
           cudaFuncSetAttribute(k_lik_pair_local<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
           k_lik_pair_local<true><<<dim3(2 * a.S * g.NGp, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
         } else {
@@ -1210,7 +1241,8 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       }
       long long total = (long long)a.S * a.B * a.K0;
       int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-      k_tc_dz_reduce<<<blocks, 256, 0, st>>>(a, ws.part, ng_used);
+      if (pair && g.Pflat > 0) k_tc_dz_reduce_flat<<<blocks, 256, 0, st>>>(a, ws.part, g.NGp, g.Pflat, g.n_tiles / 2);
+      else k_tc_dz_reduce<<<blocks, 256, 0, st>>>(a, ws.part, ng_used);
     } else if (!matrix_prior) {
       // value only: the GLOBAL kernel without likelihood produces the W_0 row sums
       LikTcArgs v = a;

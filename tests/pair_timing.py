@@ -31,6 +31,22 @@ for which in ("local", "global"):
         prof, _ = eng.profile_read(reset=True)
         out[which] = (prof["lik_main"][0] / max(prof["lik_main"][1], 1), ev0.elapsed_time(ev1) / 20)
     eng.profile(False)
-mode = "pair" if os.environ.get("SCDEF_TC_PAIR") == "1" else "single"
+mode = {"1": "pair", "2": "pair-persistent"}.get(os.environ.get("SCDEF_TC_PAIR", ""), "single")
 print(f"[{mode}] S={S}  main kernel ms/launch: LOCAL {out['local'][0]:.4f}  GLOBAL {out['global'][0]:.4f}   "
       f"whole pass ms: LOCAL {out['local'][1]:.4f}  GLOBAL {out['global'][1]:.4f}", flush=True)
+if len(sys.argv) > 3 and sys.argv[3] == "dump":   # needs a -DSCDEF_TC_TIMING build: where each role of the pair kernel spends its cycles
+    import ctypes
+    from scdef_b200 import _lib
+    lib = _lib.load()
+    buf = (ctypes.c_ulonglong * 128)()
+    lib.scdef_debug_pair_timing.argtypes = [ctypes.c_void_p]
+    lib.scdef_debug_pair_timing.restype = None
+    lib.scdef_debug_pair_timing(buf)
+    a = np.array(buf[:]).reshape(2, 4, 16)
+    names = {0: ["w_empty"], 1: ["w_full", "pw_full", "r_empty", "q_full(net)", "issue MMA1", "issue MMA2", "z_full"],
+             2: ["r_full", "q_empty", "w_full", "tmem_ld+arrive", "math", "store+fence+arrive", "top(x regs)", "dz_full", "drain"]}
+    names[3] = names[2]
+    for rank in range(2):
+        for role, rn in enumerate(["COPY", "MMA/RELAY", "EPI warp0", "EPI warp15"]):
+            print(f"  rank {rank} {rn:10s} total {int(a[rank, role, 15]):8d}  " +
+                  " ".join(f"{n}={int(a[rank, role, i])}" for i, n in enumerate(names[role])), flush=True)

@@ -66,11 +66,13 @@ def run(N, G, Ks, nb, B, S, sg=None, dump=True, **kw):
 def pair_cases():
     """CTA-pair LOCAL kernel (SCDEF_TC_PAIR=1; engaged only for B % 256 == 0).  On a trapped launch the record of the
     wait that timed out is printed: (code, blockIdx.x, warp or sub-unit, parity) -- codes in lik_tc_pair.cuh."""
-    assert os.environ.get("SCDEF_TC_PAIR") == "1", "run with SCDEF_TC_PAIR=1"
+    assert os.environ.get("SCDEF_TC_PAIR") in ("1", "2"), "run with SCDEF_TC_PAIR=1 (one item per pair) or 2 (persistent)"
     try:
         print("pair 1: one pair-tile, KP=16", flush=True); run(300, 128, (16, 4), 1, 256, 1)
         print("pair 2: C5-like layers, phantom tile", flush=True); run(600, 312, (100, 60, 30, 10), 1, 256, 2)
         print("pair 3: batches, two cell blocks", flush=True); run(700, 200, (24, 6, 1), 3, 512, 3)
+        # 100 samples x 2 pair-tiles over 74 pairs: chunks of 2-3 pair-tiles that cross sample boundaries (persistent variant)
+        print("pair 4: many samples, chunks cross samples", flush=True); run(400, 200, (24, 6, 1), 1, 256, 100, dump=False)
     finally:
         lib = _lib.load()
         rec = (ctypes.c_int * 4)()
