@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SCDEF_ABI_VERSION 5
+#define SCDEF_ABI_VERSION 6
 #define SCDEF_MAX_LAYERS 8
 
 #define SCDEF_OK 0
@@ -231,6 +231,21 @@ int scdef_csr_row_stats(const int64_t* indptr, const float* data, int64_t n_rows
                         void* cuda_stream);
 int scdef_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* rows,
                           int32_t n_rows, int32_t n_genes, float* out, void* cuda_stream);
+
+/* Post-fit Monte-Carlo assignment statistics of ONE layer (`scdef.tl.assign_confident`, tools/factor.py:1264-1379;
+   the reference does this with two jax.lax.scan passes over n_samples keys).  For each of the n_rows cells:
+   n_samples draws z = exp(mu + exp(rho) eps) of the n_cols kept factors (element (n, k) of the z block at
+   mu[n*ld + cols[k]], rho likewise; cols: device int32[n_cols]), normalised to zhat; winner = argmax_k mean_s zhat;
+   gap_s = zhat_s[winner] - max_{k != winner} zhat_s[k].
+   stats (n_rows x 6, overwritten): clip(mean gap, -1, 1), clip(SD of the gap, 0, 1), clip(quantile_level-quantile of
+   the gap with linear interpolation, 0, 1), clip(mean zhat[winner], 0, 1), max_k P(argmax = k), clip(1 - H(P)/log n_cols, 0, 1);
+   argmax (n_rows, overwritten): winner slot in [0, n_cols).
+   Noise: eps != NULL -> explicit draws (n_samples, n_rows, n_cols) (parity tests); otherwise Philox4x32-10 keyed by
+   (seed, stream_id, row0 + n, k, sample), so a cell's draws do not depend on how the cells are sharded.
+   n_cols in [2, 1024] (single-factor layers are constants, factor.py:1270-1281); 32*n_samples bytes of shared memory. */
+int scdef_assign_confident(const float* mu, const float* rho, int64_t n_rows, int32_t ld, const int32_t* cols,
+                           int32_t n_cols, int32_t n_samples, float quantile_level, uint64_t seed, int32_t stream_id,
+                           int64_t row0, const float* eps, float* stats, int32_t* argmax, void* cuda_stream);
 
 /* Writes the N(0,1) draws the kernels would use for one block in PHILOX mode (debug / parity):
    block_kind 0 cell_scale, 1 z layer `layer`, 2 gene_scale, 3 brd, 4 W layer `layer`, 5 ard,

@@ -12,6 +12,7 @@
 #include "lik_simt.cuh"
 #include "adam.cuh"
 #include "lik_tc.cuh"
+#include "tools.cuh"
 
 using namespace scdef;
 
@@ -801,6 +802,42 @@ int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib,
   if (n_rows == 0) return SCDEF_OK;
   long long blocks = (n_rows + 7) / 8;
   k_row_stats<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(X, n_rows, n_genes, lib, lgam);
+  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+}
+
+int scdef_assign_confident(const float* mu, const float* rho, int64_t n_rows, int32_t ld, const int32_t* cols,
+                           int32_t n_cols, int32_t n_samples, float quantile_level, uint64_t seed, int32_t stream_id,
+                           int64_t row0, const float* eps, float* stats, int32_t* argmax, void* cuda_stream) {
+  if (!mu || !rho || !cols || !stats || !argmax) return SCDEF_EINVAL;
+  if (n_rows < 0 || ld < 1 || n_cols < 2 || n_cols > ld || n_samples < 1 || row0 < 0) return SCDEF_EINVAL;
+  if (!(quantile_level >= 0.f && quantile_level <= 1.f)) return SCDEF_EINVAL;
+  if (n_cols > 1024) return SCDEF_EUNSUPPORTED;                 // 8 quads of 4 factors per lane
+  const size_t smem = (size_t)8 * (size_t)n_samples * sizeof(float);   // the S gaps of each of the CTA's 8 cells
+  if (smem > 200 * 1024) return SCDEF_EUNSUPPORTED;
+  if (n_rows == 0) return SCDEF_OK;
+  ConfidentArgs a;
+  a.mu = mu; a.rho = rho; a.cols = cols; a.eps = eps; a.stats = stats; a.argmax = argmax;
+  a.N = n_rows; a.row0 = row0; a.ld = ld; a.K = n_cols; a.S = n_samples; a.q_level = quantile_level;
+  a.key.k0 = (uint32_t)seed; a.key.k1 = (uint32_t)(seed >> 32);
+  a.tag.a = 0x61736366u;  /* 'ascf' */
+  a.tag.b = (uint32_t)stream_id << 8;   // the high half of the 64-bit quad counter is added to the low byte range
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (n_rows + 7) / 8;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int quads = (n_cols + 3) / 4;
+  if (quads <= 32) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_assign_confident<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_assign_confident<1><<<(unsigned)blocks, 256, smem, st>>>(a);
+  } else if (quads <= 64) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_assign_confident<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_assign_confident<2><<<(unsigned)blocks, 256, smem, st>>>(a);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_assign_confident<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_assign_confident<8><<<(unsigned)blocks, 256, smem, st>>>(a);
+  }
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 

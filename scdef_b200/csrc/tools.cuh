@@ -1,0 +1,212 @@
+// Post-fit Monte-Carlo assignment of cells to layers: the per-layer statistics of `scdef.tl.assign_confident`
+// (reference `tools/factor.py:1264-1379`), one warp per cell.
+//
+// The reference draws S reparameterised samples z^(s) = exp(mu + sigma eps) of the kept factors of a layer for every
+// cell, normalises them to zhat, and reduces over the S samples twice (two lax.scan passes with the same keys):
+//   pass 1: argmax counts and the mean of zhat               -> winner f* = argmax_k mean zhat, p = counts / S
+//   pass 2: gap^(s) = zhat[f*] - max_{g != f*} zhat[g]        -> lower (1 - credible_level) quantile, mean, SD of the gap
+// Here both passes run in one kernel: the lane that owns factor k keeps its count and zhat sum in registers, the
+// draws of pass 2 are regenerated from the same Philox counters (or re-read from the injected eps), the S gaps of the
+// cell live in the warp's slice of shared memory, and the two order statistics of the quantile are found by rank
+// counting.  HBM traffic is the 2 K parameters of the cell in and 7 numbers out; the kernel is bound by the
+// FP32 / MUFU work of 2 S K samples per cell.
+#pragma once
+#include "common.cuh"
+
+namespace scdef {
+
+struct ConfidentArgs {
+  const float* mu;      // element (n, c) at mu[n * ld + c]
+  const float* rho;
+  const int32_t* cols;  // (K) column of kept factor k
+  const float* eps;     // explicit draws (S, N, K) or nullptr -> Philox
+  float* stats;         // (N, 6): effect_size, posterior_sd, confidence, winner_mass, winner_probability, entropy_confidence
+  int32_t* argmax;      // (N) slot of the winner among the kept factors
+  long long N, row0;    // row0: global index of row 0 (data parallelism: the draws of a cell do not depend on the sharding)
+  int ld, K, S;
+  float q_level;        // 1 - credible_level
+  PhiloxKey key;
+  NoiseTag tag;
+};
+
+// (value, index) arg-max over the warp, first maximum on ties (np / jnp.argmax)
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// MAXQ: quads (4 consecutive kept factors) per lane; lane owns quads lane, lane + 32, ...
+template <int MAXQ>
+__global__ void __launch_bounds__(256) k_assign_confident(const ConfidentArgs a) {
+  extern __shared__ float gaps_all[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* gaps = gaps_all + (size_t)wib * a.S;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int K = a.K, S = a.S, Q = (K + 3) >> 2;
+  const float invS = 1.f / (float)S;
+
+  for (long long n = warp0; n < a.N; n += nwarps) {
+    float mu[MAXQ][4], sg[MAXQ][4], sz[MAXQ][4];
+    int cnt[MAXQ][4];
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = 4 * (lane + 32 * i) + c;
+        mu[i][c] = 0.f; sg[i][c] = 0.f; sz[i][c] = 0.f; cnt[i][c] = 0;
+        if (k < K) {
+          const int col = a.cols[k];
+          mu[i][c] = a.mu[n * a.ld + col];
+          sg[i][c] = expf(a.rho[n * a.ld + col]);                 // factor.py:1265
+        }
+      }
+    // zhat of sample s for the factors this lane owns (0 for k >= K); identical in both passes
+    auto sample = [&](int s, float (&zh)[MAXQ][4]) {
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXQ; ++i) {
+        const int q = lane + 32 * i;
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (q < Q) {
+          if (a.eps) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (4 * q + c < K) e[c] = a.eps[((long long)s * a.N + n) * K + 4 * q + c];
+          } else {
+            const unsigned long long qi = (unsigned long long)(a.row0 + n) * (unsigned long long)Q + (unsigned long long)q;
+            NoiseTag t = a.tag;
+            t.b += (uint32_t)(qi >> 32);
+            const float4 n4 = philox_normal4(a.key, t, (uint32_t)s, (uint32_t)qi);
+            e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool on = 4 * q + c < K;
+          zh[i][c] = on ? expf(fmaf(sg[i][c], e[c], mu[i][c])) : 0.f;   // 1289
+          part += zh[i][c];
+        }
+      }
+      const float denom = fmaxf(warp_sum(part), 1e-30f);                // 1290
+#pragma unroll
+      for (int i = 0; i < MAXQ; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) zh[i][c] = zh[i][c] / denom;
+    };
+
+    // ---- pass 1: argmax counts and the sum of zhat (factor.py:1286-1302) ----
+    for (int s = 0; s < S; ++s) {
+      float zh[MAXQ][4];
+      sample(s, zh);
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < MAXQ; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = 4 * (lane + 32 * i) + c;
+          if (k < K) {
+            sz[i][c] += zh[i][c];
+            if (zh[i][c] > best) { best = zh[i][c]; bi = k; }   // ascending k within the lane: first maximum kept
+          }
+        }
+      warp_argmax(best, bi);
+#pragma unroll
+      for (int i = 0; i < MAXQ; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cnt[i][c] += (4 * (lane + 32 * i) + c == bi) ? 1 : 0;
+    }
+    // winner = argmax of the mean zhat (1304-1305); p = counts / S (1303): its maximum and entropy (1361-1367)
+    float wbest = -INFINITY, pmax = 0.f, H = 0.f;
+    int winner = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = 4 * (lane + 32 * i) + c;
+        if (k < K) {
+          const float m = sz[i][c] * invS;
+          if (m > wbest) { wbest = m; winner = k; }
+          const float p = (float)cnt[i][c] * invS;
+          pmax = fmaxf(pmax, p);
+          H -= p * logf(fminf(fmaxf(p, 1e-30f), 1.f));
+        }
+      }
+    warp_argmax(wbest, winner);
+    pmax = warp_max(pmax);
+    H = warp_sum(H);
+
+    // ---- pass 2: the gap between the winner and its runner-up, per sample (1317-1329) ----
+    float sum_gap = 0.f, sum_wm = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float zh[MAXQ][4];
+      sample(s, zh);
+      float wm = -INFINITY, ru = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < MAXQ; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = 4 * (lane + 32 * i) + c;
+          if (k < K) {
+            if (k == winner) wm = zh[i][c];
+            else ru = fmaxf(ru, zh[i][c]);
+          }
+        }
+      wm = warp_max(wm);
+      ru = warp_max(ru);
+      const float gap = wm - ru;
+      if (lane == 0) gaps[s] = gap;
+      sum_gap += gap;
+      sum_wm += wm;
+    }
+    __syncwarp();
+    const float mean_gap = sum_gap * invS;
+    float var = 0.f;
+    for (int i = lane; i < S; i += 32) {
+      const float d = gaps[i] - mean_gap;
+      var = fmaf(d, d, var);
+    }
+    var = warp_sum(var) * invS;                                        // population SD (jnp.std), 1336
+    // empirical quantile with linear interpolation (jnp.quantile default), 1334: order statistics by rank counting
+    const float pos = a.q_level * (float)(S - 1);
+    const int lo = (int)floorf(pos), hi = min((int)ceilf(pos), S - 1);
+    const float wh = pos - (float)lo;
+    float vlo = -INFINITY, vhi = -INFINITY;
+    for (int i = lane; i < S; i += 32) {
+      const float gi = gaps[i];
+      int rank = 0;
+      for (int j = 0; j < S; ++j) {
+        const float gj = gaps[j];
+        rank += (gj < gi || (gj == gi && j < i)) ? 1 : 0;
+      }
+      if (rank == lo) vlo = gi;
+      if (rank == hi) vhi = gi;
+    }
+    vlo = warp_max(vlo);
+    vhi = warp_max(vhi);
+    const float conf = vlo * (1.f - wh) + vhi * wh;
+    if (lane == 0) {
+      float* o = a.stats + n * 6;
+      o[0] = fminf(fmaxf(mean_gap, -1.f), 1.f);                        // 1343
+      o[1] = fminf(fmaxf(sqrtf(var), 0.f), 1.f);                       // 1351
+      o[2] = fminf(fmaxf(conf, 0.f), 1.f);                             // 1354
+      o[3] = fminf(fmaxf(sum_wm * invS, 0.f), 1.f);                    // 1358
+      o[4] = fminf(fmaxf(pmax, 0.f), 1.f);                             // 1361
+      o[5] = fminf(fmaxf(1.f - H / logf((float)K), 0.f), 1.f);         // 1367
+      a.argmax[n] = winner;
+    }
+    __syncwarp();   // the warp's gap slice is reused by its next cell
+  }
+}
+
+}  // namespace scdef

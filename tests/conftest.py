@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line(
+        "markers",
+        "gpu_pending: GPU test of code written after the round's GPU minutes were spent; it has never run on a device. "
+        "Not selected by `-m gpu`; skipped without CUDA. Promote to `gpu` after its first green run "
+        "(`python -m pytest tests -m gpu_pending`).")
 
 
 def pytest_sessionstart(session):
