@@ -60,6 +60,7 @@ def run(N, G, Ks, nb, B, S, sg=None, dump=True, **kw):
         for n_, g, r in zip(names_g, gg, ref_gg):
             errs[n_] = rel_err(g, r) if np.abs(r).max() > 0 else float(np.abs(g).max())
         print(f"  {name}: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()), flush=True)
+        out[name + "_max_err"] = max(errs.values())
     return out
 
 
@@ -67,12 +68,15 @@ def pair_cases():
     """CTA-pair LOCAL kernel (SCDEF_TC_PAIR=1; engaged only for B % 256 == 0).  On a trapped launch the record of the
     wait that timed out is printed: (code, blockIdx.x, warp or sub-unit, parity) -- codes in lik_tc_pair.cuh."""
     assert os.environ.get("SCDEF_TC_PAIR") in ("1", "2"), "run with SCDEF_TC_PAIR=1 (one item per pair) or 2 (persistent)"
+    worst = 0.0
     try:
-        print("pair 1: one pair-tile, KP=16", flush=True); run(300, 128, (16, 4), 1, 256, 1)
-        print("pair 2: C5-like layers, phantom tile", flush=True); run(600, 312, (100, 60, 30, 10), 1, 256, 2)
-        print("pair 3: batches, two cell blocks", flush=True); run(700, 200, (24, 6, 1), 3, 512, 3)
+        print("pair 1: one pair-tile, KP=16", flush=True); worst = max(worst, run(300, 128, (16, 4), 1, 256, 1)["tc_max_err"])
+        print("pair 2: C5-like layers, phantom tile", flush=True); worst = max(worst, run(600, 312, (100, 60, 30, 10), 1, 256, 2)["tc_max_err"])
+        print("pair 3: batches, two cell blocks", flush=True); worst = max(worst, run(700, 200, (24, 6, 1), 3, 512, 3)["tc_max_err"])
         # 100 samples x 2 pair-tiles over 74 pairs: chunks of 2-3 pair-tiles that cross sample boundaries (persistent variant)
-        print("pair 4: many samples, chunks cross samples", flush=True); run(400, 200, (24, 6, 1), 1, 256, 100, dump=False)
+        print("pair 4: many samples, chunks cross samples", flush=True)
+        worst = max(worst, run(400, 200, (24, 6, 1), 1, 256, 100, dump=False)["tc_max_err"])
+        print(f"pair: worst relative error of the tcgen05 path {worst:.2e} (bar 1e-4)", flush=True)
     finally:
         lib = _lib.load()
         rec = (ctypes.c_int * 4)()
@@ -80,12 +84,12 @@ def pair_cases():
         lib.scdef_debug_pair_stuck.restype = None
         lib.scdef_debug_pair_stuck(rec)
         print("pair stuck record (code, block, warp/sub-unit, parity):", list(rec), flush=True)
+    return worst
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pair":
-        pair_cases()
-        sys.exit(0)
+        sys.exit(0 if pair_cases() <= 1e-4 else 1)
     print("case 1: tiny", flush=True); run(64, 64, (16, 4), 1, 32, 1)
     print("case 2: C1-like", flush=True); run(200, 120, (10, 5, 2), 1, 200, 3)
     print("case 3: ragged", flush=True); run(300, 200, (100, 60, 30, 10), 1, 257, 2)
