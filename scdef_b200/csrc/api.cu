@@ -795,6 +795,8 @@ int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t*
 void scdef_debug_tc_dump(float* p) { lik_tc_set_debug(p); }
 void scdef_debug_tc_timing(unsigned long long* out) { cudaDeviceSynchronize(); lik_tc_read_timing(out); }
 void scdef_debug_pair_stuck(int* out) { lik_tc_pair_stuck(out); }
+void scdef_debug_tc_geom(int B, int S, int K0, int G, int* out) { lik_tc_debug_geom(B, S, K0, G, out); }
+int scdef_debug_flat_chunk_of(long long f, long long T, int P) { return lik_tc_debug_flat_chunk_of(f, T, P); }
 void scdef_debug_pair_timing(unsigned long long* out) { cudaDeviceSynchronize(); lik_tc_read_pair_timing(out); }
 
 int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam, void* cuda_stream) {

@@ -1100,6 +1100,15 @@ static void pair_stuck_init() {
 }
 void lik_tc_pair_stuck(int* out) { for (int i = 0; i < 4; ++i) out[i] = g_pair_stuck_host ? g_pair_stuck_host[i] : 0; }
 
+// host logic under test (tests/test_host.py): the work decomposition for a problem shape.
+// out = {KP, n_tiles, n_chunks, NG, tiles_per_range, n_cblocks, NGp, ptiles_per_range, Pflat, pair mode}
+void lik_tc_debug_geom(int B, int S, int K0, int G, int* out) {
+  const Geom g = make_geom(B, S, K0, G);
+  const int v[10] = {g.KP, g.n_tiles, g.n_chunks, g.NG, g.tiles_per_range, g.n_cblocks, g.NGp, g.ptiles_per_range, g.Pflat, pair_mode()};
+  for (int i = 0; i < 10; ++i) out[i] = v[i];
+}
+int lik_tc_debug_flat_chunk_of(long long f, long long T, int P) { return flat_chunk_of(f, T, P); }
+
 void lik_tc_read_pair_timing(unsigned long long* out) {
 #ifdef SCDEF_TC_TIMING
   cudaMemcpyFromSymbol(out, g_pair_timing, sizeof(unsigned long long) * 2 * 4 * 16);

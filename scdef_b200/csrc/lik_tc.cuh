@@ -41,7 +41,9 @@ size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb);
 void lik_tc_set_debug(float* p);
 void lik_tc_read_timing(unsigned long long* out);
 void lik_tc_read_pair_timing(unsigned long long* out);  // [rank][role][slot] of the CTA-pair kernel (-DSCDEF_TC_TIMING)
-void lik_tc_pair_stuck(int* out);  // bring-up: which wait of the CTA-pair kernel timed out (code, block, warp, parity)
+void lik_tc_pair_stuck(int* out);
+void lik_tc_debug_geom(int B, int S, int K0, int G, int* out);   // work decomposition (host logic, CPU-testable)
+int lik_tc_debug_flat_chunk_of(long long f, long long T, int P);  // bring-up: which wait of the CTA-pair kernel timed out (code, block, warp, parity)
 int lik_tc_launch(const LikTcArgs& a, double* loss_out, int sm_count, cudaStream_t st);
 
 }  // namespace scdef
