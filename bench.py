@@ -335,7 +335,9 @@ def run_ours(args):
         torch.cuda.empty_cache()
     else:
         roof_dense = roof_adam()
-    roofs = [r for r in (roof_lik(), roof_dense if lazy and not args.no_dense_probe else roof_adam()) if r]
+    # with the lazy replay and no dense probe there is no dense-Adam launch to put on the HBM roofline (the family's
+    # timing is the lazy kernels', whose traffic is the minibatch rows only)
+    roofs = [r for r in (roof_lik(), roof_dense if not (lazy and args.no_dense_probe) else None) if r]
     roofs.sort(key=lambda r: -(r["share_of_step"] or 0))
 
     # ---- e2e: counts in host memory, per-step H2D + loss readback -------------------------------
