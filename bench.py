@@ -319,6 +319,7 @@ def run_ours(args):
 
     # the dense local Adam (the HBM-bound deliverable) is measured on a short dense run when the main run is lazy
     dense_info = None
+    roof_dense = None
     if lazy and not args.no_dense_probe:
         md = build(X, "device", lazy_adam=False)
         rd = timed_learn(md, per_step_readback=False, W=3, K=10, preroll=0, P=0)
