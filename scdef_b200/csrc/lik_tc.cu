@@ -1005,7 +1005,8 @@ __global__ void __launch_bounds__(256) k_tc_w0_final(const LikTcArgs a, const fl
 int round_up16(int k) { return (k + 15) / 16 * 16; }
 
 // SCDEF_TC_PAIR=1: the LOCAL pass runs on CTA pairs (lik_tc_pair.cuh), one item per pair; =2: the persistent
-// (flattened) variant.  Read once per process.
+// (flattened) variant; =3: the persistent variant with the whole-pair-tile epilogue (not yet run on a device).
+// Read once per process.
 int pair_mode() {
   static const int mode = getenv("SCDEF_TC_PAIR") != nullptr ? atoi(getenv("SCDEF_TC_PAIR")) : 0;
   return mode;
@@ -1039,7 +1040,7 @@ Geom make_geom(int B, int S, int K0, int G) {
   g.NGp = 0;
   g.ptiles_per_range = 0;
   g.Pflat = 0;
-  if (pair_mode() == 2) {
+  if (pair_mode() >= 2) {
     const int n_pt = g.n_tiles / 2;
     const long long T = (long long)S * n_pt;
     g.Pflat = SM_TARGET / 2 / g.n_cblocks;
@@ -1217,13 +1218,14 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
         ng_used = g.NGp;
         main_begin();
         if (g.Pflat > 0) {
-          if (a.want_loss) {
-            cudaFuncSetAttribute(k_lik_pair_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
-            k_lik_pair_flat<true><<<dim3(2 * g.Pflat, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
-          } else {
-            cudaFuncSetAttribute(k_lik_pair_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
-            k_lik_pair_flat<false><<<dim3(2 * g.Pflat, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
-          }
+          const dim3 grid(2 * g.Pflat, g.n_cblocks);
+          auto launch = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
+            kern<<<grid, PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
+          };
+          const bool wide = pair_mode() == 3;
+          if (a.want_loss) { if (wide) launch(k_lik_pair_flat<true, true>); else launch(k_lik_pair_flat<true, false>); }
+          else { if (wide) launch(k_lik_pair_flat<false, true>); else launch(k_lik_pair_flat<false, false>); }
         } else if (a.want_loss) {
           cudaFuncSetAttribute(k_lik_pair_local<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
           k_lik_pair_local<true><<<dim3(2 * a.S * g.NGp, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);

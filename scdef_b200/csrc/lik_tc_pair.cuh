@@ -518,6 +518,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
 // =============================================================================================================
 constexpr int FLAT_TMEM_DZ = 256, FLAT_DZ_STRIDE = 128;   // R[2] at 0 / 128; dz[2] at 256 / 384
 
+// tcgen05.ld split into issue and wait, so that other work can sit between them.  The wait names the destination
+// registers as in/out operands: the compiler cannot move a use of them above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 struct FlatMisc {
   uint64_t z_full, pz_full, z_empty, w_full[2], pw_full[2], w_empty[2], r_full[2], r_empty[2], q_full, q_empty, dz_full[2], dz_empty[2];
   uint32_t tmem_base, pad;
@@ -533,7 +550,10 @@ struct FlatCur {   // position in the flattened space
   __device__ __forceinline__ void next(int n_pt) { if (++pt == n_pt) { pt = 0; ++s; ++g; } }
 };
 
-template <bool WANT_LL>
+// WIDE (SCDEF_TC_PAIR=3, never run on a device yet): the epilogue handles a whole pair-tile (both 64-gene halves) per
+// barrier round instead of one half: per-element overhead (barrier fast paths, address arithmetic, tcgen05.ld issue,
+// r_empty arrival) halves, and the second half's tcgen05.ld is in flight while the first half's Q tile is stored.
+template <bool WANT_LL, bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
     k_lik_pair_flat(const LikTcArgs a, const Geom gm, const TcScratch ws, double* loss_out) {
   extern __shared__ __align__(1024) uint8_t sm[];
@@ -569,7 +589,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
       mbar_init(&mi->pw_full[i], 1);
       mbar_init(&mi->w_empty[i], 1);
       mbar_init(&mi->r_full[i], 1);
-      mbar_init(&mi->r_empty[i], 2 * 2 * E_WARPS);
+      mbar_init(&mi->r_empty[i], (WIDE ? 2 : 4) * E_WARPS);   // elected arrivals per pair-tile: 16 warps x 2 CTAs (x 2 halves)
       mbar_init(&mi->dz_full[i], 1);
       mbar_init(&mi->dz_empty[i], 2 * E_WARPS);
     }
@@ -748,6 +768,134 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
     const uint32_t r_dzempty[2] = {mapa_rank(&mi->dz_empty[0], 0), mapa_rank(&mi->dz_empty[1], 0)};
     const uint32_t r_qfull = mapa_rank(&mi->q_full, 0);
     float ll = 0.f, esum = 0.f, c = 0.f;
+    // one 64-gene half of a pair-tile: R (16 columns of this thread's cell row) -> Q, log-likelihood, sum of E
+    auto half_math = [&](const float4 (&xv4)[4], const uint32_t (&Rr)[16], const float* srow_sm, float (&q)[16], float& es) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float4 s4v = *reinterpret_cast<const float4*>(srow_sm + v * 4);
+        const float ss[4] = {s4v.x, s4v.y, s4v.z, s4v.w};
+        const float xs[4] = {xv4[v].x, xv4[v].y, xv4[v].z, xv4[v].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float Rv = __uint_as_float(Rr[v * 4 + i]);
+          const float lam = (c * ss[i]) * Rv;
+          const float E = xs[i] - lam;
+          q[v * 4 + i] = __fdividef(E, fmaxf(Rv, 1e-37f));
+          if (WANT_LL) {
+            const float t = xs[i] * __logf(lam);
+            ll += (xs[i] > 0.f ? t : 0.f) - lam;
+          }
+          es += E;
+        }
+      }
+    };
+    auto store_q = [&](const float (&q)[16]) {
+      uint4 hi, lo;
+      const uint32_t off = L.q + (uint32_t)(r >> 3) * Q_RS + (uint32_t)(r & 7) * 16u + (uint32_t)(cq * 2) * 128u;
+      split8(q, hi, lo);
+      *reinterpret_cast<uint4*>(sm + off) = hi;
+      *reinterpret_cast<uint4*>(sm + off + L.q_plane) = lo;
+      split8(q + 8, hi, lo);
+      *reinterpret_cast<uint4*>(sm + off + 128u) = hi;
+      *reinterpret_cast<uint4*>(sm + off + 128u + L.q_plane) = lo;
+      fence_async_q();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(r_qfull);
+    };
+    // the sample's dz0 is complete: drain its accumulator (cell row r, every 4th 16-column chunk of k0)
+    auto drain_segment = [&](const FlatCur& p) {
+      const uint32_t dzb = (uint32_t)p.g & 1u;
+      PT_WAIT(7, pair_wait(&mi->dz_full[dzb], ((uint32_t)p.g >> 1) & 1u, 13));
+      tc_fence_after();
+      PT_MARK();
+      const int slot = chunk - flat_chunk_of((long long)p.s * n_pt, T, P);
+      float* dst = ws.part + (((long long)p.s * gm.NGp + slot) * a.B + j) * a.K0;
+      const uint32_t tdz = tmem + FLAT_TMEM_DZ + dzb * FLAT_DZ_STRIDE + (lane_base << 16);
+      const bool vec4 = (a.K0 & 3) == 0;
+      for (int ch = cq; ch < KP / 16; ch += 4) {
+        float v[16];
+        tmem_ld16(tdz + (uint32_t)(ch * 16), v);
+        if (valid) {
+          if (vec4) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              if (ch * 16 + i < a.K0) *reinterpret_cast<float4*>(dst + ch * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (ch * 16 + i < a.K0) dst[ch * 16 + i] = v[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(r_dzempty[dzb]);
+      if (valid && esum != 0.f) atomicAdd(&a.G_c[(long long)p.s * a.B + j], a.scale * esum / c);
+      esum = 0.f;
+      PT_LAP(8);
+    };
+    if (WIDE) {
+      // this thread's first float4 of 64-gene tile t of the count image sits at x_base + t * x_tile
+      const long long x_tile = (long long)units_total_B * (4 * 16 * 128);
+      const float* x_base = ws.ximg + (((long long)unit_u * 4 + (warp & 3)) * 16 + cq * 4) * 128 + lane * 4;
+      float4 xa[4], xb[4];   // counts of half 0 / half 1, loaded one pair-tile ahead
+      FlatCur cc = cur0;
+      if (n_outer > 0) {
+        const float* xi = x_base + (long long)(2 * cc.pt) * x_tile;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { xa[v] = *reinterpret_cast<const float4*>(xi + v * 128); xb[v] = *reinterpret_cast<const float4*>(xi + x_tile + v * 128); }
+      }
+      for (int oi = 0; oi < n_outer; ++oi) {
+        const int st = oi & 1;
+        const uint32_t par = (uint32_t)(oi >> 1) & 1u;
+        const bool more = oi + 1 < n_outer;
+        FlatCur cn = cc;
+        cn.next(n_pt);
+        const float* xnext = x_base + (long long)(2 * cn.pt) * x_tile;
+        if (first_in_seg(oi, cc)) c = valid ? a.smp_c[(long long)cc.s * a.B + j] : 0.f;
+        const float* sg0 = reinterpret_cast<const float*>(sm + L.w[st] + L.sg_off) + brow * TG + cq * 16;
+        const uint32_t taddr = tmem + (lane_base << 16) + (uint32_t)(st * (2 * TG) + cq * 16);
+        PT_MARK();
+        PT_WAIT(2, pair_wait(&mi->w_full[st], par, 10));
+        PT_WAIT(0, pair_wait(&mi->r_full[st], par, 11));
+        tc_fence_after();
+        PT_MARK();
+        uint32_t R0[16], R1[16];
+        float q[16];
+        tmem_ld16_issue(taddr, R0);
+        tmem_ld16_wait(R0);
+        PT_LAP(3);
+        float es = 0.f;
+        half_math(xa, R0, sg0, q, es);
+        if (more) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) xa[v] = *reinterpret_cast<const float4*>(xnext + v * 128);
+        }
+        tmem_ld16_issue(taddr + (uint32_t)TG, R1);   // in flight while the first half's Q tile is stored
+        PT_LAP(4);
+        PT_WAIT(1, pair_wait(&mi->q_empty, 1u, 12));  // sub-unit 2 oi: parity (u & 1) ^ 1 with u even
+        PT_MARK();
+        store_q(q);
+        tmem_ld16_wait(R1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(r_rempty[st]);   // both halves of R[st] are in registers
+        PT_LAP(5);
+        half_math(xb, R1, sg0 + MAX_NB * TG, q, es);
+        if (more) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) xb[v] = *reinterpret_cast<const float4*>(xnext + x_tile + v * 128);
+        }
+        PT_LAP(4);
+        PT_WAIT(1, pair_wait(&mi->q_empty, 0u, 12));  // sub-unit 2 oi + 1
+        PT_MARK();
+        store_q(q);
+        PT_LAP(5);
+        esum += es;
+        if (last_in_seg(oi, cc)) drain_segment(cc);
+        cc = cn;
+      }
+    } else {
     FlatCur cc = cur0, cx = cur0;   // cursors of the sub-unit being processed and of the counts being prefetched
     auto x_ptr = [&](const FlatCur& p, int h) {
       const int tile_u = 2 * p.pt + h;
@@ -865,6 +1013,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
         cc.next(n_pt);
       }
     }
+    }   // !WIDE
     double v = warp_sum_d((double)ll);
     if (lane == 0) mi->red[e] = v;
     named_bar_sync(2, E_THREADS);
