@@ -121,3 +121,57 @@ def test_float32_oracle_calibrates_tolerance():
     for a, b in zip(cl32 + cg32, cl64 + cg64):
         if np.abs(b).max() > 0:
             assert rel_err(a, b) < 1e-4
+
+
+# ---- the third-party arithmetic the oracle restates (tensorflow-probability, jax.scipy, optax are not
+# ---- in the reference tree) against INDEPENDENT implementations of the same published definitions -----------------
+def test_distribution_primitives_match_scipy_and_torch_distributions():
+    """`jax_utils.py:6-46` are thin wrappers over tfd.LogNormal / tfd.Gamma and `_scdef.py:2119` over
+    jax.scipy.stats.poisson: the oracle's closed forms must agree with scipy.stats and torch.distributions, which
+    implement the same distributions independently."""
+    import scipy.stats as st
+
+    rng = np.random.default_rng(0)
+    x = rng.gamma(2.0, 1.0, size=(6, 5)) + 1e-3
+    shape = rng.uniform(0.05, 4.0, size=(6, 5))
+    rate = rng.uniform(0.1, 9.0, size=(6, 5))
+    got = float(elbo_ref.gamma_logpdf(torch.as_tensor(x), torch.as_tensor(shape), torch.as_tensor(rate)))
+    assert got == pytest.approx(float(st.gamma.logpdf(x, shape, scale=1.0 / rate).sum()), rel=1e-12)
+    td_g = torch.distributions.Gamma(torch.as_tensor(shape), torch.as_tensor(rate)).log_prob(torch.as_tensor(x)).sum()
+    assert got == pytest.approx(float(td_g), rel=1e-12)
+
+    m, s = rng.normal(size=(4, 7)), rng.uniform(0.05, 2.0, size=(4, 7))
+    got = float(elbo_ref.lognormal_entropy(torch.as_tensor(m), torch.as_tensor(s)))
+    assert got == pytest.approx(float(st.lognorm.entropy(s, scale=np.exp(m)).sum()), rel=1e-12)
+    assert got == pytest.approx(float(torch.distributions.LogNormal(torch.as_tensor(m), torch.as_tensor(s)).entropy().sum()), rel=1e-12)
+
+    k = rng.poisson(3.0, size=(5, 8)).astype(np.float64)
+    mu = rng.uniform(0.01, 10.0, size=(5, 8))
+    got = elbo_ref.poisson_logpmf(torch.as_tensor(k), torch.as_tensor(mu)).numpy()
+    np.testing.assert_allclose(got, st.poisson.logpmf(k, mu), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(got, torch.distributions.Poisson(torch.as_tensor(mu)).log_prob(torch.as_tensor(k)).numpy(), rtol=1e-12, atol=1e-12)
+
+    eps = rng.normal(size=(3, 4))
+    got = elbo_ref.lognormal_sample(torch.as_tensor(eps), torch.as_tensor(m[:3, :4]), torch.as_tensor(s[:3, :4])).numpy()
+    base = torch.distributions.Normal(torch.as_tensor(m[:3, :4]), torch.as_tensor(s[:3, :4]))
+    want = torch.distributions.LogNormal(base.loc, base.scale).icdf(torch.distributions.Normal(0.0, 1.0).cdf(torch.as_tensor(eps))).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+
+
+def test_adam_restatement_matches_torch_adam():
+    """optax.adam(lr) (`_scdef.py:3079-3082`) = bias-corrected moments, update -lr m_hat / (sqrt(v_hat) + eps): the same
+    published algorithm as torch.optim.Adam (amsgrad off, no weight decay).  20 steps, float64."""
+    rng = np.random.default_rng(1)
+    p0 = [rng.normal(size=(2, 5, 3)), rng.normal(size=(2, 4, 1))]
+    grads = [[rng.normal(size=p.shape) * (1.0 + it) for p in p0] for it in range(20)]
+    opt = host_ref.Adam(p0, 1e-2, dtype=np.float64)
+    params = [p.copy() for p in p0]
+    tp = [torch.tensor(p, dtype=torch.float64, requires_grad=True) for p in p0]
+    topt = torch.optim.Adam(tp, lr=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    for g in grads:
+        params = opt.update(params, g)
+        for t, gi in zip(tp, g):
+            t.grad = torch.tensor(gi, dtype=torch.float64)
+        topt.step()
+    for a, t in zip(params, tp):
+        np.testing.assert_allclose(a, t.detach().numpy(), rtol=1e-10, atol=1e-12)
