@@ -247,6 +247,13 @@ int scdef_assign_confident(const float* mu, const float* rho, int64_t n_rows, in
                            int32_t n_cols, int32_t n_samples, float quantile_level, uint64_t seed, int32_t stream_id,
                            int64_t row0, const float* eps, float* stats, int32_t* argmax, void* cuda_stream);
 
+/* Cold start of a LogNormal block from Gamma draws, on the device (`init_var_params`, _scdef.py:1639-1648 for the z layers):
+   m = clip(Gamma(shape, 1) / shape, clip_lo, clip_hi), v = m / var_div, (mu, rho = log sigma) = the LogNormal with mean m and
+   variance v.  Element (n, k) is written at mu[n*ld + k] / rho[n*ld + k].  The reference draws with JAX keys, so parity is
+   distributional; the draws here are Philox4x32-10 keyed by (seed, stream_id, row0 + n, k). */
+int scdef_init_gamma_block(float* mu, float* rho, int64_t n_rows, int32_t n_cols, int32_t ld, float shape, float clip_lo,
+                           float clip_hi, float var_div, uint64_t seed, int32_t stream_id, int64_t row0, void* cuda_stream);
+
 /* Writes the N(0,1) draws the kernels would use for one block in PHILOX mode (debug / parity):
    block_kind 0 cell_scale, 1 z layer `layer`, 2 gene_scale, 3 brd, 4 W layer `layer`, 5 ard,
    6 alpha; out is (S, rows, cols). */

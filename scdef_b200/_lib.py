@@ -109,7 +109,7 @@ EXPORTS = [
     "scdef_workspace_bytes", "scdef_elbo_grad", "scdef_adam_local", "scdef_adam_global",
     "scdef_posterior", "scdef_row_stats", "scdef_noise_fill", "scdef_profile_enable", "scdef_profile_read",
     "scdef_adam_local_lazy", "scdef_adam_bias_table", "scdef_assignment_counts",
-    "scdef_csr_row_stats", "scdef_csr_gather_rows", "scdef_assign_confident",
+    "scdef_csr_row_stats", "scdef_csr_gather_rows", "scdef_assign_confident", "scdef_init_gamma_block",
 ]
 LAZY_CATCHUP, LAZY_UPDATE, LAZY_CATCHUP_ALL = 0, 1, 2
 PROF_KINDS = ["lik", "adam_local_z", "hier", "sample", "wprior", "finish", "adam_global", "priors", "adam_local_c", "lik_main"]
@@ -182,6 +182,9 @@ def load():
                                            C.c_float, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]
     lib.scdef_assign_confident.restype = C.c_int
+    lib.scdef_init_gamma_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                           C.c_float, C.c_float, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p]
+    lib.scdef_init_gamma_block.restype = C.c_int
     lib.scdef_row_stats.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.scdef_row_stats.restype = C.c_int
     lib.scdef_noise_fill.argtypes = [C.c_void_p, C.POINTER(Noise), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

@@ -795,6 +795,12 @@ int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t*
 void scdef_debug_tc_dump(float* p) { lik_tc_set_debug(p); }
 void scdef_debug_tc_timing(unsigned long long* out) { cudaDeviceSynchronize(); lik_tc_read_timing(out); }
 void scdef_debug_pair_stuck(int* out) { lik_tc_pair_stuck(out); }
+/* host logic under test: n draws of the device initialiser's Gamma(shape, 1) sampler, computed on the HOST from the same code */
+void scdef_debug_gamma_host(float shape, unsigned long long seed, int stream_id, long long n, float* out_host) {
+  PhiloxKey key; key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32);
+  NoiseTag tag; tag.a = 0x696e6974u; tag.b = (uint32_t)stream_id << 8;
+  for (long long i = 0; i < n; ++i) out_host[i] = philox_gamma(shape, key, tag, (unsigned long long)i);
+}
 void scdef_debug_tc_geom(int B, int S, int K0, int G, int* out) { lik_tc_debug_geom(B, S, K0, G, out); }
 int scdef_debug_flat_chunk_of(long long f, long long T, int P) { return lik_tc_debug_flat_chunk_of(f, T, P); }
 void scdef_debug_pair_timing(unsigned long long* out) { cudaDeviceSynchronize(); lik_tc_read_pair_timing(out); }
@@ -840,6 +846,26 @@ int scdef_assign_confident(const float* mu, const float* rho, int64_t n_rows, in
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_assign_confident<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_assign_confident<8><<<(unsigned)blocks, 256, smem, st>>>(a);
   }
+  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+}
+
+int scdef_init_gamma_block(float* mu, float* rho, int64_t n_rows, int32_t n_cols, int32_t ld, float shape, float clip_lo,
+                           float clip_hi, float var_div, uint64_t seed, int32_t stream_id, int64_t row0, void* cuda_stream) {
+  if (!mu || !rho || n_rows < 0 || n_cols < 1 || ld < n_cols || row0 < 0) return SCDEF_EINVAL;
+  if (!(shape > 0.f) || !(clip_lo > 0.f) || !(clip_hi >= clip_lo) || !(var_div > 0.f)) return SCDEF_EINVAL;
+  if (n_rows == 0) return SCDEF_OK;
+  InitGammaArgs a;
+  a.mu = mu; a.rho = rho; a.N = n_rows; a.row0 = row0; a.K = n_cols; a.ld = ld;
+  a.shape = shape; a.clip_lo = clip_lo; a.clip_hi = clip_hi; a.var_div = var_div;
+  a.key.k0 = (uint32_t)seed; a.key.k1 = (uint32_t)(seed >> 32);
+  a.tag.a = 0x696e6974u;  /* 'init' */
+  a.tag.b = (uint32_t)stream_id << 8;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (n_rows * n_cols + 255) / 256;
+  if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+  k_init_gamma_block<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 

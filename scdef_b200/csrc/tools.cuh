@@ -209,4 +209,61 @@ __global__ void __launch_bounds__(256) k_assign_confident(const ConfidentArgs a)
   }
 }
 
+// =====================================================================================================================
+// Cold start of a LogNormal block from Gamma draws on the device (`init_var_params`, reference
+// `models/_scdef.py:1639-1648` for z: mean m = clip(Gamma(a, 1) / a), variance m / var_div, moment-matched to (mu, log sigma);
+// SURVEY.md §8 f3).  The reference draws with JAX keys, the host path of this package with NumPy's Generator: parity is at
+// the level of the distribution only, so the draws here come from the package's Philox stream (Marsaglia-Tsang
+// squeeze, boosted by U^(1/a) for a < 1).  One thread per element; the draw of element (row0 + n, k) does not depend
+// on how the cells are sharded.
+// =====================================================================================================================
+struct InitGammaArgs {
+  float* mu;     // element (n, k) at mu[n * ld + k]
+  float* rho;
+  long long N, row0;
+  int K, ld;
+  float shape, clip_lo, clip_hi, var_div;
+  PhiloxKey key;
+  NoiseTag tag;
+};
+
+// host + device: the CPU test draws from the same code (`scdef_debug_gamma_host`)
+__host__ __device__ inline float philox_gamma(float a, PhiloxKey key, NoiseTag tag, unsigned long long elem) {
+  const float k32 = 2.3283064365386963e-10f;   // 2^-32
+  const bool boost = a < 1.f;
+  const float aa = boost ? a + 1.f : a;
+  const float d = aa - 0.33333333f, c = 1.f / sqrtf(9.f * d);
+  NoiseTag t = tag;
+  t.b += (uint32_t)(elem >> 32);
+  float g = d;   // the mode, should all attempts be rejected (probability < 1e-20)
+  float ub = 0.5f;
+  for (uint32_t attempt = 0; attempt < 16u; ++attempt) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)elem, t.a, t.b, attempt), key);
+    const float u1 = fminf(((float)r.x + 0.5f) * k32, 0.99999994f), u2 = ((float)r.y + 0.5f) * k32;
+    const float x = sqrtf(-2.f * logf(u1)) * cosf(6.283185307179586f * u2);   // N(0,1)
+    const float u = fminf(((float)r.z + 0.5f) * k32, 0.99999994f);
+    if (attempt == 0u) ub = fminf(((float)r.w + 0.5f) * k32, 0.99999994f);
+    float v = 1.f + c * x;
+    if (v <= 0.f) continue;
+    v = v * v * v;
+    if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) { g = d * v; break; }
+  }
+  if (boost) g *= expf(logf(ub) / a);                                           // Gamma(a) = Gamma(a + 1) U^(1/a)
+  return g;
+}
+
+__global__ void __launch_bounds__(256) k_init_gamma_block(const InitGammaArgs a) {
+  const long long total = a.N * a.K;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long n = e / a.K;
+    const int k = (int)(e - n * a.K);
+    const float g = philox_gamma(a.shape, a.key, a.tag, (unsigned long long)(a.row0 + n) * (unsigned long long)a.K + (unsigned long long)k);
+    const double m = (double)fminf(fmaxf(g / a.shape, a.clip_lo), a.clip_hi);
+    const double v = m / (double)a.var_div;
+    // LogNormal with mean m and variance v (`_scdef.py:1496-1505`): mu = log(m^2 / sqrt(m^2 + v)), sigma^2 = log(1 + v / m^2)
+    a.mu[n * a.ld + k] = (float)log(m * m / sqrt(m * m + v));
+    a.rho[n * a.ld + k] = (float)log(sqrt(log1p(v / (m * m))));
+  }
+}
+
 }  // namespace scdef

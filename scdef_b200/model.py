@@ -297,9 +297,13 @@ class scDEF:
     # ------------------------------------------------------------------------------------------
     def init_var_params(self, init_budgets=True, init_alpha=True, init_z=None, init_w=None,
                         init_brd=None, init_ard=None, init_gene_scale=None, nmf_init=False,
-                        z_init_concentration=0.05, **kwargs):
+                        z_init_concentration=0.05, device_init=False, **kwargs):
         """Cold / warm start of every block.  The reference draws its Gamma variates with JAX
-        keys; here NumPy's Generator(seed) — distribution-level equivalence."""
+        keys; here NumPy's Generator(seed) — distribution-level equivalence.
+
+        device_init=True (opt-in): the per-cell z layers without an `init_z` — N x sum K Gamma draws, the
+        only part whose cost grows with the number of cells — are drawn on the GPU by `scdef_init_gamma_block` (Philox
+        stream; a cell's draws do not depend on the sharding) and copied into the host arrays."""
         if nmf_init:
             raise NotImplementedError("nmf_init is host-side preprocessing outside the hot path")
         rng = np.random.default_rng(None if self.seed is None else int(self.seed) + 1000 * self._shard.rank)
@@ -341,6 +345,11 @@ class scDEF:
             if l == L - 1:
                 a = 100.0
             zi = layer_init(init_z, l)
+            if zi is None and device_init:
+                mu, rho = self._device_gamma_block(N, Ks[l], a, clip, 4.0, 100.0 if l == 0 else 10.0, stream_id=l)
+                z_mu.append(mu)
+                z_rho.append(rho)
+                continue
             if zi is not None:
                 m = np.clip(zi, clip, 1e6).astype(np.float64)
                 m = np.clip(rng.gamma(z_init_concentration, m / z_init_concentration), clip, 1e6)
@@ -378,6 +387,31 @@ class scDEF:
         self._local_params = [np.ascontiguousarray(p, dtype=np.float32) for p in local]
         self._global_params = [np.ascontiguousarray(p, dtype=np.float32) for p in glob]
         self._engine_stale = True
+
+    def _device_gamma_block(self, n_rows, n_cols, shape, clip_lo, clip_hi, var_div, stream_id):
+        """(mu, rho) of an (n_rows, n_cols) block drawn by `scdef_init_gamma_block`; NumPy arrays."""
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("device_init=True needs a CUDA device (there is no CPU fallback for it; use device_init=False)")
+        lib = _lib.load()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        out = torch.empty((2, int(n_rows), int(n_cols)), dtype=torch.float32, device=dev)
+        seed = 0 if self.seed is None else int(self.seed)
+        row0 = int(_dist.shard_bounds(self.n_cells, self._shard)[0]) if self._shard.world > 1 else 0   # global index of this rank's first cell
+        with torch.cuda.device(dev):
+            rc = lib.scdef_init_gamma_block(C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()), int(n_rows), int(n_cols),
+                                            int(n_cols), float(shape), float(clip_lo), float(clip_hi), float(var_div),
+                                            seed & (2**64 - 1), int(stream_id), row0,
+                                            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"scdef_init_gamma_block failed ({rc})")
+        host = out.cpu().numpy()
+        return host[0], host[1]
 
     @property
     def local_params(self):
