@@ -1,0 +1,28 @@
+#!/usr/bin/env bash
+# Everything that was written after round 1's GPU minutes were spent, in ONE gpurun call (about 6-8 minutes of box time):
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/r02_first_call.sh'
+# Results land in gpurun_out/r02_*.log.  Nothing here can hang the device: the pair kernels and the probes bound their waits.
+set -u
+cd "$(dirname "$0")/.."
+out=gpurun_out
+mkdir -p $out
+t() { echo "=== $* ($(date +%T))" | tee -a $out/r02_summary.log; }
+
+t "1. pending GPU tests (assign_confident kernel, device init, pair mode 3)"
+timeout 300 python -m pytest tests -q -m gpu_pending -p no:cacheprovider > $out/r02_pending.log 2>&1; echo "rc=$?" | tee -a $out/r02_summary.log
+tail -n 5 $out/r02_pending.log | tee -a $out/r02_summary.log
+
+t "2. the full GPU suite with the persistent CTA-pair LOCAL kernel as the default path"
+SCDEF_TC_PAIR=2 timeout 420 python -m pytest tests -q -m gpu -p no:cacheprovider > $out/r02_suite_pair2.log 2>&1; echo "rc=$?" | tee -a $out/r02_summary.log
+tail -n 5 $out/r02_suite_pair2.log | tee -a $out/r02_summary.log
+
+t "3. per-launch time of the likelihood kernels: single CTA, pair persistent, pair persistent + whole-pair-tile epilogue"
+for mode in 0 2 3; do
+  SCDEF_TC_PAIR=$mode timeout 60 python tests/pair_timing.py 2>&1 | tail -n 1 | tee -a $out/r02_summary.log
+done
+
+t "4. semantics probes for the GLOBAL pair kernel (one question per process)"
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/mma_probe3 scripts/mma_probe3.cu 2>> $out/r02_summary.log
+for q in 1 2 3; do timeout 30 scripts/mma_probe3 $q 2>&1 | tee -a $out/r02_summary.log; done
+
+t "done"
