@@ -1,4 +1,5 @@
-"""CTA-pair LOCAL likelihood kernel (`lik_tc_pair.cuh`, opt-in with SCDEF_TC_PAIR): the bring-up cases of
+"""(Named test_zz_* so that it runs last: the driver runs the GPU suite with -x.)
+CTA-pair LOCAL likelihood kernel (`lik_tc_pair.cuh`, opt-in with SCDEF_TC_PAIR): the bring-up cases of
 tests/tc_bringup.py against the float64 oracle, in a subprocess because the switch is read once per process.
 Bar: 1e-4 on the loss and on every gradient tensor (same as tests/test_parity_gpu.py).  The persistent variant (=2) is the one tested here; these four cases ran green on a
 B200 in round 1 (profiles/r01_pair_flat_bringup.txt)."""
