@@ -36,6 +36,16 @@ namespace {
 
 enum { BLK_C = 0, BLK_S = 1, BLK_TAU = 2, BLK_OM = 3, BLK_A = 4, BLK_W = 5, BLK_Z = 5 + SCDEF_MAX_LAYERS };
 
+// k_sample implementation: 1 = the validated kernel, 2 = k_sample_v2 (opt-in: SCDEF_SAMPLE_V2=1, or the debug setter)
+int g_sample_impl = 0;
+int sample_impl() {
+  if (g_sample_impl == 0) {
+    const char* e = getenv("SCDEF_SAMPLE_V2");
+    g_sample_impl = (e && atoi(e) != 0) ? 2 : 1;
+  }
+  return g_sample_impl;
+}
+
 int fail(scdef_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) {
     va_list ap;
@@ -326,7 +336,31 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     if (gx > (size_t)ctx->sm_count * 16) gx = (size_t)ctx->sm_count * 16;
     if (gx < 1) gx = 1;
     ProfScope ps(ctx, SCDEF_PROF_SAMPLE, st);
-    k_sample<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key, loss_out, gw);
+    if (sample_impl() == 2) {
+      // one-dimensional grid sized per block; a thread owns a quad for a chunk of the samples (kernels_small.cuh)
+      SampleGrid sgrid;
+      long long quads_total = 0;
+      int nq[MAX_BLOCKS];
+      for (int i = 0; i < t.n; ++i) {
+        const long long e0 = t.b[i].noise_e0, per = (long long)t.b[i].rows * t.b[i].cols;
+        nq[i] = (int)(((e0 + per + 3) >> 2) - (e0 >> 2));
+        quads_total += nq[i];
+      }
+      const long long target = (long long)ctx->sm_count * 2048;   // resident threads of the whole GPU
+      int sch = (int)((target + quads_total - 1) / (quads_total > 0 ? quads_total : 1));
+      if (sch < 1) sch = 1;
+      if (sch > S) sch = S;
+      int cta = 0;
+      for (int i = 0; i < t.n; ++i) {
+        sgrid.cta0[i] = cta;
+        sgrid.sch[i] = sch;
+        cta += (int)(((long long)nq[i] * sch + 255) / 256);
+      }
+      sgrid.cta0[t.n] = cta;
+      if (cta > 0) k_sample_v2<<<(unsigned)cta, 256, 0, st>>>(t, sgrid, S, key, loss_out, gw);
+    } else {
+      k_sample<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key, loss_out, gw);
+    }
     if ((rc = check_launch(ctx, "k_sample"))) return rc;
   }
 
@@ -795,6 +829,7 @@ int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t*
 void scdef_debug_tc_dump(float* p) { lik_tc_set_debug(p); }
 void scdef_debug_tc_timing(unsigned long long* out) { cudaDeviceSynchronize(); lik_tc_read_timing(out); }
 void scdef_debug_pair_stuck(int* out) { lik_tc_pair_stuck(out); }
+void scdef_debug_set_sample_impl(int v) { g_sample_impl = (v == 2) ? 2 : 1; }
 /* host logic under test: n draws of the device initialiser's Gamma(shape, 1) sampler, computed on the HOST from the same code */
 void scdef_debug_gamma_host(float shape, unsigned long long seed, int stream_id, long long n, float* out_host) {
   PhiloxKey key; key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32);

@@ -60,6 +60,86 @@ __global__ void __launch_bounds__(256) k_sample(const BlockTable tab, int S, Phi
 }
 
 // -----------------------------------------------------------------------------------------
+// k_sample, second version (opt-in: SCDEF_SAMPLE_V2=1 or scdef_debug_set_sample_impl(2); same draws, same arithmetic,
+// bit-identical samples; NOT YET RUN ON A DEVICE).  k_sample launches ceil(max_elems/4/256) CTAs for EVERY block of the
+// table, so at C5 eleven of the thirteen block rows are thousands of CTAs without work, and every (sample, quad) thread
+// redoes the gather, two integer divisions and an expf(rho) per element.  Here the grid is one dimension sized per
+// block (`SampleGrid.cta0`), a thread owns one quad (4 consecutive elements) for a CHUNK of the S samples and keeps
+// (clip(mu), sigma) of its elements in registers.
+// -----------------------------------------------------------------------------------------
+struct SampleGrid {
+  int cta0[MAX_BLOCKS + 1];   // first CTA of each table block; cta0[n] = total
+  int sch[MAX_BLOCKS];        // sample chunks per quad of the block
+};
+
+__global__ void __launch_bounds__(256) k_sample_v2(const BlockTable tab, const SampleGrid sg, int S, PhiloxKey key,
+                                                   double* loss_out, float global_weight) {
+  (void)global_weight;
+  __shared__ double red[32];
+  int bi = 0;
+  while (bi + 1 < tab.n && (int)blockIdx.x >= sg.cta0[bi + 1]) ++bi;
+  const BlockDesc& b = tab.b[bi];
+  const int per = b.rows * b.cols;
+  const long long e0 = b.noise_e0;
+  const long long q0 = e0 >> 2;
+  const int nquad = (int)(((e0 + per + 3) >> 2) - q0);
+  const int sch = sg.sch[bi];
+  const long long t = (long long)((int)blockIdx.x - sg.cta0[bi]) * 256 + threadIdx.x;
+  const int chunk = (int)(t / nquad), qd = (int)(t - (long long)chunk * nquad);
+  double ent = 0.0;
+  if (chunk < sch) {
+    const int s_begin = (int)((long long)chunk * S / sch), s_end = (int)((long long)(chunk + 1) * S / sch);
+    // the thread's four elements: flat index, clipped mean, sigma (or the pinned value)
+    int idx[4];
+    float mut[4], sig[4], fixedv[4];
+    long long eps_off[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long gi = (q0 + qd) * 4 + q - e0;
+      idx[q] = -1; mut[q] = 0.f; sig[q] = 0.f; fixedv[q] = 0.f; eps_off[q] = 0;
+      if (gi < 0 || gi >= per) continue;
+      const int i = (int)gi;
+      const int r = i / b.cols, c = i - r * b.cols;
+      const long long row = b.gather ? b.gather[r] : r;
+      idx[q] = i;
+      if (b.fixed) {
+        fixedv[q] = b.fixed[row * b.cols + c];
+      } else {
+        const float mu = b.mu[row * b.ld + b.col0 + c];
+        const float rho = b.rho[row * b.ld + b.col0 + c];
+        mut[q] = fminf(fmaxf(mu, LOG_1E_10), b.mu_hi);
+        const float rhot = fminf(fmaxf(rho, LOG_1E_10), LOG_1E10);
+        sig[q] = expf(rhot);
+        eps_off[q] = (long long)r * b.eps_ld + b.eps_col0 + c;
+        if (chunk == 0) ent += (double)(mut[q] + rhot + HALF_LOG_2PI_PLUS_HALF);   // the s == 0 slice carries the entropy
+      }
+    }
+    for (int s = s_begin; s < s_end; ++s) {
+      float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!b.eps && !b.fixed) n4 = philox_normal4(key, b.tag, (uint32_t)s, (uint32_t)(q0 + qd));
+      const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (idx[q] < 0) continue;
+        float v;
+        if (b.fixed) {
+          v = fixedv[q];
+        } else {
+          const float eps = b.eps ? b.eps[(long long)s * b.rows * b.eps_ld + eps_off[q]] : nn[q];
+          v = fminf(fmaxf(expf(mut[q] + sig[q] * eps), V_LO), V_HI);
+        }
+        b.smp[(long long)s * per + idx[q]] = v;
+      }
+    }
+  }
+  double tot = block_sum_d(ent, red);
+  if (threadIdx.x == 0 && tot != 0.0 && b.active) {
+    bool is_local = b.gather != nullptr;
+    atomicAdd(&loss_out[is_local ? 0 : 1], -tot * (double)b.ent_weight);
+  }
+}
+
+// -----------------------------------------------------------------------------------------
 // Final assembly (A.1): d loss/d mu = -1[mu in clip] ( (1/S) sum_s 1[v in clip] G v + w_H ),
 //                       d loss/d rho = -1[rho in clip]( (1/S) sum_s 1[..] G v eps sigma + w_H ).
 // grid = (ceil(max_elems/256), n_blocks); only blocks of the requested pass are in `tab`.

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# Everything that was written after round 1's GPU minutes were spent, in ONE gpurun call (about 6-8 minutes of box time):
+# Everything that was written after round 1's GPU minutes were spent, in ONE gpurun call (about 10 minutes of box time):
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/r02_first_call.sh'
 # Results land in gpurun_out/r02_*.log.  Nothing here can hang the device: the pair kernels and the probes bound their waits.
 set -u
@@ -17,12 +17,26 @@ SCDEF_TC_PAIR=2 timeout 420 python -m pytest tests -q -m gpu -p no:cacheprovider
 tail -n 5 $out/r02_suite_pair2.log | tee -a $out/r02_summary.log
 
 t "3. per-launch time of the likelihood kernels: single CTA, pair persistent, pair persistent + whole-pair-tile epilogue"
-for mode in 0 2 3; do
+for mode in 0 2 3; do  # SCDEF_SAMPLE_V2=1 in front of a run times k_sample_v2 as well
   SCDEF_TC_PAIR=$mode timeout 60 python tests/pair_timing.py 2>&1 | tail -n 1 | tee -a $out/r02_summary.log
 done
 
 t "4. semantics probes for the GLOBAL pair kernel (one question per process)"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/mma_probe3 scripts/mma_probe3.cu 2>> $out/r02_summary.log
 for q in 1 2 3; do timeout 30 scripts/mma_probe3 $q 2>&1 | tee -a $out/r02_summary.log; done
+
+t "5. whole train step at C5: default build, then with the opt-in variants (pair persistent LOCAL kernel + k_sample_v2)"
+timeout 240 python bench.py --steps 50 --warmup 3 --no-e2e --no-cpu --no-dense-probe > $out/r02_bench_default.json 2>> $out/r02_summary.log
+SCDEF_TC_PAIR=2 SCDEF_SAMPLE_V2=1 timeout 240 python bench.py --steps 50 --warmup 3 --no-e2e --no-cpu --no-dense-probe > $out/r02_bench_variants.json 2>> $out/r02_summary.log
+python - <<'PY' | tee -a $out/r02_summary.log
+import json
+for name in ("default", "variants"):
+    try:
+        d = json.loads(open(f"gpurun_out/r02_bench_{name}.json").read().strip().splitlines()[-1])
+        k = d["kernels"]
+        print(name, "ms/step", round(d["ms_per_step"], 4), {n: round(v["ms_avg"] * v["launches_per_step"], 4) for n, v in k.items()})
+    except Exception as e:  # noqa: BLE001
+        print(name, "no result:", e)
+PY
 
 t "done"
