@@ -1131,6 +1131,8 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   LikTcArgs a = a_in;
   static const int dbg_nsplit = getenv("SCDEF_TC_NSPLIT") ? atoi(getenv("SCDEF_TC_NSPLIT")) : 3;  // timing experiments only
   a.dbg_nsplit = dbg_nsplit;
+  static const int l2pf = getenv("SCDEF_TC_L2PF") ? atoi(getenv("SCDEF_TC_L2PF")) : 0;   // opt-in, not measured yet
+  a.l2_prefetch = l2pf;
   if (!lik_tc_supported(a.K0, a.G, a.nb)) return SCDEF_EUNSUPPORTED;
   const bool matrix_prior = a.P || a.R;   // iscDEF: Gamma shape / rate of W_0 per (k, g)
   if (a.B <= 0) a.lik_on = 0;

@@ -174,6 +174,14 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
         TWAIT(1, &mi->w_empty[st], ((oi >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&mi->w_full[st], w_bytes);
         bulk_g2s(sbase + L.w[st], ws.wimg + ((long long)s * gm.n_tiles + tile) * L.w_unit, w_bytes, &mi->w_full[st]);
+        if (a.l2_prefetch && oi + 2 < n_outer) {
+          // opt-in (SCDEF_TC_L2PF=1, not measured yet): pull the W image this stage will receive NEXT (two outer steps
+          // ahead) into L2 now; the stage is only refilled once epilogue 2 has released it, which leaves about one unit
+          // of time for the copy (the MMA thread waits ~3k cycles per sample on w_full in the GLOBAL kernel)
+          const uint8_t* nxt = GLOBAL ? ws.wimg + ((long long)(s + 2) * gm.n_tiles + tile) * L.w_unit
+                                      : ws.wimg + ((long long)s * gm.n_tiles + tile + 2) * L.w_unit;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"(w_bytes) : "memory");
+        }
         if (GLOBAL) {
           for (int cb = 0; cb < units_per_outer; ++cb, ++u) {
             const int zs = u & 1;
