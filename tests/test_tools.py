@@ -96,3 +96,98 @@ def test_no_cpu_fallback():
         tools.assign_confident(object())
     with pytest.raises(tools.ScdefToolsError):
         tools.layer_confidence_stats(torch.zeros(2, 3), torch.zeros(2, 3), [0, 1], 4, 0.1)
+
+
+# ---- the device kernel's ALGORITHM, emulated lane by lane in float32 NumPy (scdef_b200/csrc/tools.cuh) --------------
+# Not the CUDA code itself, but the same decomposition: lane l owns the quads l, l+32, ... of 4 consecutive kept
+# factors; butterfly (xor) reductions for sums / maxima / arg-maxima with "first maximum" ties; the two order statistics
+# of the quantile by rank counting with index tie-break; linear interpolation in float32.  It must agree with the
+# line-by-line restatement of the reference, which pins the index arithmetic and the tie rules the kernel relies on.
+def _butterfly(vals, op):
+    v = list(vals)
+    o = 16
+    while o > 0:
+        v = [op(v[i], v[i ^ o]) for i in range(32)]
+        o >>= 1
+    return v[0]
+
+
+def _emulate_cell(mu, sigma, eps, q_level):
+    F = np.float32
+    S, K = eps.shape
+    Q = (K + 3) // 4
+    maxq = (Q + 31) // 32
+    own = [[4 * (lane + 32 * i) + c for i in range(maxq) for c in range(4) if 4 * (lane + 32 * i) + c < K] for lane in range(32)]
+    assert sorted(k for ks in own for k in ks) == list(range(K))          # every factor owned exactly once
+
+    def amax(a, b):   # (value, index): larger value wins, lower index on ties; empty lanes carry (-inf, huge)
+        return b if (b[0] > a[0] or (b[0] == a[0] and b[1] < a[1])) else a
+
+    def sample(s):
+        z = {k: F(np.exp(F(F(sigma[k]) * F(eps[s, k]) + F(mu[k])))) for k in range(K)}
+        part = [F(sum((z[k] for k in own[lane]), F(0))) for lane in range(32)]
+        denom = max(_butterfly(part, lambda a, b: F(a + b)), F(1e-30))
+        return {k: F(z[k] / denom) for k in range(K)}
+
+    sz = {k: F(0) for k in range(K)}
+    cnt = {k: 0 for k in range(K)}
+    for s in range(S):
+        zh = sample(s)
+        loc = []
+        for lane in range(32):
+            best = (F(-np.inf), 0x7FFFFFFF)
+            for k in own[lane]:
+                sz[k] = F(sz[k] + zh[k])
+                if zh[k] > best[0]:
+                    best = (zh[k], k)
+            loc.append(best)
+        cnt[_butterfly(loc, amax)[1]] += 1
+    invS = F(1.0) / F(S)
+    loc = []
+    for lane in range(32):
+        best = (F(-np.inf), 0x7FFFFFFF)
+        for k in own[lane]:
+            m = F(sz[k] * invS)
+            if m > best[0]:
+                best = (m, k)
+        loc.append(best)
+    winner = _butterfly(loc, amax)[1]
+    p = {k: F(F(cnt[k]) * invS) for k in range(K)}
+    H = F(-sum(float(p[k]) * np.log(min(max(float(p[k]), 1e-30), 1.0)) for k in range(K)))
+    gaps = np.zeros(S, dtype=F)
+    sum_gap, sum_wm = F(0), F(0)
+    for s in range(S):
+        zh = sample(s)
+        wm = zh[winner]
+        ru = max(zh[k] for k in range(K) if k != winner)
+        gaps[s] = F(wm - ru)
+        sum_gap, sum_wm = F(sum_gap + gaps[s]), F(sum_wm + wm)
+    mean_gap = F(sum_gap * invS)
+    var = F(np.sum((gaps - mean_gap).astype(F) ** 2, dtype=F) * invS)
+    pos = F(F(q_level) * F(S - 1))
+    lo, hi = int(np.floor(pos)), min(int(np.ceil(pos)), S - 1)
+    wh = F(pos - F(lo))
+    rank = [sum(1 for j in range(S) if gaps[j] < gaps[i] or (gaps[j] == gaps[i] and j < i)) for i in range(S)]
+    assert sorted(rank) == list(range(S))                                  # a permutation, ties included
+    vlo, vhi = gaps[rank.index(lo)], gaps[rank.index(hi)]
+    conf = F(vlo * (F(1) - wh) + vhi * wh)
+    clip = lambda x, a, b: float(min(max(float(x), a), b))                 # noqa: E731
+    return dict(effect_size=clip(mean_gap, -1, 1), posterior_sd=clip(np.sqrt(var), 0, 1), confidence=clip(conf, 0, 1),
+                winner_mass=clip(sum_wm * invS, 0, 1), winner_probability=clip(max(p.values()), 0, 1),
+                entropy_confidence=clip(1.0 - float(H) / np.log(K), 0, 1), argmax=winner)
+
+
+@pytest.mark.parametrize("N,K,S,level", [(6, 5, 33, 0.9), (3, 137, 20, 0.9), (4, 3, 64, 0.95), (5, 2, 1, 0.5), (4, 6, 40, 0.9)])
+def test_kernel_algorithm_emulated_lane_by_lane_matches_the_oracle(N, K, S, level):
+    rng = np.random.default_rng(N * 100 + K + S)
+    mu, rho = _params(N, K, seed=K)
+    eps = rng.normal(size=(S, N, K)).astype(np.float32)
+    if K == 6:                      # exact ties: duplicated factors and a duplicated draw
+        mu[:, 3], rho[:, 3], eps[:, :, 3] = mu[:, 1], rho[:, 1], eps[:, :, 1]
+        eps[7] = eps[5]
+    want = tools_ref.layer_stats(mu, rho, eps, credible_level=level)
+    for n in range(N):
+        got = _emulate_cell(mu[n], np.exp(rho[n]).astype(np.float32), eps[:, n, :], 1.0 - level)
+        assert got["argmax"] == want["argmax"][n]
+        for name in tools.STAT_NAMES:
+            assert got[name] == pytest.approx(float(want[name][n]), abs=2e-5), (name, n)
