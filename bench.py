@@ -401,7 +401,10 @@ def run_ours(args):
                                      if res.get("reshard") else ("static block ownership" if world > 1 else "single rank")),
                        "lik_impl": {0: "auto", 1: "simt", 2: "tcgen05"}[args.lik_impl], "noise": "philox, reference coupling",
                        "local_adam": "exact lazy replay (bit-identical to the dense kernel)" if lazy else "dense",
-                       "preroll_steps": preroll},
+                       "preroll_steps": preroll,
+                       # opt-in kernel variants selected through the environment (all off in the default run)
+                       "variants": {k: os.environ[k] for k in ("SCDEF_TC_PAIR", "SCDEF_SAMPLE_V2", "SCDEF_TC_L2PF", "SCDEF_TC_MONO",
+                                                                "SCDEF_HIER_OLD", "SCDEF_TC_NSPLIT") if k in os.environ}},
             "steps_per_s": 1e3 / ms_step, "clocks": res["clocks"], "gpu_launches": int(res["launches"]),
             "epoch_reshard": res.get("reshard"), "per_rank": res.get("per_rank"), "step_ms": res.get("step_ms"),
             "e2e": e2e, "roofline": roofs[0] if roofs else None, "roofline_other": roofs[1:],
