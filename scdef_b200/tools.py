@@ -131,6 +131,14 @@ def assign_confident(model, n_samples: int = 500, tau: float = 0.3, credible_lev
     layer_names = [str(model.layer_names[i]) for i in range(n_layers)]
     n_samples = int(n_samples)
 
+    # data parallelism: this rank holds a block of the cells; the draws of a cell are keyed by its global index
+    row0 = 0
+    shard = getattr(model, "_shard", None)
+    if shard is not None and getattr(shard, "world", 1) > 1:
+        from . import dist as _dist
+
+        row0 = int(_dist.shard_bounds(n_cells, shard)[0])
+
     mats = {name: np.zeros((n_cells, n_layers), dtype=float) for name in STAT_NAMES}
     argmax_mat = np.full((n_cells, n_layers), -1, dtype=int)
     label_mat = np.empty((n_cells, n_layers), dtype=object)
@@ -150,7 +158,7 @@ def assign_confident(model, n_samples: int = 500, tau: float = 0.3, credible_lev
             label_mat[:, layer_idx] = names_arr[np.zeros(n_cells, dtype=int)]
             continue
         stats, amax = layer_confidence_stats(mu_full, rho_full, start + kept, n_samples, 1.0 - float(credible_level),
-                                             seed=seed, stream_id=layer_idx)
+                                             seed=seed, stream_id=layer_idx, row0=row0)
         stats = stats.cpu().numpy().astype(float)
         amax = amax.cpu().numpy().astype(int)
         for c, name in enumerate(STAT_NAMES):
