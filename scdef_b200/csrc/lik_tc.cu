@@ -1005,7 +1005,8 @@ __global__ void __launch_bounds__(256) k_tc_w0_final(const LikTcArgs a, const fl
 int round_up16(int k) { return (k + 15) / 16 * 16; }
 
 // SCDEF_TC_PAIR=1: the LOCAL pass runs on CTA pairs (lik_tc_pair.cuh), one item per pair; =2: the persistent
-// (flattened) variant; =3: the persistent variant with the whole-pair-tile epilogue (not yet run on a device).
+// (flattened) variant; =3: the persistent variant with the whole-pair-tile epilogue, =4: 3 + the per-k-step Q hand-off
+// (3 and 4 not yet run on a device).
 // Read once per process.
 int pair_mode() {
   static const int mode = getenv("SCDEF_TC_PAIR") != nullptr ? atoi(getenv("SCDEF_TC_PAIR")) : 0;
@@ -1225,9 +1226,16 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
             kern<<<grid, PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
           };
-          const bool wide = pair_mode() == 3;
-          if (a.want_loss) { if (wide) launch(k_lik_pair_flat<true, true>); else launch(k_lik_pair_flat<true, false>); }
-          else { if (wide) launch(k_lik_pair_flat<false, true>); else launch(k_lik_pair_flat<false, false>); }
+          const int pm = pair_mode();   // 2: narrow epilogue, 3: whole-pair-tile epilogue, 4: 3 + per-k-step Q hand-off
+          if (a.want_loss) {
+            if (pm == 4) launch(k_lik_pair_flat<true, true, true>);
+            else if (pm == 3) launch(k_lik_pair_flat<true, true, false>);
+            else launch(k_lik_pair_flat<true, false, false>);
+          } else {
+            if (pm == 4) launch(k_lik_pair_flat<false, true, true>);
+            else if (pm == 3) launch(k_lik_pair_flat<false, true, false>);
+            else launch(k_lik_pair_flat<false, false, false>);
+          }
         } else if (a.want_loss) {
           cudaFuncSetAttribute(k_lik_pair_local<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
           k_lik_pair_local<true><<<dim3(2 * a.S * g.NGp, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);

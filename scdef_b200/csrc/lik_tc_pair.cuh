@@ -537,6 +537,7 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
 
 struct FlatMisc {
   uint64_t z_full, pz_full, z_empty, w_full[2], pw_full[2], w_empty[2], r_full[2], r_empty[2], q_full, q_empty, dz_full[2], dz_empty[2];
+  uint64_t q_full4[4], q_empty4[4];   // FINE: the Q hand-off per k-step of the second GEMM (= per 16-gene quarter cq)
   uint32_t tmem_base, pad;
   double red[32];
 };
@@ -553,7 +554,11 @@ struct FlatCur {   // position in the flattened space
 // WIDE (SCDEF_TC_PAIR=3, never run on a device yet): the epilogue handles a whole pair-tile (both 64-gene halves) per
 // barrier round instead of one half: per-element overhead (barrier fast paths, address arithmetic, tcgen05.ld issue,
 // r_empty arrival) halves, and the second half's tcgen05.ld is in flight while the first half's Q tile is stored.
-template <bool WANT_LL, bool WIDE>
+// FINE (SCDEF_TC_PAIR=4 = WIDE + FINE, never run on a device yet): the Q tile is handed over per k-step of the second
+// GEMM.  The four warps that own the 16-gene quarter cq arrive on q_full4[cq]; the MMA thread issues that k-step's three
+// MMAs as soon as they have, and commits q_empty4[cq].  The quarters stop moving in lockstep (each is released ~0.3k
+// cycles after the previous one) and a warp waits only for its own slice.  Modelled in tests/test_pair_protocol.py.
+template <bool WANT_LL, bool WIDE, bool FINE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
     k_lik_pair_flat(const LikTcArgs a, const Geom gm, const TcScratch ws, double* loss_out) {
   extern __shared__ __align__(1024) uint8_t sm[];
@@ -595,6 +600,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
     }
     mbar_init(&mi->q_full, 2 * E_WARPS);
     mbar_init(&mi->q_empty, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&mi->q_full4[i], 2 * E_WARPS / 4);   // the quarter's 4 warps in each CTA
+      mbar_init(&mi->q_empty4[i], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -647,7 +656,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
         const int uses = (n_outer + 1 - st) / 2;
         if (uses > 0) pair_wait(&mi->w_empty[st], (uint32_t)(uses - 1) & 1u, 15);
       }
-      if (U > 0) pair_wait(&mi->q_empty, (uint32_t)(U - 1) & 1u, 16);
+      if (U > 0) {
+        if (FINE) { for (int i = 0; i < 4; ++i) pair_wait(&mi->q_empty4[i], (uint32_t)(U - 1) & 1u, 16); }
+        else pair_wait(&mi->q_empty, (uint32_t)(U - 1) & 1u, 16);
+      }
       if (n_seg > 0) pair_wait(&mi->z_empty, (uint32_t)(n_seg - 1) & 1u, 18);
     }
     __syncwarp();
@@ -713,6 +725,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
         c1.next(n_pt);
       };
       int next1 = 0;
+      uint64_t* const q_gate = FINE ? &mi->q_full4[0] : &mi->q_full;
       for (int u = 0; u < U; ++u) {
         const int oi = u >> 1, h = u & 1, st = oi & 1;
         long long t_poll = 0;
@@ -721,8 +734,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
 #endif
         for (;;) {
           if (next1 < n_outer && next1 <= oi + 1 && (next1 == oi || ready1(next1))) { issue_mma1(next1); ++next1; continue; }
-          if (mbar_test_remote(&mi->q_full, (uint32_t)u & 1u)) break;
-          if (next1 > oi + 1 || next1 >= n_outer) { pair_wait_remote(&mi->q_full, (uint32_t)u & 1u, 9); break; }
+          if (mbar_test_remote(q_gate, (uint32_t)u & 1u)) break;
+          if (next1 > oi + 1 || next1 >= n_outer) { pair_wait_remote(q_gate, (uint32_t)u & 1u, 9); break; }
           if (t_poll == 0) t_poll = clock64();
           else if (clock64() - t_poll > PAIR_DEADLINE) pair_stuck(14, (int)blockIdx.x, u, next1);
         }
@@ -736,6 +749,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
         PT_MARK();
         const uint32_t d = tmem + FLAT_TMEM_DZ + dzb * FLAT_DZ_STRIDE;
         uint64_t da = dq_k, db = db2_k[st] + (uint64_t)(2 * h) * b2pl;
+        if (FINE) {
+#pragma unroll
+          for (int ks = 0; ks < TG / 16; ++ks) {
+            if (ks > 0) {   // the gate above was quarter 0
+              PT_WAIT(3, pair_wait_remote(&mi->q_full4[ks], (uint32_t)u & 1u, 20));
+              tc_fence_after();
+            }
+            umma2_bf16(d, da + qpl, db, idesc2, (seg_first && ks == 0) ? 0u : 1u);
+            umma2_bf16(d, da, db + b2pl, idesc2, 1u);
+            umma2_bf16(d, da, db, idesc2, 1u);
+            umma2_commit(&mi->q_empty4[ks]);
+            da += 16;
+            db += 16;
+          }
+        } else {
         umma2_bf16(d, da + qpl, db, idesc2, seg_first ? 0u : 1u);
         umma2_bf16(d, da, db + b2pl, idesc2, 1u);
         umma2_bf16(d, da, db, idesc2, 1u);
@@ -748,6 +776,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
           umma2_bf16(d, da, db, idesc2, 1u);
         }
         umma2_commit(&mi->q_empty);
+        }
         if (h == 1) umma2_commit(&mi->w_empty[st]);
         if (seg_last) umma2_commit(&mi->dz_full[dzb]);
         PT_LAP(5);
@@ -766,7 +795,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
     const int brow = valid ? ws.brow[j] : 0;
     const uint32_t r_rempty[2] = {mapa_rank(&mi->r_empty[0], 0), mapa_rank(&mi->r_empty[1], 0)};
     const uint32_t r_dzempty[2] = {mapa_rank(&mi->dz_empty[0], 0), mapa_rank(&mi->dz_empty[1], 0)};
-    const uint32_t r_qfull = mapa_rank(&mi->q_full, 0);
+    const uint32_t r_qfull = mapa_rank(FINE ? &mi->q_full4[cq] : &mi->q_full, 0);
+    uint64_t* const q_empty_bar = FINE ? &mi->q_empty4[cq] : &mi->q_empty;
     float ll = 0.f, esum = 0.f, c = 0.f;
     // one 64-gene half of a pair-tile: R (16 columns of this thread's cell row) -> Q, log-likelihood, sum of E
     auto half_math = [&](const float4 (&xv4)[4], const uint32_t (&Rr)[16], const float* srow_sm, float (&q)[16], float& es) {
@@ -873,7 +903,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
         }
         tmem_ld16_issue(taddr + (uint32_t)TG, R1);   // in flight while the first half's Q tile is stored
         PT_LAP(4);
-        PT_WAIT(1, pair_wait(&mi->q_empty, 1u, 12));  // sub-unit 2 oi: parity (u & 1) ^ 1 with u even
+        PT_WAIT(1, pair_wait(q_empty_bar, 1u, 12));  // sub-unit 2 oi: parity (u & 1) ^ 1 with u even
         PT_MARK();
         store_q(q);
         tmem_ld16_wait(R1);
@@ -887,7 +917,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
           for (int v = 0; v < 4; ++v) xb[v] = *reinterpret_cast<const float4*>(xnext + x_tile + v * 128);
         }
         PT_LAP(4);
-        PT_WAIT(1, pair_wait(&mi->q_empty, 0u, 12));  // sub-unit 2 oi + 1
+        PT_WAIT(1, pair_wait(q_empty_bar, 0u, 12));  // sub-unit 2 oi + 1
         PT_MARK();
         store_q(q);
         PT_LAP(5);
@@ -959,7 +989,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
           if (g0 + i < a.G) g_dbg_R[((long long)cc.s * a.B + j) * a.G + g0 + i] = R[i];
       }
       PT_LAP(4);
-      PT_WAIT(1, pair_wait(&mi->q_empty, ((uint32_t)u & 1u) ^ 1u, 12));
+      PT_WAIT(1, pair_wait(q_empty_bar, ((uint32_t)u & 1u) ^ 1u, 12));
       PT_MARK();
       {
         uint4 hi, lo;

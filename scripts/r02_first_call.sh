@@ -16,8 +16,8 @@ t "2. the full GPU suite with the persistent CTA-pair LOCAL kernel as the defaul
 SCDEF_TC_PAIR=2 timeout 420 python -m pytest tests -q -m gpu -p no:cacheprovider > $out/r02_suite_pair2.log 2>&1; echo "rc=$?" | tee -a $out/r02_summary.log
 tail -n 5 $out/r02_suite_pair2.log | tee -a $out/r02_summary.log
 
-t "3. per-launch time of the likelihood kernels: single CTA, pair persistent, pair persistent + whole-pair-tile epilogue"
-for mode in 0 2 3; do  # SCDEF_SAMPLE_V2=1 in front of a run times k_sample_v2 as well
+t "3. per-launch time of the likelihood kernels: single CTA, pair persistent, + whole-pair-tile epilogue, + per-k-step Q hand-off"
+for mode in 0 2 3 4; do  # SCDEF_SAMPLE_V2=1 in front of a run times k_sample_v2 as well
   SCDEF_TC_PAIR=$mode timeout 60 python tests/pair_timing.py 2>&1 | tail -n 1 | tee -a $out/r02_summary.log
 done
 

@@ -11,12 +11,14 @@ asynchronous agents, and checks: every agent finishes (no deadlock), no barrier 
 per phase, and no buffer is written while an earlier reader is still in flight or read before its writer finished.
 
 Both epilogue variants are modelled: `wide=False` (SCDEF_TC_PAIR=2, the one that ran on the B200) and `wide=True`
-(SCDEF_TC_PAIR=3, not run yet).  If the kernel's protocol changes, change it here first."""
+(SCDEF_TC_PAIR=3, not run yet), and the per-k-step Q hand-off (`fine=True`, SCDEF_TC_PAIR=4, not run yet).  If the kernel's
+protocol changes, change it here first."""
 import random
 
 import pytest
 
-E_WARPS = 3   # epilogue warps per CTA in the model (16 in the kernel: the counts below are written in terms of it)
+E_WARPS = 4   # epilogue warps per CTA in the model (16 in the kernel: the counts below are written in terms of it)
+NQ = 2        # groups of epilogue warps by the k-step of the second GEMM their Q columns feed (4 in the kernel)
 
 
 class Barrier:
@@ -73,9 +75,9 @@ class Resource:
 
 
 class Sim:
-    def __init__(self, n_outer, n_pt, pt0, wide, seed):
+    def __init__(self, n_outer, n_pt, pt0, wide, seed, fine=False):
         self.rng = random.Random(seed)
-        self.n_outer, self.n_pt, self.pt0, self.wide = n_outer, n_pt, pt0, wide
+        self.n_outer, self.n_pt, self.pt0, self.wide, self.fine = n_outer, n_pt, pt0, wide, fine
         self.async_ops = []      # [due_time, callback]
         self.now = 0
         self.bars = [dict(), dict()]
@@ -83,6 +85,9 @@ class Sim:
             b = self.bars[r]
             for name, cnt in (("z_full", 1), ("pz_full", 1), ("z_empty", 1), ("q_full", 2 * E_WARPS), ("q_empty", 1)):
                 b[name] = Barrier(f"{name}@{r}", cnt)
+            for k in range(NQ):     # fine mode: one Q hand-off per k-step group
+                b[f"q_full_k{k}"] = Barrier(f"q_full_k{k}@{r}", 2 * E_WARPS // NQ)
+                b[f"q_empty_k{k}"] = Barrier(f"q_empty_k{k}@{r}", 1)
             for i in range(2):
                 b[f"w_full{i}"] = Barrier(f"w_full{i}@{r}", 1)
                 b[f"pw_full{i}"] = Barrier(f"pw_full{i}@{r}", 1)
@@ -92,7 +97,7 @@ class Sim:
                 b[f"dz_full{i}"] = Barrier(f"dz_full{i}@{r}", 1)
                 b[f"dz_empty{i}"] = Barrier(f"dz_empty{i}@{r}", 2 * E_WARPS)
         # buffers: per CTA z, W stage 0/1, Q; per pair (modelled once) R[2] and dz[2] in tensor memory
-        self.res = {f"{n}@{r}": Resource(f"{n}@{r}") for r in range(2) for n in ("z", "w0", "w1", "q")}
+        self.res = {f"{n}@{r}": Resource(f"{n}@{r}") for r in range(2) for n in ["z", "w0", "w1", "q"] + [f"q_k{k}" for k in range(NQ)]}
         for n in ("R0", "R1", "dz0", "dz1"):
             self.res[n] = Resource(n)
         self.tensor_queue = []   # ops issued by the MMA thread, completed IN ORDER by the tensor pipe
@@ -171,7 +176,11 @@ class Sim:
             if uses > 0:
                 yield b[f"w_empty{st}"], (uses - 1) & 1
         if self.n_outer > 0:
-            yield b["q_empty"], (2 * self.n_outer - 1) & 1
+            if self.fine:
+                for k in range(NQ):
+                    yield b[f"q_empty_k{k}"], (2 * self.n_outer - 1) & 1
+            else:
+                yield b["q_empty"], (2 * self.n_outer - 1) & 1
             yield b["z_empty"], (n_seg - 1) & 1
 
     def relay_thread(self):            # peer only: forwards "my TMA landed" to the leader
@@ -218,10 +227,11 @@ class Sim:
                     yield from issue1(next1)
                     next1 += 1
                     continue
-                if b["q_full"].ready(u & 1):
+                gate = b["q_full_k0"] if self.fine else b["q_full"]
+                if gate.ready(u & 1):
                     break
                 if next1 > oi + 1 or next1 >= self.n_outer:
-                    yield b["q_full"], u & 1
+                    yield gate, u & 1
                     break
                 yield None                                  # poll again later
             s, pt, g, first, last = cur[oi]
@@ -229,8 +239,15 @@ class Sim:
             dzb = g & 1
             if seg_first:
                 yield b[f"dz_empty{dzb}"], ((g >> 1) & 1) ^ 1
-            self.mma(["q@0", "q@1", f"w{st}@0", f"w{st}@1"], f"dz{dzb}", fresh=seg_first, unread_after=2 * E_WARPS if seg_last else 0)
-            self.commit("q_empty")
+            if self.fine:     # one k-step group at a time: its Q columns in, its MMAs, its slice handed back
+                for k in range(NQ):
+                    yield b[f"q_full_k{k}"], u & 1
+                    self.mma([f"q_k{k}@0", f"q_k{k}@1", f"w{st}@0", f"w{st}@1"], f"dz{dzb}", fresh=seg_first and k == 0,
+                             unread_after=2 * E_WARPS if (seg_last and k == NQ - 1) else 0)
+                    self.commit(f"q_empty_k{k}")
+            else:
+                self.mma(["q@0", "q@1", f"w{st}@0", f"w{st}@1"], f"dz{dzb}", fresh=seg_first, unread_after=2 * E_WARPS if seg_last else 0)
+                self.commit("q_empty")
             if h == 1:
                 self.commit(f"w_empty{st}")
             if seg_last:
@@ -238,13 +255,16 @@ class Sim:
 
     def epilogue_warp(self, rank, w):
         b, lead = self.bars[rank], self.bars[0]
-        q = self.res[f"q@{rank}"]
+        kq = w % NQ
+        q = self.res[f"q_k{kq}@{rank}" if self.fine else f"q@{rank}"]
+        q_full = lead[f"q_full_k{kq}" if self.fine else "q_full"]
+        q_empty = b[f"q_empty_k{kq}" if self.fine else "q_empty"]
         cur = self.cursors()
 
         def store_q():
             q.begin_write()
             q.writers -= 1                      # generic-proxy stores complete before the fence + arrive
-            lead["q_full"].arrive()
+            q_full.arrive()
 
         def read_r(st):
             self.res[f"R{st}"].consume()
@@ -263,11 +283,11 @@ class Sim:
                 read_r(st)                       # first half
                 yield None
                 read_r(st)                       # second half's tcgen05.ld, issued before the first Q store
-                yield b["q_empty"], 1
+                yield q_empty, 1
                 store_q()
                 lead[f"r_empty{st}"].arrive()    # both halves are in registers
                 yield None
-                yield b["q_empty"], 0
+                yield q_empty, 0
                 store_q()
                 if last:
                     yield from drain(g)
@@ -282,7 +302,7 @@ class Sim:
                 read_r(st)
                 lead[f"r_empty{st}"].arrive()
                 yield None
-                yield b["q_empty"], (u & 1) ^ 1
+                yield q_empty, (u & 1) ^ 1
                 store_q()
                 if h == 1 and last:
                     yield from drain(g)
@@ -348,13 +368,13 @@ class Sim:
             return None
 
 
-@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("wide,fine", [(False, False), (True, False), (True, True), (False, True)])
 @pytest.mark.parametrize("n_outer,n_pt,pt0", [(1, 1, 0), (2, 2, 0), (3, 2, 1), (5, 2, 0), (6, 3, 2), (7, 40, 38), (9, 4, 3), (8, 1, 0)])
-def test_no_deadlock_no_overrun_no_hazard(wide, n_outer, n_pt, pt0):
+def test_no_deadlock_no_overrun_no_hazard(wide, fine, n_outer, n_pt, pt0):
     """Chunks of n_outer pair-tiles starting at pair-tile pt0 of a sample with n_pt pair-tiles (so they cross 0..7 sample
-    boundaries), 40 random schedules each."""
+    boundaries), 40 random schedules each.  fine: the Q hand-off per k-step group (SCDEF_TC_PAIR=4)."""
     for seed in range(40):
-        Sim(n_outer, n_pt, pt0, wide, seed).run()
+        Sim(n_outer, n_pt, pt0, wide, seed, fine).run()
 
 
 def _without_wait(role, prefix):

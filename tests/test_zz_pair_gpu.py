@@ -26,10 +26,12 @@ def test_persistent_pair_kernel_matches_the_oracle():
 
 
 @pytest.mark.gpu_pending
-def test_wide_epilogue_variant_matches_the_oracle():
-    """SCDEF_TC_PAIR=3 (whole-pair-tile epilogue): written after the round's GPU minutes were spent, never run."""
+@pytest.mark.parametrize("mode", ["3", "4"])
+def test_pending_epilogue_variants_match_the_oracle(mode):
+    """SCDEF_TC_PAIR=3 (whole-pair-tile epilogue) and 4 (+ per-k-step Q hand-off): written after the round's GPU minutes
+    were spent, never run; their barrier protocol is modelled in tests/test_pair_protocol.py."""
     import torch
 
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
-    _run("3")
+    _run(mode)
