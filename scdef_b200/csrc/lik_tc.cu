@@ -1226,13 +1226,15 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
             kern<<<grid, PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
           };
-          const int pm = pair_mode();   // 2: narrow epilogue, 3: whole-pair-tile epilogue, 4: 3 + per-k-step Q hand-off
+          const int pm = pair_mode();   // 2: narrow epilogue, 3: whole-pair-tile epilogue, 4: 3 + per-k-step Q hand-off, 5: 2 + that hand-off
           if (a.want_loss) {
             if (pm == 4) launch(k_lik_pair_flat<true, true, true>);
+            else if (pm == 5) launch(k_lik_pair_flat<true, false, true>);
             else if (pm == 3) launch(k_lik_pair_flat<true, true, false>);
             else launch(k_lik_pair_flat<true, false, false>);
           } else {
             if (pm == 4) launch(k_lik_pair_flat<false, true, true>);
+            else if (pm == 5) launch(k_lik_pair_flat<false, false, true>);
             else if (pm == 3) launch(k_lik_pair_flat<false, true, false>);
             else launch(k_lik_pair_flat<false, false, false>);
           }

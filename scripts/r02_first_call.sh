@@ -17,7 +17,7 @@ SCDEF_TC_PAIR=2 timeout 420 python -m pytest tests -q -m gpu -p no:cacheprovider
 tail -n 5 $out/r02_suite_pair2.log | tee -a $out/r02_summary.log
 
 t "3. per-launch time of the likelihood kernels: single CTA, pair persistent, + whole-pair-tile epilogue, + per-k-step Q hand-off"
-for mode in 0 2 3 4; do  # SCDEF_SAMPLE_V2=1 in front of a run times k_sample_v2 as well
+for mode in 0 2 3 4 5; do  # SCDEF_SAMPLE_V2=1 in front of a run times k_sample_v2 as well
   SCDEF_TC_PAIR=$mode timeout 60 python tests/pair_timing.py 2>&1 | tail -n 1 | tee -a $out/r02_summary.log
 done
 

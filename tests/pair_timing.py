@@ -31,7 +31,7 @@ for which in ("local", "global"):
         prof, _ = eng.profile_read(reset=True)
         out[which] = (prof["lik_main"][0] / max(prof["lik_main"][1], 1), ev0.elapsed_time(ev1) / 20)
     eng.profile(False)
-mode = {"1": "pair", "2": "pair-persistent", "3": "pair-persistent-wide", "4": "pair-persistent-wide-fine"}.get(os.environ.get("SCDEF_TC_PAIR", ""), "single")
+mode = {"1": "pair", "2": "pair-persistent", "3": "pair-persistent-wide", "4": "pair-persistent-wide-fine", "5": "pair-persistent-fine"}.get(os.environ.get("SCDEF_TC_PAIR", ""), "single")
 print(f"[{mode}] S={S}  main kernel ms/launch: LOCAL {out['local'][0]:.4f}  GLOBAL {out['global'][0]:.4f}   "
       f"whole pass ms: LOCAL {out['local'][1]:.4f}  GLOBAL {out['global'][1]:.4f}", flush=True)
 if len(sys.argv) > 3 and sys.argv[3] == "dump":   # needs a -DSCDEF_TC_TIMING build: where each role of the pair kernel spends its cycles

@@ -26,7 +26,7 @@ def test_persistent_pair_kernel_matches_the_oracle():
 
 
 @pytest.mark.gpu_pending
-@pytest.mark.parametrize("mode", ["3", "4"])
+@pytest.mark.parametrize("mode", ["3", "4", "5"])
 def test_pending_epilogue_variants_match_the_oracle(mode):
     """SCDEF_TC_PAIR=3 (whole-pair-tile epilogue) and 4 (+ per-k-step Q hand-off): written after the round's GPU minutes
     were spent, never run; their barrier protocol is modelled in tests/test_pair_protocol.py."""
