@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# Everything that was written after round 1's GPU minutes were spent, in ONE gpurun call (about 10 minutes of box time):
+# Everything that was written after round 1's GPU minutes were spent, in ONE gpurun call (about 13 minutes of box time):
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/r02_first_call.sh'
 # Results land in gpurun_out/r02_*.log.  Nothing here can hang the device: the pair kernels and the probes bound their waits.
 set -u
@@ -40,5 +40,11 @@ for name in ("default", "variants"):
     except Exception as e:  # noqa: BLE001
         print(name, "no result:", e)
 PY
+
+t "6. secondary settings of SURVEY 8(d): S = 10 (paper benchmarks) and S = 1, default build"
+for S in 10 1; do
+  timeout 200 python bench.py --samples $S --steps 50 --warmup 3 --no-e2e --no-cpu --no-dense-probe > $out/r02_bench_S$S.json 2>> $out/r02_summary.log
+  python -c "import json,sys; d=json.loads(open('gpurun_out/r02_bench_S$S.json').read().strip().splitlines()[-1]); print('S=$S ms/step', round(d['ms_per_step'],4), 'cells/s', round(d['value']))" 2>&1 | tee -a $out/r02_summary.log
+done
 
 t "done"
