@@ -415,7 +415,7 @@ def run_ours(args):
                        "local_adam": "exact lazy replay (bit-identical to the dense kernel)" if lazy else "dense",
                        "preroll_steps": preroll,
                        # opt-in kernel variants selected through the environment (all off in the default run)
-                       "variants": {k: os.environ[k] for k in ("SCDEF_TC_PAIR", "SCDEF_SAMPLE_V2", "SCDEF_TC_L2PF", "SCDEF_TC_MONO",
+                       "variants": {k: os.environ[k] for k in ("SCDEF_TC_PAIR", "SCDEF_SAMPLE_V2", "SCDEF_TC_L2PF", "SCDEF_TC_POLL", "SCDEF_TC_MONO",
                                                                 "SCDEF_HIER_OLD", "SCDEF_TC_NSPLIT") if k in os.environ}},
             "steps_per_s": 1e3 / ms_step, "clocks": res["clocks"], "gpu_launches": int(res["launches"]),
             "epoch_reshard": res.get("reshard"), "per_rank": res.get("per_rank"), "step_ms": res.get("step_ms"),

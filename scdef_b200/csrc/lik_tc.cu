@@ -1134,6 +1134,8 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   a.dbg_nsplit = dbg_nsplit;
   static const int l2pf = getenv("SCDEF_TC_L2PF") ? atoi(getenv("SCDEF_TC_L2PF")) : 0;   // opt-in, not measured yet
   a.l2_prefetch = l2pf;
+  static const int poll = getenv("SCDEF_TC_POLL") ? atoi(getenv("SCDEF_TC_POLL")) : 0;      // opt-in, not measured yet
+  a.mma_poll = poll;
   if (!lik_tc_supported(a.K0, a.G, a.nb)) return SCDEF_EUNSUPPORTED;
   const bool matrix_prior = a.P || a.R;   // iscDEF: Gamma shape / rate of W_0 per (k, g)
   if (a.B <= 0) a.lik_on = 0;

@@ -31,6 +31,7 @@ struct LikTcArgs {
   float P_scalar, R_scalar;
   int use_brd, B, G, K0, nb, pass, S, w0_stopped, lik_on, reuse_w0, want_loss, dbg_nsplit;
   int l2_prefetch;  // opt-in: the COPY thread prefetches upcoming W_0 tile images into L2 (SCDEF_TC_L2PF=1)
+  int mma_poll;     // opt-in: the MMA thread slips the next rate GEMM in only when its operands are ready (SCDEF_TC_POLL=1)
   float scale, global_weight, anneal;
   void* ws;
   size_t ws_bytes;

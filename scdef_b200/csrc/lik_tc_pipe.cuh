@@ -232,7 +232,21 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_lik_pipe(const LikTcArgs a, cons
       // single Q buffer is released as early as possible.
       int next1 = 0;  // next unit whose MMA1 has not been issued
       if (U > 0) { issue_mma1(0); next1 = 1; }
+      // opt-in (SCDEF_TC_POLL=1, not measured yet): slip the next rate GEMM in only when its operands have landed and its
+      // R buffer is free, and keep polling for that while waiting for Q — issue_mma1 blocks on w_full / z_full / r_empty,
+      // and in the GLOBAL kernel the MMA thread was seen waiting ~30 % of its time there while Q tiles were ready
+      auto ready1 = [&](int un) {
+        const int oi1 = un / units_per_outer, cb1 = un - oi1 * units_per_outer;
+        if (cb1 == 0 && !mbar_test(&mi->w_full[oi1 & 1], (oi1 >> 1) & 1)) return false;
+        if (GLOBAL && !mbar_test(&mi->z_full[un & 1], (un >> 1) & 1)) return false;
+        return mbar_test(&mi->r_empty[un & 1], ((un >> 1) & 1) ^ 1);
+      };
       for (int u = 0; u < U; ++u) {
+        if (a.mma_poll) {
+          while (!mbar_test(&mi->q_full, u & 1)) {
+            if (next1 == u + 1 && next1 < U && ready1(next1)) { issue_mma1(next1); ++next1; }
+          }
+        } else
         if (next1 == u + 1 && next1 < U && !mbar_test(&mi->q_full, u & 1)) { issue_mma1(next1); ++next1; }
         const int oi = u / units_per_outer, cb = u - oi * units_per_outer;
         const int st = oi & 1;

@@ -23,6 +23,10 @@ done
 
 SCDEF_TC_L2PF=1 timeout 60 python tests/pair_timing.py 2>&1 | tail -n 1 | sed 's/^/[L2 prefetch of W images] /' | tee -a $out/r02_summary.log
 
+SCDEF_TC_POLL=1 timeout 60 python tests/pair_timing.py 2>&1 | tail -n 1 | sed 's/^/[MMA thread polls operand readiness] /' | tee -a $out/r02_summary.log
+SCDEF_TC_POLL=1 SCDEF_TC_L2PF=1 timeout 60 python tests/pair_timing.py 2>&1 | tail -n 1 | sed 's/^/[poll + L2 prefetch] /' | tee -a $out/r02_summary.log
+SCDEF_TC_POLL=1 SCDEF_TC_L2PF=1 timeout 120 python tests/tc_bringup.py > $out/r02_bringup_poll.log 2>&1; grep "tc:" $out/r02_bringup_poll.log | tee -a $out/r02_summary.log
+
 t "4. semantics probes for the GLOBAL pair kernel (one question per process)"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/mma_probe3 scripts/mma_probe3.cu 2>> $out/r02_summary.log
 for q in 1 2 3; do timeout 30 scripts/mma_probe3 $q 2>&1 | tee -a $out/r02_summary.log; done
