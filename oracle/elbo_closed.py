@@ -1,6 +1,7 @@
 """Oracle #2 — closed-form ELBO value and gradients in NumPy (no autodiff).
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED (no jax in this image).
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Pinned to the reference's own source executed under
+`oracle/jaxshim.py` (`tests/test_ref_pin.py`, 1e-9); the third-party formulas are restated, see there.
 
 Same function as `oracle.elbo_ref` (reference `_scdef.py:1823-2181`, `jax_utils.py:6-46`)
 but with the backward pass derived by hand.  This is the

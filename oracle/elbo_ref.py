@@ -1,6 +1,7 @@
 """Oracle #1 — line-by-line restatement of the reference ELBO in torch (CPU autograd).
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED (no jax in this image).
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Pinned to the reference's own source executed under
+`oracle/jaxshim.py` (`tests/test_ref_pin.py`, 1e-11); the third-party formulas are restated, see there.
 
 Follows `/root/reference/src/scdef/models/_scdef.py`:
   * `elbo`            1823-2146   -> `elbo_sample`

@@ -1,9 +1,10 @@
 """Oracle — host-side pieces around the ELBO: constants, layer ladder, parameter
 initialisation, minibatch stream, Adam + clip, one `_learn` step.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED for the float parts
-(optax / tfp are absent); the integer parts (ladder, permutation) are pinned by the
-reference's own tests (`/root/reference/tests/test_sscdef.py:55-83`) and by NumPy itself.
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Constants, Adam / clip and the step order are pinned to
+the reference's own `__init__` / `_learn` executed under `oracle/jaxshim.py` (`tests/test_ref_pin.py`);
+the integer parts (ladder, permutation) also by the reference's own tests
+(`/root/reference/tests/test_sscdef.py:55-83`) and by NumPy itself.
 
 Restates `/root/reference/src/scdef/models/_scdef.py`:
   `load_adata` 482-578, `_geometric_layer_sizes` 580-628, `update_model_priors` 1246-1287,
@@ -200,7 +201,7 @@ def clip_params(params, min_mu=-1e10, max_mu=1e4, min_logstd=-1e10, max_logstd=1
 def learn_step(model, X_batch, indices, local_params, global_params, noise, local_opt: Adam,
                global_opt: Adam, annealing, stop_gradients, stop_cell_budgets, stop_gene_budgets,
                alpha, update_locals=True, update_globals=True, freeze_w=False,
-               freeze_z_slices=(), z_orig=None, dtype=np.float64):
+               freeze_z_slices=(), z_orig=None, dtype=np.float64, post_local=None):
     """One iteration of the hot loop (`_scdef.py:3230-3271`): local pass + Adam, optional
     z snap-back, global pass (same noise, updated locals) + Adam + freeze_w restore + clip."""
     from . import elbo_closed
@@ -215,6 +216,8 @@ def learn_step(model, X_batch, indices, local_params, global_params, noise, loca
         for (s, e) in freeze_z_slices:
             local_params[1] = np.array(local_params[1])
             local_params[1][:, :, s:e] = z_orig[:, :, s:e]
+        if post_local is not None:  # sscDEF: `_sscdef.py:892-893` runs between the two updates
+            local_params = post_local(local_params)
     if update_globals:
         loss, _, g_glob = elbo_closed.loss_and_grads(
             model, X_batch, indices, local_params, global_params, noise, annealing, stop_gradients,

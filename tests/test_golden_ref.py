@@ -1,0 +1,227 @@
+"""Golden vectors PRODUCED BY THE REFERENCE'S OWN SOURCE (`tests/golden/ref_elbo.npz`, `ref_learn.npz`, written by
+`tests/golden/make_golden_ref.py` through `oracle/ref_exec.py`) against (a) the restated oracle, on any machine,
+and (b) the CUDA path through the C ABI, on a B200.
+
+Tolerances: the oracle (float64) must reproduce the reference's float64 execution to 1e-9; the CUDA path
+(float32 arithmetic, tensor-core likelihood) must meet the north-star bar: |loss - ref| / |ref| <= 1e-4 and, per
+gradient tensor, max|g - g_ref| / max|g_ref| <= 1e-4.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import elbo_closed, host_ref
+from oracle.elbo_ref import OracleModel
+from tests import ref_cases
+from tests.helpers import make_engine, noise_to_spec, rel_err
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+ELBO = np.load(os.path.join(GOLDEN, "ref_elbo.npz"))
+LEARN = np.load(os.path.join(GOLDEN, "ref_learn.npz"))
+META = json.loads(str(ELBO["meta"]))
+TOL = 1e-4
+
+
+class _Case:
+    def __init__(self, store, name, info):
+        self.name, self.info = name, info
+        self._s = store
+
+    def __getitem__(self, k):
+        return self._s[f"{self.name}/{k}"]
+
+    def has(self, k):
+        return f"{self.name}/{k}" in self._s.files
+
+    def params(self, prefix, n):
+        return [np.asarray(self[f"{prefix}{i}"]) for i in range(n)]
+
+    def model(self) -> OracleModel:
+        Ks = [int(k) for k in self["layer_sizes"]]
+        sc = self["scalars"]
+        gr = self["gene_ratio"]
+        w_priors = []
+        for l in range(len(Ks)):
+            a, b = self[f"w_prior_shape{l}"], self[f"w_prior_rate{l}"]
+            w_priors.append([float(a) if a.ndim == 0 else a, float(b) if b.ndim == 0 else b])
+        om = OracleModel(
+            n_cells=int(self["X"].shape[0]), layer_sizes=Ks, batch_indices_onehot=self["batch_indices_onehot"],
+            batch_lib_ratio=self["batch_lib_ratio"], gene_ratio=float(gr) if gr.ndim == 0 else gr,
+            cell_alpha_factor=self["cell_alpha_factor"], w_priors=w_priors, use_brd=bool(sc[8]),
+            marginalize_alpha=bool(sc[9]), top_alpha=float(sc[1]), brd=float(sc[2]), brd_mean=float(sc[3]),
+            shrinkage_shape=float(sc[4]), shrinkage_rate=float(sc[5]), cell_scale_shape=float(sc[6]),
+            gene_scale_shape=float(sc[7]), alpha_floor=float(self.info.get("alpha_floor", 0.1)),
+            supervised_layer=self.info.get("supervised_layer"),
+            fixed_top_z=self["fixed_top_z"] if self.has("fixed_top_z") else None)
+        om.alpha = float(sc[0])
+        return om
+
+    def batch_ids(self):
+        return np.argmax(self["batch_indices_onehot"], axis=1).astype(np.int32)
+
+    def flags(self):
+        i = self.info
+        return (i.get("anneal", 1.0), [float(v) for v in i["sg"]], i.get("stop_cell", 0.0), i.get("stop_gene", 0.0))
+
+
+ELBO_NAMES = sorted(META["elbo"])
+LEARN_NAMES = sorted(META["learn"])
+
+
+def test_golden_files_say_where_they_come_from():
+    src = META["source"]
+    assert src["elbo"] == "/root/reference/src/scdef/models/_scdef.py:1823-2146"
+    assert src["batch_elbo"] == "/root/reference/src/scdef/models/_scdef.py:2148-2181"
+    assert src["ss_elbo"].startswith("/root/reference/src/scdef/models/_sscdef.py:256-")
+    assert len(ELBO_NAMES) >= 15 and len(LEARN_NAMES) >= 5
+
+
+@pytest.mark.parametrize("name", ELBO_NAMES)
+def test_oracle_reproduces_the_reference_vectors(name):
+    c = _Case(ELBO, name, META["elbo"][name])
+    om = c.model()
+    L = om.n_layers
+    idx = c["idx"]
+    noise = ref_cases.noise_from_arrays({k: c[k] for k in ("eps_c", "eps_s", "eps_tau", "eps_omega", "eps_a", "eps_z")}
+                                        | {f"eps_W{l}": c[f"eps_W{l}"] for l in range(L)}, L)
+    anneal, sg, sc, sgn = c.flags()
+    X = c["X"].astype(np.float64)
+    loss, gl, gg = elbo_closed.loss_and_grads(om, X[idx], idx, c.params("lp", 2), c.params("gp", 4 + L), noise,
+                                              anneal, sg, sc, sgn, om.alpha)
+    assert abs(loss - float(c["loss"])) <= 1e-9 * abs(float(c["loss"]))
+    for i in range(2):
+        assert rel_err(gl[i][:, idx], c[f"gl{i}"]) <= 1e-9
+    for i in range(4 + L):
+        assert rel_err(gg[i], c[f"gg{i}"]) <= 1e-9
+
+
+def _learn_replay_oracle(c, info):
+    om = c.model()
+    L = om.n_layers
+    N, B, S = info["N"], info["B"], info["S"]
+    kw = info.get("learn_kw", {})
+    sg = [0.0] * L
+    if "optimize_layers" in kw:
+        opt = [l for l in kw["optimize_layers"]
+               if not (info["kind"] == "sscDEF" and l == info["supervised_layer"])]  # `_sscdef.py:240-253`
+        sg = [0.0 if l in opt else 1.0 for l in range(L)]
+    lp, gp = c.params("lp", 2), c.params("gp", 4 + L)
+    lp = [p.astype(np.float64) for p in lp]
+    gp = [p.astype(np.float64) for p in gp]
+    return om, sg, kw, lp, gp
+
+
+@pytest.mark.parametrize("name", LEARN_NAMES)
+def test_oracle_hot_loop_reproduces_the_reference_learn(name):
+    info = META["learn"][name]
+    c = _Case(LEARN, name, info)
+    om, sg, kw, lp, gp = _learn_replay_oracle(c, info)
+    L = om.n_layers
+    lp0 = [p.copy() for p in lp]
+    X = c["X"].astype(np.float64)
+    lopt = host_ref.Adam(lp, kw.get("local_lr", 0.01), dtype=np.float64)
+    gopt = host_ref.Adam(gp, kw.get("lr", 0.1), dtype=np.float64)
+    stream = host_ref.data_stream_indices(info["N"], info["B"])
+    n_batches = -(-info["N"] // info["B"])
+    losses, step = [], 0
+    # `_sscdef.py:892-893`: between the two updates the loop re-reads the never-updated `self.local_params`
+    reset = (lambda _lp: [p.copy() for p in lp0]) if info["kind"] == "sscDEF" else None
+    for _ in range(info["n_epoch"]):
+        ep = []
+        for _ in range(n_batches):
+            idx = next(stream)
+            noise = ref_cases.noise_from_arrays(c._s, L, prefix=f"{name}/step{step}_")
+            loss, lp, gp = host_ref.learn_step(om, X[idx], idx, lp, gp, noise, lopt, gopt, kw.get("annealing", 1.0), sg,
+                                               0.0, 0.0, om.alpha, freeze_w=kw.get("freeze_w", False), post_local=reset)
+            ep.append(loss)
+            step += 1
+        losses.append(np.mean(ep))
+    assert step == int(c["n_steps"])
+    np.testing.assert_allclose(losses, c["epoch_losses"], rtol=1e-9)
+    for i in range(2):
+        assert rel_err(lp[i], c[f"lp_final{i}"]) <= 1e-8
+    for i in range(4 + L):
+        assert rel_err(gp[i], c[f"gp_final{i}"]) <= 1e-8
+
+
+# ---- the CUDA path -------------------------------------------------------------------------------------------
+def _engine(c, lp, gp, **kw):
+    om = c.model()
+    return om, make_engine(c["X"], c.batch_ids(), om, lp, gp, **kw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ELBO_NAMES)
+def test_cuda_elbo_and_gradients_match_the_reference_vectors(name):
+    c = _Case(ELBO, name, META["elbo"][name])
+    L = len(c["layer_sizes"])
+    lp, gp = c.params("lp", 2), c.params("gp", 4 + L)
+    om, eng = _engine(c, lp, gp)
+    idx = c["idx"]
+    noise = ref_cases.noise_from_arrays(c._s, L, prefix=f"{name}/", dtype=torch.float32)
+    anneal, sg, sc, sgn = c.flags()
+    idx_d = torch.as_tensor(idx, dtype=torch.int64, device="cuda")
+    kw = dict(num_samples=int(c.info["S"]), annealing=anneal, stop_gradients=sg, stop_cell_budgets=sc,
+              stop_gene_budgets=sgn, alpha=om.alpha)
+    want = float(c["loss"])
+    eng.elbo_grad("local", idx_d, noise_to_spec(noise), **kw)
+    assert abs(eng.loss_value() - want) <= TOL * abs(want)
+    for i, t in enumerate(eng.local_grads(len(idx))):
+        ref = c[f"gl{i}"]
+        if np.abs(ref).max() > 0:
+            assert rel_err(t.cpu().numpy(), ref) <= TOL, ("local", i)
+        else:
+            assert np.abs(t.cpu().numpy()).max() == 0.0
+    eng.elbo_grad("global", idx_d, noise_to_spec(noise), **kw)
+    assert abs(eng.loss_value() - want) <= TOL * abs(want)
+    for i, t in enumerate(eng.glob_grad.views):
+        ref = c[f"gg{i}"]
+        if np.abs(ref).max() > 0:
+            assert rel_err(t.cpu().numpy(), ref) <= TOL, ("global", i)
+        else:
+            assert np.abs(t.cpu().numpy()).max() == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", LEARN_NAMES)
+def test_cuda_hot_loop_follows_the_reference_learn(name):
+    """The reference's `_learn` (2 epochs, `optax.adam`, `clip_params`, RandomState(0) minibatches incl. a short last
+    one) replayed on the device with the draws the reference consumed: per-epoch loss within 1e-4, final parameters
+    within 2e-4 of their scale (float32 Adam against the float64 execution)."""
+    info = META["learn"][name]
+    c = _Case(LEARN, name, info)
+    om, sg, kw, lp, gp = _learn_replay_oracle(c, info)
+    L = om.n_layers
+    lp32, gp32 = c.params("lp", 2), c.params("gp", 4 + L)
+    _, eng = _engine(c, lp32, gp32)
+    stream = host_ref.data_stream_indices(info["N"], info["B"])
+    n_batches = -(-info["N"] // info["B"])
+    losses, step = [], 0
+    for _ in range(info["n_epoch"]):
+        ep = []
+        for _ in range(n_batches):
+            idx = next(stream)
+            noise = ref_cases.noise_from_arrays(c._s, L, prefix=f"{name}/step{step}_", dtype=torch.float32)
+            idx_d = torch.as_tensor(idx, dtype=torch.int64, device="cuda")
+            ekw = dict(num_samples=info["S"], annealing=kw.get("annealing", 1.0), stop_gradients=sg, alpha=om.alpha)
+            eng.elbo_grad("local", idx_d, noise_to_spec(noise), **ekw)
+            eng.adam_local(idx_d, kw.get("local_lr", 0.01))
+            if info["kind"] == "sscDEF":  # literal `_sscdef.py:892-893`
+                eng.local_sync()
+                eng.set_params(local_params=lp32)
+            eng.elbo_grad("global", idx_d, noise_to_spec(noise), **ekw)
+            eng.adam_global(kw.get("lr", 0.1), freeze_w=kw.get("freeze_w", False))
+            ep.append(eng.loss_value())
+            step += 1
+        losses.append(np.mean(ep))
+    np.testing.assert_allclose(losses, c["epoch_losses"], rtol=TOL)
+    got_lp, got_gp = eng.get_params()
+    for i in range(2):
+        ref = c[f"lp_final{i}"]
+        assert np.abs(got_lp[i] - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max()), ("local", i)
+    for i in range(4 + L):
+        ref = c[f"gp_final{i}"]
+        assert np.abs(got_gp[i] - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max()), ("global", i)
