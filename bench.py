@@ -32,9 +32,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-# (profiles/r01_ncu_full_final.txt, C5 shapes); None where no capture exists
-TRAFFIC = {"lik_main": 3.00e8, "adam_local_z": 9.708e9}  # bytes per launch (lik: mean of the LOCAL 288 MB and GLOBAL 311 MB captures)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the round's own `ncu --set full` capture of this
+# command: scripts/ncu_traffic.py parses the .ncu-rep into profiles/ncu_traffic.json (kernel family -> bytes per launch,
+# with the capture's file name and configuration).  No capture for a family / configuration -> null.
+def _traffic(config, samples):
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}
+    d = json.load(open(p))
+    if d.get("config") != config or int(d.get("num_samples", -1)) != int(samples):
+        return {}
+    return {k: float(v) for k, v in d.get("bytes_per_launch", {}).items()}
 
 METRIC = "ELBO+grad train step throughput (local pass + Adam, global pass + Adam), cells/s"
 
@@ -156,6 +164,7 @@ def run_ours(args):
     n_local = N // world + (1 if rank < N % world else 0)
     W, K, S, B = args.warmup, args.steps, args.samples, args.batch
     peaks = _peaks()
+    TRAFFIC = _traffic(args.config, S)
 
     t0 = time.time()
     X, batch = synth_counts_torch(n_local, G, n_batches=nb, lib=lib, seed=1000 + rank, device=dev)
@@ -166,10 +175,22 @@ def run_ours(args):
     lazy = not args.dense_adam
 
     def build(x, placement, lazy_adam=None):
-        return scDEF(MiniAnnData(x, obs=obs), batch_key="batch" if nb > 1 else None, layer_sizes=Ks, seed=42,
-                     logginglevel=30, device=str(dev), x_placement=placement,
-                     process_group="world" if world > 1 else None, lik_impl=args.lik_impl,
-                     lazy_adam=lazy if lazy_adam is None else lazy_adam, epoch_reshard=not args.static_ownership)
+        common = dict(seed=42, logginglevel=30, device=str(dev), x_placement=placement,
+                      process_group="world" if world > 1 else None, lik_impl=args.lik_impl,
+                      lazy_adam=lazy if lazy_adam is None else lazy_adam, epoch_reshard=not args.static_ownership)
+        if args.config == "C3":
+            # BASELINE config 3: iscDEF with synthetic marker gene lists: 20 cell types x 10 marker
+            # genes (disjoint, seeded), add_other=4, markers_layer=1 -> layers [48, 24, 1], matrix-valued W_0 / W_1 priors
+            from scdef_b200 import iscDEF
+
+            rng = np.random.default_rng(7)
+            pick = rng.permutation(G)[:200].reshape(20, 10)
+            markers = {f"type{i}": [f"g{int(j)}" for j in pick[i]] for i in range(20)}
+            m = iscDEF(MiniAnnData(x, var_names=[f"g{i}" for i in range(G)]), markers_dict=markers, add_other=4,
+                       markers_layer=1, **common)
+            assert list(m.layer_sizes) == list(Ks), (m.layer_sizes, Ks)
+            return m
+        return scDEF(MiniAnnData(x, obs=obs), batch_key="batch" if nb > 1 else None, layer_sizes=Ks, **common)
 
     steps_per_epoch = max(1, math.ceil(N / (B * world)))
     # The exact lazy Adam replays, for every minibatch row, the steps since the row was last touched.  In the first
@@ -221,7 +242,7 @@ def run_ours(args):
             if i == 0:
                 if not os.environ.get("SCDEF_BENCH_NO_SAMPLER"):
                     sampler.start()
-                eng.profile(True, ["lik_main", "adam_local_z"])
+                eng.profile(True, ["lik_main", "lik_main_global", "adam_local_z"])
             if i == W:
                 barrier()
                 eng.profile_read(reset=True)
@@ -254,7 +275,7 @@ def run_ours(args):
                          "argmax": int(per.argmax()), "mean_without_max": round(float((per.sum() - per.max()) / max(1, len(per) - 1)), 4)}
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
-            ksum = sum(v[0] / max(v[1], 1) * v[2] for k, v in st.get("prof_all", {}).items() if k != "lik_main") * K / max(P, 1)
+            ksum = sum(v[0] / max(v[1], 1) * v[2] for k, v in st.get("prof_all", {}).items() if not k.startswith("lik_main")) * K / max(P, 1)
             mine = torch.tensor([ms, ksum], dtype=torch.float64, device=dev)
             allr = [torch.zeros_like(mine) for _ in range(world)]
             td.all_gather(allr, mine)
@@ -286,7 +307,7 @@ def run_ours(args):
 
     P_all = 30
     prof = dict(res["prof_all"])
-    for k in ("lik_main",):           # the dominant kernel: measured over the timed region itself
+    for k in ("lik_main", "lik_main_global"):   # the fused kernels: measured over the timed region itself
         if res["prof"][k][1] > 0:
             ms_sum, n_timed, n_launched = res["prof"][k]
             prof[k] = (ms_sum, n_timed, n_launched * P_all / K)
@@ -296,15 +317,13 @@ def run_ours(args):
             kinds[k] = dict(ms_avg=ms_sum / n_timed, launches=n_launched, ms_per_step=ms_sum / n_timed * n_launched / P_all)
     share = {k: v["ms_per_step"] / ms_step for k, v in kinds.items()}
 
-    def roof_lik():
-        key = "lik_main" if "lik_main" in kinds else "lik"
+    def roof_lik(key, what):
         if key not in kinds:
             return None
         flops = 4.0 * S * B * K0 * G  # per launch: forward GEMM + one backward GEMM, 2 flop/MAC
         ach = flops / (kinds[key]["ms_avg"] * 1e-3) / 1e12
-        return {"kernel": "fused likelihood kernel k_lik_pipe (K2-K4; tcgen05 split-bf16, average of the LOCAL and GLOBAL variants)",
-                "bound": "tensor", "achieved": ach, "peak": peaks["bf16"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16"], "traffic": TRAFFIC.get("lik_main"), "peak_source": peaks["source"] + ", sustained bf16",
+        return {"kernel": what, "bound": "tensor", "achieved": ach, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16"], "traffic": TRAFFIC.get(key), "peak_source": peaks["source"] + ", sustained bf16",
                 "algorithmic": f"4*S*B*K0*G = {flops:.3e} flop/launch (forward + one backward GEMM; the 3x split-bf16 products are issued, not algorithmic)",
                 "issued_frac": 3.0 * ach / peaks["bf16"], "ms_avg": kinds[key]["ms_avg"],
                 "share_of_step": share.get(key), "share_of_step_with_pre_post_kernels": share.get("lik")}
@@ -340,7 +359,9 @@ def run_ours(args):
         roof_dense = roof_adam()
     # with the lazy replay and no dense probe there is no dense-Adam launch to put on the HBM roofline (the family's
     # timing is the lazy kernels', whose traffic is the minibatch rows only)
-    roofs = [r for r in (roof_lik(), roof_dense if not (lazy and args.no_dense_probe) else None) if r]
+    roofs = [r for r in (roof_lik("lik_main_global", "fused likelihood kernel, GLOBAL pass (K2-K4 + W_0 gradient fold; tcgen05 split-bf16)"),
+                         roof_lik("lik_main", "fused likelihood kernel, LOCAL pass (K2-K4; tcgen05 split-bf16 on CTA pairs)"),
+                         roof_dense if not (lazy and args.no_dense_probe) else None) if r]
     roofs.sort(key=lambda r: -(r["share_of_step"] or 0))
 
     # ---- e2e: counts in host memory, per-step H2D + loss readback -------------------------------
@@ -385,16 +406,41 @@ def run_ours(args):
                          f"{n_s}-cell slice; the reference's JAX path is not installable here", "ms_per_step": r["ms_per_step"]}
 
     # BASELINE.md §3.4 also asks for the `eval` step (one ELBO value + all gradients = the two passes without the Adam
-    # updates): the train step minus the time of the Adam kernel families, from the per-family CUDA-event timings.
+    # updates).  Measured directly on the engine of a fresh model: W warm-up + K timed repetitions of
+    # elbo_grad(LOCAL) + elbo_grad(GLOBAL, same noise) on fresh minibatches, CUDA events, max over ranks.
     eval_step = None
-    try:
-        adam_ms = sum(v["ms_per_step"] for k, v in kinds.items() if k.startswith("adam"))
-        ms_eval = ms_step - adam_ms
-        if ms_eval > 0:
+    if not args.no_eval:
+        try:
+            from scdef_b200.engine import NoiseSpec
+
+            me = build(X, "device")
+            eng = me._get_engine()
+            g = torch.Generator(device="cpu").manual_seed(5 + rank)
+            n_ev = min(K, 50)
+            idxs = [torch.randperm(n_local, generator=g)[:B].to(dev) for _ in range(n_ev + W)]
+            kw = dict(num_samples=S, annealing=1.0, stop_gradients=[0.0] * len(Ks), alpha=float(me.alpha),
+                      scale=N / (B * world), global_weight=1.0 / world, lik_impl=args.lik_impl)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i, idx in enumerate(idxs):
+                if i == W:
+                    barrier()
+                    e0.record(torch.cuda.current_stream(dev))
+                noise = NoiseSpec.philox(42, 10_000 + i, True)
+                eng.local_catchup(idx)
+                eng.elbo_grad("local", idx, noise, want_loss=False, **kw)
+                eng.elbo_grad("global", idx, noise, reuse_w0=True, **kw)
+            e1.record(torch.cuda.current_stream(dev))
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / n_ev], dtype=torch.float64, device=dev)
+            if world > 1:
+                td.all_reduce(t, op=td.ReduceOp.MAX)
+            ms_eval = float(t.item())
             eval_step = {"ms_per_step": ms_eval, "steps_per_s": 1e3 / ms_eval, "cells_per_s": cells_per_step / (ms_eval * 1e-3),
-                         "how": "train ms_per_step minus the Adam kernel families (adam_* in `kernels`)"}
-    except Exception as e:  # noqa: BLE001 - a derived, secondary figure must never cost the bench line
-        eval_step = {"error": repr(e)}
+                         "steps": n_ev, "how": "measured: elbo_grad(LOCAL) + elbo_grad(GLOBAL) per step on the engine, no Adam, no all-reduce"}
+            del me, eng
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001 - a secondary figure must never cost the bench line
+            eval_step = {"error": repr(e)}
 
     if rank == 0:
         line = {
@@ -414,13 +460,13 @@ def run_ours(args):
                        "lik_impl": {0: "auto", 1: "simt", 2: "tcgen05"}[args.lik_impl], "noise": "philox, reference coupling",
                        "local_adam": "exact lazy replay (bit-identical to the dense kernel)" if lazy else "dense",
                        "preroll_steps": preroll,
-                       # opt-in kernel variants selected through the environment (all off in the default run)
-                       "variants": {k: os.environ[k] for k in ("SCDEF_TC_PAIR", "SCDEF_SAMPLE_V2", "SCDEF_TC_L2PF", "SCDEF_TC_POLL", "SCDEF_TC_MONO",
+                       # kernel variants selected through the environment (none in the default run)
+                       "variants": {k: os.environ[k] for k in ("SCDEF_TC_PAIR", "SCDEF_SAMPLE_V2", "SCDEF_TC_MONO",
                                                                 "SCDEF_HIER_OLD", "SCDEF_TC_NSPLIT") if k in os.environ}},
             "steps_per_s": 1e3 / ms_step, "clocks": res["clocks"], "gpu_launches": int(res["launches"]),
             "epoch_reshard": res.get("reshard"), "per_rank": res.get("per_rank"), "step_ms": res.get("step_ms"),
             "e2e": e2e, "roofline": roofs[0] if roofs else None, "roofline_other": roofs[1:],
-            "kernels_note": "lik_main: CUDA events over the timed region; the other families: over the 30 steps after it",
+            "kernels_note": "lik_main / lik_main_global (the fused kernel alone, LOCAL / GLOBAL launch): CUDA events over the timed region; the other families: over the 30 steps after it",
             "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches_per_step": round(v["launches"] / P_all, 2), "share": round(share[k], 4)}
                         for k, v in kinds.items()},
             "cpu_baseline": cpu, "final_loss": res["loss"], "dense_adam_probe": dense_info, "eval_step": eval_step,
@@ -447,6 +493,7 @@ def main():
     ap.add_argument("--no-preroll", action="store_true")
     ap.add_argument("--no-dense-probe", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-eval", action="store_true", help="skip the directly measured eval step (two passes, no Adam)")
     ap.add_argument("--static-ownership", action="store_true",
                     help="data parallel: keep the cells on their home rank (ragged per-rank minibatches) instead of moving them each epoch")
     ap.add_argument("--cpu-cells", type=int, default=10000)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SCDEF_ABI_VERSION 6
+#define SCDEF_ABI_VERSION 7
 #define SCDEF_MAX_LAYERS 8
 
 #define SCDEF_OK 0
@@ -271,8 +271,9 @@ int scdef_noise_fill(scdef_ctx* ctx, const scdef_noise* noise, int block_kind, i
 #define SCDEF_PROF_ADAM_GLOBAL 6
 #define SCDEF_PROF_PRIORS 7
 #define SCDEF_PROF_ADAM_LOCAL_C 8 /* dense Adam over the cell-scale block */
-#define SCDEF_PROF_LIK_MAIN 9     /* the fused likelihood kernel alone (without its pre-/post-kernels) */
-#define SCDEF_PROF_KINDS 10
+#define SCDEF_PROF_LIK_MAIN 9     /* the fused likelihood kernel alone (without its pre-/post-kernels), LOCAL pass */
+#define SCDEF_PROF_LIK_MAIN_GLOBAL 10 /* the same, GLOBAL pass */
+#define SCDEF_PROF_KINDS 11
 /* on: 0 = off, 1 = every kind, otherwise a mask (bit k+1 = kind k) so that a timed region can carry the
    event pairs of its dominant kernel only (two records per launch are not free on a ~30-launch step). */
 int scdef_profile_enable(scdef_ctx* ctx, int on);

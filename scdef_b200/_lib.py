@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 MAX_LAYERS = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 PASS_LOCAL, PASS_GLOBAL = 1, 2
 NOISE_PHILOX, NOISE_EXPLICIT = 0, 1
@@ -112,7 +112,7 @@ EXPORTS = [
     "scdef_csr_row_stats", "scdef_csr_gather_rows", "scdef_assign_confident", "scdef_init_gamma_block",
 ]
 LAZY_CATCHUP, LAZY_UPDATE, LAZY_CATCHUP_ALL = 0, 1, 2
-PROF_KINDS = ["lik", "adam_local_z", "hier", "sample", "wprior", "finish", "adam_global", "priors", "adam_local_c", "lik_main"]
+PROF_KINDS = ["lik", "adam_local_z", "hier", "sample", "wprior", "finish", "adam_global", "priors", "adam_local_c", "lik_main", "lik_main_global"]
 
 _LIB = None
 

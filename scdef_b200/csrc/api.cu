@@ -36,12 +36,14 @@ namespace {
 
 enum { BLK_C = 0, BLK_S = 1, BLK_TAU = 2, BLK_OM = 3, BLK_A = 4, BLK_W = 5, BLK_Z = 5 + SCDEF_MAX_LAYERS };
 
-// k_sample implementation: 1 = the validated kernel, 2 = k_sample_v2 (opt-in: SCDEF_SAMPLE_V2=1, or the debug setter)
+// k_sample implementation: 2 = k_sample_v2 (default since round 2: 0.119 -> 0.057 ms per step at C5, bit-identical
+// samples, profiles/r02_first_call_summary.txt), 1 = the first kernel (SCDEF_SAMPLE_V2=0, or the debug setter; kept as
+// the cross-check of tests/test_variants_gpu.py)
 int g_sample_impl = 0;
 int sample_impl() {
   if (g_sample_impl == 0) {
     const char* e = getenv("SCDEF_SAMPLE_V2");
-    g_sample_impl = (e && atoi(e) != 0) ? 2 : 1;
+    g_sample_impl = (e && atoi(e) == 0) ? 1 : 2;
   }
   return g_sample_impl;
 }
@@ -519,11 +521,13 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       a.ws = ws + plan.tc_off; a.ws_bytes = plan.tc_bytes;
       {
         ProfScope ps(ctx, SCDEF_PROF_LIK, st);
-        const bool pm = ctx->prof_on && ctx->prof_ready && lik_run && ((ctx->prof_mask >> SCDEF_PROF_LIK_MAIN) & 1u);
-        const int slot = (int)(ctx->prof_count[SCDEF_PROF_LIK_MAIN] % PROF_RING);
-        if (pm) { a.ev0 = ctx->prof_ev[SCDEF_PROF_LIK_MAIN][slot][0]; a.ev1 = ctx->prof_ev[SCDEF_PROF_LIK_MAIN][slot][1]; }
+        // the fused kernel alone, LOCAL and GLOBAL launches timed separately
+        const int mk = pass == SCDEF_PASS_GLOBAL ? SCDEF_PROF_LIK_MAIN_GLOBAL : SCDEF_PROF_LIK_MAIN;
+        const bool pm = ctx->prof_on && ctx->prof_ready && lik_run && ((ctx->prof_mask >> mk) & 1u);
+        const int slot = (int)(ctx->prof_count[mk] % PROF_RING);
+        if (pm) { a.ev0 = ctx->prof_ev[mk][slot][0]; a.ev1 = ctx->prof_ev[mk][slot][1]; }
         rc = lik_tc_launch(a, loss_out, ctx->sm_count, st);
-        if (pm && rc == 0) ctx->prof_count[SCDEF_PROF_LIK_MAIN]++;
+        if (pm && rc == 0) ctx->prof_count[mk]++;
       }
       ctx->launches += 4;
       if (rc) return fail(ctx, rc, "lik_tc_launch failed (%d)", rc);
@@ -540,7 +544,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       dim3 grid((G + LT - 1) / LT, (B + LT - 1) / LT, S);
       {
         ProfScope ps(ctx, SCDEF_PROF_LIK, st);
-        ProfScope pm(ctx, SCDEF_PROF_LIK_MAIN, st);
+        ProfScope pm(ctx, pass == SCDEF_PASS_GLOBAL ? SCDEF_PROF_LIK_MAIN_GLOBAL : SCDEF_PROF_LIK_MAIN, st);
         k_lik_simt<<<grid, 256, smem, st>>>(a, S, loss_out);
       }
       if ((rc = check_launch(ctx, "k_lik_simt"))) return rc;

@@ -1004,12 +1004,12 @@ __global__ void __launch_bounds__(256) k_tc_w0_final(const LikTcArgs a, const fl
 
 int round_up16(int k) { return (k + 15) / 16 * 16; }
 
-// SCDEF_TC_PAIR=1: the LOCAL pass runs on CTA pairs (lik_tc_pair.cuh), one item per pair; =2: the persistent
-// (flattened) variant; =3: the persistent variant with the whole-pair-tile epilogue, =4: 3 + the per-k-step Q hand-off
-// (3 and 4 not yet run on a device).
-// Read once per process.
+// LOCAL pass on CTA pairs (lik_tc_pair.cuh).  Default 3: the persistent (flattened) variant with the whole-pair-tile
+// epilogue (0.262 ms per launch at C5 against 0.365 for the single-CTA pipeline; full GPU suite green with it,
+// profiles/r02_first_call_summary.txt).  SCDEF_TC_PAIR=0 selects the single-CTA pipeline (A/B checks), 2 the narrow
+// epilogue.  Read once per process.
 int pair_mode() {
-  static const int mode = getenv("SCDEF_TC_PAIR") != nullptr ? atoi(getenv("SCDEF_TC_PAIR")) : 0;
+  static const int mode = getenv("SCDEF_TC_PAIR") != nullptr ? atoi(getenv("SCDEF_TC_PAIR")) : 3;
   return mode;
 }
 

@@ -35,6 +35,32 @@ def _moment_match(m, v):
             np.log(np.sqrt(np.log1p(v / m**2))).astype(np.float32))
 
 
+def geometric_ladder(n_factors: int, top_factors: int, n_layers: int, root: bool = True) -> List[int]:
+    """Layer widths from `n_factors` down to `top_factors` in `n_layers` geometric steps, strictly decreasing where
+    rounding allows, plus a width-1 root when `root` and `top_factors > 1`.
+    MIRRORED ON PURPOSE: the integers must equal `scDEF._geometric_layer_sizes` (`_scdef.py:580-628`; without the root
+    `sscDEF._geometric_layer_sizes_no_root`, `_sscdef.py:44-77`) for every input — pinned by the reference's own values
+    (`/root/reference/tests/test_sscdef.py:55-83`) in tests/test_host.py."""
+    n_layers = max(2, int(n_layers))
+    k_lo, k_hi = float(n_factors), int(top_factors)
+    if n_layers == 2:
+        widths = [max(1, int(round(k_lo)), k_hi), k_hi]
+    else:
+        step = k_hi / max(k_lo, 1.0)
+        widths: List[int] = []
+        for l in range(n_layers - 1):
+            k = max(1, int(round(k_lo * step ** (l / float(n_layers - 1)))))
+            if widths and k >= widths[-1]:
+                k = max(1, widths[-1] - 1)
+            widths.append(k)
+        widths.append(k_hi)
+        for i in range(n_layers - 2, -1, -1):   # never narrower than the layer above
+            widths[i] = max(widths[i], widths[i + 1])
+    if root and k_hi > 1:
+        widths.append(1)
+    return widths
+
+
 class scDEF:
     """Single-cell Deep Exponential Families — B200-native training path."""
 
@@ -225,31 +251,7 @@ class scDEF:
     # model size / priors — `_scdef.py:580-628, 1175-1287`
     # ------------------------------------------------------------------------------------------
     def _geometric_layer_sizes(self, n_layers: int) -> List[int]:
-        n_layers = max(2, int(n_layers))
-        min_k, top_k = float(self.n_factors), float(self.top_factors)
-        ratio = top_k / max(min_k, 1.0)
-        add_root = int(self.top_factors) > 1
-        if n_layers == 2:
-            out = [max(1, int(round(min_k))), int(self.top_factors)]
-            out[0] = max(out[0], out[1])
-        else:
-            out: List[int] = []
-            prev = None
-            for l in range(n_layers):
-                if l == n_layers - 1:
-                    k_i = int(self.top_factors)
-                else:
-                    k_i = max(1, int(round(min_k * ratio ** (l / float(n_layers - 1)))))
-                    if prev is not None and k_i >= prev:
-                        k_i = max(1, prev - 1)
-                out.append(k_i)
-                prev = k_i
-            out[-1] = int(self.top_factors)
-            for i in range(len(out) - 2, -1, -1):
-                out[i] = max(out[i], out[i + 1])
-        if add_root:
-            out.append(1)
-        return out
+        return geometric_ladder(self.n_factors, self.top_factors, n_layers, root=True)
 
     def update_model_size(self, max_n_factors=None, n_layers=None, layer_sizes=None,
                           use_decay_factor_schedule: bool = False):
@@ -509,8 +511,32 @@ class scDEF:
         return self._engine
 
     def _engine_signature(self):
-        return (tuple(self.layer_sizes), bool(self.marginalize_alpha), bool(self.use_brd), float(self.top_alpha),
-                self.x_placement, self.supervised_layer, float(self.alpha_floor))
+        """Everything the engine copies into its device-side model description ONCE: a change of any of it after the
+        first `_get_engine()` (`set_geneset_prior`, `set_connectivity_prior`, `update_model_priors`, `model.brd = ...`)
+        must rebuild the engine, or training would silently keep the old priors."""
+        import hashlib
+
+        h = hashlib.blake2b(digest_size=16)
+
+        def feed(v):
+            if v is None:
+                h.update(b"none")
+            elif hasattr(v, "is_cuda"):   # torch tensor (possibly on the device): identity + shape is enough
+                h.update(repr((int(v.data_ptr()), tuple(v.shape), str(v.dtype))).encode())
+            else:
+                a = np.ascontiguousarray(np.asarray(v, dtype=np.float64))
+                h.update(repr(a.shape).encode())
+                h.update(a.tobytes())
+
+        for shape, rate in self.w_priors:
+            feed(shape)
+            feed(rate)
+        for v in (self.cell_alpha_factor, self.gene_ratio, self.batch_lib_ratio, getattr(self, "_fixed_top_z", None),
+                  [self.brd, self.brd_mean, self.shrinkage_shape, self.shrinkage_rate, self.cell_scale_shape,
+                   self.gene_scale_shape, self.top_alpha, self.alpha_floor]):
+            feed(v)
+        return (tuple(self.layer_sizes), bool(self.marginalize_alpha), bool(self.use_brd), self.x_placement,
+                self.supervised_layer, h.hexdigest())
 
     def _pull_params(self):
         lp, gp = self._engine.get_params()
@@ -745,7 +771,17 @@ class scDEF:
         stop_message, interrupted = None, False
         trace, trace_epochs = [], []
         gene_budgets_frozen = bool(stop_gene_budgets >= 1.0)
-        loss_dev = torch.zeros(num_batches, dtype=torch.float64, device=eng.device)
+        loss_dev = torch.zeros(num_batches + 1, dtype=torch.float64, device=eng.device)   # last element: stop flag
+        # data parallel: a Ctrl-C on one rank must not leave that rank alone in (or out of) the collectives.  SIGINT
+        # only sets a flag; the flag rides with the per-epoch loss all-reduce, and every rank leaves at the same epoch.
+        import signal
+        import threading
+
+        sigint = {"hit": False, "old": None}
+        if shard.world > 1 and threading.current_thread() is threading.main_thread():
+            def _on_sigint(signum, frame):
+                sigint["hit"] = True
+            sigint["old"] = signal.signal(signal.SIGINT, _on_sigint)
         steps_done = 0
         limit = self.max_steps_per_learn
 
@@ -765,6 +801,8 @@ class scDEF:
                     step_counter += 1
                     noise = NoiseSpec.philox(self.seed or 0, step_counter, self.noise_coupling, *stream.noise_window(it))
                     idx, Xb, n_glob = stream.batch(it)
+                    if Xb is None and eng.X_csr is not None and int(idx.numel()) > 0:
+                        Xb = eng.gather_rows(idx)   # CSR placement: densify the minibatch ONCE for both passes
                     kw = dict(num_samples=int(num_samples), annealing=annealing_parameter,
                               stop_gradients=stop_gradients, stop_cell_budgets=stop_cell_budgets,
                               stop_gene_budgets=stop_gene_budgets, alpha=alpha_f, scale=n_total / n_glob,
@@ -788,8 +826,11 @@ class scDEF:
                     if limit is not None and steps_done >= int(limit):
                         break
                 if shard.world > 1:
+                    loss_dev[num_batches] = 1.0 if sigint["hit"] else 0.0
                     _dist.all_reduce_sum(loss_dev, shard)
                 current_loss = float(loss_dev[:n_it].mean().item())  # one host sync per epoch (3273)
+                if shard.world > 1 and float(loss_dev[num_batches].item()) > 0.0:
+                    raise KeyboardInterrupt   # agreed on by all ranks: everybody takes the "exit safely" path
                 all_losses.append(current_loss)
                 total_epochs += 1
                 trace.append(float(annealing_parameter))
@@ -838,11 +879,19 @@ class scDEF:
             interrupted = True
             self.logger.info("Interrupted. Exiting safely...")
         finally:
+            if sigint["old"] is not None:
+                signal.signal(signal.SIGINT, sigint["old"])
             if pbar is not None:
                 pbar.close()
-            if self._step_hook is not None:
+            import sys as _sys
+
+            failing = _sys.exc_info()[0] is not None   # a rank-local error is propagating (KeyboardInterrupt is caught above)
+            if self._step_hook is not None and not failing:
                 self._step_hook(steps_done, eng, stream)
-            stream.finish()  # position-based ownership: the rows go back to block order before anything reads them
+            # position-based ownership: the rows go back to block order before anything reads them.  Not on a
+            # rank-local error: the way home is a collective the other ranks will never enter — fail fast instead
+            # (torchrun tears the job down) and leave the rows where they are.
+            stream.finish(collective=not (failing and shard.world > 1))
 
         if stop_message is None and not interrupted:
             stop_message = f"Stopping learning: reached max epochs (n_epoch={int(n_epoch)})."

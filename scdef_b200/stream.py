@@ -102,6 +102,10 @@ class MinibatchStream:
             m = (perm >= self.start) & (perm < self.start + self.n_local)
             local = perm[m] - self.start
             offs = np.concatenate([[0], np.cumsum(np.add.reduceat(m.astype(np.int64), bounds[:-1]))])
+            # static ownership: the members of a slice that fall into the lower ranks' blocks come first in the
+            # noise numbering, so every rank draws its per-cell normals from a DISJOINT window of the slice's stream
+            # (with (0, 0) all ranks would read rows [0, B) of the same stream: correlated noise across ranks)
+            self.row0 = np.add.reduceat((perm < self.start).astype(np.int64), bounds[:-1])
         self.perm_host = np.ascontiguousarray(local, dtype=np.int64)
         self.offs = offs
         self.perm_dev = torch.from_numpy(self.perm_host).to(self.device, non_blocking=False)
@@ -132,14 +136,17 @@ class MinibatchStream:
         self._staged = {}
 
     def noise_window(self, it: int):
-        """(row offset, total rows) of this rank's rows inside global minibatch `it` for the per-cell Philox
-        draws; (0, 0) under static ownership, where a rank's members are not a contiguous range of the slice."""
+        """(row offset, total rows) of this rank's rows inside global minibatch `it` for the per-cell Philox draws.
+        Position-based ownership: the rank's rows ARE the range [offset, offset + B) of the slice, so an R-rank run
+        draws the single-rank run's normals.  Static ownership: a disjoint window per rank (members of lower ranks
+        first) — independent across ranks, though not the single-rank numbering."""
         if self.row0 is None or self.shard.world == 1:
             return 0, 0
         return int(self.row0[it]), int(self.n_glob[it])
 
-    def finish(self):
-        """Return every per-cell row to its home rank and row (block order) after the last epoch."""
+    def finish(self, collective: bool = True):
+        """Return every per-cell row to its home rank and row (block order) after the last epoch.
+        collective=False: only stop the helper threads (a rank that is failing must not enter the all-to-all)."""
         ahead = getattr(self, "_ahead", None)
         if ahead is not None:
             ahead[0].join()
@@ -149,7 +156,7 @@ class MinibatchStream:
                 f.cancel()
             self._pool.shutdown(wait=True)
             self._pool, self._staged = None, {}
-        if self.migrator is not None and not self.migrator.at_home:
+        if collective and self.migrator is not None and not self.migrator.at_home:
             self.migrator.go_home(self.tensors_fn())
 
     def reshard_ms(self):

@@ -12,9 +12,8 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line(
         "markers",
-        "gpu_pending: GPU test of code written after the round's GPU minutes were spent; it has never run on a device. "
-        "Not selected by `-m gpu`; skipped without CUDA. Promote to `gpu` after its first green run "
-        "(`python -m pytest tests -m gpu_pending`).")
+        "gpu_pending: GPU test of code that has not had its first run on a device yet (none at the moment: the 16 of "
+        "round 1 ran green in round 2's first GPU call and are ordinary `gpu` tests now). Not selected by `-m gpu`.")
 
 
 def pytest_sessionstart(session):

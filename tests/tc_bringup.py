@@ -67,7 +67,7 @@ def run(N, G, Ks, nb, B, S, sg=None, dump=True, **kw):
 def pair_cases():
     """CTA-pair LOCAL kernel (SCDEF_TC_PAIR=1; engaged only for B % 256 == 0).  On a trapped launch the record of the
     wait that timed out is printed: (code, blockIdx.x, warp or sub-unit, parity) -- codes in lik_tc_pair.cuh."""
-    assert os.environ.get("SCDEF_TC_PAIR") in ("1", "2", "3", "4", "5"), "run with SCDEF_TC_PAIR=1 (one item per pair), 2 (persistent), 3 (+ whole-pair-tile epilogue) or 4 (+ per-k-step Q hand-off)"
+    # SCDEF_TC_PAIR: unset / 3 = the default persistent pair kernel, 2 = narrow epilogue, 0 = the single-CTA pipeline
     worst = 0.0
     try:
         print("pair 1: one pair-tile, KP=16", flush=True); worst = max(worst, run(300, 128, (16, 4), 1, 256, 1)["tc_max_err"])

@@ -57,7 +57,7 @@ def test_device_init_fails_loudly_without_cuda():
         m.init_var_params(device_init=True)
 
 
-@pytest.mark.gpu_pending
+@pytest.mark.gpu
 @pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")
 def test_kernel_writes_the_moment_matched_draws():
     lib = _lib.load()
@@ -76,7 +76,7 @@ def test_kernel_writes_the_moment_matched_draws():
     assert close.mean() > 0.999
 
 
-@pytest.mark.gpu_pending
+@pytest.mark.gpu
 @pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")
 def test_device_init_of_the_model_trains():
     from scdef_b200.synth import synth_counts_numpy

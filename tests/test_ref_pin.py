@@ -297,3 +297,26 @@ def test_restated_iscdef_priors_and_elbo_equal_the_reference_execution(ref, mark
     assert abs(float(l1) - loss_l) <= TOL * abs(loss_l)
     for a, b in zip(gg1, g_glob):
         assert rel_err(a.numpy(), b) <= TOL
+
+
+@needs_reference
+def test_layer_ladder_equals_the_reference_method(ref):
+    """`scDEF._geometric_layer_sizes` (`_scdef.py:580-628`) and `sscDEF._geometric_layer_sizes_no_root`
+    (`_sscdef.py:44-77`) executed from the reference vs the oracle's and the product's ladder, over a grid."""
+    import itertools
+    import types
+
+    from scdef_b200.model import geometric_ladder
+
+    n = 0
+    for nf, tf, nl in itertools.product([1, 2, 5, 8, 20, 33, 64, 100, 128], [1, 2, 3, 5, 10, 24], [1, 2, 3, 4, 5, 6, 8]):
+        if tf > nf:
+            continue
+        me = types.SimpleNamespace(n_factors=nf, top_factors=tf)
+        want = [int(k) for k in ref.scDEF._geometric_layer_sizes(me, nl)]
+        assert host_ref.geometric_layer_sizes(nf, tf, nl) == want, (nf, tf, nl)
+        assert geometric_ladder(nf, tf, nl, root=True) == want, (nf, tf, nl)
+        want_nr = [int(k) for k in ref.sscDEF._geometric_layer_sizes_no_root(nf, tf, nl)]
+        assert geometric_ladder(nf, tf, nl, root=False) == want_nr, (nf, tf, nl)
+        n += 1
+    assert n > 200

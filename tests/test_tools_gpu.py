@@ -1,6 +1,6 @@
 """`scdef_assign_confident` on the device vs the NumPy restatement of the reference (`oracle/tools_ref.py`), same
 injected draws.  Tolerances: statistics 2e-5 absolute (they live in [0, 1]; float32 sums in a different order),
-winner slots equal.  PENDING: written after the round's GPU minutes were spent — see the `gpu_pending` marker."""
+winner slots equal."""
 import numpy as np
 import pytest
 import torch
@@ -8,7 +8,7 @@ import torch
 from oracle import tools_ref
 from scdef_b200 import MiniAnnData, scDEF, tools
 
-pytestmark = [pytest.mark.gpu_pending, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
 ATOL = 2e-5
 
 

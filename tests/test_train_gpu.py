@@ -314,15 +314,20 @@ def test_lazy_adam_is_bit_identical_to_dense(freeze_z):
     assert int(lazy.row_step.max().item()) == 0
 
 
-def test_sscdef_fit_keeps_the_top_layer_pinned():
-    """/root/reference/tests/test_sscdef.py:36-49: after fit, the top layer's posterior mean is the label one-hot."""
+@pytest.mark.parametrize("local_updates", ["reference", "keep"])
+def test_sscdef_fit_keeps_the_top_layer_pinned(local_updates):
+    """/root/reference/tests/test_sscdef.py:36-49: after fit, the top layer's posterior mean is the label one-hot.
+    Default = the reference's literal loop (`_sscdef.py:892-893`: every local update is discarded, shown on the
+    reference itself by tests/test_ref_pin.py); `local_updates="keep"` trains the per-cell blocks below the pinned layer."""
     from scdef_b200 import MiniAnnData, sscDEF
     from scdef_b200.synth import synth_counts_numpy
 
     X, _ = synth_counts_numpy(80, 120, seed=0)
     types = np.random.RandomState(0).choice(["A", "B"], size=80)
-    m = sscDEF(MiniAnnData(X, obs={"cell_type": types}), top_key="cell_type", n_layers=2, n_factors=4, seed=1, logginglevel=30)
+    m = sscDEF(MiniAnnData(X, obs={"cell_type": types}), top_key="cell_type", n_layers=2, n_factors=4, seed=1,
+               logginglevel=30, local_updates=local_updates)
     before = [p.copy() for p in m.local_params]
+    gbefore = [p.copy() for p in m.global_params]
     m.fit(n_epoch=2, n_rounds=1, num_samples=5)
     top = m._supervised_top_z
     np.testing.assert_allclose(m.pmeans["cell_typez"], top, rtol=1e-5, atol=1e-5)
@@ -330,7 +335,9 @@ def test_sscdef_fit_keeps_the_top_layer_pinned():
     zs, zr = m.local_params[1]
     np.testing.assert_allclose(np.exp(zs[:, start:end] + 0.5 * np.exp(zr[:, start:end]) ** 2), top, rtol=1e-3, atol=1e-3)
     assert len(m.elbos) == 2 and all(np.all(np.isfinite(e)) for e in m.elbos)   # main fit + root phase (root_epochs=10)
-    assert np.any(m.local_params[1][0][:, :start] != before[1][0][:, :start])   # the other layers did learn
+    assert np.any(m.global_params[2] != gbefore[2])                             # the globals always learn
+    moved = np.any(m.local_params[1][0][:, :start] != before[1][0][:, :start])
+    assert moved == (local_updates == "keep")
 
 
 # ---- data parallel with position-based ownership: two ranks == one rank with twice the batch ---------------------
@@ -480,3 +487,28 @@ def test_iscdef_fit_runs_with_matrix_priors():
                   add_other=1, n_layers=2, seed=1, logginglevel=30)
     flat.fit(n_epoch=2, num_samples=5)
     assert len(flat.elbos) == 1 and np.all(np.isfinite(flat.elbos[0]))
+
+
+def test_prior_changes_after_the_first_learn_reach_the_device():
+    """The engine copies the W priors and prior hyper-parameters into its device-side description once; editing them
+    afterwards (`update_model_priors`, `set_geneset_prior`, `model.brd = ...`) must rebuild it.  Same parameters, same
+    noise step: the loss must move when a prior moves, and come back when it is restored."""
+    from scdef_b200 import MiniAnnData, scDEF
+    from scdef_b200.synth import synth_counts_numpy
+
+    X, _ = synth_counts_numpy(120, 80, seed=0)
+    m = scDEF(MiniAnnData(X), layer_sizes=[8, 4, 2], seed=1, logginglevel=30)
+    m._learn(n_epoch=1, num_samples=3, filter=False, annotate=False)
+    idx = np.arange(64)
+    args = (X[idx], idx, m.local_params, m.global_params, 7, 1.0, [0, 0, 0], 0.0, 0.0, m.alpha)
+    base, _ = m.global_loss_grad(*args, num_samples=3)
+    m.brd = 3.0                                     # a scalar hyper-parameter
+    moved, _ = m.global_loss_grad(*args, num_samples=3)
+    assert abs(moved - base) > 1e-6 * abs(base)
+    m.brd = 1.0
+    back, _ = m.global_loss_grad(*args, num_samples=3)
+    assert back == pytest.approx(base, rel=1e-6)
+    m.factor_shape = 0.5                            # W priors rebuilt by update_model_priors (`_scdef.py:1246-1287`)
+    m.update_model_priors()
+    moved2, _ = m.global_loss_grad(*args, num_samples=3)
+    assert abs(moved2 - base) > 1e-6 * abs(base)

@@ -1,5 +1,4 @@
-"""Opt-in kernel variants written after round 1's GPU minutes were spent (never run on a device yet): they must
-reproduce the validated kernels.  `k_sample_v2` draws the same Philox normals and does the same arithmetic as
+"""Kernel variants must reproduce each other.  `k_sample_v2` draws the same Philox normals and does the same arithmetic as
 `k_sample`, so every sample — and with it the loss and every gradient — must agree to the last bits (1e-6 leaves room
 for the float atomics of the kernels downstream)."""
 import ctypes
@@ -13,7 +12,7 @@ from scdef_b200 import _lib
 from scdef_b200.engine import NoiseSpec
 from tests.helpers import make_engine, noise_to_spec, rel_err, small_problem
 
-pytestmark = [pytest.mark.gpu_pending, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
 
 
 def _set_sample_impl(v):

@@ -1,8 +1,7 @@
 """(Named test_zz_* so that it runs last: the driver runs the GPU suite with -x.)
-CTA-pair LOCAL likelihood kernel (`lik_tc_pair.cuh`, opt-in with SCDEF_TC_PAIR): the bring-up cases of
+CTA-pair LOCAL likelihood kernel (`lik_tc_pair.cuh`, the default LOCAL path; SCDEF_TC_PAIR selects a variant): the bring-up cases of
 tests/tc_bringup.py against the float64 oracle, in a subprocess because the switch is read once per process.
-Bar: 1e-4 on the loss and on every gradient tensor (same as tests/test_parity_gpu.py).  The persistent variant (=2) is the one tested here; these four cases ran green on a
-B200 in round 1 (profiles/r01_pair_flat_bringup.txt)."""
+Bar: 1e-4 on the loss and on every gradient tensor (same as tests/test_parity_gpu.py)."""
 import os
 import subprocess
 import sys
@@ -21,17 +20,8 @@ def _run(mode):
 
 
 @pytest.mark.gpu
-def test_persistent_pair_kernel_matches_the_oracle():
-    _run("2")
-
-
-@pytest.mark.gpu_pending
-@pytest.mark.parametrize("mode", ["3", "4", "5"])
-def test_pending_epilogue_variants_match_the_oracle(mode):
-    """SCDEF_TC_PAIR=3 (whole-pair-tile epilogue) and 4 (+ per-k-step Q hand-off): written after the round's GPU minutes
-    were spent, never run; their barrier protocol is modelled in tests/test_pair_protocol.py."""
-    import torch
-
-    if not torch.cuda.is_available():
-        pytest.skip("needs a CUDA device")
+@pytest.mark.parametrize("mode", ["3", "2", "0"])
+def test_likelihood_kernel_variants_match_the_oracle(mode):
+    """3 = the default (persistent CTA pairs, whole-pair-tile epilogue), 2 = its narrow-epilogue sibling, 0 = the
+    single-CTA pipeline that odd batch sizes still take.  All green on a B200 (profiles/r02_first_call_summary.txt)."""
     _run(mode)
