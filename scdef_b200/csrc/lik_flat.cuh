@@ -1,0 +1,762 @@
+// The fused Poisson-likelihood kernel of BOTH passes: one persistent CTA-pair kernel, two orientations
+// (included by lik_tc.cu inside its anonymous namespace, after lik_tc_pair.cuh whose PTX wrappers it uses).
+//
+// Algebra that takes the rank-1 terms out of the tile loop (reference `_scdef.py:2096-2136`):
+//   Lambda = c s R,   Q = (x - Lambda) / R = x / R - c s^T            with  R = z0 W
+//   dz0 = Q W^T   = (X/R) W^T - c (W s_b)^T            (X/R) is zero wherever x = 0, i.e. for ~90 % of the entries
+//   dW  = z0^T Q  = z0^T (X/R) - sum_b ctilde_b s_b^T        ctilde_b = sum_{n in b} c_n z_n
+//   dc_n = (rowsum_g x_ng - c_n z_n . (W s_b)) / c_n
+//   ll  = sum_{x>0} x log R + sum_n rowsumX_n log c_n + sum_{b,g} colsumX_b[g] log s_bg - sum_n c_n z_n . (W s_b) - lgamma terms
+// so the tile loop needs ONLY x and R:  q = x > 0 ? x / R : 0  (one MUFU.RCP, one multiply, one select per element) and,
+// when the loss is wanted, x log R.  The cell scale, the gene-scale tile, Lambda and E are gone from the epilogue; the rank-1
+// corrections are a K0-dot per (sample, cell) (`k_tc_rank1`) and nb FMAs per element of the W_0 fold.
+//
+// One kernel template, two orientations of the same tile pipeline ("rows" = the M dimension of the pair MMAs):
+//   LOCAL  (GENES = false): rows = cells.  ROW unit A1 = z0^s of 128 cells (K-major), static per segment (rb = cell block, s);
+//          COL stream = W_0^s tile images, pair-tile = 128 genes.  D2 = dz0[rows, k0] accumulated over the segment,
+//          drained to the partial buffer (`k_tc_rank1` sums the slots and adds the rank-1 term).
+//   GLOBAL (GENES = true):  rows = genes.  ROW unit A1 = W_0^s of 128 genes (MN-major, assembled from two 64-gene tile
+//          images with 1 KB bulk copies), static per segment (rb = gene block, s); COL stream = z0^s, pair-tile = 128 cells
+//          (image `zimg_g`: one 56 KB bulk copy per stage).  D2 = dW^T[rows, k0] accumulated over the segment's cells, then
+//          FOLDED per sample:  t = W (scale dW' - sum_b ctS_b[k] s_b[g] - gw B_k) + gw (A_k - 1),  d mu += t,
+//          sum t log W += t log W  (thread = gene row; d mu lives in tensor memory, the other sum in registers), flushed to
+//          the partial buffer when the gene block changes.
+// Rate GEMM   D1[256 rows, 128 cols] = A1 B1      (cta_group::2, M = 256, N = 128 split over the pair, K = KP, 3 split-bf16 products)
+// second GEMM D2[256 rows, KP]      += Q_h B2_h   (M = 256, N = KP split over the pair, K = 64 cols of half h)
+// Flattened work f = (rb * S + s) * n_pt + pt, cut into P contiguous chunks, one per CTA pair (148 SMs -> 74 pairs).
+// Barrier protocol: that of k_lik_pair_flat (lik_tc_pair.cuh; modelled in tests/test_pair_protocol.py); in the GLOBAL
+// orientation the ROW unit is released after the fold has read it (z_empty: the commit + the 16 epilogue warps).
+#pragma once
+
+struct FlatGeom {
+  int KP;
+  int n_rblk;   // row blocks (256 rows each): LOCAL cell blocks, GLOBAL gene blocks
+  int n_pt;     // column pair-tiles (128 columns) per segment: LOCAL gene pair-tiles, GLOBAL cell pair-tiles
+  int P;        // CTA pairs
+  int slots;    // partial-buffer slots: LOCAL per (sample), GLOBAL per gene block
+  int n_units;  // 128-row units in the count image of this orientation (= 2 * n_rblk)
+};
+
+struct FlatSmem {
+  uint32_t a1, st[2], q, tab, misc, total;
+  uint32_t a1_plane, b1_plane, b2_piece, b2_off, stage, q_plane;
+  uint32_t z_rs, zb_rs, u_rs;
+};
+__host__ __device__ inline FlatSmem plan_flat_smem(int KP) {
+  FlatSmem s;
+  s.z_rs = (uint32_t)(KP / 8) * 128u;     // [row][k0] layouts: bytes per 8-row group
+  s.zb_rs = (uint32_t)(KP / 16) * 128u;   // the same for a k0 half
+  s.u_rs = 16u * 128u;                    // assembled W unit [k0][128 genes]: bytes per 8-k0 group
+  s.a1_plane = (uint32_t)KP * 256u;       // 128 rows x KP x bf16
+  s.b1_plane = (uint32_t)KP * 128u;       // 64 columns x KP
+  s.b2_piece = (uint32_t)KP * 64u;        // 64 columns x KP/2
+  s.b2_off = 2u * s.b1_plane;
+  s.stage = s.b2_off + 4u * s.b2_piece;
+  s.q_plane = 16u * Q_RS;
+  uint32_t o = 0;
+  s.a1 = o; o += 2u * s.a1_plane;
+  s.st[0] = o; o += s.stage;
+  s.st[1] = o; o += s.stage;
+  s.q = o; o += 2u * s.q_plane;
+  s.tab = o; o += (uint32_t)((2 + MAX_NB) * KP * 4 + 127) / 128u * 128u;
+  s.misc = o;
+  s.total = o + 1024u;
+  return s;
+}
+
+struct FlatPos {   // position in the flattened space
+  int rb, s, pt, g;
+  __device__ __forceinline__ void next(int n_pt, int S) {
+    if (++pt == n_pt) { pt = 0; ++g; if (++s == S) { s = 0; ++rb; } }
+  }
+};
+
+constexpr uint32_t FLAT_TMEM_D2 = 256, FLAT_TMEM_ACC = 384;
+
+// W_0 prior parameters and rank-1 factors of the fold, per (sample, k0): [a1 | bm | ctS_0 .. ctS_{nb-1}], rows of KP floats.
+// scalar priors: a1 = gw (A - 1), bm = gw B;  matrix priors (MAT): a1 = 1 / tau, bm = 1 / (tau omega)
+__global__ void __launch_bounds__(128) k_tc_foldtab(const LikTcArgs a, const float* ctilde, float* tab, int KP, int mat) {
+  const int s = blockIdx.x;
+  float* t = tab + (long long)s * (2 + a.nb) * KP;
+  for (int k = threadIdx.x; k < KP; k += blockDim.x) {
+    float a1 = 0.f, bm = 0.f;
+    if (k < a.K0) {
+      float tau = 1.f, om = 1.f;
+      if (a.use_brd) { tau = a.smp_tau[(long long)s * a.K0 + k]; om = a.smp_om[(long long)s * a.K0 + k]; }
+      if (mat) { a1 = 1.f / tau; bm = 1.f / (tau * om); }
+      else {
+        const float A = a.use_brd ? a.P_scalar / tau : a.P_scalar;
+        const float Bm = a.R_scalar * (float)a.K0 / (tau * om);
+        a1 = a.global_weight * (A - 1.f);
+        bm = a.global_weight * Bm;
+      }
+    }
+    t[k] = a1;
+    t[KP + k] = bm;
+    for (int b = 0; b < a.nb; ++b) t[(2 + b) * KP + k] = (k < a.K0 && a.lik_on) ? a.scale * ctilde[((long long)s * a.nb + b) * a.K0 + k] : 0.f;
+  }
+}
+
+// z0 samples -> GLOBAL-orientation column images: per (s, 128-cell pair-tile, rank) one contiguous stage
+//   [B1 hi | B1 lo | B2[0] hi | B2[0] lo | B2[1] hi | B2[1] lo]
+// B1   = z[cells 64 rank .. +64][all k0]            [cell][k0], 8-row-group stride z_rs          (K-major B of the rate GEMM)
+// B2[h] = z[cells 64 h .. +64][k0 in KP/2 rank ..]   [cell][k0 half], 8-row-group stride zb_rs    (MN-major B of the second GEMM)
+__global__ void __launch_bounds__(256) k_tc_zprep_g(const LikTcArgs a, uint8_t* zimg, int KP, int n_ptc) {
+  const FlatSmem L = plan_flat_smem(KP);
+  const int nchunk = KP / 8, half_chunks = KP / 16;
+  const long long per_pt = 128ll * nchunk;   // (cell of the pair-tile, k0 chunk)
+  const long long total = (long long)a.S * n_ptc * per_pt;
+  const bool vec = (a.K0 & 3) == 0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long sp = t / per_pt;
+    const int i = (int)(t - sp * per_pt);
+    const int s = (int)(sp / n_ptc), pt = (int)(sp - (long long)s * n_ptc);
+    const int cl = i % 128, c = i / 128;          // cell of the pair-tile, k0 chunk
+    const int j = pt * 128 + cl, k = c * 8;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = 0.f;
+    if (j < a.B) {
+      const float* row = a.smp_z0 + ((long long)s * a.B + j) * a.K0;
+      if (vec) {
+        if (k + 4 <= a.K0) { float4 v = *reinterpret_cast<const float4*>(row + k); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+        if (k + 8 <= a.K0) { float4 v = *reinterpret_cast<const float4*>(row + k + 4); x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (k + e < a.K0) x[e] = row[k + e];
+      }
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    uint8_t* base = zimg + sp * (2ll * L.stage);
+    const int h = cl >> 6, r = cl & 63;           // 64-cell half, row inside it
+    // B1 of the rank that owns this half
+    {
+      uint8_t* d = base + (long long)h * L.stage + (uint32_t)(r >> 3) * L.z_rs + (uint32_t)c * 128u + (uint32_t)(r & 7) * 16u;
+      *reinterpret_cast<uint4*>(d) = hi;
+      *reinterpret_cast<uint4*>(d + L.b1_plane) = lo;
+    }
+    // B2[h] of the rank that owns this k0 half
+    {
+      const int rk = c / half_chunks, cc = c - rk * half_chunks;
+      uint8_t* d = base + (long long)rk * L.stage + L.b2_off + (uint32_t)(2 * h) * L.b2_piece + (uint32_t)(r >> 3) * L.zb_rs +
+                   (uint32_t)cc * 128u + (uint32_t)(r & 7) * 16u;
+      *reinterpret_cast<uint4*>(d) = hi;
+      *reinterpret_cast<uint4*>(d + L.b2_piece) = lo;
+    }
+  }
+}
+
+// minibatch counts -> GLOBAL-orientation image (row = gene, column = cell), same addressing as k_tc_xprep:
+// element (gene = unit*128 + q*32 + lane, cell = tile*64 + v*4 + i) at ((((tile*units + unit)*4 + q)*16 + v)*32 + lane)*4 + i
+__global__ void __launch_bounds__(256) k_tc_xprep_t(const LikTcArgs a, float* ximg, int n_ctiles, int n_units) {
+  const long long total = (long long)n_ctiles * n_units * 4 * 16 * 32;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int lane = (int)(t % 32);               // consecutive threads = consecutive genes of one cell: coalesced reads
+    long long rest = t / 32;
+    const int q = (int)(rest % 4); rest /= 4;
+    const int unit = (int)(rest % n_units); rest /= n_units;
+    const int v = (int)(rest % 16);
+    const int tile = (int)(rest / 16);
+    const int g = unit * 128 + q * 32 + lane, j0 = tile * 64 + v * 4;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g < a.G) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (j0 + i < a.B) x[i] = a.X[(a.idx_x ? a.idx_x[j0 + i] : (long long)(j0 + i)) * a.G + g];
+    }
+    *reinterpret_cast<float4*>(ximg + ((((((long long)tile * n_units + unit) * 4 + q) * 16 + v) * 32 + lane) * 4)) = make_float4(x[0], x[1], x[2], x[3]);
+  }
+}
+
+// row sums of the minibatch counts (one warp per row)
+__global__ void __launch_bounds__(256) k_tc_rowsum(const LikTcArgs a, float* rowsum) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= a.B) return;
+  const float* row = a.X + (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
+  float acc = 0.f;
+  for (int g = lane; g < a.G; g += 32) acc += row[g];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) rowsum[j] = acc;
+}
+
+// sum_{b,g} colsumX_b[g] log s^s_{b,g}  (the gene-scale part of sum x log Lambda), all samples
+__global__ void __launch_bounds__(256) k_tc_loss_gs(const LikTcArgs a, const float* colsumX, double* loss_out) {
+  __shared__ double red[32];
+  const long long n = (long long)a.S * a.nb * a.G, per = (long long)a.nb * a.G;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float cx = colsumX[i % per];
+    if (cx > 0.f) acc += (double)(cx * __logf(a.smp_s[i]));
+  }
+  const double tot = block_sum_d(acc, red);
+  if (threadIdx.x == 0 && tot != 0.0) atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)a.S);
+}
+
+// The rank-1 parts, one warp per (sample, cell):  dot = z_n . (W s_b)
+//   LOCAL : G_z0[s][j][k] += scale (sum_slots part - c Ws_b[k]),   G_c[s][j] += scale (rowsumX_j / c - dot)
+//   loss  : - scale / S * (rowsumX_j log c - c dot)
+__global__ void __launch_bounds__(256) k_tc_rank1(const LikTcArgs a, const TcScratch ws, const float* part, int slots_ld,
+                                                  long long T, int P, int n_pt, int do_grad, int do_loss, double* loss_out) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), total = (long long)a.S * a.B;
+  double lacc = 0.0;
+  if (w < total) {
+    const int s = (int)(w / a.B), j = (int)(w - (long long)s * a.B);
+    const float c = a.smp_c[w];
+    const int b = ws.brow[j];
+    const float* Wsb = ws.Ws + ((long long)s * a.nb + b) * a.K0;
+    const float* z = a.smp_z0 + w * a.K0;
+    int nsl = 0;
+    long long pbase = 0;
+    if (do_grad) {
+      // the chunks that hold a piece of segment (rb, s): rb = j / 256
+      const long long f0 = ((long long)(j / CB) * a.S + s) * n_pt;
+      nsl = flat_chunk_of(f0 + n_pt - 1, T, P) - flat_chunk_of(f0, T, P) + 1;
+      pbase = ((long long)s * slots_ld * a.B + j) * a.K0;
+    }
+    float dot = 0.f;
+    for (int k = lane; k < a.K0; k += 32) {
+      const float wsk = Wsb[k];
+      dot = fmaf(z[k], wsk, dot);
+      if (do_grad) {
+        float acc = 0.f;
+        for (int q = 0; q < nsl; ++q) acc += part[pbase + (long long)q * a.B * a.K0 + k];
+        a.G_z0[w * a.K0 + k] += a.scale * (acc - c * wsk);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) {
+      const float rs = ws.rowsumx[j];
+      if (do_grad) a.G_c[w] += a.scale * (rs / c - dot);
+      if (do_loss) lacc = (double)(rs * __logf(c) - c * dot);
+    }
+  }
+  if (do_loss) {
+    const double tot = block_sum_d(lacc, red);
+    if (threadIdx.x == 0) atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)a.S);
+  }
+}
+
+// W_0: entropy value and the final (mu, rho) gradients from the gene-block slots of the GLOBAL orientation
+__global__ void __launch_bounds__(256) k_tc_w0_final_flat(const LikTcArgs a, const float* part, long long T, int P, int per_rb,
+                                                          double* loss_out) {
+  __shared__ double red[32];
+  const long long n = (long long)a.K0 * a.G;
+  const float wH = a.anneal * a.global_weight, invS = 1.f / (float)a.S;
+  double ent = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float mu = a.mu_W0[i], rho = a.rho_W0[i];
+    ent += (double)(fminf(fmaxf(mu, LOG_1E_10), LOG_1E6) + fminf(fmaxf(rho, LOG_1E_10), LOG_1E10) + HALF_LOG_2PI_PLUS_HALF);
+    if (a.gmu_W0) {
+      float dmu = 0.f, drho = 0.f;
+      if (!a.w0_stopped) {
+        const int rb = (int)((i % a.G) / 256);
+        const long long f0 = (long long)rb * per_rb;
+        const int nsl = part ? flat_chunk_of(f0 + per_rb - 1, T, P) - flat_chunk_of(f0, T, P) + 1 : 0;
+        float gv = 0.f, glw = 0.f;
+        for (int c = 0; c < nsl; ++c) {
+          gv += part[((long long)c * 2 + 0) * n + i];
+          glw += part[((long long)c * 2 + 1) * n + i];
+        }
+        const float gve = glw - fminf(fmaxf(mu, LOG_1E_10), LOG_1E6) * gv;   // sum_s t_s (sigma eps)_s, sigma eps = log W - mu~
+        const bool in_mu = mu >= LOG_1E_10 && mu <= LOG_1E6, in_rho = rho >= LOG_1E_10 && rho <= LOG_1E10;
+        dmu = in_mu ? -(gv * invS + wH) : 0.f;
+        drho = in_rho ? -(gve * invS + wH) : 0.f;
+      }
+      a.gmu_W0[i] = dmu;
+      a.grho_W0[i] = drho;
+    }
+  }
+  const double tot = block_sum_d(ent, red);
+  if (threadIdx.x == 0) atomicAdd(&loss_out[1], -tot * (double)wH);
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------------
+template <bool GENES, bool WANT_LL, bool MAT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
+    k_lik_flat(const LikTcArgs a, const FlatGeom gm, const TcScratch ws, double* loss_out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const int KP = gm.KP;
+  const FlatSmem L = plan_flat_smem(KP);
+  FlatMisc* mi = reinterpret_cast<FlatMisc*>(sm + L.misc);
+  const uint32_t sbase = smem_u32(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  PT_DECL;
+
+  // ---- work of this pair ----
+  const int n_pt = gm.n_pt, P = gm.P, S = a.S;
+  const long long T = (long long)gm.n_rblk * S * n_pt;
+  const int chunk = blockIdx.x >> 1;
+  const long long f0 = (long long)chunk * T / P, f1 = (long long)(chunk + 1) * T / P;
+  const int n_outer = (int)(f1 - f0);
+  const int U = 2 * n_outer;
+  FlatPos cur0;
+  {
+    const long long sg = f0 / n_pt;
+    cur0.rb = (int)(sg / S); cur0.s = (int)(sg % S); cur0.pt = (int)(f0 % n_pt); cur0.g = 0;
+  }
+  const int n_seg = n_outer > 0 ? (int)((f1 - 1) / n_pt - f0 / n_pt) + 1 : 0;
+  constexpr int ND2 = GENES ? 1 : 2;   // D2 accumulators in tensor memory
+
+  // ---- prologue ----
+  if (threadIdx.x == 0) {
+    mbar_init(&mi->z_full, 1);
+    mbar_init(&mi->pz_full, 1);
+    mbar_init(&mi->z_empty, GENES ? 1 + E_WARPS : 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&mi->w_full[i], 1);
+      mbar_init(&mi->pw_full[i], 1);
+      mbar_init(&mi->w_empty[i], 1);
+      mbar_init(&mi->r_full[i], 1);
+      mbar_init(&mi->r_empty[i], 2 * E_WARPS);
+      mbar_init(&mi->dz_full[i], 1);
+      mbar_init(&mi->dz_empty[i], 2 * E_WARPS);
+    }
+    mbar_init(&mi->q_full, 2 * E_WARPS);
+    mbar_init(&mi->q_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&mi->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = mi->tmem_base;
+  const PipeSmem IL = plan_pipe_smem(KP);   // layout of one W_0 tile image in global memory (k_tc_wgen)
+  const uint32_t tab_bytes = (uint32_t)((2 + a.nb) * KP * 4);
+  auto first_in_seg = [&](int oi, const FlatPos& c) { return c.pt == 0 || oi == 0; };
+  auto last_in_seg = [&](int oi, const FlatPos& c) { return c.pt == n_pt - 1 || oi == n_outer - 1; };
+
+  if (warp == COPY_WARP) {
+    // =========================================== COPY (TMA), each CTA for itself ===========================
+    if (lane == 0) {
+      FlatPos c = cur0;
+      for (int oi = 0; oi < n_outer; ++oi, c.next(n_pt, S)) {
+        const int st = oi & 1;
+        PT_WAIT(0, pair_wait(&mi->w_empty[st], ((oi >> 1) & 1) ^ 1, 1));
+        mbar_arrive_expect_tx(&mi->w_full[st], L.stage);
+        const uint32_t dst = sbase + L.st[st];
+        if (GENES) {
+          bulk_g2s(dst, ws.zimg_g + (((long long)c.s * n_pt + c.pt) * 2 + rank) * L.stage, L.stage, &mi->w_full[st]);
+        } else {
+          const uint8_t* img0 = ws.wimg + ((long long)c.s * (2 * n_pt) + 2 * c.pt) * IL.w_unit;
+          const uint8_t* img1 = img0 + IL.w_unit;
+          bulk_g2s(dst, rank ? img1 : img0, 2u * L.b1_plane, &mi->w_full[st]);                      // B1: hi | lo of the own image
+          const uint32_t row_off = rank * L.b2_piece;                                                // k0 rows [KP/2 rank, +KP/2)
+          bulk_g2s(dst + L.b2_off + 0u * L.b2_piece, img0 + row_off, L.b2_piece, &mi->w_full[st]);
+          bulk_g2s(dst + L.b2_off + 1u * L.b2_piece, img0 + IL.w_plane + row_off, L.b2_piece, &mi->w_full[st]);
+          bulk_g2s(dst + L.b2_off + 2u * L.b2_piece, img1 + row_off, L.b2_piece, &mi->w_full[st]);
+          bulk_g2s(dst + L.b2_off + 3u * L.b2_piece, img1 + IL.w_plane + row_off, L.b2_piece, &mi->w_full[st]);
+        }
+        if (first_in_seg(oi, c)) {
+          // the ROW unit of the new segment replaces the old one once the tensor core (LOCAL) / the fold (GLOBAL) is done with it
+          PT_WAIT(1, pair_wait(&mi->z_empty, ((uint32_t)c.g & 1u) ^ 1u, 17));
+          const uint32_t unit = (uint32_t)(2 * c.rb) + rank;
+          if (GENES) {
+            mbar_arrive_expect_tx(&mi->z_full, 2u * L.a1_plane + tab_bytes);
+            const int nkg = KP / 8, n_img = a.n_wimg;
+            for (int hsel = 0; hsel < 2; ++hsel) {
+              const int img = (int)unit * 2 + hsel;   // 64-gene tile image of this half of the unit
+              const uint8_t* src = ws.wimg + ((long long)c.s * n_img + img) * IL.w_unit;
+              for (int pl = 0; pl < 2; ++pl)
+                for (int kg = 0; kg < nkg; ++kg)
+                  bulk_g2s(sbase + L.a1 + (uint32_t)pl * L.a1_plane + (uint32_t)kg * L.u_rs + (uint32_t)hsel * 1024u,
+                           src + (uint32_t)pl * IL.w_plane + (uint32_t)kg * W_RS, 1024u, &mi->z_full);
+            }
+            bulk_g2s(sbase + L.tab, ws.foldtab + (long long)c.s * (2 + a.nb) * KP, tab_bytes, &mi->z_full);
+          } else {
+            mbar_arrive_expect_tx(&mi->z_full, 2u * L.a1_plane);
+            bulk_g2s(sbase + L.a1, ws.zimg + ((long long)c.s * gm.n_units + unit) * (2u * L.a1_plane), 2u * L.a1_plane, &mi->z_full);
+          }
+        }
+      }
+      // see the last multicast commits land before this CTA can exit
+      for (int st = 0; st < 2; ++st) {
+        const int uses = (n_outer + 1 - st) / 2;
+        if (uses > 0) pair_wait(&mi->w_empty[st], (uint32_t)(uses - 1) & 1u, 15);
+      }
+      if (U > 0) pair_wait(&mi->q_empty, (uint32_t)(U - 1) & 1u, 16);
+      if (n_seg > 0) pair_wait(&mi->z_empty, (uint32_t)(n_seg - 1) & 1u, 18);
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    if (lane == 0 && !leader) {
+      // =========================================== RELAY (peer) ==========================================
+      const uint32_t r_pz = mapa_rank(&mi->pz_full, 0), r_pw0 = mapa_rank(&mi->pw_full[0], 0), r_pw1 = mapa_rank(&mi->pw_full[1], 0);
+      FlatPos c = cur0;
+      for (int oi = 0; oi < n_outer; ++oi, c.next(n_pt, S)) {
+        PT_WAIT(0, pair_wait(&mi->w_full[oi & 1], (oi >> 1) & 1, 3));
+        mbar_arrive_remote((oi & 1) ? r_pw1 : r_pw0);
+        if (first_in_seg(oi, c)) {
+          PT_WAIT(1, pair_wait(&mi->z_full, (uint32_t)c.g & 1u, 2));
+          mbar_arrive_remote(r_pz);
+        }
+      }
+    } else if (lane == 0) {
+      // =========================================== MMA ISSUER (leader) ===================================
+      // descriptor: lbo = byte stride between core matrices along K, sbo = along M / N (see lik_tc.cu)
+      const uint32_t idesc1 = GENES ? umma_idesc(256, 2 * TG, 1, 0) : umma_idesc(256, 2 * TG, 0, 1);
+      const uint32_t idesc2 = GENES ? umma_idesc(256, KP, 0, 1) : umma_idesc(256, KP, 0, 0);
+      const uint64_t d_a1 = GENES ? umma_desc(sbase + L.a1, L.u_rs, 128u) : umma_desc(sbase + L.a1, 128u, L.z_rs);
+      const uint64_t a1_k = GENES ? (uint64_t)(2u * (L.u_rs >> 4)) : 16ull;
+      uint64_t d_b1[2], d_b2[2];
+      for (int i = 0; i < 2; ++i) {
+        d_b1[i] = GENES ? umma_desc(sbase + L.st[i], 128u, L.z_rs) : umma_desc(sbase + L.st[i], W_RS, 128u);
+        d_b2[i] = GENES ? umma_desc(sbase + L.st[i] + L.b2_off, L.zb_rs, 128u) : umma_desc(sbase + L.st[i] + L.b2_off, 128u, W_RS);
+      }
+      const uint64_t b1_k = GENES ? 16ull : (uint64_t)(2u * (W_RS >> 4));
+      const uint64_t b2_k = GENES ? (uint64_t)(2u * (L.zb_rs >> 4)) : 16ull;
+      const uint64_t dq_k = umma_desc(sbase + L.q, 128u, Q_RS);
+      const uint64_t a1pl = L.a1_plane >> 4, b1pl = L.b1_plane >> 4, qpl = L.q_plane >> 4, b2pl = L.b2_piece >> 4;
+      const int nk1 = KP / 16;
+      FlatPos c1 = cur0, c2 = cur0;
+      auto ready1 = [&](int oi) {
+        const int st = oi & 1;
+        const uint32_t par = (uint32_t)(oi >> 1) & 1u;
+        if (first_in_seg(oi, c1) && !(mbar_test(&mi->z_full, (uint32_t)c1.g & 1u) && mbar_test_remote(&mi->pz_full, (uint32_t)c1.g & 1u)))
+          return false;
+        return mbar_test(&mi->w_full[st], par) && mbar_test_remote(&mi->pw_full[st], par) &&
+               mbar_test_remote(&mi->r_empty[st], par ^ 1u);
+      };
+      auto issue_mma1 = [&](int oi) {
+        const int st = oi & 1;
+        const uint32_t par = (uint32_t)(oi >> 1) & 1u;
+        if (first_in_seg(oi, c1)) {
+          PT_WAIT(6, pair_wait(&mi->z_full, (uint32_t)c1.g & 1u, 7));
+          PT_WAIT(6, pair_wait_remote(&mi->pz_full, (uint32_t)c1.g & 1u, 8));
+        }
+        PT_WAIT(0, pair_wait(&mi->w_full[st], par, 4));
+        PT_WAIT(1, pair_wait_remote(&mi->pw_full[st], par, 5));
+        PT_WAIT(2, pair_wait_remote(&mi->r_empty[st], par ^ 1u, 6));
+        tc_fence_after();
+        PT_MARK();
+        uint64_t da = d_a1, db = d_b1[st];
+        const uint32_t d = tmem + (uint32_t)st * (2 * TG);
+        umma2_bf16(d, da + a1pl, db, idesc1, 0u);
+        umma2_bf16(d, da, db + b1pl, idesc1, 1u);
+        umma2_bf16(d, da, db, idesc1, 1u);
+        for (int ks = 1; ks < nk1; ++ks) {
+          da += a1_k;
+          db += b1_k;
+          umma2_bf16(d, da + a1pl, db, idesc1, 1u);
+          umma2_bf16(d, da, db + b1pl, idesc1, 1u);
+          umma2_bf16(d, da, db, idesc1, 1u);
+        }
+        umma2_commit(&mi->r_full[st]);
+        if (last_in_seg(oi, c1)) umma2_commit(&mi->z_empty);   // the segment's ROW unit has been read by its last rate GEMM
+        PT_LAP(4);
+        c1.next(n_pt, S);
+      };
+      int next1 = 0;
+      for (int u = 0; u < U; ++u) {
+        const int oi = u >> 1, h = u & 1, st = oi & 1;
+        long long t_poll = 0;
+#ifdef SCDEF_TC_TIMING
+        const long long t_loop0 = clock64(), t_in1 = tacc[0] + tacc[1] + tacc[2] + tacc[4] + tacc[6];
+#endif
+        for (;;) {
+          if (next1 < n_outer && next1 <= oi + 1 && (next1 == oi || ready1(next1))) { issue_mma1(next1); ++next1; continue; }
+          if (mbar_test_remote(&mi->q_full, (uint32_t)u & 1u)) break;
+          if (next1 > oi + 1 || next1 >= n_outer) { pair_wait_remote(&mi->q_full, (uint32_t)u & 1u, 9); break; }
+          if (t_poll == 0) t_poll = clock64();
+          else if (clock64() - t_poll > PAIR_DEADLINE) pair_stuck(14, (int)blockIdx.x, u, next1);
+        }
+#ifdef SCDEF_TC_TIMING
+        tacc[3] += (clock64() - t_loop0) - (tacc[0] + tacc[1] + tacc[2] + tacc[4] + tacc[6] - t_in1);
+#endif
+        const bool seg_first = first_in_seg(oi, c2) && h == 0, seg_last = last_in_seg(oi, c2) && h == 1;
+        const uint32_t dzb = GENES ? 0u : ((uint32_t)c2.g & 1u);
+        const uint32_t dz_use = GENES ? (uint32_t)c2.g : ((uint32_t)c2.g >> 1);
+        if (seg_first) PT_WAIT(7, pair_wait_remote(&mi->dz_empty[dzb], (dz_use & 1u) ^ 1u, 19));   // drained / folded
+        tc_fence_after();
+        PT_MARK();
+        const uint32_t d = tmem + FLAT_TMEM_D2 + dzb * FLAT_DZ_STRIDE;
+        uint64_t da = dq_k, db = d_b2[st] + (uint64_t)(2 * h) * b2pl;
+        umma2_bf16(d, da + qpl, db, idesc2, seg_first ? 0u : 1u);
+        umma2_bf16(d, da, db + b2pl, idesc2, 1u);
+        umma2_bf16(d, da, db, idesc2, 1u);
+#pragma unroll
+        for (int ks = 1; ks < TG / 16; ++ks) {
+          da += 16;
+          db += b2_k;
+          umma2_bf16(d, da + qpl, db, idesc2, 1u);
+          umma2_bf16(d, da, db + b2pl, idesc2, 1u);
+          umma2_bf16(d, da, db, idesc2, 1u);
+        }
+        umma2_commit(&mi->q_empty);
+        if (h == 1) umma2_commit(&mi->w_empty[st]);
+        if (seg_last) umma2_commit(&mi->dz_full[dzb]);
+        PT_LAP(5);
+        if (h == 1) c2.next(n_pt, S);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================== EPILOGUE (both CTAs) ====================================
+    const int e = warp;
+    const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+    const int r = (int)lane_base + lane;   // row of this CTA's unit: cell (LOCAL) or gene (GLOBAL)
+    const int cq = e >> 2;                 // 16-column quarter of a 64-column half
+    const uint32_t r_rempty[2] = {mapa_rank(&mi->r_empty[0], 0), mapa_rank(&mi->r_empty[1], 0)};
+    const uint32_t r_dzempty[2] = {mapa_rank(&mi->dz_empty[0], 0), mapa_rank(&mi->dz_empty[1], 0)};
+    const uint32_t r_qfull = mapa_rank(&mi->q_full, 0);
+    float ll = 0.f;
+    // one 64-column half: R (16 columns of this thread's row) -> q = x / R where x > 0; sum x log R
+    auto half_math = [&](const float4 (&xv4)[4], const uint32_t (&Rr)[16], float (&q)[16]) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float xs[4] = {xv4[v].x, xv4[v].y, xv4[v].z, xv4[v].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float Rv = __uint_as_float(Rr[v * 4 + i]);
+          const bool nz = xs[i] > 0.f;
+          q[v * 4 + i] = nz ? __fdividef(xs[i], Rv) : 0.f;
+          if (WANT_LL) ll += nz ? xs[i] * __logf(Rv) : 0.f;
+        }
+      }
+    };
+    auto store_q = [&](const float (&q)[16]) {
+      uint4 hi, lo;
+      const uint32_t off = L.q + (uint32_t)(r >> 3) * Q_RS + (uint32_t)(r & 7) * 16u + (uint32_t)(cq * 2) * 128u;
+      split8(q, hi, lo);
+      *reinterpret_cast<uint4*>(sm + off) = hi;
+      *reinterpret_cast<uint4*>(sm + off + L.q_plane) = lo;
+      split8(q + 8, hi, lo);
+      *reinterpret_cast<uint4*>(sm + off + 128u) = hi;
+      *reinterpret_cast<uint4*>(sm + off + 128u + L.q_plane) = lo;
+      fence_async_q();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(r_qfull);
+    };
+
+    // ---- LOCAL: the segment's dz0 is complete: drain its accumulator (cell row r, every 4th 16-column chunk of k0) ----
+    auto drain_segment = [&](const FlatPos& p) {
+      const uint32_t dzb = (uint32_t)p.g & 1u;
+      PT_WAIT(7, pair_wait(&mi->dz_full[dzb], ((uint32_t)p.g >> 1) & 1u, 13));
+      tc_fence_after();
+      PT_MARK();
+      const int j = p.rb * CB + (int)rank * UC + r;
+      const long long fseg = ((long long)p.rb * S + p.s) * n_pt;
+      const int slot = chunk - flat_chunk_of(fseg, T, P);
+      float* dst = ws.part + (((long long)p.s * gm.slots + slot) * a.B + j) * a.K0;
+      const uint32_t tdz = tmem + FLAT_TMEM_D2 + dzb * FLAT_DZ_STRIDE + (lane_base << 16);
+      const bool vec4 = (a.K0 & 3) == 0, valid = j < a.B;
+      for (int ch = cq; ch < KP / 16; ch += 4) {
+        float v[16];
+        tmem_ld16(tdz + (uint32_t)(ch * 16), v);
+        if (valid) {
+          if (vec4) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              if (ch * 16 + i < a.K0) *reinterpret_cast<float4*>(dst + ch * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (ch * 16 + i < a.K0) dst[ch * 16 + i] = v[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(r_dzempty[dzb]);
+      PT_LAP(8);
+    };
+
+    // ---- GLOBAL: fold dW^T of the segment into d mu (tensor memory) and sum t log W (registers) ----
+    float acc_lw[32];
+    bool acc_live = false;   // the accumulators hold a partial sum of the current gene block
+    if (GENES) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc_lw[i] = 0.f;
+    }
+    const uint32_t tacc_mu = tmem + FLAT_TMEM_ACC + (lane_base << 16);
+    auto fold_segment = [&](const FlatPos& p) {
+      PT_WAIT(7, pair_wait(&mi->dz_full[0], (uint32_t)p.g & 1u, 13));
+      tc_fence_after();
+      PT_MARK();
+      const int g = (p.rb * 2 + (int)rank) * UC + r;
+      const bool gok = g < a.G;
+      const float* tab = reinterpret_cast<const float*>(sm + L.tab);
+      float sgv[MAX_NB];
+#pragma unroll
+      for (int b = 0; b < MAX_NB; ++b) sgv[b] = (b < a.nb && gok && a.lik_on) ? a.smp_s[((long long)p.s * a.nb + b) * a.G + g] : 0.f;
+      const uint32_t td2 = tmem + FLAT_TMEM_D2 + (lane_base << 16);
+      const uint32_t wrow = L.a1 + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 2u;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int ch = cq + 4 * cc;
+        if (ch < KP / 16) {
+          float dW[16], am[16];
+          tmem_ld16(td2 + (uint32_t)(ch * 16), dW);
+          if (acc_live) tmem_ld16(tacc_mu + (uint32_t)(ch * 16), am);
+          else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) am[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = ch * 16 + i;
+            const uint32_t wo = wrow + (uint32_t)(k >> 3) * L.u_rs + (uint32_t)(k & 7) * 16u;
+            const float W = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(sm + wo)) << 16) +
+                            __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(sm + wo + L.a1_plane)) << 16);
+            float a1 = tab[k], bm = tab[KP + k];
+            if (MAT) {
+              const float Pv = (a.P && gok && k < a.K0) ? __ldg(a.P + (long long)k * a.G + g) : a.P_scalar;
+              const float Rv = (a.R && gok && k < a.K0) ? __ldg(a.R + (long long)k * a.G + g) : a.R_scalar;
+              bm = a.global_weight * Rv * (float)a.K0 * bm;                        // gw B,  B = R K0 / (tau omega)
+              a1 = a.global_weight * ((a.use_brd ? Pv * a1 : Pv) - 1.f);           // gw (A - 1),  A = P / tau
+            }
+            float cs = bm;
+#pragma unroll
+            for (int b = 0; b < MAX_NB; ++b)
+              if (b < a.nb) cs = fmaf(tab[(2 + b) * KP + k], sgv[b], cs);
+            const float t = fmaf(W, fmaf(a.scale, dW[i], -cs), a1);
+            if (W > V_LO_M && W < V_HI_M && gok && k < a.K0) {
+              am[i] += t;
+              acc_lw[cc * 16 + i] = fmaf(t, __logf(W), acc_lw[cc * 16 + i]);
+            }
+          }
+          tmem_st16(tacc_mu + (uint32_t)(ch * 16), am);
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      acc_live = true;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_remote(r_dzempty[0]);   // D2 may be overwritten by the next segment
+        mbar_arrive(&mi->z_empty);          // ... and this CTA's ROW unit replaced
+      }
+      PT_LAP(8);
+    };
+    auto flush_block = [&](const FlatPos& p) {
+      // partial sums of gene block p.rb held by this pair -> slot of the (slots, 2, K0, G) buffer
+      const int g = (p.rb * 2 + (int)rank) * UC + r;
+      const long long per_rb = (long long)S * n_pt;
+      const int slot = chunk - flat_chunk_of((long long)p.rb * per_rb, T, P);
+      const long long n = (long long)a.K0 * a.G;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int ch = cq + 4 * cc;
+        if (ch < KP / 16) {
+          float am[16];
+          tmem_ld16(tacc_mu + (uint32_t)(ch * 16), am);
+          if (g < a.G) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int k = ch * 16 + i;
+              if (k < a.K0) {
+                ws.part[((long long)slot * 2 + 0) * n + (long long)k * a.G + g] = am[i];
+                ws.part[((long long)slot * 2 + 1) * n + (long long)k * a.G + g] = acc_lw[cc * 16 + i];
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc_lw[cc * 16 + i] = 0.f;
+        }
+      }
+      acc_live = false;
+    };
+
+    // this thread's first float4 of 64-column tile t of the count image sits at x_base + t * x_tile
+    const long long x_tile = (long long)gm.n_units * (4 * 16 * 128);
+    const float* x_img = GENES ? ws.ximg_t : ws.ximg;
+    float4 xa[4], xb[4];   // counts of half 0 / half 1, loaded one pair-tile ahead
+    FlatPos cc = cur0;
+    auto x_ptr = [&](const FlatPos& p) {
+      const int unit = p.rb * 2 + (int)rank;
+      return x_img + (((long long)unit * 4 + (warp & 3)) * 16 + cq * 4) * 128 + lane * 4 + (long long)(2 * p.pt) * x_tile;
+    };
+    if (n_outer > 0) {
+      const float* xi = x_ptr(cc);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { xa[v] = *reinterpret_cast<const float4*>(xi + v * 128); xb[v] = *reinterpret_cast<const float4*>(xi + x_tile + v * 128); }
+    }
+    for (int oi = 0; oi < n_outer; ++oi) {
+      const int st = oi & 1;
+      const uint32_t par = (uint32_t)(oi >> 1) & 1u;
+      const bool more = oi + 1 < n_outer;
+      FlatPos cn = cc;
+      cn.next(n_pt, S);
+      const float* xnext = x_ptr(cn);
+      const uint32_t taddr = tmem + (lane_base << 16) + (uint32_t)(st * (2 * TG) + cq * 16);
+      PT_MARK();
+      PT_WAIT(0, pair_wait(&mi->r_full[st], par, 11));
+      tc_fence_after();
+      PT_MARK();
+      uint32_t R0[16], R1[16];
+      float q[16];
+      tmem_ld16_issue(taddr, R0);
+      tmem_ld16_wait(R0);
+      PT_LAP(3);
+      half_math(xa, R0, q);
+      if (more) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) xa[v] = *reinterpret_cast<const float4*>(xnext + v * 128);
+      }
+      tmem_ld16_issue(taddr + (uint32_t)TG, R1);   // in flight while the first half's Q tile is stored
+      PT_LAP(4);
+      PT_WAIT(1, pair_wait(&mi->q_empty, 1u, 12));  // sub-unit 2 oi: parity (u & 1) ^ 1 with u even
+      PT_MARK();
+      store_q(q);
+      tmem_ld16_wait(R1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(r_rempty[st]);   // both halves of R[st] are in registers
+      PT_LAP(5);
+      half_math(xb, R1, q);
+      if (more) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) xb[v] = *reinterpret_cast<const float4*>(xnext + x_tile + v * 128);
+      }
+      PT_LAP(4);
+      PT_WAIT(1, pair_wait(&mi->q_empty, 0u, 12));  // sub-unit 2 oi + 1
+      PT_MARK();
+      store_q(q);
+      PT_LAP(5);
+      if (last_in_seg(oi, cc)) {
+        if (GENES) {
+          fold_segment(cc);
+          if (!more || cn.rb != cc.rb) flush_block(cc);
+        } else {
+          drain_segment(cc);
+        }
+      }
+      cc = cn;
+    }
+    if (WANT_LL) {
+      double v = warp_sum_d((double)ll);
+      if (lane == 0) mi->red[e] = v;
+      named_bar_sync(2, E_THREADS);
+      if (e == 0 && lane == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < E_WARPS; ++i) tot += mi->red[i];
+        atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)a.S);
+      }
+    }
+  }
+
+#ifdef SCDEF_TC_TIMING
+  if ((int)(blockIdx.x >> 1) == (int)(gridDim.x >> 2) && lane == 0 &&
+      (warp == COPY_WARP || warp == MMA_WARP || warp == 0 || warp == 15)) {
+    const int role = warp == COPY_WARP ? 0 : (warp == MMA_WARP ? 1 : (warp == 0 ? 2 : 3));
+    for (int i = 0; i < 15; ++i) g_pair_timing[rank][role][i] = (unsigned long long)tacc[i];
+    g_pair_timing[rank][role][15] = (unsigned long long)(clock64() - t_start);
+  }
+#endif
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
