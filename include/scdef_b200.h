@@ -222,6 +222,20 @@ int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t*
 int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam,
                     void* cuda_stream);
 
+/* Counts kept as uint16 on the device (raw UMI counts fit; half the HBM of float32): the per-cell constants, and the
+   minibatch rows converted to the dense float32 `X_batch` of scdef_elbo_grad. */
+int scdef_u16_row_stats(const uint16_t* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam, void* cuda_stream);
+int scdef_u16_gather_rows(const uint16_t* X, const int64_t* rows, int32_t n_rows, int32_t n_genes, float* out,
+                          void* cuda_stream);
+
+/* The count statistics behind the constants of `load_adata` (src/scdef/models/_scdef.py:498-573), on the device:
+   batch_stats[(b, {n cells, sum lib, sum lib^2})] for b = 0..n_batches-1 and, in slot n_batches, over all cells;
+   gene_sums[(b, g)] likewise ((n_batches + 1) x n_genes); lib[n] (optional) = library size of every cell.
+   X: float32 or uint16 (x_is_u16), row-major n_rows x n_genes; batch_id may be NULL when n_batches == 1.
+   Outputs are device doubles, overwritten; a data-parallel caller all-reduces them over the ranks. */
+int scdef_count_stats(const void* X, int32_t x_is_u16, const int32_t* batch_id, int64_t n_rows, int32_t n_genes,
+                      int32_t n_batches, double* batch_stats, double* gene_sums, float* lib, void* cuda_stream);
+
 /* Counts kept as CSR on the device (float32 data, int32 column indices, int64 row pointers; the reference
    densifies `adata.X`, _scdef.py:491-496 — 40 GB of host memory at 1M x 5k — this keeps ~10 % of that in HBM).
    scdef_csr_row_stats: the per-cell constants of scdef_row_stats from the CSR rows.

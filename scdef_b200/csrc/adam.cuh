@@ -354,6 +354,88 @@ __global__ void __launch_bounds__(256) k_row_stats(const float* X, long long n_r
   }
 }
 
+// ---- counts stored as uint16 (half the HBM of float32: 10 GB instead of 20 GB at 1M x 5000) -------------------------
+// per-cell constants, as k_row_stats
+__global__ void __launch_bounds__(256) k_u16_row_stats(const uint16_t* X, long long n_rows, int G, float* lib, float* lgam) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  float sl = 0.f, sg = 0.f;
+  for (int g = lane; g < G; g += 32) {
+    const float x = (float)X[row * G + g];
+    sl += x;
+    if (x > 1.5f) sg += lgammaf(x + 1.f);
+  }
+  sl = warp_sum(sl);
+  sg = warp_sum(sg);
+  if (lane == 0) {
+    if (lib) lib[row] = sl;
+    if (lgam) lgam[row] = sg;
+  }
+}
+// out[j, :] = float(X[rows[j], :]) : the minibatch as the dense float32 X_batch every kernel downstream reads
+__global__ void __launch_bounds__(256) k_u16_gather_rows(const uint16_t* X, const long long* rows, int n_rows, int G, float* out) {
+  const long long total = (long long)n_rows * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i / G), g = (int)(i - (long long)j * G);
+    out[i] = (float)X[rows[j] * G + g];
+  }
+}
+
+// ---- the count statistics of load_adata (`_scdef.py:498-573`) on the device ------------------------------------------
+// Per batch b (and over all cells, slot nb): [number of cells, sum of library sizes, sum of squared library sizes] and the
+// per-gene totals.  T = float or uint16_t.  One block = 32 rows x all genes: the gene sums of the block's rows are
+// accumulated per batch in registers over the rows (rows of one block mostly share few batches) and added with double atomics.
+template <typename T>
+__global__ void __launch_bounds__(256) k_count_stats(const T* X, const int* batch_id, long long n_rows, int G, int nb,
+                                                     double* st, double* gs, float* lib_out) {
+  __shared__ float lib_sm[32];
+  __shared__ int b_sm[32];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int rows = (int)min((long long)32, n_rows - r0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // library sizes: 8 warps x 4 rows
+  for (int rr = warp; rr < rows; rr += 8) {
+    const T* row = X + (r0 + rr) * G;
+    float acc = 0.f;
+    for (int g = lane; g < G; g += 32) acc += (float)row[g];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      lib_sm[rr] = acc;
+      b_sm[rr] = batch_id ? batch_id[r0 + rr] : 0;
+      if (lib_out) lib_out[r0 + rr] = acc;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int rr = 0; rr < rows; ++rr) {
+      const double l = (double)lib_sm[rr];
+      const int b = b_sm[rr];
+      atomicAdd(&st[nb * 3 + 0], 1.0); atomicAdd(&st[nb * 3 + 1], l); atomicAdd(&st[nb * 3 + 2], l * l);
+      if (nb > 1) { atomicAdd(&st[b * 3 + 0], 1.0); atomicAdd(&st[b * 3 + 1], l); atomicAdd(&st[b * 3 + 2], l * l); }
+    }
+  }
+  // gene sums: thread = gene (strided), rows in order; a run of rows of the same batch is summed before it is flushed
+  for (int g = threadIdx.x; g < G; g += 256) {
+    float all = 0.f, run = 0.f;
+    int cur = b_sm[0];
+    for (int rr = 0; rr < rows; ++rr) {
+      const float x = (float)X[(r0 + rr) * G + g];
+      all += x;
+      if (nb > 1) {
+        if (b_sm[rr] != cur) {
+          if (run != 0.f) atomicAdd(&gs[(long long)cur * G + g], (double)run);
+          run = 0.f;
+          cur = b_sm[rr];
+        }
+        run += x;
+      }
+    }
+    if (nb > 1 && run != 0.f) atomicAdd(&gs[(long long)cur * G + g], (double)run);
+    if (all != 0.f) atomicAdd(&gs[(long long)nb * G + g], (double)all);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_noise_fill(float* out, int S, int per, PhiloxKey key, NoiseTag tag, long long e0) {
   const long long total = (long long)S * per;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;

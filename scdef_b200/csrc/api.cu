@@ -112,6 +112,7 @@ Plan make_plan(const scdef_ctx* c, int B, int S, int lik_impl) {
     p.G[i] = o; o += align_up(n);
   }
   p.tc_off = o;
+  lik_tc_set_sm_count(c->sm_count);
   p.tc_bytes = (lik_impl == SCDEF_LIK_TC) ? lik_tc_workspace_bytes(B, S, c->K0, c->d.n_genes, c->d.n_batches) : 0;
   o += align_up(p.tc_bytes);
   p.total = o;
@@ -808,6 +809,37 @@ int scdef_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const f
   cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_rows * n_genes, st);
   k_csr_gather_rows<<<(n_rows + 7) / 8, 256, 0, st>>>(reinterpret_cast<const long long*>(indptr), indices, data,
                                                       reinterpret_cast<const long long*>(rows), n_rows, n_genes, out);
+  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+}
+
+int scdef_u16_row_stats(const uint16_t* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam, void* cuda_stream) {
+  if (!X || n_rows < 0 || n_genes < 1) return SCDEF_EINVAL;
+  if (n_rows == 0) return SCDEF_OK;
+  k_u16_row_stats<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)cuda_stream>>>(X, n_rows, n_genes, lib, lgam);
+  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+}
+
+int scdef_u16_gather_rows(const uint16_t* X, const int64_t* rows, int32_t n_rows, int32_t n_genes, float* out, void* cuda_stream) {
+  if (!X || !out || n_rows < 0 || n_genes < 1) return SCDEF_EINVAL;
+  if (n_rows == 0) return SCDEF_OK;
+  if (!rows) return SCDEF_EINVAL;
+  const long long total = (long long)n_rows * n_genes;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  k_u16_gather_rows<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(X, reinterpret_cast<const long long*>(rows), n_rows, n_genes, out);
+  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+}
+
+int scdef_count_stats(const void* X, int32_t x_is_u16, const int32_t* batch_id, int64_t n_rows, int32_t n_genes,
+                      int32_t n_batches, double* batch_stats, double* gene_sums, float* lib, void* cuda_stream) {
+  if (!X || !batch_stats || !gene_sums || n_rows < 0 || n_genes < 1 || n_batches < 1) return SCDEF_EINVAL;
+  if (n_batches > 1 && !batch_id) return SCDEF_EINVAL;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cudaMemsetAsync(batch_stats, 0, sizeof(double) * 3 * (size_t)(n_batches + 1), st);
+  cudaMemsetAsync(gene_sums, 0, sizeof(double) * (size_t)(n_batches + 1) * n_genes, st);
+  if (n_rows == 0) return SCDEF_OK;
+  const unsigned blocks = (unsigned)((n_rows + 31) / 32);
+  if (x_is_u16) k_count_stats<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)X, batch_id, n_rows, n_genes, n_batches, batch_stats, gene_sums, lib);
+  else k_count_stats<float><<<blocks, 256, 0, st>>>((const float*)X, batch_id, n_rows, n_genes, n_batches, batch_stats, gene_sums, lib);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 

@@ -25,7 +25,7 @@
 // second GEMM D2[256 rows, KP]      += Q_h B2_h   (M = 256, N = KP split over the pair, K = 64 cols of half h)
 // Flattened work f = (rb * S + s) * n_pt + pt, cut into P contiguous chunks, one per CTA pair (148 SMs -> 74 pairs).
 // Barrier protocol: that of k_lik_pair_flat (lik_tc_pair.cuh; modelled in tests/test_pair_protocol.py); in the GLOBAL
-// orientation the ROW unit is released after the fold has read it (z_empty: the commit + the 16 epilogue warps).
+// orientation the fold reads W^s from the tile images in global memory, so the ROW unit is released by the tensor core as in LOCAL.
 #pragma once
 
 struct FlatGeom {
@@ -37,8 +37,11 @@ struct FlatGeom {
   int n_units;  // 128-row units in the count image of this orientation (= 2 * n_rblk)
 };
 
+constexpr uint32_t FOLD_GRP = 144;                 // 8 k0 rows x 16 B of one 8-gene group, padded so that the 4 groups of a warp fall into different banks
+constexpr uint32_t FOLD_SCRATCH = 2 * 4 * FOLD_GRP;   // hi and lo plane
+
 struct FlatSmem {
-  uint32_t a1, st[2], q, tab, misc, total;
+  uint32_t a1, st[2], q, fold, misc, total;
   uint32_t a1_plane, b1_plane, b2_piece, b2_off, stage, q_plane;
   uint32_t z_rs, zb_rs, u_rs;
 };
@@ -58,10 +61,38 @@ __host__ __device__ inline FlatSmem plan_flat_smem(int KP) {
   s.st[0] = o; o += s.stage;
   s.st[1] = o; o += s.stage;
   s.q = o; o += 2u * s.q_plane;
-  s.tab = o; o += (uint32_t)((2 + MAX_NB) * KP * 4 + 127) / 128u * 128u;
+  s.fold = o; o += 16u * FOLD_SCRATCH;   // GLOBAL: per epilogue warp, the W lines of one 8-k0 step of the fold
   s.misc = o;
   s.total = o + 1024u;
   return s;
+}
+
+
+// 32 lanes x 4 consecutive 32-bit columns (the fold works in groups of four elements to keep its live state small)
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_wait3(uint32_t (&a)[8], uint32_t (&b)[8], uint32_t (&c)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                 "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
 }
 
 struct FlatPos {   // position in the flattened space
@@ -71,7 +102,11 @@ struct FlatPos {   // position in the flattened space
   }
 };
 
-constexpr uint32_t FLAT_TMEM_D2 = 256, FLAT_TMEM_ACC = 384;
+// tensor-memory columns.  LOCAL: R[2] at 0 / 128, dz0[2] at 256 / 384.  GLOBAL: ONE R buffer at 0 (the whole-pair-tile
+// epilogue has both halves of R in registers ~1k cycles after the rate GEMM commits, and the next rate GEMM's result is
+// only needed a pair-tile later), dW^T at 128, and the two fold accumulators at 256 / 384 (d mu, sum t log W): the
+// accumulators of a gene block never occupy registers.
+constexpr uint32_t FLAT_TMEM_D2_LOCAL = 256, FLAT_TMEM_D2_GENES = 128, FLAT_TMEM_ACC_MU = 256, FLAT_TMEM_ACC_LW = 384;
 
 // W_0 prior parameters and rank-1 factors of the fold, per (sample, k0): [a1 | bm | ctS_0 .. ctS_{nb-1}], rows of KP floats.
 // scalar priors: a1 = gw (A - 1), bm = gw B;  matrix priors (MAT): a1 = 1 / tau, bm = 1 / (tau omega)
@@ -277,7 +312,7 @@ __global__ void __launch_bounds__(256) k_tc_w0_final_flat(const LikTcArgs a, con
 
 // ---- the kernel ------------------------------------------------------------------------------------------------
 template <bool GENES, bool WANT_LL, bool MAT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 registers: 112 x 576 threads is refused at launch
     k_lik_flat(const LikTcArgs a, const FlatGeom gm, const TcScratch ws, double* loss_out) {
   extern __shared__ __align__(1024) uint8_t sm[];
   const int KP = gm.KP;
@@ -308,7 +343,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
   if (threadIdx.x == 0) {
     mbar_init(&mi->z_full, 1);
     mbar_init(&mi->pz_full, 1);
-    mbar_init(&mi->z_empty, GENES ? 1 + E_WARPS : 1);
+    mbar_init(&mi->z_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&mi->w_full[i], 1);
       mbar_init(&mi->pw_full[i], 1);
@@ -334,7 +369,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
   tc_fence_after();
   const uint32_t tmem = mi->tmem_base;
   const PipeSmem IL = plan_pipe_smem(KP);   // layout of one W_0 tile image in global memory (k_tc_wgen)
-  const uint32_t tab_bytes = (uint32_t)((2 + a.nb) * KP * 4);
   auto first_in_seg = [&](int oi, const FlatPos& c) { return c.pt == 0 || oi == 0; };
   auto last_in_seg = [&](int oi, const FlatPos& c) { return c.pt == n_pt - 1 || oi == n_outer - 1; };
 
@@ -360,11 +394,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
           bulk_g2s(dst + L.b2_off + 3u * L.b2_piece, img1 + IL.w_plane + row_off, L.b2_piece, &mi->w_full[st]);
         }
         if (first_in_seg(oi, c)) {
-          // the ROW unit of the new segment replaces the old one once the tensor core (LOCAL) / the fold (GLOBAL) is done with it
+          // the ROW unit of the new segment replaces the old one once the segment's last rate GEMM has read it
           PT_WAIT(1, pair_wait(&mi->z_empty, ((uint32_t)c.g & 1u) ^ 1u, 17));
           const uint32_t unit = (uint32_t)(2 * c.rb) + rank;
           if (GENES) {
-            mbar_arrive_expect_tx(&mi->z_full, 2u * L.a1_plane + tab_bytes);
+            mbar_arrive_expect_tx(&mi->z_full, 2u * L.a1_plane);
             const int nkg = KP / 8, n_img = a.n_wimg;
             for (int hsel = 0; hsel < 2; ++hsel) {
               const int img = (int)unit * 2 + hsel;   // 64-gene tile image of this half of the unit
@@ -374,7 +408,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
                   bulk_g2s(sbase + L.a1 + (uint32_t)pl * L.a1_plane + (uint32_t)kg * L.u_rs + (uint32_t)hsel * 1024u,
                            src + (uint32_t)pl * IL.w_plane + (uint32_t)kg * W_RS, 1024u, &mi->z_full);
             }
-            bulk_g2s(sbase + L.tab, ws.foldtab + (long long)c.s * (2 + a.nb) * KP, tab_bytes, &mi->z_full);
           } else {
             mbar_arrive_expect_tx(&mi->z_full, 2u * L.a1_plane);
             bulk_g2s(sbase + L.a1, ws.zimg + ((long long)c.s * gm.n_units + unit) * (2u * L.a1_plane), 2u * L.a1_plane, &mi->z_full);
@@ -427,7 +460,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
         if (first_in_seg(oi, c1) && !(mbar_test(&mi->z_full, (uint32_t)c1.g & 1u) && mbar_test_remote(&mi->pz_full, (uint32_t)c1.g & 1u)))
           return false;
         return mbar_test(&mi->w_full[st], par) && mbar_test_remote(&mi->pw_full[st], par) &&
-               mbar_test_remote(&mi->r_empty[st], par ^ 1u);
+               mbar_test_remote(&mi->r_empty[GENES ? 0 : st], (GENES ? ((uint32_t)oi & 1u) : par) ^ 1u);
       };
       auto issue_mma1 = [&](int oi) {
         const int st = oi & 1;
@@ -438,11 +471,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
         }
         PT_WAIT(0, pair_wait(&mi->w_full[st], par, 4));
         PT_WAIT(1, pair_wait_remote(&mi->pw_full[st], par, 5));
-        PT_WAIT(2, pair_wait_remote(&mi->r_empty[st], par ^ 1u, 6));
+        // R: double-buffered with the stage (LOCAL) or a single buffer (GLOBAL: barrier 0, one phase per pair-tile)
+        const int rs = GENES ? 0 : st;
+        const uint32_t rpar = GENES ? ((uint32_t)oi & 1u) : par;
+        PT_WAIT(2, pair_wait_remote(&mi->r_empty[rs], rpar ^ 1u, 6));
         tc_fence_after();
         PT_MARK();
         uint64_t da = d_a1, db = d_b1[st];
-        const uint32_t d = tmem + (uint32_t)st * (2 * TG);
+        const uint32_t d = tmem + (uint32_t)rs * (2 * TG);
         umma2_bf16(d, da + a1pl, db, idesc1, 0u);
         umma2_bf16(d, da, db + b1pl, idesc1, 1u);
         umma2_bf16(d, da, db, idesc1, 1u);
@@ -453,7 +489,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
           umma2_bf16(d, da, db + b1pl, idesc1, 1u);
           umma2_bf16(d, da, db, idesc1, 1u);
         }
-        umma2_commit(&mi->r_full[st]);
+        umma2_commit(&mi->r_full[rs]);
         if (last_in_seg(oi, c1)) umma2_commit(&mi->z_empty);   // the segment's ROW unit has been read by its last rate GEMM
         PT_LAP(4);
         c1.next(n_pt, S);
@@ -481,7 +517,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
         if (seg_first) PT_WAIT(7, pair_wait_remote(&mi->dz_empty[dzb], (dz_use & 1u) ^ 1u, 19));   // drained / folded
         tc_fence_after();
         PT_MARK();
-        const uint32_t d = tmem + FLAT_TMEM_D2 + dzb * FLAT_DZ_STRIDE;
+        const uint32_t d = tmem + (GENES ? FLAT_TMEM_D2_GENES : FLAT_TMEM_D2_LOCAL + dzb * FLAT_DZ_STRIDE);
         uint64_t da = dq_k, db = d_b2[st] + (uint64_t)(2 * h) * b2pl;
         umma2_bf16(d, da + qpl, db, idesc2, seg_first ? 0u : 1u);
         umma2_bf16(d, da, db + b2pl, idesc2, 1u);
@@ -526,13 +562,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
         }
       }
     };
+    // split of 8 values into bf16 hi (round to nearest: F2FP, the conversion pipe is the epilogue's bottleneck together
+    // with MUFU.RCP) and lo = the upper 16 bits of (x - hi) (truncation: one PRMT on the integer pipe).  hi + lo carries
+    // 15 bits beyond hi's 8; the truncation error has the sign of lo, which is random because hi is rounded to nearest.
+    auto split8t = [](const float* x, uint4& hi, uint4& lo) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+        const float r0 = x[2 * i] - __uint_as_float(h[i] << 16);
+        const float r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
+        l[i] = __byte_perm(__float_as_uint(r0), __float_as_uint(r1), 0x7632);   // {r1[31:16], r0[31:16]}
+      }
+      hi = make_uint4(h[0], h[1], h[2], h[3]);
+      lo = make_uint4(l[0], l[1], l[2], l[3]);
+    };
     auto store_q = [&](const float (&q)[16]) {
       uint4 hi, lo;
       const uint32_t off = L.q + (uint32_t)(r >> 3) * Q_RS + (uint32_t)(r & 7) * 16u + (uint32_t)(cq * 2) * 128u;
-      split8(q, hi, lo);
+      split8t(q, hi, lo);
       *reinterpret_cast<uint4*>(sm + off) = hi;
       *reinterpret_cast<uint4*>(sm + off + L.q_plane) = lo;
-      split8(q + 8, hi, lo);
+      split8t(q + 8, hi, lo);
       *reinterpret_cast<uint4*>(sm + off + 128u) = hi;
       *reinterpret_cast<uint4*>(sm + off + 128u + L.q_plane) = lo;
       fence_async_q();
@@ -550,7 +601,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
       const long long fseg = ((long long)p.rb * S + p.s) * n_pt;
       const int slot = chunk - flat_chunk_of(fseg, T, P);
       float* dst = ws.part + (((long long)p.s * gm.slots + slot) * a.B + j) * a.K0;
-      const uint32_t tdz = tmem + FLAT_TMEM_D2 + dzb * FLAT_DZ_STRIDE + (lane_base << 16);
+      const uint32_t tdz = tmem + FLAT_TMEM_D2_LOCAL + dzb * FLAT_DZ_STRIDE + (lane_base << 16);
       const bool vec4 = (a.K0 & 3) == 0, valid = j < a.B;
       for (int ch = cq; ch < KP / 16; ch += 4) {
         float v[16];
@@ -573,71 +624,103 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
       PT_LAP(8);
     };
 
-    // ---- GLOBAL: fold dW^T of the segment into d mu (tensor memory) and sum t log W (registers) ----
-    float acc_lw[32];
+    // ---- GLOBAL: fold dW^T of the segment into the two accumulators of the gene block (tensor memory) ----
     bool acc_live = false;   // the accumulators hold a partial sum of the current gene block
-    if (GENES) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc_lw[i] = 0.f;
-    }
-    const uint32_t tacc_mu = tmem + FLAT_TMEM_ACC + (lane_base << 16);
+    const uint32_t tacc_mu = tmem + FLAT_TMEM_ACC_MU + (lane_base << 16), tacc_lw = tmem + FLAT_TMEM_ACC_LW + (lane_base << 16);
     auto fold_segment = [&](const FlatPos& p) {
+      // W^s of this thread's gene comes from the tile image in global memory (L2: the COPY thread streamed it a segment
+      // ago), NOT from the ROW unit in shared memory: the unit is released by the segment's last rate GEMM, so the next
+      // segment's unit loads while this one is still being processed and folded (no bubble in the tensor pipeline).
+      // Per step of 8 k0 rows a warp fetches its 4 x 128 B image lines with one 16 B load per lane and plane (lane =
+      // (gene group, k0 row)), parks them in its private scratch and reads its own gene's column back; the next step's
+      // lines are in flight meanwhile, and the first step's are requested before the wait for the segment's last GEMM.
+      const int g = (p.rb * 2 + (int)rank) * UC + r;
+      const bool gok = g < a.G;
+      const float* tab = ws.foldtab + (long long)p.s * (2 + a.nb) * KP;
+      const uint8_t* wline = ws.wimg + ((long long)p.s * a.n_wimg + (p.rb * 2 + (int)rank) * 2 + (r >> 6)) * IL.w_unit +
+                             (uint32_t)((r & 63) >> 3) * 128u + (uint32_t)(r & 7) * 16u;   // + plane * w_plane + kg * W_RS
+      const int n_steps = 2 * ((KP / 16 - cq + 3) / 4);   // 8-k0 steps of this thread's chunks cq, cq + 4, ...
+      auto step_kg = [&](int t) { return 2 * (cq + 4 * (t >> 1)) + (t & 1); };
+      uint4 nh = make_uint4(0, 0, 0, 0), nl = nh;
+      if (n_steps > 0) {
+        const uint8_t* q0 = wline + (uint32_t)step_kg(0) * W_RS;
+        nh = __ldg(reinterpret_cast<const uint4*>(q0));
+        nl = __ldg(reinterpret_cast<const uint4*>(q0 + IL.w_plane));
+      }
+      // A chunk boundary may cut a segment in two: the terms that do not depend on dW' (the W_0 prior gradient and the
+      // rank-1 part) belong to the piece that holds the segment's first pair-tile only.
+      const float own = (p.g > 0 || cur0.pt == 0) ? 1.f : 0.f;
+      float sgv[MAX_NB];
+#pragma unroll
+      for (int b = 0; b < MAX_NB; ++b) sgv[b] = (b < a.nb && gok && a.lik_on) ? own * a.smp_s[((long long)p.s * a.nb + b) * a.G + g] : 0.f;
       PT_WAIT(7, pair_wait(&mi->dz_full[0], (uint32_t)p.g & 1u, 13));
       tc_fence_after();
       PT_MARK();
-      const int g = (p.rb * 2 + (int)rank) * UC + r;
-      const bool gok = g < a.G;
-      const float* tab = reinterpret_cast<const float*>(sm + L.tab);
-      float sgv[MAX_NB];
+      const uint32_t td2 = tmem + FLAT_TMEM_D2_GENES + (lane_base << 16);
+      uint8_t* scr = sm + L.fold + (uint32_t)e * FOLD_SCRATCH;
+      const uint32_t scr_w = (uint32_t)(lane >> 3) * FOLD_GRP + (uint32_t)(lane & 7) * 16u;   // where this lane parks its line piece
+      const uint32_t scr_r = (uint32_t)(lane >> 3) * FOLD_GRP + (uint32_t)(lane & 7) * 2u;    // its own gene's column: + kk * 16
+      float t_a1 = 0.f, t_bm = 0.f, t_ct[MAX_NB];
+#pragma unroll 1
+      for (int t = 0; t < n_steps; ++t) {
+        const int kg = step_kg(t), k0 = kg * 8;
+        if ((t & 1) == 0) {
+          // the table row of this chunk: lanes 0..15 hold one k each, the element loop reads them by shuffle
+          const int kl = k0 + (lane & 15);
+          t_a1 = own * __ldg(tab + kl);
+          t_bm = own * __ldg(tab + KP + kl);
 #pragma unroll
-      for (int b = 0; b < MAX_NB; ++b) sgv[b] = (b < a.nb && gok && a.lik_on) ? a.smp_s[((long long)p.s * a.nb + b) * a.G + g] : 0.f;
-      const uint32_t td2 = tmem + FLAT_TMEM_D2 + (lane_base << 16);
-      const uint32_t wrow = L.a1 + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 2u;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int ch = cq + 4 * cc;
-        if (ch < KP / 16) {
-          float dW[16], am[16];
-          tmem_ld16(td2 + (uint32_t)(ch * 16), dW);
-          if (acc_live) tmem_ld16(tacc_mu + (uint32_t)(ch * 16), am);
-          else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) am[i] = 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k = ch * 16 + i;
-            const uint32_t wo = wrow + (uint32_t)(k >> 3) * L.u_rs + (uint32_t)(k & 7) * 16u;
-            const float W = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(sm + wo)) << 16) +
-                            __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(sm + wo + L.a1_plane)) << 16);
-            float a1 = tab[k], bm = tab[KP + k];
-            if (MAT) {
-              const float Pv = (a.P && gok && k < a.K0) ? __ldg(a.P + (long long)k * a.G + g) : a.P_scalar;
-              const float Rv = (a.R && gok && k < a.K0) ? __ldg(a.R + (long long)k * a.G + g) : a.R_scalar;
-              bm = a.global_weight * Rv * (float)a.K0 * bm;                        // gw B,  B = R K0 / (tau omega)
-              a1 = a.global_weight * ((a.use_brd ? Pv * a1 : Pv) - 1.f);           // gw (A - 1),  A = P / tau
-            }
-            float cs = bm;
-#pragma unroll
-            for (int b = 0; b < MAX_NB; ++b)
-              if (b < a.nb) cs = fmaf(tab[(2 + b) * KP + k], sgv[b], cs);
-            const float t = fmaf(W, fmaf(a.scale, dW[i], -cs), a1);
-            if (W > V_LO_M && W < V_HI_M && gok && k < a.K0) {
-              am[i] += t;
-              acc_lw[cc * 16 + i] = fmaf(t, __logf(W), acc_lw[cc * 16 + i]);
-            }
-          }
-          tmem_st16(tacc_mu + (uint32_t)(ch * 16), am);
+          for (int b = 0; b < MAX_NB; ++b) t_ct[b] = b < a.nb ? __ldg(tab + (2 + b) * KP + kl) : 0.f;
         }
+        *reinterpret_cast<uint4*>(scr + scr_w) = nh;
+        *reinterpret_cast<uint4*>(scr + 4 * FOLD_GRP + scr_w) = nl;
+        __syncwarp();
+        if (t + 1 < n_steps) {
+          const uint8_t* qn = wline + (uint32_t)step_kg(t + 1) * W_RS;
+          nh = __ldg(reinterpret_cast<const uint4*>(qn));
+          nl = __ldg(reinterpret_cast<const uint4*>(qn + IL.w_plane));
+        }
+        uint32_t dW[8], am[8], al[8];
+        tmem_ld8_issue(td2 + (uint32_t)k0, dW);
+        if (acc_live) {
+          tmem_ld8_issue(tacc_mu + (uint32_t)k0, am);
+          tmem_ld8_issue(tacc_lw + (uint32_t)k0, al);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { am[i] = 0u; al[i] = 0u; }
+        }
+        tmem_ld8_wait3(dW, am, al);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = k0 + i, src = (t & 1) * 8 + i;
+          const float W = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(scr + scr_r + i * 16)) << 16) +
+                          __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(scr + 4 * FOLD_GRP + scr_r + i * 16)) << 16);
+          float a1 = __shfl_sync(0xffffffffu, t_a1, src), bm = __shfl_sync(0xffffffffu, t_bm, src);
+          if (MAT) {
+            const float Pv = (a.P && gok && k < a.K0) ? __ldg(a.P + (long long)k * a.G + g) : a.P_scalar;
+            const float Rv = (a.R && gok && k < a.K0) ? __ldg(a.R + (long long)k * a.G + g) : a.R_scalar;
+            bm = a.global_weight * Rv * (float)a.K0 * bm;   // gw B,  B = R K0 / (tau omega); table: own / (tau omega)
+            a1 = a.global_weight * (Pv * a1 - own);         // gw (A - 1),  A = P / tau; table: own / tau
+          }
+          float cs = bm;
+#pragma unroll
+          for (int b = 0; b < MAX_NB; ++b)
+            if (b < a.nb) cs = fmaf(__shfl_sync(0xffffffffu, t_ct[b], src), sgv[b], cs);
+          const float tt = fmaf(W, fmaf(a.scale, __uint_as_float(dW[i]), -cs), a1);
+          if (W > V_LO_M && W < V_HI_M && gok && k < a.K0) {
+            am[i] = __float_as_uint(__uint_as_float(am[i]) + tt);
+            al[i] = __float_as_uint(fmaf(tt, __logf(W), __uint_as_float(al[i])));
+          }
+        }
+        tmem_st8(tacc_mu + (uint32_t)k0, am);
+        tmem_st8(tacc_lw + (uint32_t)k0, al);
+        __syncwarp();   // everybody has read the scratch before the next step overwrites it
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       acc_live = true;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_remote(r_dzempty[0]);   // D2 may be overwritten by the next segment
-        mbar_arrive(&mi->z_empty);          // ... and this CTA's ROW unit replaced
-      }
+      if (lane == 0) mbar_arrive_remote(r_dzempty[0]);   // D2 may be overwritten by the next segment
       PT_LAP(8);
     };
     auto flush_block = [&](const FlatPos& p) {
@@ -646,24 +729,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
       const long long per_rb = (long long)S * n_pt;
       const int slot = chunk - flat_chunk_of((long long)p.rb * per_rb, T, P);
       const long long n = (long long)a.K0 * a.G;
+#pragma unroll 1
+      for (int ch = cq; ch < KP / 16; ch += 4) {
+        float am[16], al[16];
+        tmem_ld16(tacc_mu + (uint32_t)(ch * 16), am);
+        tmem_ld16(tacc_lw + (uint32_t)(ch * 16), al);
+        if (g < a.G) {
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int ch = cq + 4 * cc;
-        if (ch < KP / 16) {
-          float am[16];
-          tmem_ld16(tacc_mu + (uint32_t)(ch * 16), am);
-          if (g < a.G) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int k = ch * 16 + i;
-              if (k < a.K0) {
-                ws.part[((long long)slot * 2 + 0) * n + (long long)k * a.G + g] = am[i];
-                ws.part[((long long)slot * 2 + 1) * n + (long long)k * a.G + g] = acc_lw[cc * 16 + i];
-              }
+          for (int i = 0; i < 16; ++i) {
+            const int k = ch * 16 + i;
+            if (k < a.K0) {
+              ws.part[((long long)slot * 2 + 0) * n + (long long)k * a.G + g] = am[i];
+              ws.part[((long long)slot * 2 + 1) * n + (long long)k * a.G + g] = al[i];
             }
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) acc_lw[cc * 16 + i] = 0.f;
         }
       }
       acc_live = false;
@@ -690,9 +769,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
       FlatPos cn = cc;
       cn.next(n_pt, S);
       const float* xnext = x_ptr(cn);
-      const uint32_t taddr = tmem + (lane_base << 16) + (uint32_t)(st * (2 * TG) + cq * 16);
+      const int rs = GENES ? 0 : st;
+      const uint32_t rpar = GENES ? ((uint32_t)oi & 1u) : par;
+      const uint32_t taddr = tmem + (lane_base << 16) + (uint32_t)(rs * (2 * TG) + cq * 16);
       PT_MARK();
-      PT_WAIT(0, pair_wait(&mi->r_full[st], par, 11));
+      PT_WAIT(0, pair_wait(&mi->r_full[rs], rpar, 11));
       tc_fence_after();
       PT_MARK();
       uint32_t R0[16], R1[16];
@@ -701,7 +782,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
       tmem_ld16_wait(R0);
       PT_LAP(3);
       half_math(xa, R0, q);
-      if (more) {
+      // the next pair-tile's counts are fetched while this one is processed -- except across a fold (GLOBAL), whose
+      // working set needs the registers: there they are fetched after it
+      const bool x_early = more && !(GENES && last_in_seg(oi, cc));
+      if (x_early) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) xa[v] = *reinterpret_cast<const float4*>(xnext + v * 128);
       }
@@ -713,10 +797,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
       tmem_ld16_wait(R1);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(r_rempty[st]);   // both halves of R[st] are in registers
+      if (lane == 0) mbar_arrive_remote(r_rempty[rs]);   // both halves of R are in registers
       PT_LAP(5);
       half_math(xb, R1, q);
-      if (more) {
+      if (x_early) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) xb[v] = *reinterpret_cast<const float4*>(xnext + x_tile + v * 128);
       }
@@ -729,6 +813,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)
         if (GENES) {
           fold_segment(cc);
           if (!more || cn.rb != cc.rb) flush_block(cc);
+          if (more) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { xa[v] = *reinterpret_cast<const float4*>(xnext + v * 128); xb[v] = *reinterpret_cast<const float4*>(xnext + x_tile + v * 128); }
+          }
         } else {
           drain_segment(cc);
         }

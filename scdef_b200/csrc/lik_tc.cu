@@ -342,6 +342,12 @@ struct TcScratch {
   uint8_t* wimg;    // (S, n_tiles) W_0 sample tiles: [hi plane | lo plane | gene-scale tile (MAX_NB x 64 f32)]
   int* brow;        // (B) batch of each minibatch row
   long long* xoff;  // (B) element offset of each minibatch row in X
+  // unified pair kernel (lik_flat.cuh)
+  float* Ws;        // (S,nb,K0)  sum_g W^s[k][g] s^s[b][g]           } persist from the LOCAL to the GLOBAL pass
+  float* rowsumx;   // (B)        sum_g x[j][g]
+  uint8_t* zimg_g;  // (S, cell pair-tiles, 2 ranks) z0 column stages of the GLOBAL orientation
+  float* ximg_t;    // counts, row = gene (GLOBAL orientation)
+  float* foldtab;   // (S, 2 + nb, KP) W_0 prior parameters and rank-1 factors of the fold
 };
 
 // =====================================================================================================
@@ -612,6 +618,7 @@ __global__ void __launch_bounds__(NT, 1) k_lik_tc_global(const LikTcArgs a, cons
 
 #include "lik_tc_pipe.cuh"
 #include "lik_tc_pair.cuh"
+#include "lik_flat.cuh"
 
 // ---- pre-kernels of the pipelined path -----------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_tc_wprep(const LikTcArgs a, float* wmu, float* wsig) {
@@ -629,8 +636,7 @@ __global__ void __launch_bounds__(256) k_tc_rowprep(const LikTcArgs a, int* brow
 }
 // minibatch counts -> image in which the epilogue's "lane = cell row, 16 B per lane" loads are contiguous:
 // element (row = unit*128 + q*32 + lane, gene = tile*64 + v*4 + i) at ((((tile*units + unit)*4 + q)*16 + v)*32 + lane)*4 + i
-__global__ void __launch_bounds__(256) k_tc_xprep(const LikTcArgs a, float* ximg, int n_tiles) {
-  const int units = (a.B + UC - 1) / UC;
+__global__ void __launch_bounds__(256) k_tc_xprep(const LikTcArgs a, float* ximg, int n_tiles, int units) {
   const long long total = (long long)n_tiles * units * 4 * 16 * 32;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     // decode so that consecutive threads read consecutive genes of one row (coalesced reads)
@@ -648,8 +654,8 @@ __global__ void __launch_bounds__(256) k_tc_xprep(const LikTcArgs a, float* ximg
 }
 
 // z0 samples (S,B,K0) fp32 -> per (s, 128-cell unit) image [hi plane | lo plane] in the canonical layout
-__global__ void __launch_bounds__(256) k_tc_zprep(const LikTcArgs a, uint8_t* zimg, int KP) {
-  const int nchunk = KP / 8, units = (a.B + UC - 1) / UC;
+__global__ void __launch_bounds__(256) k_tc_zprep(const LikTcArgs a, uint8_t* zimg, int KP, int units) {
+  const int nchunk = KP / 8;
   const uint32_t z_rs = (uint32_t)nchunk * 128u, z_plane = 16u * z_rs;
   const long long per_unit = (long long)UC * nchunk, total = (long long)a.S * units * per_unit;
   const bool vec = (a.K0 & 3) == 0;
@@ -684,13 +690,13 @@ __global__ void __launch_bounds__(256) k_tc_zprep(const LikTcArgs a, uint8_t* zi
 // Also: the per-row sums (sum_g log W, sum_g W) of the W_0 prior, and the gene-scale sample tile.
 __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScratch ws, int KP, int n_tiles, uint32_t w_plane,
                                                  uint32_t w_unit) {
-  __shared__ float rowacc[128][2];
+  __shared__ float rowacc[128][2 + MAX_NB];   // per k0 row: sum log W, sum W, sum_g W s_b[g] (the rank-1 vector W s_b)
   const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const int kk = tid & 7, cgl = tid >> 3;
   const int g = blockIdx.x * 256 + cgl * 8;
   const int tile = g / TG, cg = (g % TG) / 8;
   const int nkg = KP / 8;
-  for (int i = tid; i < 256; i += 256) (&rowacc[0][0])[i] = 0.f;
+  for (int i = tid; i < 128 * (2 + MAX_NB); i += 256) (&rowacc[0][0])[i] = 0.f;
   __syncthreads();
   if (tile < n_tiles) {
     uint8_t* unit = ws.wimg + ((long long)s * n_tiles + tile) * w_unit;
@@ -736,6 +742,18 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
         atomicAdd(&rowacc[k][0], su);
         atomicAdd(&rowacc[k][1], sw);
       }
+      // (W s_b)[k] += sum over this thread's 8 genes; the gene-scale samples come through L1 (same for every kg)
+      for (int b = 0; b < a.nb; ++b) {
+        float d = 0.f;
+        if (k < a.K0 && gok) {
+          const float* sp = a.smp_s + ((long long)s * a.nb + b) * a.G + g;
+          const float4 t0 = *reinterpret_cast<const float4*>(sp), t1 = *reinterpret_cast<const float4*>(sp + 4);
+          d = w[0] * t0.x + w[1] * t0.y + w[2] * t0.z + w[3] * t0.w + w[4] * t1.x + w[5] * t1.y + w[6] * t1.z + w[7] * t1.w;
+        }
+        d += __shfl_xor_sync(0xffffffffu, d, 8);
+        d += __shfl_xor_sync(0xffffffffu, d, 16);
+        if (lane < 8 && k < a.K0) atomicAdd(&rowacc[k][2 + b], d);
+      }
     }
   }
   // gene-scale sample tile(s) of this block's 256 genes
@@ -752,6 +770,7 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
     if (rowacc[k][0] != 0.f || rowacc[k][1] != 0.f) {
       atomicAdd(&ws.rowstats[((long long)s * a.K0 + k) * 2 + 0], rowacc[k][0]);
       atomicAdd(&ws.rowstats[((long long)s * a.K0 + k) * 2 + 1], rowacc[k][1]);
+      for (int b = 0; b < a.nb; ++b) atomicAdd(&ws.Ws[((long long)s * a.nb + b) * a.K0 + k], rowacc[k][2 + b]);
     }
   }
 }
@@ -1072,6 +1091,66 @@ Geom make_geom(int B, int S, int K0, int G) {
 
 size_t a256(size_t x) { return (x + 255) / 256 * 256; }
 
+// The unified CTA-pair kernel of lik_flat.cuh is the default for both passes.  SCDEF_TC_FLAT=0 selects the round-1
+// kernels (k_lik_pair_flat for LOCAL, the single-CTA k_lik_pipe for GLOBAL) for A/B checks.  Read once per process.
+int flat_mode() {
+  static const int mode = getenv("SCDEF_TC_FLAT") != nullptr ? atoi(getenv("SCDEF_TC_FLAT")) : 1;
+  return mode;
+}
+int g_sm_count = 148;   // set by lik_tc_launch / lik_tc_workspace_bytes callers through lik_tc_set_sm_count
+
+FlatGeom make_flat_geom(bool genes, int B, int S, int K0, int G) {
+  FlatGeom g;
+  g.KP = round_up16(K0);
+  const int n_gb = (G + 255) / 256, Bp = B > 0 ? B : 1;
+  if (genes) { g.n_rblk = n_gb; g.n_pt = (Bp + 127) / 128; }
+  else { g.n_rblk = (Bp + 255) / 256; g.n_pt = 2 * n_gb; }
+  g.n_units = 2 * g.n_rblk;
+  const long long T = (long long)g.n_rblk * S * g.n_pt;
+  long long P = g_sm_count / 2;
+  if (P < 1) P = 1;
+  if (P > T) P = T > 0 ? T : 1;
+  g.P = (int)P;
+  int slots = 1;
+  if (genes) {
+    const long long per_rb = (long long)S * g.n_pt;
+    for (int rb = 0; rb < g.n_rblk; ++rb) {
+      const int n = flat_chunk_of((rb + 1) * per_rb - 1, T, g.P) - flat_chunk_of(rb * per_rb, T, g.P) + 1;
+      if (n > slots) slots = n;
+    }
+  } else {
+    for (long long sg = 0; sg < (long long)g.n_rblk * S; ++sg) {
+      const int n = flat_chunk_of((sg + 1) * g.n_pt - 1, T, g.P) - flat_chunk_of(sg * g.n_pt, T, g.P) + 1;
+      if (n > slots) slots = n;
+    }
+  }
+  g.slots = slots;
+  return g;
+}
+
+struct FlatSizes {
+  size_t part, zimg, ximg, zimg_g, ximg_t, foldtab, Ws, rowsumx, wimg;
+  int n_tiles;
+};
+FlatSizes flat_sizes(int B, int S, int K0, int G, int nb) {
+  const FlatGeom gl = make_flat_geom(false, B, S, K0, G), gg = make_flat_geom(true, B, S, K0, G);
+  const FlatSmem L = plan_flat_smem(gl.KP);
+  const size_t Bp = (size_t)(B > 0 ? B : 1);
+  FlatSizes z;
+  z.n_tiles = 4 * ((G + 255) / 256);
+  const size_t pl = (size_t)S * gl.slots * Bp * K0 * 4, pg = (size_t)gg.slots * 2 * K0 * G * 4;
+  z.part = pl > pg ? pl : pg;
+  z.zimg = (size_t)S * gl.n_units * 2 * L.a1_plane;
+  z.ximg = (size_t)z.n_tiles * gl.n_units * 128 * 64 * 4;
+  z.zimg_g = (size_t)S * gg.n_pt * 2 * L.stage;
+  z.ximg_t = (size_t)(2 * gg.n_pt) * gg.n_units * 128 * 64 * 4;
+  z.foldtab = (size_t)S * (2 + nb) * gl.KP * 4;
+  z.Ws = (size_t)S * nb * K0 * 4;
+  z.rowsumx = Bp * 4;
+  z.wimg = (size_t)S * z.n_tiles * plan_pipe_smem(gl.KP).w_unit;
+  return z;
+}
+
 }  // namespace
 
 bool lik_tc_supported(int K0, int G, int nb) { return K0 >= 1 && K0 <= 112 && (G % 8) == 0 && nb >= 1 && nb <= MAX_NB; }
@@ -1081,12 +1160,21 @@ size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb) {
   size_t part_local = (size_t)S * (g.NG > g.NGp ? g.NG : g.NGp) * (size_t)(B > 0 ? B : 1) * K0 * 4;
   size_t part_global = (size_t)g.n_chunks * 2 * K0 * G * 4;
   const size_t Bp = (size_t)(B > 0 ? B : 1), units = (Bp + 127) / 128;
-  const size_t zimg = (size_t)S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
-  return a256((size_t)S * K0 * 2 * 4) + a256((size_t)S * nb * K0 * 4) + a256((size_t)nb * G * 4) +
-         a256(part_local > part_global ? part_local : part_global) + 2 * a256((size_t)K0 * G * 4) + a256(zimg) +
-         a256(Bp * 4) + a256(Bp * 8) + a256((size_t)S * g.n_tiles * plan_pipe_smem(g.KP).w_unit) +
-         a256((size_t)g.n_tiles * units * 128 * 64 * 4) + 1024;
+  const FlatSizes f = flat_sizes(B, S, K0, G, nb);
+  size_t part = part_local > part_global ? part_local : part_global;
+  if (f.part > part) part = f.part;
+  size_t zimg = (size_t)S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
+  if (f.zimg > zimg) zimg = f.zimg;
+  size_t wimg = (size_t)S * g.n_tiles * plan_pipe_smem(g.KP).w_unit;
+  if (f.wimg > wimg) wimg = f.wimg;
+  size_t ximg = (size_t)g.n_tiles * units * 128 * 64 * 4;
+  if (f.ximg > ximg) ximg = f.ximg;
+  return a256((size_t)S * K0 * 2 * 4) + a256((size_t)S * nb * K0 * 4) + a256((size_t)nb * G * 4) + a256(part) +
+         2 * a256((size_t)K0 * G * 4) + a256(zimg) + a256(Bp * 4) + a256(Bp * 8) + a256(wimg) + a256(ximg) +
+         a256(f.Ws) + a256(f.rowsumx) + a256(f.zimg_g) + a256(f.ximg_t) + a256(f.foldtab) + 1024;
 }
+
+void lik_tc_set_sm_count(int n) { if (n > 1) g_sm_count = n; }
 
 void lik_tc_set_debug(float* p) { cudaMemcpyToSymbol(g_dbg_R, &p, sizeof(p)); }
 
@@ -1128,7 +1216,7 @@ void lik_tc_read_timing(unsigned long long* out) {
 }
 
 int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStream_t st) {
-  (void)sm_count;
+  lik_tc_set_sm_count(sm_count);
   LikTcArgs a = a_in;
   static const int dbg_nsplit = getenv("SCDEF_TC_NSPLIT") ? atoi(getenv("SCDEF_TC_NSPLIT")) : 3;  // timing experiments only
   a.dbg_nsplit = dbg_nsplit;
@@ -1142,24 +1230,38 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   const Geom g = make_geom(a.B, a.S, a.K0, a.G);
   char* w = (char*)a.ws;
   TcScratch ws;
+  const FlatSizes fz = flat_sizes(a.B, a.S, a.K0, a.G, a.nb);
+  const bool flat = flat_mode() != 0;
   ws.rowstats = (float*)w; w += a256((size_t)a.S * a.K0 * 2 * 4);
   ws.ctilde = (float*)w;   w += a256((size_t)a.S * a.nb * a.K0 * 4);
   ws.colsumX = (float*)w;  w += a256((size_t)a.nb * a.G * 4);
   ws.part = (float*)w;
-  {
-    size_t part_local = (size_t)a.S * (g.NG > g.NGp ? g.NG : g.NGp) * (size_t)(a.B > 0 ? a.B : 1) * a.K0 * 4;
-    size_t part_global = (size_t)g.n_chunks * 2 * a.K0 * a.G * 4;
-    w += a256(part_local > part_global ? part_local : part_global);
-  }
   const size_t Bp = (size_t)(a.B > 0 ? a.B : 1), units = (Bp + 127) / 128;
-  const size_t zimg_bytes = (size_t)a.S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
+  {
+    size_t part_local = (size_t)a.S * (g.NG > g.NGp ? g.NG : g.NGp) * Bp * a.K0 * 4;
+    size_t part_global = (size_t)g.n_chunks * 2 * a.K0 * a.G * 4;
+    size_t part = part_local > part_global ? part_local : part_global;
+    if (fz.part > part) part = fz.part;
+    w += a256(part);
+  }
+  size_t zimg_bytes = (size_t)a.S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
+  if (fz.zimg > zimg_bytes) zimg_bytes = fz.zimg;
+  size_t wimg_bytes = (size_t)a.S * g.n_tiles * plan_pipe_smem(g.KP).w_unit;
+  if (fz.wimg > wimg_bytes) wimg_bytes = fz.wimg;
+  size_t ximg_bytes = (size_t)g.n_tiles * units * 128 * 64 * 4;
+  if (fz.ximg > ximg_bytes) ximg_bytes = fz.ximg;
   ws.wmu = (float*)w;      w += a256((size_t)a.K0 * a.G * 4);
   ws.wsig = (float*)w;     w += a256((size_t)a.K0 * a.G * 4);
   ws.zimg = (uint8_t*)w;   w += a256(zimg_bytes);
   ws.brow = (int*)w;       w += a256(Bp * 4);
   ws.xoff = (long long*)w; w += a256(Bp * 8);
-  ws.wimg = (uint8_t*)w;   w += a256((size_t)a.S * g.n_tiles * plan_pipe_smem(g.KP).w_unit);
-  ws.ximg = (float*)w;     w += a256((size_t)g.n_tiles * units * 128 * 64 * 4);
+  ws.wimg = (uint8_t*)w;   w += a256(wimg_bytes);
+  ws.ximg = (float*)w;     w += a256(ximg_bytes);
+  ws.Ws = (float*)w;       w += a256(fz.Ws);
+  ws.rowsumx = (float*)w;  w += a256(fz.rowsumx);
+  ws.zimg_g = (uint8_t*)w; w += a256(fz.zimg_g);
+  ws.ximg_t = (float*)w;   w += a256(fz.ximg_t);
+  ws.foldtab = (float*)w;  w += a256(fz.foldtab);
   if ((size_t)(w - (char*)a.ws) > a.ws_bytes) return SCDEF_EWORKSPACE;
   const Smem L = plan_smem(g.KP);
   const PipeSmem PL = plan_pipe_smem(g.KP);
@@ -1170,7 +1272,72 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   cudaEvent_t ev0 = a.ev0, ev1 = a.ev1;
   a.ev0 = a.ev1 = nullptr;
   const bool reuse = pipe && a.reuse_w0;  // W_0 image + row sums of the previous pass (same noise, same W_0) are still valid
-  if (!reuse) cudaMemsetAsync(ws.rowstats, 0, (size_t)a.S * a.K0 * 2 * 4, st);
+  if (!reuse) {
+    cudaMemsetAsync(ws.rowstats, 0, (size_t)a.S * a.K0 * 2 * 4, st);
+    cudaMemsetAsync(ws.Ws, 0, (size_t)a.S * a.nb * a.K0 * 4, st);
+  }
+  a.n_wimg = flat ? fz.n_tiles : g.n_tiles;
+  if (pipe && flat) {
+    // ================= unified CTA-pair kernel (lik_flat.cuh) =================
+    const int n_tiles = fz.n_tiles;
+    const FlatGeom fg = make_flat_geom(global_pass, a.B, a.S, a.K0, a.G);
+    const FlatSmem FL = plan_flat_smem(fg.KP);
+    const int nblk = g_sm_count * 4;
+    const long long T = (long long)fg.n_rblk * a.S * fg.n_pt;
+    pair_stuck_init();
+    k_tc_rowprep<<<(a.B + 255) / 256, 256, 0, st>>>(a, ws.brow, ws.xoff);
+    k_tc_rowsum<<<(a.B + 7) / 8, 256, 0, st>>>(a, ws.rowsumx);
+    if (!reuse) {
+      k_tc_wprep<<<g_sm_count * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
+      k_tc_wgen<<<dim3(n_tiles / 4, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit);
+    }
+    auto launch = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total);
+      if (ev0) cudaEventRecord(ev0, st);
+      kern<<<dim3(2 * fg.P), PIPE_NT, FL.total, st>>>(a, fg, ws, loss_out);
+      if (ev1 && ev0) cudaEventRecord(ev1, st);
+    };
+    const int rank1_blocks = (int)(((long long)a.S * a.B + 7) / 8);
+    auto loss_terms = [&]() {
+      k_tc_loss_gs<<<g_sm_count, 256, 0, st>>>(a, ws.colsumX, loss_out);
+      if (matrix_prior)
+        k_tc_w0_prior_mat<<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out, 0);
+      else k_tc_w0_prior<<<(a.S * a.K0 + 127) / 128, 128, 0, st>>>(a, ws.rowstats, loss_out);
+    };
+    if (global_pass) {
+      k_tc_zprep_g<<<nblk, 256, 0, st>>>(a, ws.zimg_g, fg.KP, fg.n_pt);
+      k_tc_xprep_t<<<nblk, 256, 0, st>>>(a, ws.ximg_t, 2 * fg.n_pt, fg.n_units);
+      k_tc_ctilde<<<a.S, 1024, 0, st>>>(a, ws.ctilde);
+      k_tc_colsum<<<(a.G + 63) / 64, 1024, 0, st>>>(a, ws.colsumX);
+      k_tc_foldtab<<<a.S, 128, 0, st>>>(a, ws.ctilde, ws.foldtab, fg.KP, matrix_prior ? 1 : 0);
+      if (a.nb == 1) k_tc_colw<1><<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit);
+      else k_tc_colw<MAX_NB><<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit);
+      if (matrix_prior) launch(k_lik_flat<true, true, true>);
+      else launch(k_lik_flat<true, true, false>);
+      k_tc_rank1<<<rank1_blocks, 256, 0, st>>>(a, ws, nullptr, 0, T, fg.P, fg.n_pt, 0, 1, loss_out);
+      loss_terms();
+      k_tc_w0_final_flat<<<g_sm_count * 4, 256, 0, st>>>(a, ws.part, T, fg.P, a.S * fg.n_pt, loss_out);
+    } else {
+      k_tc_zprep<<<nblk, 256, 0, st>>>(a, ws.zimg, fg.KP, fg.n_units);
+      k_tc_xprep<<<nblk, 256, 0, st>>>(a, ws.ximg, n_tiles, fg.n_units);
+      if (a.want_loss) launch(k_lik_flat<false, true, false>);
+      else launch(k_lik_flat<false, false, false>);
+      k_tc_rank1<<<rank1_blocks, 256, 0, st>>>(a, ws, ws.part, fg.slots, T, fg.P, fg.n_pt, 1, a.want_loss ? 1 : 0, loss_out);
+      if (a.want_loss) {
+        k_tc_colsum<<<(a.G + 63) / 64, 1024, 0, st>>>(a, ws.colsumX);
+        loss_terms();
+        LikTcArgs v = a;
+        v.gmu_W0 = nullptr;   // LOCAL pass: the entropy value only
+        k_tc_w0_final_flat<<<g_sm_count * 4, 256, 0, st>>>(v, nullptr, T, fg.P, a.S * fg.n_pt, loss_out);
+      }
+    }
+    const cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) {
+      fprintf(stderr, "scdef_b200: lik_tc_launch (pair kernel): %s (smem %u)\n", cudaGetErrorString(e2), FL.total);
+      return SCDEF_ECUDA;
+    }
+    return SCDEF_OK;
+  }
   // matrix prior without the main kernel (likelihood off = W_0 frozen, or a rank without minibatch rows): the tile
   // images are still needed for the prior value and the brd / ard gradients
   const bool fold_prior_grad = matrix_prior && !pipe && global_pass && !a.w0_stopped;
@@ -1181,8 +1348,8 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   }
   if (pipe) {
     k_tc_rowprep<<<(a.B + 255) / 256, 256, 0, st>>>(a, ws.brow, ws.xoff);
-    k_tc_zprep<<<148 * 4, 256, 0, st>>>(a, ws.zimg, g.KP);
-    k_tc_xprep<<<148 * 4, 256, 0, st>>>(a, ws.ximg, g.n_tiles);
+    k_tc_zprep<<<148 * 4, 256, 0, st>>>(a, ws.zimg, g.KP, (int)units);
+    k_tc_xprep<<<148 * 4, 256, 0, st>>>(a, ws.ximg, g.n_tiles, (int)units);
     if (!reuse) {
       k_tc_wprep<<<148 * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
       k_tc_wgen<<<dim3((a.G + 255) / 256, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);

@@ -79,6 +79,50 @@ def shard_bounds(n_local: int, shard: ShardInfo):
     return start, int(sum(counts)), counts
 
 
+def _device_lib(X):
+    """Library sizes of device-resident counts (float32 / uint16) through the C ABI (`scdef_row_stats`)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+
+    lib = _lib.load()
+    n, G = int(X.shape[0]), int(X.shape[1])
+    out = torch.empty(max(n, 1), dtype=torch.float32, device=X.device)
+    st = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+    fn = lib.scdef_u16_row_stats if X.dtype in (torch.uint16, torch.int16) else lib.scdef_row_stats
+    rc = fn(C.c_void_p(X.data_ptr()), n, G, C.c_void_p(out.data_ptr()), None, st)
+    if rc != 0:
+        raise RuntimeError(f"row statistics failed ({rc})")
+    return out[:n].double().cpu().numpy()
+
+
+def _device_count_stats(X, batch_id, nb):
+    """(per-batch [n, sum lib, sum lib^2], per-batch gene sums), slot nb = all cells: `scdef_count_stats` on the device."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+
+    lib = _lib.load()
+    n, G = int(X.shape[0]), int(X.shape[1])
+    dev = X.device
+    st = torch.zeros((nb + 1, 3), dtype=torch.float64, device=dev)
+    gs = torch.zeros((nb + 1, G), dtype=torch.float64, device=dev)
+    bid = torch.as_tensor(np.ascontiguousarray(batch_id, dtype=np.int32), device=dev)
+    is16 = 1 if X.dtype in (torch.uint16, torch.int16) else 0
+    if not is16 and X.dtype != torch.float32:
+        raise TypeError("device-resident counts must be float32 or uint16")
+    rc = lib.scdef_count_stats(C.c_void_p(X.data_ptr()), is16, C.c_void_p(bid.data_ptr()), n, G, nb,
+                               C.c_void_p(st.data_ptr()), C.c_void_p(gs.data_ptr()), None,
+                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"scdef_count_stats failed ({rc})")
+    return st.cpu().numpy(), gs.cpu().numpy()
+
+
 def count_statistics(X, batch_labels, shard: ShardInfo, eps=1e-12):
     """The constants `load_adata` / `update_model_priors` derive from the counts
     (`_scdef.py:498-573, 1279-1287`), computed over ALL ranks' cells.  float64 throughout."""
@@ -86,7 +130,10 @@ def count_statistics(X, batch_labels, shard: ShardInfo, eps=1e-12):
     is_sparse = hasattr(X, "tocsr")
     dev = X.device if (is_torch and X.is_cuda and shard.world > 1) else None
     n_local, G = int(X.shape[0]), int(X.shape[1])
-    if is_sparse:
+    on_device = bool(is_torch and X.is_cuda)
+    if on_device:
+        lib = _device_lib(X)
+    elif is_sparse:
         lib = np.asarray(X.sum(axis=1, dtype=np.float64)).ravel()
     elif is_torch:
         import torch
@@ -117,15 +164,19 @@ def count_statistics(X, batch_labels, shard: ShardInfo, eps=1e-12):
         return rows.sum(0, dtype=np.float64)
 
     # sufficient statistics: per batch [count, sum lib, sum lib^2] and gene sums
-    st = np.zeros((nb + 1, 3))
-    gs = np.zeros((nb + 1, G))
-    st[nb] = [n_local, lib.sum(), (lib**2).sum()]
-    gs[nb] = gene_sums()
-    if nb > 1:
-        for i in range(nb):
-            m = batch_id == i
-            st[i] = [m.sum(), lib[m].sum(), (lib[m] ** 2).sum()]
-            gs[i] = gene_sums(np.where(m)[0])
+    if on_device:
+        # counts resident in HBM (float32 or uint16): one pass of `scdef_count_stats` over them
+        st, gs = _device_count_stats(X, batch_id, nb)
+    else:
+        st = np.zeros((nb + 1, 3))
+        gs = np.zeros((nb + 1, G))
+        st[nb] = [n_local, lib.sum(), (lib**2).sum()]
+        gs[nb] = gene_sums()
+        if nb > 1:
+            for i in range(nb):
+                m = batch_id == i
+                st[i] = [m.sum(), lib[m].sum(), (lib[m] ** 2).sum()]
+                gs[i] = gene_sums(np.where(m)[0])
     st = _allreduce_np(st, shard, dev)
     gs = _allreduce_np(gs, shard, dev)
     n_total = int(round(st[nb, 0]))

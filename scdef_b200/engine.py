@@ -101,7 +101,7 @@ class Engine:
                  batch_id, batch_lib_ratio, cell_alpha_factor, gene_ratio, w_priors,
                  use_brd=True, marginalize_alpha=False, top_alpha=1.0, brd=1.0, brd_mean=1.0,
                  shrinkage_shape=1.0, shrinkage_rate=1.0, cell_scale_shape=1.0, gene_scale_shape=1.0,
-                 alpha_floor=0.1, supervised_layer=None, fixed_top_z=None, X=None, X_csr=None,
+                 alpha_floor=0.1, supervised_layer=None, fixed_top_z=None, X=None, X_csr=None, X_u16=None,
                  device="cuda:0", batch_max=256, lazy_adam=True):
         if not torch.cuda.is_available():
             raise ScdefError("scdef_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
@@ -141,6 +141,21 @@ class Engine:
             rc = self.lib.scdef_csr_row_stats(_ptr(self.X_csr[0]), _ptr(self.X_csr[2]), self.N, None, _ptr(self.x_lgamma), self._stream())
             if rc != 0:
                 raise ScdefError(f"scdef_csr_row_stats failed ({rc})")
+            self._xb_scratch = None
+        # counts kept as uint16 on the device (half of float32's HBM); a minibatch is converted per call
+        # (`scdef_u16_gather_rows`) into the dense float32 X_batch, like the CSR rows
+        self.X_u16 = None
+        if X_u16 is not None:
+            if self.X is not None or self.X_csr is not None:
+                raise ScdefError("give one of X, X_csr, X_u16")
+            t = X_u16 if isinstance(X_u16, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X_u16))
+            if t.dtype not in (torch.uint16, torch.int16):
+                t = t.to(torch.uint16)
+            self.X_u16 = t.to(dev).contiguous()
+            self.x_lgamma = torch.empty(max(self.N, 1), dtype=torch.float32, device=dev)
+            rc = self.lib.scdef_u16_row_stats(_ptr(self.X_u16), self.N, self.G, None, _ptr(self.x_lgamma), self._stream())
+            if rc != 0:
+                raise ScdefError(f"scdef_u16_row_stats failed ({rc})")
             self._xb_scratch = None
         if self.X is not None and self.N > 0:
             self.x_lgamma = torch.empty(self.N, dtype=torch.float32, device=dev)
@@ -274,7 +289,8 @@ class Engine:
         constants, the local blocks and their Adam moments (mu and rho planes), the lazy-Adam row clock.
         This is what `dist.RowMigrator` moves when the cells change ranks at an epoch boundary."""
         out = []
-        for t in (self.X, self.batch_id, self.batch_lib_ratio, self.cell_alpha_factor, self.x_lgamma,
+        x16 = None if self.X_u16 is None else self.X_u16.view(torch.int16)   # NCCL moves it as int16 bits
+        for t in (self.X, x16, self.batch_id, self.batch_lib_ratio, self.cell_alpha_factor, self.x_lgamma,
                   self.row_step, self.fixed_top_z):
             if t is not None and t.numel() > 0:
                 out.append(t.view(self.N, -1))
@@ -320,7 +336,7 @@ class Engine:
         B = int(indices.numel())
         self._ensure_batch(B)
         self._ensure_workspace(B, int(num_samples), lik_impl)
-        if X_batch is None and self.X_csr is not None and B > 0:
+        if X_batch is None and (self.X_csr is not None or self.X_u16 is not None) and B > 0:
             X_batch = self.gather_rows(indices)
         call = Call()
         call.pass_ = _lib.PASS_LOCAL if which == "local" else _lib.PASS_GLOBAL
@@ -354,11 +370,16 @@ class Engine:
         return self.loss_buf
 
     def gather_rows(self, indices: torch.Tensor) -> torch.Tensor:
-        """CSR-resident counts: the dense (B, G) rows of this rank's cells `indices` (a view of a reused scratch)."""
+        """CSR- or uint16-resident counts: the dense float32 (B, G) rows of this rank's cells `indices` (a view of a reused scratch)."""
         B = int(indices.numel())
         if self._xb_scratch is None or self._xb_scratch.shape[0] < B:
             self._xb_scratch = torch.empty((max(B, self.batch_max), self.G), dtype=torch.float32, device=self.device)
         out = self._xb_scratch[:B]
+        if self.X_u16 is not None:
+            rc = self.lib.scdef_u16_gather_rows(_ptr(self.X_u16), _ptr(indices), B, self.G, _ptr(out), self._stream())
+            if rc != 0:
+                raise ScdefError(f"scdef_u16_gather_rows failed ({rc})")
+            return out
         ip, ix, dv = self.X_csr
         rc = self.lib.scdef_csr_gather_rows(_ptr(ip), _ptr(ix), _ptr(dv), _ptr(indices), B, self.G, _ptr(out), self._stream())
         if rc != 0:

@@ -109,8 +109,8 @@ class scDEF:
         self.device = device
         # "device": dense counts resident in HBM; "csr": CSR counts resident in HBM (a minibatch is densified per
         # step); "host": dense counts in host memory, streamed per step
-        if x_placement not in ("device", "csr", "host"):
-            raise ValueError("x_placement must be 'device', 'csr' or 'host'")
+        if x_placement not in ("device", "device_u16", "csr", "host"):
+            raise ValueError("x_placement must be 'device', 'device_u16', 'csr' or 'host'")
         self.x_placement = x_placement
         self.noise_coupling = bool(noise_coupling)
         self.lik_impl = int(lik_impl)
@@ -210,6 +210,22 @@ class scDEF:
                 raise TypeError("x_placement='csr' takes a scipy sparse or NumPy count matrix")
             X = sp.csr_matrix(X, dtype=np.float32)
             X.sort_indices()
+        elif self.x_placement == "device_u16":   # raw counts as uint16 in HBM (a quarter of the reference's float64 copy)
+            import torch
+
+            if sp.issparse(X):
+                X = X.toarray()
+            if not self._X_is_torch:
+                Xn = np.asarray(X)
+                if Xn.size and (Xn.min() < 0 or Xn.max() > 65535 or np.any(Xn != np.rint(Xn))):
+                    raise ValueError("x_placement='device_u16' needs integer counts in [0, 65535]")
+                X = torch.from_numpy(np.ascontiguousarray(Xn.astype(np.uint16)))
+            elif X.dtype not in (torch.uint16, torch.int16):
+                X = X.to(torch.uint16)
+            if not torch.cuda.is_available():
+                raise RuntimeError("x_placement='device_u16' needs a CUDA device; there is no CPU fallback")
+            X = X.to(self.device or f"cuda:{self._shard.local_rank}")   # the statistics below are computed on the device
+            self._X_is_torch = True
         else:
             if sp.issparse(X):
                 X = X.toarray()
@@ -498,6 +514,7 @@ class scDEF:
                 gene_scale_shape=self.gene_scale_shape, alpha_floor=self.alpha_floor,
                 supervised_layer=self.supervised_layer, fixed_top_z=getattr(self, "_fixed_top_z", None),
                 X=self.X if self.x_placement == "device" else None,
+                X_u16=self.X if self.x_placement == "device_u16" else None,
                 X_csr=(self.X.indptr.astype(np.int64), self.X.indices.astype(np.int32), self.X.data.astype(np.float32))
                 if self.x_placement == "csr" else None, device=dev, lazy_adam=self.lazy_adam)
             self._engine_key = self._engine_signature()
@@ -801,7 +818,7 @@ class scDEF:
                     step_counter += 1
                     noise = NoiseSpec.philox(self.seed or 0, step_counter, self.noise_coupling, *stream.noise_window(it))
                     idx, Xb, n_glob = stream.batch(it)
-                    if Xb is None and eng.X_csr is not None and int(idx.numel()) > 0:
+                    if Xb is None and (eng.X_csr is not None or eng.X_u16 is not None) and int(idx.numel()) > 0:
                         Xb = eng.gather_rows(idx)   # CSR placement: densify the minibatch ONCE for both passes
                     kw = dict(num_samples=int(num_samples), annealing=annealing_parameter,
                               stop_gradients=stop_gradients, stop_cell_budgets=stop_cell_budgets,

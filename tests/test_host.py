@@ -142,7 +142,7 @@ def test_sharded_stream_partitions_the_reference_batch():
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "scdef_b200.h")).read()
-    declared = set(re.findall(r"\b(scdef_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(scdef_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     path = _lib.lib_path()
     assert os.path.exists(path), "build the extension first (__graft_entry__.build())"
