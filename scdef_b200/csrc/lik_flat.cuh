@@ -17,12 +17,17 @@
 //          drained to the partial buffer (`k_tc_rank1` sums the slots and adds the rank-1 term).
 //   GLOBAL (GENES = true):  rows = genes.  ROW unit A1 = W_0^s of 128 genes (MN-major, assembled from two 64-gene tile
 //          images with 1 KB bulk copies), static per segment (rb = gene block, s); COL stream = z0^s, pair-tile = 128 cells
-//          (image `zimg_g`: one 56 KB bulk copy per stage).  D2 = dW^T[rows, k0] accumulated over the segment's cells, then
-//          FOLDED per sample:  t = W (scale dW' - sum_b ctS_b[k] s_b[g] - gw B_k) + gw (A_k - 1),  d mu += t,
-//          sum t log W += t log W  (thread = gene row; d mu lives in tensor memory, the other sum in registers), flushed to
-//          the partial buffer when the gene block changes.
+//          (image `zimg_g`: one 56 KB bulk copy per stage = both 64-cell halves, the CTA's own first).
+//          The second GEMM runs PER CTA (cta_group::1): D2[k0 (M = 128), the CTA's 128 genes (N)] += z_h^T Q_h^T, i.e.
+//          A = z of half h (MN-major, M = k0), B = the CTA's Q tile (K-major, N = genes), K = 64 cells — the contraction is
+//          over the cells, which the rate GEMM has as columns, and the result comes out with k0 on the tensor-memory lanes.
+//          So the FOLD  t = W (scale dW' - sum_b ctS_b[k] s_b[g] - gw B_k) + gw (A_k - 1),  d mu += t,  sum t log W += t log W
+//          runs with thread = k0 row: A_k, B_k, ctS_b[k] are per-thread constants and W^s[k][32 genes] is four 16 B loads per
+//          plane.  Both accumulators (128 lanes x 128 genes each) live in tensor memory next to R and D2 (4 x 128 columns),
+//          and are flushed to the partial buffer when the gene block changes.
 // Rate GEMM   D1[256 rows, 128 cols] = A1 B1      (cta_group::2, M = 256, N = 128 split over the pair, K = KP, 3 split-bf16 products)
-// second GEMM D2[256 rows, KP]      += Q_h B2_h   (M = 256, N = KP split over the pair, K = 64 cols of half h)
+// second GEMM LOCAL : D2[256 rows, KP] += Q_h B2_h   (cta_group::2, M = 256, N = KP split over the pair, K = 64 cols of half h)
+//             GLOBAL: see above (cta_group::1, each CTA's own issuing thread; the peer's doubles as the TMA relay)
 // Flattened work f = (rb * S + s) * n_pt + pt, cut into P contiguous chunks, one per CTA pair (148 SMs -> 74 pairs).
 // Barrier protocol: that of k_lik_pair_flat (lik_tc_pair.cuh; modelled in tests/test_pair_protocol.py); in the GLOBAL
 // orientation the fold reads W^s from the tile images in global memory, so the ROW unit is released by the tensor core as in LOCAL.
@@ -61,7 +66,7 @@ __host__ __device__ inline FlatSmem plan_flat_smem(int KP) {
   s.st[0] = o; o += s.stage;
   s.st[1] = o; o += s.stage;
   s.q = o; o += 2u * s.q_plane;
-  s.fold = o; o += 16u * FOLD_SCRATCH;   // GLOBAL: per epilogue warp, the W lines of one 8-k0 step of the fold
+  s.fold = o;
   s.misc = o;
   s.total = o + 1024u;
   return s;
@@ -104,41 +109,17 @@ struct FlatPos {   // position in the flattened space
 
 // tensor-memory columns.  LOCAL: R[2] at 0 / 128, dz0[2] at 256 / 384.  GLOBAL: ONE R buffer at 0 (the whole-pair-tile
 // epilogue has both halves of R in registers ~1k cycles after the rate GEMM commits, and the next rate GEMM's result is
-// only needed a pair-tile later), dW^T at 128, and the two fold accumulators at 256 / 384 (d mu, sum t log W): the
-// accumulators of a gene block never occupy registers.
+// only needed a pair-tile later), D2 = dW[k0, 128 genes] at 128, and the two fold accumulators at 256 / 384 (d mu,
+// sum t log W; 128 genes each): the accumulators of a gene block never occupy registers.
 constexpr uint32_t FLAT_TMEM_D2_LOCAL = 256, FLAT_TMEM_D2_GENES = 128, FLAT_TMEM_ACC_MU = 256, FLAT_TMEM_ACC_LW = 384;
 
-// W_0 prior parameters and rank-1 factors of the fold, per (sample, k0): [a1 | bm | ctS_0 .. ctS_{nb-1}], rows of KP floats.
-// scalar priors: a1 = gw (A - 1), bm = gw B;  matrix priors (MAT): a1 = 1 / tau, bm = 1 / (tau omega)
-__global__ void __launch_bounds__(128) k_tc_foldtab(const LikTcArgs a, const float* ctilde, float* tab, int KP, int mat) {
-  const int s = blockIdx.x;
-  float* t = tab + (long long)s * (2 + a.nb) * KP;
-  for (int k = threadIdx.x; k < KP; k += blockDim.x) {
-    float a1 = 0.f, bm = 0.f;
-    if (k < a.K0) {
-      float tau = 1.f, om = 1.f;
-      if (a.use_brd) { tau = a.smp_tau[(long long)s * a.K0 + k]; om = a.smp_om[(long long)s * a.K0 + k]; }
-      if (mat) { a1 = 1.f / tau; bm = 1.f / (tau * om); }
-      else {
-        const float A = a.use_brd ? a.P_scalar / tau : a.P_scalar;
-        const float Bm = a.R_scalar * (float)a.K0 / (tau * om);
-        a1 = a.global_weight * (A - 1.f);
-        bm = a.global_weight * Bm;
-      }
-    }
-    t[k] = a1;
-    t[KP + k] = bm;
-    for (int b = 0; b < a.nb; ++b) t[(2 + b) * KP + k] = (k < a.K0 && a.lik_on) ? a.scale * ctilde[((long long)s * a.nb + b) * a.K0 + k] : 0.f;
-  }
-}
-
 // z0 samples -> GLOBAL-orientation column images: per (s, 128-cell pair-tile, rank) one contiguous stage
-//   [B1 hi | B1 lo | B2[0] hi | B2[0] lo | B2[1] hi | B2[1] lo]
-// B1   = z[cells 64 rank .. +64][all k0]            [cell][k0], 8-row-group stride z_rs          (K-major B of the rate GEMM)
-// B2[h] = z[cells 64 h .. +64][k0 in KP/2 rank ..]   [cell][k0 half], 8-row-group stride zb_rs    (MN-major B of the second GEMM)
+//   [Z_own hi | Z_own lo | Z_other hi | Z_other lo],  Z_x = z[the 64 cells of half x][all k0]  as [cell][k0], 8-row-group stride z_rs
+// Z_own (half = rank) is the CTA's N-half of the rate GEMM's B (K-major); Z_0 / Z_1 are the A operands (MN-major, M = k0) of
+// the CTA's second GEMMs of the two halves.
 __global__ void __launch_bounds__(256) k_tc_zprep_g(const LikTcArgs a, uint8_t* zimg, int KP, int n_ptc) {
   const FlatSmem L = plan_flat_smem(KP);
-  const int nchunk = KP / 8, half_chunks = KP / 16;
+  const int nchunk = KP / 8;
   const long long per_pt = 128ll * nchunk;   // (cell of the pair-tile, k0 chunk)
   const long long total = (long long)a.S * n_ptc * per_pt;
   const bool vec = (a.K0 & 3) == 0;
@@ -165,19 +146,11 @@ __global__ void __launch_bounds__(256) k_tc_zprep_g(const LikTcArgs a, uint8_t* 
     split8(x, hi, lo);
     uint8_t* base = zimg + sp * (2ll * L.stage);
     const int h = cl >> 6, r = cl & 63;           // 64-cell half, row inside it
-    // B1 of the rank that owns this half
-    {
-      uint8_t* d = base + (long long)h * L.stage + (uint32_t)(r >> 3) * L.z_rs + (uint32_t)c * 128u + (uint32_t)(r & 7) * 16u;
+    const uint32_t off = (uint32_t)(r >> 3) * L.z_rs + (uint32_t)c * 128u + (uint32_t)(r & 7) * 16u;
+    for (int rk = 0; rk < 2; ++rk) {              // own half first in each rank's stage
+      uint8_t* d = base + (long long)rk * L.stage + (rk == h ? 0u : 2u * L.b1_plane) + off;
       *reinterpret_cast<uint4*>(d) = hi;
       *reinterpret_cast<uint4*>(d + L.b1_plane) = lo;
-    }
-    // B2[h] of the rank that owns this k0 half
-    {
-      const int rk = c / half_chunks, cc = c - rk * half_chunks;
-      uint8_t* d = base + (long long)rk * L.stage + L.b2_off + (uint32_t)(2 * h) * L.b2_piece + (uint32_t)(r >> 3) * L.zb_rs +
-                   (uint32_t)cc * 128u + (uint32_t)(r & 7) * 16u;
-      *reinterpret_cast<uint4*>(d) = hi;
-      *reinterpret_cast<uint4*>(d + L.b2_piece) = lo;
     }
   }
 }
@@ -202,18 +175,6 @@ __global__ void __launch_bounds__(256) k_tc_xprep_t(const LikTcArgs a, float* xi
     }
     *reinterpret_cast<float4*>(ximg + ((((((long long)tile * n_units + unit) * 4 + q) * 16 + v) * 32 + lane) * 4)) = make_float4(x[0], x[1], x[2], x[3]);
   }
-}
-
-// row sums of the minibatch counts (one warp per row)
-__global__ void __launch_bounds__(256) k_tc_rowsum(const LikTcArgs a, float* rowsum) {
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (j >= a.B) return;
-  const float* row = a.X + (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
-  float acc = 0.f;
-  for (int g = lane; g < a.G; g += 32) acc += row[g];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) rowsum[j] = acc;
 }
 
 // sum_{b,g} colsumX_b[g] log s^s_{b,g}  (the gene-scale part of sum x log Lambda), all samples
@@ -347,13 +308,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&mi->w_full[i], 1);
       mbar_init(&mi->pw_full[i], 1);
-      mbar_init(&mi->w_empty[i], 1);
+      // GLOBAL: a stage is read by the pair's rate GEMM (leader's commit, multicast) and by this CTA's second GEMMs
+      mbar_init(&mi->w_empty[i], GENES ? 2 : 1);
       mbar_init(&mi->r_full[i], 1);
       mbar_init(&mi->r_empty[i], 2 * E_WARPS);
       mbar_init(&mi->dz_full[i], 1);
-      mbar_init(&mi->dz_empty[i], 2 * E_WARPS);
+      mbar_init(&mi->dz_empty[i], GENES ? E_WARPS : 2 * E_WARPS);   // GLOBAL: D2 and the Q hand-off are per CTA
     }
-    mbar_init(&mi->q_full, 2 * E_WARPS);
+    mbar_init(&mi->q_full, GENES ? E_WARPS : 2 * E_WARPS);
     mbar_init(&mi->q_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -424,32 +386,85 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
     }
     __syncwarp();
   } else if (warp == MMA_WARP) {
+    // GLOBAL: the second GEMM of a sub-unit, by THIS CTA's issuing thread (cta_group::1):
+    //   D2[k0 (M = 128), the CTA's 128 genes] (+)= z_h^T Q^T     A = z of half h (MN-major, M = k0), B = Q (K-major, N = genes)
+    const uint32_t idesc2g = umma_idesc(128, 128, 1, 0);
+    const uint64_t dqb = umma_desc(sbase + L.q, 128u, Q_RS);
+    auto issue_mma2g = [&](int u, const FlatPos& c2, int n_outer_) {
+      const int oi = u >> 1, h = u & 1, st = oi & 1;
+      const bool seg_first = (c2.pt == 0 || oi == 0) && h == 0, seg_last = (c2.pt == n_pt - 1 || oi == n_outer_ - 1) && h == 1;
+      if (seg_first) PT_WAIT(7, pair_wait(&mi->dz_empty[0], ((uint32_t)c2.g & 1u) ^ 1u, 19));   // the fold has read D2
+      tc_fence_after();
+      PT_MARK();
+      const uint32_t d = tmem + FLAT_TMEM_D2_GENES;
+      uint64_t da = umma_desc(sbase + L.st[st] + ((uint32_t)h == rank ? 0u : 2u * L.b1_plane), L.z_rs, 128u), db = dqb;
+      const uint64_t apl = L.b1_plane >> 4, bpl = L.q_plane >> 4, a_k = (uint64_t)(2u * (L.z_rs >> 4));
+      umma_bf16(d, da + apl, db, idesc2g, seg_first ? 0u : 1u);
+      umma_bf16(d, da, db + bpl, idesc2g, 1u);
+      umma_bf16(d, da, db, idesc2g, 1u);
+#pragma unroll
+      for (int ks = 1; ks < TG / 16; ++ks) {
+        da += a_k;
+        db += 16;
+        umma_bf16(d, da + apl, db, idesc2g, 1u);
+        umma_bf16(d, da, db + bpl, idesc2g, 1u);
+        umma_bf16(d, da, db, idesc2g, 1u);
+      }
+      umma_commit(&mi->q_empty);
+      if (h == 1) umma_commit(&mi->w_empty[st]);
+      if (seg_last) umma_commit(&mi->dz_full[0]);
+      PT_LAP(5);
+    };
     if (lane == 0 && !leader) {
       // =========================================== RELAY (peer) ==========================================
+      // forwards "my TMA landed" to the leader; GLOBAL: also issues this CTA's second GEMMs
       const uint32_t r_pz = mapa_rank(&mi->pz_full, 0), r_pw0 = mapa_rank(&mi->pw_full[0], 0), r_pw1 = mapa_rank(&mi->pw_full[1], 0);
-      FlatPos c = cur0;
-      for (int oi = 0; oi < n_outer; ++oi, c.next(n_pt, S)) {
-        PT_WAIT(0, pair_wait(&mi->w_full[oi & 1], (oi >> 1) & 1, 3));
-        mbar_arrive_remote((oi & 1) ? r_pw1 : r_pw0);
-        if (first_in_seg(oi, c)) {
-          PT_WAIT(1, pair_wait(&mi->z_full, (uint32_t)c.g & 1u, 2));
-          mbar_arrive_remote(r_pz);
+      if (!GENES) {
+        FlatPos c = cur0;
+        for (int oi = 0; oi < n_outer; ++oi, c.next(n_pt, S)) {
+          PT_WAIT(0, pair_wait(&mi->w_full[oi & 1], (oi >> 1) & 1, 3));
+          mbar_arrive_remote((oi & 1) ? r_pw1 : r_pw0);
+          if (first_in_seg(oi, c)) {
+            PT_WAIT(1, pair_wait(&mi->z_full, (uint32_t)c.g & 1u, 2));
+            mbar_arrive_remote(r_pz);
+          }
         }
+      } else {
+        FlatPos cz = cur0, c2 = cur0;   // cursors of the next ROW unit to announce and of the next second GEMM
+        int rw = 0, rz = 0, u = 0;      // stages / ROW units announced, sub-units issued
+        const long long t_begin = clock64();
+        while (rw < n_outer || rz < n_seg || u < U) {
+          bool moved = false;
+          if (rw < n_outer && mbar_test(&mi->w_full[rw & 1], (uint32_t)(rw >> 1) & 1u)) {
+            mbar_arrive_remote((rw & 1) ? r_pw1 : r_pw0);
+            ++rw; moved = true;
+          }
+          if (rz < n_seg && mbar_test(&mi->z_full, (uint32_t)rz & 1u)) {
+            mbar_arrive_remote(r_pz);
+            ++rz; moved = true;
+          }
+          if (u < U && mbar_test(&mi->q_full, (uint32_t)u & 1u)) {
+            issue_mma2g(u, c2, n_outer);
+            if (u & 1) c2.next(n_pt, S);
+            ++u; moved = true;
+          }
+          if (!moved && clock64() - t_begin > 4 * PAIR_DEADLINE) pair_stuck(22, (int)blockIdx.x, u, rw);
+        }
+        (void)cz;
       }
     } else if (lane == 0) {
       // =========================================== MMA ISSUER (leader) ===================================
       // descriptor: lbo = byte stride between core matrices along K, sbo = along M / N (see lik_tc.cu)
       const uint32_t idesc1 = GENES ? umma_idesc(256, 2 * TG, 1, 0) : umma_idesc(256, 2 * TG, 0, 1);
-      const uint32_t idesc2 = GENES ? umma_idesc(256, KP, 0, 1) : umma_idesc(256, KP, 0, 0);
+      const uint32_t idesc2 = umma_idesc(256, KP, 0, 0);
       const uint64_t d_a1 = GENES ? umma_desc(sbase + L.a1, L.u_rs, 128u) : umma_desc(sbase + L.a1, 128u, L.z_rs);
       const uint64_t a1_k = GENES ? (uint64_t)(2u * (L.u_rs >> 4)) : 16ull;
       uint64_t d_b1[2], d_b2[2];
       for (int i = 0; i < 2; ++i) {
         d_b1[i] = GENES ? umma_desc(sbase + L.st[i], 128u, L.z_rs) : umma_desc(sbase + L.st[i], W_RS, 128u);
-        d_b2[i] = GENES ? umma_desc(sbase + L.st[i] + L.b2_off, L.zb_rs, 128u) : umma_desc(sbase + L.st[i] + L.b2_off, 128u, W_RS);
+        d_b2[i] = umma_desc(sbase + L.st[i] + L.b2_off, 128u, W_RS);
       }
       const uint64_t b1_k = GENES ? 16ull : (uint64_t)(2u * (W_RS >> 4));
-      const uint64_t b2_k = GENES ? (uint64_t)(2u * (L.zb_rs >> 4)) : 16ull;
       const uint64_t dq_k = umma_desc(sbase + L.q, 128u, Q_RS);
       const uint64_t a1pl = L.a1_plane >> 4, b1pl = L.b1_plane >> 4, qpl = L.q_plane >> 4, b2pl = L.b2_piece >> 4;
       const int nk1 = KP / 16;
@@ -490,6 +505,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
           umma2_bf16(d, da, db, idesc1, 1u);
         }
         umma2_commit(&mi->r_full[rs]);
+        if (GENES) umma2_commit(&mi->w_empty[st]);               // the pair's rate GEMM has read both CTAs' stage
         if (last_in_seg(oi, c1)) umma2_commit(&mi->z_empty);   // the segment's ROW unit has been read by its last rate GEMM
         PT_LAP(4);
         c1.next(n_pt, S);
@@ -503,21 +519,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
 #endif
         for (;;) {
           if (next1 < n_outer && next1 <= oi + 1 && (next1 == oi || ready1(next1))) { issue_mma1(next1); ++next1; continue; }
-          if (mbar_test_remote(&mi->q_full, (uint32_t)u & 1u)) break;
-          if (next1 > oi + 1 || next1 >= n_outer) { pair_wait_remote(&mi->q_full, (uint32_t)u & 1u, 9); break; }
+          if (GENES ? mbar_test(&mi->q_full, (uint32_t)u & 1u) : mbar_test_remote(&mi->q_full, (uint32_t)u & 1u)) break;
+          if (next1 > oi + 1 || next1 >= n_outer) {
+            if (GENES) pair_wait(&mi->q_full, (uint32_t)u & 1u, 9);
+            else pair_wait_remote(&mi->q_full, (uint32_t)u & 1u, 9);
+            break;
+          }
           if (t_poll == 0) t_poll = clock64();
           else if (clock64() - t_poll > PAIR_DEADLINE) pair_stuck(14, (int)blockIdx.x, u, next1);
         }
 #ifdef SCDEF_TC_TIMING
         tacc[3] += (clock64() - t_loop0) - (tacc[0] + tacc[1] + tacc[2] + tacc[4] + tacc[6] - t_in1);
 #endif
+        if (GENES) {
+          issue_mma2g(u, c2, n_outer);
+          if (h == 1) c2.next(n_pt, S);
+          continue;
+        }
         const bool seg_first = first_in_seg(oi, c2) && h == 0, seg_last = last_in_seg(oi, c2) && h == 1;
-        const uint32_t dzb = GENES ? 0u : ((uint32_t)c2.g & 1u);
-        const uint32_t dz_use = GENES ? (uint32_t)c2.g : ((uint32_t)c2.g >> 1);
-        if (seg_first) PT_WAIT(7, pair_wait_remote(&mi->dz_empty[dzb], (dz_use & 1u) ^ 1u, 19));   // drained / folded
+        const uint32_t dzb = (uint32_t)c2.g & 1u;
+        if (seg_first) PT_WAIT(7, pair_wait_remote(&mi->dz_empty[dzb], (((uint32_t)c2.g >> 1) & 1u) ^ 1u, 19));   // drained two segments ago
         tc_fence_after();
         PT_MARK();
-        const uint32_t d = tmem + (GENES ? FLAT_TMEM_D2_GENES : FLAT_TMEM_D2_LOCAL + dzb * FLAT_DZ_STRIDE);
+        const uint32_t d = tmem + FLAT_TMEM_D2_LOCAL + dzb * FLAT_DZ_STRIDE;
         uint64_t da = dq_k, db = d_b2[st] + (uint64_t)(2 * h) * b2pl;
         umma2_bf16(d, da + qpl, db, idesc2, seg_first ? 0u : 1u);
         umma2_bf16(d, da, db + b2pl, idesc2, 1u);
@@ -525,7 +549,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
 #pragma unroll
         for (int ks = 1; ks < TG / 16; ++ks) {
           da += 16;
-          db += b2_k;
+          db += 16;
           umma2_bf16(d, da + qpl, db, idesc2, 1u);
           umma2_bf16(d, da, db + b2pl, idesc2, 1u);
           umma2_bf16(d, da, db, idesc2, 1u);
@@ -588,7 +612,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       *reinterpret_cast<uint4*>(sm + off + 128u + L.q_plane) = lo;
       fence_async_q();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(r_qfull);
+      if (lane == 0) {
+        if (GENES) mbar_arrive(&mi->q_full);   // the Q hand-off is per CTA
+        else mbar_arrive_remote(r_qfull);
+      }
     };
 
     // ---- LOCAL: the segment's dz0 is complete: drain its accumulator (cell row r, every 4th 16-column chunk of k0) ----
@@ -624,123 +651,122 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       PT_LAP(8);
     };
 
-    // ---- GLOBAL: fold dW^T of the segment into the two accumulators of the gene block (tensor memory) ----
+    // ---- GLOBAL: fold dW of the segment into the two accumulators of the gene block (tensor memory) ----
+    // thread = k0 row r (tensor-memory lane), the 32 genes [32 cq, 32 cq + 32) of this CTA's unit
     bool acc_live = false;   // the accumulators hold a partial sum of the current gene block
     const uint32_t tacc_mu = tmem + FLAT_TMEM_ACC_MU + (lane_base << 16), tacc_lw = tmem + FLAT_TMEM_ACC_LW + (lane_base << 16);
     auto fold_segment = [&](const FlatPos& p) {
-      // W^s of this thread's gene comes from the tile image in global memory (L2: the COPY thread streamed it a segment
-      // ago), NOT from the ROW unit in shared memory: the unit is released by the segment's last rate GEMM, so the next
-      // segment's unit loads while this one is still being processed and folded (no bubble in the tensor pipeline).
-      // Per step of 8 k0 rows a warp fetches its 4 x 128 B image lines with one 16 B load per lane and plane (lane =
-      // (gene group, k0 row)), parks them in its private scratch and reads its own gene's column back; the next step's
-      // lines are in flight meanwhile, and the first step's are requested before the wait for the segment's last GEMM.
-      const int g = (p.rb * 2 + (int)rank) * UC + r;
-      const bool gok = g < a.G;
+      // W^s[k][genes] comes from the tile image in global memory (L2: the COPY thread streamed it a segment ago), NOT
+      // from the ROW unit in shared memory: the unit is released by the segment's last rate GEMM, so the next segment's
+      // unit loads while this one is still being processed and folded (no bubble in the tensor pipeline).  Four steps of
+      // 8 genes: one 16 B load per plane and step, the next step's in flight, the first requested before the wait.
+      const int g0 = (p.rb * 2 + (int)rank) * UC + cq * 32;
+      const bool kok = r < a.K0;
       const float* tab = ws.foldtab + (long long)p.s * (2 + a.nb) * KP;
-      const uint8_t* wline = ws.wimg + ((long long)p.s * a.n_wimg + (p.rb * 2 + (int)rank) * 2 + (r >> 6)) * IL.w_unit +
-                             (uint32_t)((r & 63) >> 3) * 128u + (uint32_t)(r & 7) * 16u;   // + plane * w_plane + kg * W_RS
-      const int n_steps = 2 * ((KP / 16 - cq + 3) / 4);   // 8-k0 steps of this thread's chunks cq, cq + 4, ...
-      auto step_kg = [&](int t) { return 2 * (cq + 4 * (t >> 1)) + (t & 1); };
-      uint4 nh = make_uint4(0, 0, 0, 0), nl = nh;
-      if (n_steps > 0) {
-        const uint8_t* q0 = wline + (uint32_t)step_kg(0) * W_RS;
-        nh = __ldg(reinterpret_cast<const uint4*>(q0));
-        nl = __ldg(reinterpret_cast<const uint4*>(q0 + IL.w_plane));
-      }
+      const int rr = r < KP ? r : 0;
+      // image of the 64-gene tile that holds these 32 genes; + plane * w_plane + step * 128
+      const uint8_t* wline = ws.wimg + ((long long)p.s * a.n_wimg + (p.rb * 2 + (int)rank) * 2 + (cq >> 1)) * IL.w_unit +
+                             (uint32_t)(rr >> 3) * W_RS + (uint32_t)((cq & 1) * 4) * 128u + (uint32_t)(rr & 7) * 16u;
+      uint4 nh = __ldg(reinterpret_cast<const uint4*>(wline)), nl = __ldg(reinterpret_cast<const uint4*>(wline + IL.w_plane));
       // A chunk boundary may cut a segment in two: the terms that do not depend on dW' (the W_0 prior gradient and the
       // rank-1 part) belong to the piece that holds the segment's first pair-tile only.
       const float own = (p.g > 0 || cur0.pt == 0) ? 1.f : 0.f;
-      float sgv[MAX_NB];
+      const float t_a1 = kok ? own * __ldg(tab + r) : 0.f, t_bm = kok ? own * __ldg(tab + KP + r) : 0.f;
+      float t_ct[MAX_NB];
 #pragma unroll
-      for (int b = 0; b < MAX_NB; ++b) sgv[b] = (b < a.nb && gok && a.lik_on) ? own * a.smp_s[((long long)p.s * a.nb + b) * a.G + g] : 0.f;
+      for (int b = 0; b < MAX_NB; ++b) t_ct[b] = (b < a.nb && kok && a.lik_on) ? own * __ldg(tab + (2 + b) * KP + r) : 0.f;
       PT_WAIT(7, pair_wait(&mi->dz_full[0], (uint32_t)p.g & 1u, 13));
       tc_fence_after();
       PT_MARK();
       const uint32_t td2 = tmem + FLAT_TMEM_D2_GENES + (lane_base << 16);
-      uint8_t* scr = sm + L.fold + (uint32_t)e * FOLD_SCRATCH;
-      const uint32_t scr_w = (uint32_t)(lane >> 3) * FOLD_GRP + (uint32_t)(lane & 7) * 16u;   // where this lane parks its line piece
-      const uint32_t scr_r = (uint32_t)(lane >> 3) * FOLD_GRP + (uint32_t)(lane & 7) * 2u;    // its own gene's column: + kk * 16
-      float t_a1 = 0.f, t_bm = 0.f, t_ct[MAX_NB];
 #pragma unroll 1
-      for (int t = 0; t < n_steps; ++t) {
-        const int kg = step_kg(t), k0 = kg * 8;
-        if ((t & 1) == 0) {
-          // the table row of this chunk: lanes 0..15 hold one k each, the element loop reads them by shuffle
-          const int kl = k0 + (lane & 15);
-          t_a1 = own * __ldg(tab + kl);
-          t_bm = own * __ldg(tab + KP + kl);
-#pragma unroll
-          for (int b = 0; b < MAX_NB; ++b) t_ct[b] = b < a.nb ? __ldg(tab + (2 + b) * KP + kl) : 0.f;
+      for (int t = 0; t < 4; ++t) {
+        const uint4 ch = nh, cl = nl;
+        if (t + 1 < 4) {
+          nh = __ldg(reinterpret_cast<const uint4*>(wline + (t + 1) * 128));
+          nl = __ldg(reinterpret_cast<const uint4*>(wline + IL.w_plane + (t + 1) * 128));
         }
-        *reinterpret_cast<uint4*>(scr + scr_w) = nh;
-        *reinterpret_cast<uint4*>(scr + 4 * FOLD_GRP + scr_w) = nl;
-        __syncwarp();
-        if (t + 1 < n_steps) {
-          const uint8_t* qn = wline + (uint32_t)step_kg(t + 1) * W_RS;
-          nh = __ldg(reinterpret_cast<const uint4*>(qn));
-          nl = __ldg(reinterpret_cast<const uint4*>(qn + IL.w_plane));
-        }
+        const int gb = g0 + t * 8;            // first of this step's 8 genes
+        const uint32_t col = (uint32_t)(cq * 32 + t * 8);
         uint32_t dW[8], am[8], al[8];
-        tmem_ld8_issue(td2 + (uint32_t)k0, dW);
+        tmem_ld8_issue(td2 + col, dW);
         if (acc_live) {
-          tmem_ld8_issue(tacc_mu + (uint32_t)k0, am);
-          tmem_ld8_issue(tacc_lw + (uint32_t)k0, al);
+          tmem_ld8_issue(tacc_mu + col, am);
+          tmem_ld8_issue(tacc_lw + col, al);
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) { am[i] = 0u; al[i] = 0u; }
         }
+        // sum_b ctS_b[k] s_b[g] for the 8 genes (the gene-scale samples: the same 32 B for every lane)
+        float cs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cs[i] = t_bm;
+        if (gb < a.G) {
+#pragma unroll
+          for (int b = 0; b < MAX_NB; ++b) {
+            if (b < a.nb) {
+              const float* sp = a.smp_s + ((long long)p.s * a.nb + b) * a.G + gb;
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp)), s1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
+              const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) cs[i] = fmaf(t_ct[b], sv[i], cs[i]);
+            }
+          }
+        }
+        float Pv[8], Rv[8];
+        if (MAT) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            Pv[i] = (a.P && kok && gb + i < a.G) ? __ldg(a.P + (long long)r * a.G + gb + i) : a.P_scalar;
+            Rv[i] = (a.R && kok && gb + i < a.G) ? __ldg(a.R + (long long)r * a.G + gb + i) : a.R_scalar;
+          }
+        }
         tmem_ld8_wait3(dW, am, al);
+        const uint32_t hw[4] = {ch.x, ch.y, ch.z, ch.w}, lw[4] = {cl.x, cl.y, cl.z, cl.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int k = k0 + i, src = (t & 1) * 8 + i;
-          const float W = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(scr + scr_r + i * 16)) << 16) +
-                          __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(scr + 4 * FOLD_GRP + scr_r + i * 16)) << 16);
-          float a1 = __shfl_sync(0xffffffffu, t_a1, src), bm = __shfl_sync(0xffffffffu, t_bm, src);
+          const uint32_t hv = hw[i >> 1], lv = lw[i >> 1];
+          const float W = (i & 1) ? (bf16hi(hv) + bf16hi(lv)) : (bf16lo(hv) + bf16lo(lv));
+          float a1 = t_a1, c1 = cs[i];
           if (MAT) {
-            const float Pv = (a.P && gok && k < a.K0) ? __ldg(a.P + (long long)k * a.G + g) : a.P_scalar;
-            const float Rv = (a.R && gok && k < a.K0) ? __ldg(a.R + (long long)k * a.G + g) : a.R_scalar;
-            bm = a.global_weight * Rv * (float)a.K0 * bm;   // gw B,  B = R K0 / (tau omega); table: own / (tau omega)
-            a1 = a.global_weight * (Pv * a1 - own);         // gw (A - 1),  A = P / tau; table: own / tau
+            c1 = cs[i] - t_bm + a.global_weight * Rv[i] * (float)a.K0 * t_bm;   // gw B, B = R K0 / (tau omega); table: own / (tau omega)
+            a1 = a.global_weight * (Pv[i] * t_a1 - own);                       // gw (A - 1), A = P / tau; table: own / tau
           }
-          float cs = bm;
-#pragma unroll
-          for (int b = 0; b < MAX_NB; ++b)
-            if (b < a.nb) cs = fmaf(__shfl_sync(0xffffffffu, t_ct[b], src), sgv[b], cs);
-          const float tt = fmaf(W, fmaf(a.scale, __uint_as_float(dW[i]), -cs), a1);
-          if (W > V_LO_M && W < V_HI_M && gok && k < a.K0) {
+          const float tt = fmaf(W, fmaf(a.scale, __uint_as_float(dW[i]), -c1), a1);
+          if (W > V_LO_M && W < V_HI_M && kok && gb + i < a.G) {
             am[i] = __float_as_uint(__uint_as_float(am[i]) + tt);
             al[i] = __float_as_uint(fmaf(tt, __logf(W), __uint_as_float(al[i])));
           }
         }
-        tmem_st8(tacc_mu + (uint32_t)k0, am);
-        tmem_st8(tacc_lw + (uint32_t)k0, al);
-        __syncwarp();   // everybody has read the scratch before the next step overwrites it
+        tmem_st8(tacc_mu + col, am);
+        tmem_st8(tacc_lw + col, al);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       acc_live = true;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(r_dzempty[0]);   // D2 may be overwritten by the next segment
+      if (lane == 0) mbar_arrive(&mi->dz_empty[0]);   // D2 may be overwritten by this CTA's next segment
       PT_LAP(8);
     };
     auto flush_block = [&](const FlatPos& p) {
       // partial sums of gene block p.rb held by this pair -> slot of the (slots, 2, K0, G) buffer
-      const int g = (p.rb * 2 + (int)rank) * UC + r;
+      const int g0 = (p.rb * 2 + (int)rank) * UC + cq * 32;
       const long long per_rb = (long long)S * n_pt;
       const int slot = chunk - flat_chunk_of((long long)p.rb * per_rb, T, P);
       const long long n = (long long)a.K0 * a.G;
+      float* pm = ws.part + ((long long)slot * 2 + 0) * n + (long long)r * a.G + g0;
+      float* pl = ws.part + ((long long)slot * 2 + 1) * n + (long long)r * a.G + g0;
 #pragma unroll 1
-      for (int ch = cq; ch < KP / 16; ch += 4) {
+      for (int t = 0; t < 2; ++t) {
         float am[16], al[16];
-        tmem_ld16(tacc_mu + (uint32_t)(ch * 16), am);
-        tmem_ld16(tacc_lw + (uint32_t)(ch * 16), al);
-        if (g < a.G) {
+        tmem_ld16(tacc_mu + (uint32_t)(cq * 32 + t * 16), am);
+        tmem_ld16(tacc_lw + (uint32_t)(cq * 32 + t * 16), al);
+        if (r < a.K0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k = ch * 16 + i;
-            if (k < a.K0) {
-              ws.part[((long long)slot * 2 + 0) * n + (long long)k * a.G + g] = am[i];
-              ws.part[((long long)slot * 2 + 1) * n + (long long)k * a.G + g] = al[i];
+          for (int i = 0; i < 16; i += 4) {
+            if (g0 + t * 16 + i < a.G) {   // G is a multiple of 8
+              *reinterpret_cast<float4*>(pm + t * 16 + i) = make_float4(am[i], am[i + 1], am[i + 2], am[i + 3]);
+              *reinterpret_cast<float4*>(pl + t * 16 + i) = make_float4(al[i], al[i + 1], al[i + 2], al[i + 3]);
             }
           }
         }

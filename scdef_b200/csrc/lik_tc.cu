@@ -634,6 +634,25 @@ __global__ void __launch_bounds__(256) k_tc_rowprep(const LikTcArgs a, int* brow
   brow[j] = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
   xoff[j] = (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
 }
+// the same plus the row sums of the minibatch counts, one warp per row (unified pair kernel)
+__global__ void __launch_bounds__(256) k_tc_rowprep_sum(const LikTcArgs a, int* brow, long long* xoff, float* rowsum) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= a.B) return;
+  const long long off = (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
+  const float* row = a.X + off;
+  float acc = 0.f;
+  for (int g = lane * 4; g < a.G; g += 128) {   // G is a multiple of 8, rows are 16 B aligned
+    const float4 v = *reinterpret_cast<const float4*>(row + g);
+    acc += (v.x + v.y) + (v.z + v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    rowsum[j] = acc;
+    brow[j] = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
+    xoff[j] = off;
+  }
+}
 // minibatch counts -> image in which the epilogue's "lane = cell row, 16 B per lane" loads are contiguous:
 // element (row = unit*128 + q*32 + lane, gene = tile*64 + v*4 + i) at ((((tile*units + unit)*4 + q)*16 + v)*32 + lane)*4 + i
 __global__ void __launch_bounds__(256) k_tc_xprep(const LikTcArgs a, float* ximg, int n_tiles, int units) {
@@ -701,6 +720,11 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
   if (tile < n_tiles) {
     uint8_t* unit = ws.wimg + ((long long)s * n_tiles + tile) * w_unit;
     const bool gok = g < a.G;
+    float4 sv0 = make_float4(0.f, 0.f, 0.f, 0.f), sv1 = sv0;
+    if (gok) {
+      const float* sp = a.smp_s + (long long)s * a.nb * a.G + g;
+      sv0 = *reinterpret_cast<const float4*>(sp); sv1 = *reinterpret_cast<const float4*>(sp + 4);
+    }
     for (int kg = 0; kg < nkg; ++kg) {
       const int k = kg * 8 + kk;
       float w[8];
@@ -742,12 +766,16 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
         atomicAdd(&rowacc[k][0], su);
         atomicAdd(&rowacc[k][1], sw);
       }
-      // (W s_b)[k] += sum over this thread's 8 genes; the gene-scale samples come through L1 (same for every kg)
+      // (W s_b)[k] += sum over this thread's 8 genes (batch 0's gene-scale samples are held in registers; further
+      // batches come through L1, the same 32 B for every kg)
       for (int b = 0; b < a.nb; ++b) {
         float d = 0.f;
         if (k < a.K0 && gok) {
-          const float* sp = a.smp_s + ((long long)s * a.nb + b) * a.G + g;
-          const float4 t0 = *reinterpret_cast<const float4*>(sp), t1 = *reinterpret_cast<const float4*>(sp + 4);
+          float4 t0 = sv0, t1 = sv1;
+          if (b > 0) {
+            const float* sp = a.smp_s + ((long long)s * a.nb + b) * a.G + g;
+            t0 = *reinterpret_cast<const float4*>(sp); t1 = *reinterpret_cast<const float4*>(sp + 4);
+          }
           d = w[0] * t0.x + w[1] * t0.y + w[2] * t0.z + w[3] * t0.w + w[4] * t1.x + w[5] * t1.y + w[6] * t1.z + w[7] * t1.w;
         }
         d += __shfl_xor_sync(0xffffffffu, d, 8);
@@ -779,7 +807,7 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
 //   G_s[s,b,g] += scale * ( colsumX[b][g] / s_{b,g} - sum_k ctilde[s][b][k] W^s[k][g] ).   grid = (n_tiles, S), block = 256
 template <int NBT>
 __global__ void __launch_bounds__(256) k_tc_colw(const LikTcArgs a, const TcScratch ws, int KP, int n_tiles, uint32_t w_plane,
-                                                 uint32_t w_unit) {
+                                                 uint32_t w_unit, double* loss_out = nullptr) {
   __shared__ float colacc[NBT][TG];
   __shared__ float ct_sm[NBT][128];
   const int tile = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
@@ -829,20 +857,34 @@ __global__ void __launch_bounds__(256) k_tc_colw(const LikTcArgs a, const TcScra
     }
   }
   __syncthreads();
+  float lgs = 0.f;   // unified pair kernel: sum_{b,g} colsumX_b[g] log s_bg, the gene-scale part of sum x log Lambda
   if (tid < TG) {
     const int g = tile * TG + tid;
     const float* stile = reinterpret_cast<const float*>(unit + 2 * w_plane);
-    if (g < a.G && a.G_s)
-      for (int b = 0; b < a.nb; ++b)
-        a.G_s[((long long)s * a.nb + b) * a.G + g] += a.scale * (ws.colsumX[(long long)b * a.G + g] / stile[b * TG + tid] - colacc[b][tid]);
+    if (g < a.G)
+      for (int b = 0; b < a.nb; ++b) {
+        const float cx = ws.colsumX[(long long)b * a.G + g], sv = stile[b * TG + tid];
+        if (a.G_s) a.G_s[((long long)s * a.nb + b) * a.G + g] += a.scale * (cx / sv - colacc[b][tid]);
+        if (loss_out && cx > 0.f) lgs += cx * __logf(sv);
+      }
+  }
+  if (loss_out && tid < 64) {   // TG = 64: two warps
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lgs += __shfl_xor_sync(0xffffffffu, lgs, o);
+    if ((tid & 31) == 0 && lgs != 0.f) atomicAdd(&loss_out[0], -(double)lgs * (double)a.scale / (double)a.S);
   }
 }
 
 // ---- small companions ---------------------------------------------------------------------------------
 // ctilde[s][b][k] = sum_{n in batch b} c_n^s z_nk^s ;  grid = S, block = 1024 (k = tid & 127, 8 row groups)
-__global__ void __launch_bounds__(1024) k_tc_ctilde(const LikTcArgs a, float* ctilde) {
+// With `loss_out` (GLOBAL pass of the unified pair kernel) it also adds the cell-scale parts of the log-likelihood of its
+// sample:  sum_j rowsumX_j log c_j - sum_{b,k} ctilde_b[k] (W s_b)[k]   (= sum_n c_n z_n . (W s_b), the sum of all rates).
+__global__ void __launch_bounds__(1024) k_tc_ctilde(const LikTcArgs a, float* ctilde, float* foldtab = nullptr, int KP = 0, int mat = 0,
+                                                    const float* rowsumx = nullptr, const float* Ws = nullptr, double* loss_out = nullptr) {
   __shared__ float part[8][MAX_NB][128];
+  __shared__ double red[32];
   const int s = blockIdx.x, k = threadIdx.x & 127, rg = threadIdx.x >> 7;
+  double lacc = 0.0;
   float acc[MAX_NB];
 #pragma unroll
   for (int b = 0; b < MAX_NB; ++b) acc[b] = 0.f;
@@ -863,6 +905,35 @@ __global__ void __launch_bounds__(1024) k_tc_ctilde(const LikTcArgs a, float* ct
 #pragma unroll
     for (int r = 0; r < 8; ++r) t += part[r][b][kk];
     ctilde[((long long)s * a.nb + b) * a.K0 + kk] = t;
+    if (foldtab) foldtab[((long long)s * (2 + a.nb) + 2 + b) * KP + kk] = a.scale * t;   // ctS_b[k]
+    if (loss_out) lacc -= (double)(t * Ws[((long long)s * a.nb + b) * a.K0 + kk]);
+  }
+  if (loss_out) {
+    for (int j = threadIdx.x; j < a.B; j += 1024) lacc += (double)(rowsumx[j] * __logf(a.smp_c[(long long)s * a.B + j]));
+    const double tot = block_sum_d(lacc, red);
+    if (threadIdx.x == 0) atomicAdd(&loss_out[0], -tot * (double)a.scale / (double)a.S);
+  }
+  // unified pair kernel: the per-(sample, k0) constants of the W_0 fold, rows [a1 | bm | ctS_0 .. ctS_{nb-1}] of KP floats.
+  // scalar priors: a1 = gw (A - 1), bm = gw B;  matrix priors: a1 = 1 / tau, bm = 1 / (tau omega)
+  if (foldtab) {
+    float* t = foldtab + (long long)s * (2 + a.nb) * KP;
+    for (int kk = threadIdx.x; kk < KP; kk += 1024) {
+      float a1 = 0.f, bm = 0.f;
+      if (kk < a.K0) {
+        float tau = 1.f, om = 1.f;
+        if (a.use_brd) { tau = a.smp_tau[(long long)s * a.K0 + kk]; om = a.smp_om[(long long)s * a.K0 + kk]; }
+        if (mat) { a1 = 1.f / tau; bm = 1.f / (tau * om); }
+        else {
+          const float A = a.use_brd ? a.P_scalar / tau : a.P_scalar;
+          a1 = a.global_weight * (A - 1.f);
+          bm = a.global_weight * a.R_scalar * (float)a.K0 / (tau * om);
+        }
+      } else {
+        for (int b = 0; b < a.nb; ++b) t[(2 + b) * KP + kk] = 0.f;
+      }
+      t[kk] = a1;
+      t[KP + kk] = bm;
+    }
   }
 }
 
@@ -1285,8 +1356,7 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
     const int nblk = g_sm_count * 4;
     const long long T = (long long)fg.n_rblk * a.S * fg.n_pt;
     pair_stuck_init();
-    k_tc_rowprep<<<(a.B + 255) / 256, 256, 0, st>>>(a, ws.brow, ws.xoff);
-    k_tc_rowsum<<<(a.B + 7) / 8, 256, 0, st>>>(a, ws.rowsumx);
+    k_tc_rowprep_sum<<<(a.B + 7) / 8, 256, 0, st>>>(a, ws.brow, ws.xoff, ws.rowsumx);
     if (!reuse) {
       k_tc_wprep<<<g_sm_count * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
       k_tc_wgen<<<dim3(n_tiles / 4, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit);
@@ -1298,8 +1368,8 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       if (ev1 && ev0) cudaEventRecord(ev1, st);
     };
     const int rank1_blocks = (int)(((long long)a.S * a.B + 7) / 8);
-    auto loss_terms = [&]() {
-      k_tc_loss_gs<<<g_sm_count, 256, 0, st>>>(a, ws.colsumX, loss_out);
+    auto loss_terms = [&](bool gene_scale_term) {
+      if (gene_scale_term) k_tc_loss_gs<<<g_sm_count, 256, 0, st>>>(a, ws.colsumX, loss_out);
       if (matrix_prior)
         k_tc_w0_prior_mat<<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out, 0);
       else k_tc_w0_prior<<<(a.S * a.K0 + 127) / 128, 128, 0, st>>>(a, ws.rowstats, loss_out);
@@ -1307,15 +1377,13 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
     if (global_pass) {
       k_tc_zprep_g<<<nblk, 256, 0, st>>>(a, ws.zimg_g, fg.KP, fg.n_pt);
       k_tc_xprep_t<<<nblk, 256, 0, st>>>(a, ws.ximg_t, 2 * fg.n_pt, fg.n_units);
-      k_tc_ctilde<<<a.S, 1024, 0, st>>>(a, ws.ctilde);
+      k_tc_ctilde<<<a.S, 1024, 0, st>>>(a, ws.ctilde, ws.foldtab, fg.KP, matrix_prior ? 1 : 0, ws.rowsumx, ws.Ws, loss_out);
       k_tc_colsum<<<(a.G + 63) / 64, 1024, 0, st>>>(a, ws.colsumX);
-      k_tc_foldtab<<<a.S, 128, 0, st>>>(a, ws.ctilde, ws.foldtab, fg.KP, matrix_prior ? 1 : 0);
-      if (a.nb == 1) k_tc_colw<1><<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit);
-      else k_tc_colw<MAX_NB><<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit);
+      if (a.nb == 1) k_tc_colw<1><<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out);
+      else k_tc_colw<MAX_NB><<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out);
       if (matrix_prior) launch(k_lik_flat<true, true, true>);
       else launch(k_lik_flat<true, true, false>);
-      k_tc_rank1<<<rank1_blocks, 256, 0, st>>>(a, ws, nullptr, 0, T, fg.P, fg.n_pt, 0, 1, loss_out);
-      loss_terms();
+      loss_terms(false);   // the cell-scale terms of the loss came with k_tc_ctilde, the gene-scale term with k_tc_colw
       k_tc_w0_final_flat<<<g_sm_count * 4, 256, 0, st>>>(a, ws.part, T, fg.P, a.S * fg.n_pt, loss_out);
     } else {
       k_tc_zprep<<<nblk, 256, 0, st>>>(a, ws.zimg, fg.KP, fg.n_units);
@@ -1325,7 +1393,7 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       k_tc_rank1<<<rank1_blocks, 256, 0, st>>>(a, ws, ws.part, fg.slots, T, fg.P, fg.n_pt, 1, a.want_loss ? 1 : 0, loss_out);
       if (a.want_loss) {
         k_tc_colsum<<<(a.G + 63) / 64, 1024, 0, st>>>(a, ws.colsumX);
-        loss_terms();
+        loss_terms(true);
         LikTcArgs v = a;
         v.gmu_W0 = nullptr;   // LOCAL pass: the entropy value only
         k_tc_w0_final_flat<<<g_sm_count * 4, 256, 0, st>>>(v, nullptr, T, fg.P, a.S * fg.n_pt, loss_out);
