@@ -359,8 +359,8 @@ def run_ours(args):
         roof_dense = roof_adam()
     # with the lazy replay and no dense probe there is no dense-Adam launch to put on the HBM roofline (the family's
     # timing is the lazy kernels', whose traffic is the minibatch rows only)
-    roofs = [r for r in (roof_lik("lik_main_global", "fused likelihood kernel, GLOBAL pass (K2-K4 + W_0 gradient fold; tcgen05 split-bf16)"),
-                         roof_lik("lik_main", "fused likelihood kernel, LOCAL pass (K2-K4; tcgen05 split-bf16 on CTA pairs)"),
+    roofs = [r for r in (roof_lik("lik_main_global", "k_lik_flat<GLOBAL>: fused likelihood kernel, rows = genes (K2-K4 + W_0 gradient fold; tcgen05 split-bf16 on CTA pairs)"),
+                         roof_lik("lik_main", "k_lik_flat<LOCAL>: fused likelihood kernel, rows = cells (K2-K4; tcgen05 split-bf16 on CTA pairs)"),
                          roof_dense if not (lazy and args.no_dense_probe) else None) if r]
     roofs.sort(key=lambda r: -(r["share_of_step"] or 0))
 
@@ -461,8 +461,7 @@ def run_ours(args):
                        "local_adam": "exact lazy replay (bit-identical to the dense kernel)" if lazy else "dense",
                        "preroll_steps": preroll,
                        # kernel variants selected through the environment (none in the default run)
-                       "variants": {k: os.environ[k] for k in ("SCDEF_TC_PAIR", "SCDEF_SAMPLE_V2", "SCDEF_TC_MONO",
-                                                                "SCDEF_HIER_OLD", "SCDEF_TC_NSPLIT") if k in os.environ}},
+                       "variants": {k: os.environ[k] for k in ("SCDEF_SAMPLE_V2", "SCDEF_TC_MONO", "SCDEF_HIER_OLD") if k in os.environ}},
             "steps_per_s": 1e3 / ms_step, "clocks": res["clocks"], "gpu_launches": int(res["launches"]),
             "epoch_reshard": res.get("reshard"), "per_rank": res.get("per_rank"), "step_ms": res.get("step_ms"),
             "e2e": e2e, "roofline": roofs[0] if roofs else None, "roofline_other": roofs[1:],

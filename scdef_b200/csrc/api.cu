@@ -863,7 +863,6 @@ int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t*
 
 /* bring-up hook (not part of the public header): dump the tcgen05 rate tile R as (S,B,G) */
 void scdef_debug_tc_dump(float* p) { lik_tc_set_debug(p); }
-void scdef_debug_tc_timing(unsigned long long* out) { cudaDeviceSynchronize(); lik_tc_read_timing(out); }
 void scdef_debug_pair_stuck(int* out) { lik_tc_pair_stuck(out); }
 void scdef_debug_set_sample_impl(int v) { g_sample_impl = (v == 2) ? 2 : 1; }
 /* host logic under test: n draws of the device initialiser's Gamma(shape, 1) sampler, computed on the HOST from the same code */

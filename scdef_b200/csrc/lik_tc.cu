@@ -135,10 +135,8 @@ struct Misc {                  // lives at Smem.misc
   float rowU[128], rowW[128];  // per-k0 sums of log W and W over the tile's genes (prior terms)
 };
 
-struct Geom {
+struct Geom {   // work decomposition of the monolithic kernels (likelihood-off phases, SCDEF_TC_MONO)
   int KP, n_tiles, n_chunks, NG, tiles_per_range, n_cblocks;
-  int NGp, ptiles_per_range;   // CTA-pair LOCAL kernel: ranges of 128-gene pair-tiles (0 when pair mode is off)
-  int Pflat;                   // persistent variant: CTA pairs per cell block (NGp = partial slots per sample then)
 };
 
 // ---- (a) z0^s block -> bf16 hi/lo planes --------------------------------------------------------
@@ -1094,21 +1092,11 @@ __global__ void __launch_bounds__(256) k_tc_w0_final(const LikTcArgs a, const fl
 
 int round_up16(int k) { return (k + 15) / 16 * 16; }
 
-// LOCAL pass on CTA pairs (lik_tc_pair.cuh).  Default 3: the persistent (flattened) variant with the whole-pair-tile
-// epilogue (0.262 ms per launch at C5 against 0.365 for the single-CTA pipeline; full GPU suite green with it,
-// profiles/r02_first_call_summary.txt).  SCDEF_TC_PAIR=0 selects the single-CTA pipeline (A/B checks), 2 the narrow
-// epilogue.  Read once per process.
-int pair_mode() {
-  static const int mode = getenv("SCDEF_TC_PAIR") != nullptr ? atoi(getenv("SCDEF_TC_PAIR")) : 3;
-  return mode;
-}
-
 // work decomposition: balance (items / 148 SMs rounded up) x (work per item)
 Geom make_geom(int B, int S, int K0, int G) {
   Geom g;
   g.KP = round_up16(K0);
   g.n_tiles = (G + TG - 1) / TG;
-  if (pair_mode()) g.n_tiles = (g.n_tiles + 1) / 2 * 2;   // a pair-tile is two tile images; the phantom one is all zeros
   g.n_cblocks = B > 0 ? (B + CB - 1) / CB : 1;
   double best = 1e30;
   g.n_chunks = 1;
@@ -1128,46 +1116,11 @@ Geom make_geom(int B, int S, int K0, int G) {
   }
   g.tiles_per_range = (g.n_tiles + g.NG - 1) / g.NG;
   g.NG = (g.n_tiles + g.tiles_per_range - 1) / g.tiles_per_range;
-  g.NGp = 0;
-  g.ptiles_per_range = 0;
-  g.Pflat = 0;
-  if (pair_mode() >= 2) {
-    const int n_pt = g.n_tiles / 2;
-    const long long T = (long long)S * n_pt;
-    g.Pflat = SM_TARGET / 2 / g.n_cblocks;
-    if (g.Pflat < 1) g.Pflat = 1;
-    if ((long long)g.Pflat > T) g.Pflat = (int)(T > 0 ? T : 1);
-    int slots = 1;
-    for (int s2 = 0; s2 < S; ++s2) {
-      const int n = flat_chunk_of((long long)(s2 + 1) * n_pt - 1, T, g.Pflat) - flat_chunk_of((long long)s2 * n_pt, T, g.Pflat) + 1;
-      if (n > slots) slots = n;
-    }
-    g.NGp = slots;
-  } else if (pair_mode()) {
-    // pairs of CTAs: 74 pair slots; item = (s, range of pair-tiles, 256-cell block)
-    const int n_pt = g.n_tiles / 2;
-    best = 1e30;
-    g.NGp = 1;
-    for (int ng = 1; ng <= n_pt; ++ng) {
-      const long long items = (long long)S * ng * g.n_cblocks;
-      const double waves = (double)((items + SM_TARGET / 2 - 1) / (SM_TARGET / 2));
-      const double cost = waves * ((double)((n_pt + ng - 1) / ng) + 1.0) + 0.01 * ng;   // +1: per-item z load / dz drain
-      if (cost < best - 1e-9) { best = cost; g.NGp = ng; }
-    }
-    g.ptiles_per_range = (n_pt + g.NGp - 1) / g.NGp;
-    g.NGp = (n_pt + g.ptiles_per_range - 1) / g.ptiles_per_range;
-  }
   return g;
 }
 
 size_t a256(size_t x) { return (x + 255) / 256 * 256; }
 
-// The unified CTA-pair kernel of lik_flat.cuh is the default for both passes.  SCDEF_TC_FLAT=0 selects the round-1
-// kernels (k_lik_pair_flat for LOCAL, the single-CTA k_lik_pipe for GLOBAL) for A/B checks.  Read once per process.
-int flat_mode() {
-  static const int mode = getenv("SCDEF_TC_FLAT") != nullptr ? atoi(getenv("SCDEF_TC_FLAT")) : 1;
-  return mode;
-}
 int g_sm_count = 148;   // set by lik_tc_launch / lik_tc_workspace_bytes callers through lik_tc_set_sm_count
 
 FlatGeom make_flat_geom(bool genes, int B, int S, int K0, int G) {
@@ -1228,20 +1181,14 @@ bool lik_tc_supported(int K0, int G, int nb) { return K0 >= 1 && K0 <= 112 && (G
 
 size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb) {
   const Geom g = make_geom(B, S, K0, G);
-  size_t part_local = (size_t)S * (g.NG > g.NGp ? g.NG : g.NGp) * (size_t)(B > 0 ? B : 1) * K0 * 4;
-  size_t part_global = (size_t)g.n_chunks * 2 * K0 * G * 4;
-  const size_t Bp = (size_t)(B > 0 ? B : 1), units = (Bp + 127) / 128;
+  const size_t Bp = (size_t)(B > 0 ? B : 1);
   const FlatSizes f = flat_sizes(B, S, K0, G, nb);
-  size_t part = part_local > part_global ? part_local : part_global;
+  size_t part = (size_t)S * g.NG * Bp * K0 * 4;                       // monolithic LOCAL
+  const size_t part_global = (size_t)g.n_chunks * 2 * K0 * G * 4;     // monolithic GLOBAL
+  if (part_global > part) part = part_global;
   if (f.part > part) part = f.part;
-  size_t zimg = (size_t)S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
-  if (f.zimg > zimg) zimg = f.zimg;
-  size_t wimg = (size_t)S * g.n_tiles * plan_pipe_smem(g.KP).w_unit;
-  if (f.wimg > wimg) wimg = f.wimg;
-  size_t ximg = (size_t)g.n_tiles * units * 128 * 64 * 4;
-  if (f.ximg > ximg) ximg = f.ximg;
   return a256((size_t)S * K0 * 2 * 4) + a256((size_t)S * nb * K0 * 4) + a256((size_t)nb * G * 4) + a256(part) +
-         2 * a256((size_t)K0 * G * 4) + a256(zimg) + a256(Bp * 4) + a256(Bp * 8) + a256(wimg) + a256(ximg) +
+         2 * a256((size_t)K0 * G * 4) + a256(f.zimg) + a256(Bp * 4) + a256(Bp * 8) + a256(f.wimg) + a256(f.ximg) +
          a256(f.Ws) + a256(f.rowsumx) + a256(f.zimg_g) + a256(f.ximg_t) + a256(f.foldtab) + 1024;
 }
 
@@ -1261,11 +1208,11 @@ static void pair_stuck_init() {
 }
 void lik_tc_pair_stuck(int* out) { for (int i = 0; i < 4; ++i) out[i] = g_pair_stuck_host ? g_pair_stuck_host[i] : 0; }
 
-// host logic under test (tests/test_host.py): the work decomposition for a problem shape.
-// out = {KP, n_tiles, n_chunks, NG, tiles_per_range, n_cblocks, NGp, ptiles_per_range, Pflat, pair mode}
+// host logic under test (tests/test_host.py): the work decomposition of the CTA-pair kernel for a problem shape.
+// out = {KP, W_0 tile images per sample, LOCAL: n_rblk, n_pt, P, slots, GLOBAL: n_rblk, n_pt, P, slots}
 void lik_tc_debug_geom(int B, int S, int K0, int G, int* out) {
-  const Geom g = make_geom(B, S, K0, G);
-  const int v[10] = {g.KP, g.n_tiles, g.n_chunks, g.NG, g.tiles_per_range, g.n_cblocks, g.NGp, g.ptiles_per_range, g.Pflat, pair_mode()};
+  const FlatGeom l = make_flat_geom(false, B, S, K0, G), g = make_flat_geom(true, B, S, K0, G);
+  const int v[10] = {l.KP, 4 * ((G + 255) / 256), l.n_rblk, l.n_pt, l.P, l.slots, g.n_rblk, g.n_pt, g.P, g.slots};
   for (int i = 0; i < 10; ++i) out[i] = v[i];
 }
 int lik_tc_debug_flat_chunk_of(long long f, long long T, int P) { return flat_chunk_of(f, T, P); }
@@ -1278,56 +1225,35 @@ void lik_tc_read_pair_timing(unsigned long long* out) {
 #endif
 }
 
-void lik_tc_read_timing(unsigned long long* out) {
-#ifdef SCDEF_TC_TIMING
-  cudaMemcpyFromSymbol(out, g_tc_timing, sizeof(unsigned long long) * 2 * 4 * 16);
-#else
-  for (int i = 0; i < 128; ++i) out[i] = 0;
-#endif
-}
-
 int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStream_t st) {
   lik_tc_set_sm_count(sm_count);
   LikTcArgs a = a_in;
-  static const int dbg_nsplit = getenv("SCDEF_TC_NSPLIT") ? atoi(getenv("SCDEF_TC_NSPLIT")) : 3;  // timing experiments only
-  a.dbg_nsplit = dbg_nsplit;
-  static const int l2pf = getenv("SCDEF_TC_L2PF") ? atoi(getenv("SCDEF_TC_L2PF")) : 0;   // opt-in, not measured yet
-  a.l2_prefetch = l2pf;
-  static const int poll = getenv("SCDEF_TC_POLL") ? atoi(getenv("SCDEF_TC_POLL")) : 0;      // opt-in, not measured yet
-  a.mma_poll = poll;
   if (!lik_tc_supported(a.K0, a.G, a.nb)) return SCDEF_EUNSUPPORTED;
   const bool matrix_prior = a.P || a.R;   // iscDEF: Gamma shape / rate of W_0 per (k, g)
   if (a.B <= 0) a.lik_on = 0;
   const Geom g = make_geom(a.B, a.S, a.K0, a.G);
+  const FlatSizes fz = flat_sizes(a.B, a.S, a.K0, a.G, a.nb);
+  const size_t Bp = (size_t)(a.B > 0 ? a.B : 1);
   char* w = (char*)a.ws;
   TcScratch ws;
-  const FlatSizes fz = flat_sizes(a.B, a.S, a.K0, a.G, a.nb);
-  const bool flat = flat_mode() != 0;
   ws.rowstats = (float*)w; w += a256((size_t)a.S * a.K0 * 2 * 4);
   ws.ctilde = (float*)w;   w += a256((size_t)a.S * a.nb * a.K0 * 4);
   ws.colsumX = (float*)w;  w += a256((size_t)a.nb * a.G * 4);
   ws.part = (float*)w;
-  const size_t Bp = (size_t)(a.B > 0 ? a.B : 1), units = (Bp + 127) / 128;
   {
-    size_t part_local = (size_t)a.S * (g.NG > g.NGp ? g.NG : g.NGp) * Bp * a.K0 * 4;
-    size_t part_global = (size_t)g.n_chunks * 2 * a.K0 * a.G * 4;
-    size_t part = part_local > part_global ? part_local : part_global;
+    size_t part = (size_t)a.S * g.NG * Bp * a.K0 * 4;
+    const size_t part_global = (size_t)g.n_chunks * 2 * a.K0 * a.G * 4;
+    if (part_global > part) part = part_global;
     if (fz.part > part) part = fz.part;
     w += a256(part);
   }
-  size_t zimg_bytes = (size_t)a.S * units * 2 * 16 * (size_t)(g.KP / 8) * 128;
-  if (fz.zimg > zimg_bytes) zimg_bytes = fz.zimg;
-  size_t wimg_bytes = (size_t)a.S * g.n_tiles * plan_pipe_smem(g.KP).w_unit;
-  if (fz.wimg > wimg_bytes) wimg_bytes = fz.wimg;
-  size_t ximg_bytes = (size_t)g.n_tiles * units * 128 * 64 * 4;
-  if (fz.ximg > ximg_bytes) ximg_bytes = fz.ximg;
   ws.wmu = (float*)w;      w += a256((size_t)a.K0 * a.G * 4);
   ws.wsig = (float*)w;     w += a256((size_t)a.K0 * a.G * 4);
-  ws.zimg = (uint8_t*)w;   w += a256(zimg_bytes);
+  ws.zimg = (uint8_t*)w;   w += a256(fz.zimg);
   ws.brow = (int*)w;       w += a256(Bp * 4);
   ws.xoff = (long long*)w; w += a256(Bp * 8);
-  ws.wimg = (uint8_t*)w;   w += a256(wimg_bytes);
-  ws.ximg = (float*)w;     w += a256(ximg_bytes);
+  ws.wimg = (uint8_t*)w;   w += a256(fz.wimg);
+  ws.ximg = (float*)w;     w += a256(fz.ximg);
   ws.Ws = (float*)w;       w += a256(fz.Ws);
   ws.rowsumx = (float*)w;  w += a256(fz.rowsumx);
   ws.zimg_g = (uint8_t*)w; w += a256(fz.zimg_g);
@@ -1336,21 +1262,21 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   if ((size_t)(w - (char*)a.ws) > a.ws_bytes) return SCDEF_EWORKSPACE;
   const Smem L = plan_smem(g.KP);
   const PipeSmem PL = plan_pipe_smem(g.KP);
-  static const bool mono = getenv("SCDEF_TC_MONO") != nullptr;  // A/B switch: the monolithic v2a kernels
+  static const bool mono = getenv("SCDEF_TC_MONO") != nullptr;  // A/B switch: the monolithic kernels with the likelihood on
   const bool global_pass = a.pass == SCDEF_PASS_GLOBAL;
-  const bool pipe = a.lik_on && !mono;
+  const bool pair = a.lik_on && !mono;   // the CTA-pair kernel runs whenever the likelihood is on
   if (matrix_prior && mono) return SCDEF_EUNSUPPORTED;   // the monolithic kernels only know scalar W_0 priors
   cudaEvent_t ev0 = a.ev0, ev1 = a.ev1;
   a.ev0 = a.ev1 = nullptr;
-  const bool reuse = pipe && a.reuse_w0;  // W_0 image + row sums of the previous pass (same noise, same W_0) are still valid
+  const bool reuse = pair && a.reuse_w0;  // W_0 images + row sums of the previous pass (same noise, same W_0) are still valid
   if (!reuse) {
     cudaMemsetAsync(ws.rowstats, 0, (size_t)a.S * a.K0 * 2 * 4, st);
     cudaMemsetAsync(ws.Ws, 0, (size_t)a.S * a.nb * a.K0 * 4, st);
   }
-  a.n_wimg = flat ? fz.n_tiles : g.n_tiles;
-  if (pipe && flat) {
-    // ================= unified CTA-pair kernel (lik_flat.cuh) =================
-    const int n_tiles = fz.n_tiles;
+  const int n_tiles = fz.n_tiles;   // W_0 tile images per sample
+  a.n_wimg = n_tiles;
+  if (pair) {
+    // ================= the CTA-pair kernel (lik_flat.cuh) =================
     const FlatGeom fg = make_flat_geom(global_pass, a.B, a.S, a.K0, a.G);
     const FlatSmem FL = plan_flat_smem(fg.KP);
     const int nblk = g_sm_count * 4;
@@ -1406,103 +1332,36 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
     }
     return SCDEF_OK;
   }
-  // matrix prior without the main kernel (likelihood off = W_0 frozen, or a rank without minibatch rows): the tile
-  // images are still needed for the prior value and the brd / ard gradients
-  const bool fold_prior_grad = matrix_prior && !pipe && global_pass && !a.w0_stopped;
-  if (!pipe && matrix_prior) {
-    k_tc_wprep<<<148 * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
-    k_tc_wgen<<<dim3((a.G + 255) / 256, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
+
+  // ================= likelihood off (layer 0 frozen, or a rank without minibatch rows), or SCDEF_TC_MONO =================
+  // W_0 prior and entropy: value, and — GLOBAL pass of a rank without rows — their gradients.  The monolithic kernels
+  // sample W_0 in the kernel; matrix-valued priors walk the tile images instead.
+  const bool fold_prior_grad = matrix_prior && global_pass && !a.w0_stopped;
+  if (matrix_prior) {
+    k_tc_wprep<<<g_sm_count * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
+    k_tc_wgen<<<dim3(n_tiles / 4, a.S), 256, 0, st>>>(a, ws, g.KP, n_tiles, PL.w_plane, PL.w_unit);
     if (fold_prior_grad) cudaMemsetAsync(ws.part, 0, (size_t)g.n_chunks * 2 * a.K0 * a.G * 4, st);
   }
-  if (pipe) {
-    k_tc_rowprep<<<(a.B + 255) / 256, 256, 0, st>>>(a, ws.brow, ws.xoff);
-    k_tc_zprep<<<148 * 4, 256, 0, st>>>(a, ws.zimg, g.KP, (int)units);
-    k_tc_xprep<<<148 * 4, 256, 0, st>>>(a, ws.ximg, g.n_tiles, (int)units);
-    if (!reuse) {
-      k_tc_wprep<<<148 * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
-      k_tc_wgen<<<dim3((a.G + 255) / 256, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
-    }
-  }
-  bool ev_started = false;
-  auto main_begin = [&]() { if (ev0) { cudaEventRecord(ev0, st); ev_started = true; } };
-  auto main_end = [&]() { if (ev1 && ev_started) cudaEventRecord(ev1, st); };
   if (global_pass) {
     if (a.lik_on) {
       k_tc_ctilde<<<a.S, 1024, 0, st>>>(a, ws.ctilde);
       k_tc_colsum<<<(a.G + 63) / 64, 1024, 0, st>>>(a, ws.colsumX);
     }
-    if (a.lik_on && !mono) {
-      if (a.nb == 1) k_tc_colw<1><<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
-      else k_tc_colw<MAX_NB><<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit);
-      main_begin();
-      if (matrix_prior) {
-        cudaFuncSetAttribute(k_lik_pipe<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
-        k_lik_pipe<true, true, true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
-      } else {
-        cudaFuncSetAttribute(k_lik_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
-        k_lik_pipe<true, true><<<g.n_tiles * g.n_chunks, PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
-      }
-      main_end();
-    } else if (!matrix_prior) {
+    if (!matrix_prior) {
       cudaFuncSetAttribute(k_lik_tc_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+      if (ev0 && a.lik_on) cudaEventRecord(ev0, st);
       k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(a, g, ws, loss_out);
+      if (ev1 && ev0 && a.lik_on) cudaEventRecord(ev1, st);
     }
   } else {
-    // CTA-pair LOCAL kernel (opt-in): whole 256-cell blocks only; anything else takes the single-CTA pipeline
-    const bool pair = pipe && pair_mode() && a.B > 0 && (a.B % CB) == 0 && g.NGp > 0 && a.dbg_nsplit != 1;
-    int ng_used = g.NG;
     if (a.lik_on) {
-      if (pair) {
-        const PairSmem QL = plan_pair_smem(g.KP);
-        pair_stuck_init();
-        ng_used = g.NGp;
-        main_begin();
-        if (g.Pflat > 0) {
-          const dim3 grid(2 * g.Pflat, g.n_cblocks);
-          auto launch = [&](auto kern) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
-            kern<<<grid, PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
-          };
-          const int pm = pair_mode();   // 2: narrow epilogue, 3: whole-pair-tile epilogue, 4: 3 + per-k-step Q hand-off, 5: 2 + that hand-off
-          if (a.want_loss) {
-            if (pm == 4) launch(k_lik_pair_flat<true, true, true>);
-            else if (pm == 5) launch(k_lik_pair_flat<true, false, true>);
-            else if (pm == 3) launch(k_lik_pair_flat<true, true, false>);
-            else launch(k_lik_pair_flat<true, false, false>);
-          } else {
-            if (pm == 4) launch(k_lik_pair_flat<false, true, true>);
-            else if (pm == 5) launch(k_lik_pair_flat<false, false, true>);
-            else if (pm == 3) launch(k_lik_pair_flat<false, true, false>);
-            else launch(k_lik_pair_flat<false, false, false>);
-          }
-        } else if (a.want_loss) {
-          cudaFuncSetAttribute(k_lik_pair_local<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
-          k_lik_pair_local<true><<<dim3(2 * a.S * g.NGp, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
-        } else {
-          cudaFuncSetAttribute(k_lik_pair_local<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QL.total);
-          k_lik_pair_local<false><<<dim3(2 * a.S * g.NGp, g.n_cblocks), PIPE_NT, QL.total, st>>>(a, g, ws, loss_out);
-        }
-        main_end();
-      } else if (!mono) {
-        if (a.want_loss) {
-          cudaFuncSetAttribute(k_lik_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
-          main_begin();
-          k_lik_pipe<false, true><<<dim3(a.S * g.NG, g.n_cblocks), PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
-          main_end();
-        } else {
-          cudaFuncSetAttribute(k_lik_pipe<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL.total);
-          main_begin();
-          k_lik_pipe<false, false><<<dim3(a.S * g.NG, g.n_cblocks), PIPE_NT, PL.total, st>>>(a, g, ws, loss_out);
-          main_end();
-        }
-      } else {
-        cudaFuncSetAttribute(k_lik_tc_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-        k_lik_tc_local<<<dim3(a.S * g.NG, g.n_cblocks), NT, L.total, st>>>(a, g, ws, loss_out);
-      }
-      long long total = (long long)a.S * a.B * a.K0;
-      int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-      if (pair && g.Pflat > 0) k_tc_dz_reduce_flat<<<blocks, 256, 0, st>>>(a, ws.part, g.NGp, g.Pflat, g.n_tiles / 2);
-      else k_tc_dz_reduce<<<blocks, 256, 0, st>>>(a, ws.part, ng_used);
+      cudaFuncSetAttribute(k_lik_tc_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+      if (ev0) cudaEventRecord(ev0, st);
+      k_lik_tc_local<<<dim3(a.S * g.NG, g.n_cblocks), NT, L.total, st>>>(a, g, ws, loss_out);
+      if (ev1 && ev0) cudaEventRecord(ev1, st);
+      const long long total = (long long)a.S * a.B * a.K0;
+      const int blocks = (int)((total + 255) / 256 < g_sm_count * 8 ? (total + 255) / 256 : g_sm_count * 8);
+      k_tc_dz_reduce<<<blocks, 256, 0, st>>>(a, ws.part, g.NG);
     } else if (!matrix_prior) {
       // value only: the GLOBAL kernel without likelihood produces the W_0 row sums
       LikTcArgs v = a;
@@ -1511,9 +1370,9 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
       k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(v, g, ws, loss_out);
     }
   }
-  // LOCAL pass with the loss discarded: the W_0 prior and entropy VALUES are all these two kernels would produce
+  // LOCAL pass with the loss discarded: the W_0 prior and entropy VALUES are all the kernels below would produce
   if (!global_pass && !a.want_loss) {
-    cudaError_t e0 = cudaGetLastError();
+    const cudaError_t e0 = cudaGetLastError();
     if (e0 != cudaSuccess) {
       fprintf(stderr, "scdef_b200: lik_tc_launch: %s\n", cudaGetErrorString(e0));
       return SCDEF_ECUDA;
@@ -1521,12 +1380,12 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
     return SCDEF_OK;
   }
   if (matrix_prior)
-    k_tc_w0_prior_mat<<<dim3(g.n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, g.n_tiles, PL.w_plane, PL.w_unit, loss_out, fold_prior_grad ? 1 : 0);
+    k_tc_w0_prior_mat<<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out, fold_prior_grad ? 1 : 0);
   else k_tc_w0_prior<<<(a.S * a.K0 + 127) / 128, 128, 0, st>>>(a, ws.rowstats, loss_out);
-  k_tc_w0_final<<<148 * 4, 256, 0, st>>>(a, ws.part, g.n_chunks, loss_out);
-  cudaError_t err = cudaGetLastError();
+  k_tc_w0_final<<<g_sm_count * 4, 256, 0, st>>>(a, ws.part, g.n_chunks, loss_out);
+  const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
-    fprintf(stderr, "scdef_b200: lik_tc_launch: %s (smem mono %u, pipe %u)\n", cudaGetErrorString(err), L.total, PL.total);
+    fprintf(stderr, "scdef_b200: lik_tc_launch: %s (smem %u)\n", cudaGetErrorString(err), L.total);
     return SCDEF_ECUDA;
   }
   return SCDEF_OK;

@@ -29,10 +29,8 @@ struct LikTcArgs {
   const float* P;  // W_0 prior matrices or nullptr
   const float* R;
   float P_scalar, R_scalar;
-  int use_brd, B, G, K0, nb, pass, S, w0_stopped, lik_on, reuse_w0, want_loss, dbg_nsplit;
+  int use_brd, B, G, K0, nb, pass, S, w0_stopped, lik_on, reuse_w0, want_loss;
   int n_wimg;       // W_0 tile images per MC sample in the workspace (set by lik_tc_launch)
-  int l2_prefetch;  // opt-in: the COPY thread prefetches upcoming W_0 tile images into L2 (SCDEF_TC_L2PF=1)
-  int mma_poll;     // opt-in: the MMA thread slips the next rate GEMM in only when its operands are ready (SCDEF_TC_POLL=1)
   float scale, global_weight, anneal;
   void* ws;
   size_t ws_bytes;
@@ -43,7 +41,6 @@ bool lik_tc_supported(int K0, int G, int nb);
 size_t lik_tc_workspace_bytes(int B, int S, int K0, int G, int nb);
 void lik_tc_set_debug(float* p);
 void lik_tc_set_sm_count(int n);   // SMs of the device (decomposition of the persistent kernels); default 148
-void lik_tc_read_timing(unsigned long long* out);
 void lik_tc_read_pair_timing(unsigned long long* out);  // [rank][role][slot] of the CTA-pair kernel (-DSCDEF_TC_TIMING)
 void lik_tc_pair_stuck(int* out);
 void lik_tc_debug_geom(int B, int S, int K0, int G, int* out);   // work decomposition (host logic, CPU-testable)

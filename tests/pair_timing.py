@@ -1,6 +1,6 @@
 """Per-launch time of the fused likelihood kernel, LOCAL and GLOBAL pass separately, at C5 shapes (256 cells x 5000
-genes, layers [100,60,30,10], 100 MC samples).  Run twice to compare the single-CTA pipeline with the CTA-pair LOCAL
-kernel:   python tests/pair_timing.py ;  SCDEF_TC_PAIR=1 python tests/pair_timing.py"""
+genes, layers [100,60,30,10], 100 MC samples):   python tests/pair_timing.py [cells] [samples] [dump]
+(`dump` needs a -DSCDEF_TC_TIMING build and prints where each role of the CTA-pair kernel spends its cycles.)"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -53,6 +53,6 @@ for which in ("local", "global"):
     if len(sys.argv) > 3 and sys.argv[3] == "dump":
         dump(which)
     eng.profile(False)
-mode = "unified pair kernel" if os.environ.get("SCDEF_TC_FLAT", "1") != "0" else "round-1 kernels (SCDEF_TC_FLAT=0), LOCAL pair mode " + os.environ.get("SCDEF_TC_PAIR", "3")
+mode = "monolithic kernels" if os.environ.get("SCDEF_TC_MONO") else "CTA-pair kernel"
 print(f"[{mode}] S={S}  main kernel ms/launch: LOCAL {out['local'][0]:.4f}  GLOBAL {out['global'][0]:.4f}   "
       f"whole pass ms: LOCAL {out['local'][1]:.4f}  GLOBAL {out['global'][1]:.4f}", flush=True)

@@ -65,9 +65,8 @@ def run(N, G, Ks, nb, B, S, sg=None, dump=True, **kw):
 
 
 def pair_cases():
-    """CTA-pair LOCAL kernel (SCDEF_TC_PAIR=1; engaged only for B % 256 == 0).  On a trapped launch the record of the
-    wait that timed out is printed: (code, blockIdx.x, warp or sub-unit, parity) -- codes in lik_tc_pair.cuh."""
-    # SCDEF_TC_PAIR: unset / 3 = the default persistent pair kernel, 2 = narrow epilogue, 0 = the single-CTA pipeline
+    """The CTA-pair kernel (both passes; SCDEF_TC_MONO=1: the monolithic kernels).  On a trapped launch the record of the
+    wait that timed out is printed: (code, blockIdx.x, warp or sub-unit, parity) -- codes in lik_flat.cuh."""
     worst = 0.0
     try:
         print("pair 1: one pair-tile, KP=16", flush=True); worst = max(worst, run(300, 128, (16, 4), 1, 256, 1)["tc_max_err"])

@@ -338,12 +338,11 @@ def test_iscdef_priors_match_the_loop_restatement(markers_layer, add_other, pena
 
 
 def test_persistent_pair_kernel_work_decomposition():
-    """Chunks of the flattened (sample, pair-tile) space and the partial-buffer slots of the persistent CTA-pair kernel
-    (lik_tc_pair.cuh), checked through the library's own arithmetic for 65 shapes; SCDEF_TC_PAIR is read once per
-    process, hence the subprocess.  No CUDA call."""
+    """Chunks of the flattened (row block, sample, pair-tile) space and the partial-buffer slots of the persistent
+    CTA-pair kernel (csrc/lik_flat.cuh), both orientations, checked through the library's own arithmetic for 68 shapes
+    (in a subprocess: plain ctypes, no torch).  No CUDA call."""
     import subprocess
     import sys
 
-    env = dict(os.environ, SCDEF_TC_PAIR="2")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_flat_plan_check.py")], env=env, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_flat_plan_check.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "flat plan ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,4 +1,6 @@
-"""Protocol model of the persistent CTA-pair LOCAL kernel (`scdef_b200/csrc/lik_tc_pair.cuh::k_lik_pair_flat`), CPU only.
+"""Protocol model of the persistent CTA-pair likelihood kernel in its LOCAL orientation (`scdef_b200/csrc/lik_flat.cuh::k_lik_flat`,
+barrier block and wrappers in `lik_tc_pair.cuh`), CPU only.  (The GLOBAL orientation shares the rate-GEMM half of the
+protocol; its second GEMM and Q hand-off are per CTA — plain single-CTA full/empty pairs.)
 
 The kernel is five kinds of agents (per CTA: a COPY thread, epilogue warps; in the leader the MMA issuer, in the peer the
 relay thread; plus the hardware: TMA copies and the tensor pipe complete asynchronously) that hand buffers to each
@@ -10,9 +12,10 @@ expressions) as Python coroutines, runs them under many random interleavings and
 asynchronous agents, and checks: every agent finishes (no deadlock), no barrier is arrived on more often than its count
 per phase, and no buffer is written while an earlier reader is still in flight or read before its writer finished.
 
-Both epilogue variants are modelled: `wide=False` (SCDEF_TC_PAIR=2, the one that ran on the B200) and `wide=True`
-(SCDEF_TC_PAIR=3, not run yet), and the per-k-step Q hand-off (`fine=True`, SCDEF_TC_PAIR=4, not run yet).  If the kernel's
-protocol changes, change it here first."""
+The model covers the kernel's whole-pair-tile epilogue (`wide=True`, the shipped form) and the two variants it was chosen
+from in round 2 (`wide=False`: one 64-gene half per barrier round; `fine=True`: the Q hand-off per k-step — both measured
+slower or equal on a B200, profiles/r02_first_call_summary.txt, and removed from the kernel).  If the kernel's protocol
+changes, change it here first."""
 import random
 
 import pytest
@@ -372,7 +375,7 @@ class Sim:
 @pytest.mark.parametrize("n_outer,n_pt,pt0", [(1, 1, 0), (2, 2, 0), (3, 2, 1), (5, 2, 0), (6, 3, 2), (7, 40, 38), (9, 4, 3), (8, 1, 0)])
 def test_no_deadlock_no_overrun_no_hazard(wide, fine, n_outer, n_pt, pt0):
     """Chunks of n_outer pair-tiles starting at pair-tile pt0 of a sample with n_pt pair-tiles (so they cross 0..7 sample
-    boundaries), 40 random schedules each.  fine: the Q hand-off per k-step group (SCDEF_TC_PAIR=4)."""
+    boundaries), 40 random schedules each.  fine: the Q hand-off per k-step group."""
     for seed in range(40):
         Sim(n_outer, n_pt, pt0, wide, seed, fine).run()
 
