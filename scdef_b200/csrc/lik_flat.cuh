@@ -214,13 +214,32 @@ __global__ void __launch_bounds__(256) k_tc_rank1(const LikTcArgs a, const TcScr
       pbase = ((long long)s * slots_ld * a.B + j) * a.K0;
     }
     float dot = 0.f;
-    for (int k = lane; k < a.K0; k += 32) {
-      const float wsk = Wsb[k];
-      dot = fmaf(z[k], wsk, dot);
-      if (do_grad) {
-        float acc = 0.f;
-        for (int q = 0; q < nsl; ++q) acc += part[pbase + (long long)q * a.B * a.K0 + k];
-        a.G_z0[w * a.K0 + k] += a.scale * (acc - c * wsk);
+    if ((a.K0 & 3) == 0) {
+      // one float4 per lane and array: a single round of loads for K0 <= 128
+      for (int k = lane * 4; k < a.K0; k += 128) {
+        const float4 z4 = *reinterpret_cast<const float4*>(z + k), w4 = *reinterpret_cast<const float4*>(Wsb + k);
+        dot = fmaf(z4.x, w4.x, fmaf(z4.y, w4.y, fmaf(z4.z, w4.z, fmaf(z4.w, w4.w, dot))));
+        if (do_grad) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < nsl; ++q) {
+            const float4 p4 = *reinterpret_cast<const float4*>(part + pbase + (long long)q * a.B * a.K0 + k);
+            acc.x += p4.x; acc.y += p4.y; acc.z += p4.z; acc.w += p4.w;
+          }
+          float4 g4 = *reinterpret_cast<float4*>(a.G_z0 + w * a.K0 + k);
+          g4.x += a.scale * (acc.x - c * w4.x); g4.y += a.scale * (acc.y - c * w4.y);
+          g4.z += a.scale * (acc.z - c * w4.z); g4.w += a.scale * (acc.w - c * w4.w);
+          *reinterpret_cast<float4*>(a.G_z0 + w * a.K0 + k) = g4;
+        }
+      }
+    } else {
+      for (int k = lane; k < a.K0; k += 32) {
+        const float wsk = Wsb[k];
+        dot = fmaf(z[k], wsk, dot);
+        if (do_grad) {
+          float acc = 0.f;
+          for (int q = 0; q < nsl; ++q) acc += part[pbase + (long long)q * a.B * a.K0 + k];
+          a.G_z0[w * a.K0 + k] += a.scale * (acc - c * wsk);
+        }
       }
     }
 #pragma unroll
@@ -477,39 +496,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
         return mbar_test(&mi->w_full[st], par) && mbar_test_remote(&mi->pw_full[st], par) &&
                mbar_test_remote(&mi->r_empty[GENES ? 0 : st], (GENES ? ((uint32_t)oi & 1u) : par) ^ 1u);
       };
-      auto issue_mma1 = [&](int oi) {
+      // The rate GEMM of a pair-tile is issued in CHUNKS of k-steps: the tensor pipe executes in issue order, so a whole
+      // rate GEMM (21 MMAs, ~2k cycles) slipped in ahead would delay the second GEMM of a Q tile that arrives meanwhile
+      // by that much, and with it the release of the single Q buffer the epilogue warps wait for.
+      int ks1 = 0;                 // k-steps of the pending rate GEMM (pair-tile next1) issued so far
+      uint64_t da1 = 0, db1 = 0;
+      auto issue_mma1 = [&](int oi, int max_steps) {
         const int st = oi & 1;
         const uint32_t par = (uint32_t)(oi >> 1) & 1u;
-        if (first_in_seg(oi, c1)) {
-          PT_WAIT(6, pair_wait(&mi->z_full, (uint32_t)c1.g & 1u, 7));
-          PT_WAIT(6, pair_wait_remote(&mi->pz_full, (uint32_t)c1.g & 1u, 8));
-        }
-        PT_WAIT(0, pair_wait(&mi->w_full[st], par, 4));
-        PT_WAIT(1, pair_wait_remote(&mi->pw_full[st], par, 5));
         // R: double-buffered with the stage (LOCAL) or a single buffer (GLOBAL: barrier 0, one phase per pair-tile)
         const int rs = GENES ? 0 : st;
-        const uint32_t rpar = GENES ? ((uint32_t)oi & 1u) : par;
-        PT_WAIT(2, pair_wait_remote(&mi->r_empty[rs], rpar ^ 1u, 6));
-        tc_fence_after();
-        PT_MARK();
-        uint64_t da = d_a1, db = d_b1[st];
         const uint32_t d = tmem + (uint32_t)rs * (2 * TG);
-        umma2_bf16(d, da + a1pl, db, idesc1, 0u);
-        umma2_bf16(d, da, db + b1pl, idesc1, 1u);
-        umma2_bf16(d, da, db, idesc1, 1u);
-        for (int ks = 1; ks < nk1; ++ks) {
-          da += a1_k;
-          db += b1_k;
-          umma2_bf16(d, da + a1pl, db, idesc1, 1u);
-          umma2_bf16(d, da, db + b1pl, idesc1, 1u);
-          umma2_bf16(d, da, db, idesc1, 1u);
+        if (ks1 == 0) {
+          if (first_in_seg(oi, c1)) {
+            PT_WAIT(6, pair_wait(&mi->z_full, (uint32_t)c1.g & 1u, 7));
+            PT_WAIT(6, pair_wait_remote(&mi->pz_full, (uint32_t)c1.g & 1u, 8));
+          }
+          PT_WAIT(0, pair_wait(&mi->w_full[st], par, 4));
+          PT_WAIT(1, pair_wait_remote(&mi->pw_full[st], par, 5));
+          const uint32_t rpar = GENES ? ((uint32_t)oi & 1u) : par;
+          PT_WAIT(2, pair_wait_remote(&mi->r_empty[rs], rpar ^ 1u, 6));
+          tc_fence_after();
+          da1 = d_a1;
+          db1 = d_b1[st];
         }
+        PT_MARK();
+        for (int n = 0; n < max_steps && ks1 < nk1; ++n, ++ks1) {
+          umma2_bf16(d, da1 + a1pl, db1, idesc1, ks1 > 0 ? 1u : 0u);
+          umma2_bf16(d, da1, db1 + b1pl, idesc1, 1u);
+          umma2_bf16(d, da1, db1, idesc1, 1u);
+          da1 += a1_k;
+          db1 += b1_k;
+        }
+        PT_LAP(4);
+        if (ks1 < nk1) return false;
         umma2_commit(&mi->r_full[rs]);
         if (GENES) umma2_commit(&mi->w_empty[st]);               // the pair's rate GEMM has read both CTAs' stage
         if (last_in_seg(oi, c1)) umma2_commit(&mi->z_empty);   // the segment's ROW unit has been read by its last rate GEMM
-        PT_LAP(4);
         c1.next(n_pt, S);
+        ks1 = 0;
+        return true;
       };
+      constexpr int MMA1_CHUNK = 2;   // k-steps (6 MMAs, ~0.6k cycles of tensor pipe) per slipped-in chunk
       int next1 = 0;
       for (int u = 0; u < U; ++u) {
         const int oi = u >> 1, h = u & 1, st = oi & 1;
@@ -518,8 +546,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
         const long long t_loop0 = clock64(), t_in1 = tacc[0] + tacc[1] + tacc[2] + tacc[4] + tacc[6];
 #endif
         for (;;) {
-          if (next1 < n_outer && next1 <= oi + 1 && (next1 == oi || ready1(next1))) { issue_mma1(next1); ++next1; continue; }
+          // this pair-tile's own rate GEMM: nothing else can happen before it
+          if (next1 == oi) { if (issue_mma1(next1, nk1)) ++next1; continue; }
           if (GENES ? mbar_test(&mi->q_full, (uint32_t)u & 1u) : mbar_test_remote(&mi->q_full, (uint32_t)u & 1u)) break;
+          // the next pair-tile's, a chunk at a time while Q is not there
+          if (next1 < n_outer && next1 == oi + 1 && (ks1 > 0 || ready1(next1))) { if (issue_mma1(next1, MMA1_CHUNK)) ++next1; continue; }
           if (next1 > oi + 1 || next1 >= n_outer) {
             if (GENES) pair_wait(&mi->q_full, (uint32_t)u & 1u, 9);
             else pair_wait_remote(&mi->q_full, (uint32_t)u & 1u, 9);
@@ -668,6 +699,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       const uint8_t* wline = ws.wimg + ((long long)p.s * a.n_wimg + (p.rb * 2 + (int)rank) * 2 + (cq >> 1)) * IL.w_unit +
                              (uint32_t)(rr >> 3) * W_RS + (uint32_t)((cq & 1) * 4) * 128u + (uint32_t)(rr & 7) * 16u;
       uint4 nh = __ldg(reinterpret_cast<const uint4*>(wline)), nl = __ldg(reinterpret_cast<const uint4*>(wline + IL.w_plane));
+      // gene-scale samples of the step's 8 genes (batch 0; the same 32 B for every lane), fetched one step ahead as well
+      const float* sline = a.smp_s + (long long)p.s * a.nb * a.G + g0;
+      const bool s_ok = a.lik_on && g0 < a.G;   // G is a multiple of 8 and g0 of 32: a step is inside or outside
+      float4 ns0 = make_float4(0.f, 0.f, 0.f, 0.f), ns1 = ns0;
+      if (s_ok) { ns0 = __ldg(reinterpret_cast<const float4*>(sline)); ns1 = __ldg(reinterpret_cast<const float4*>(sline + 4)); }
       // A chunk boundary may cut a segment in two: the terms that do not depend on dW' (the W_0 prior gradient and the
       // rank-1 part) belong to the piece that holds the segment's first pair-tile only.
       const float own = (p.g > 0 || cur0.pt == 0) ? 1.f : 0.f;
@@ -682,9 +718,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
 #pragma unroll 1
       for (int t = 0; t < 4; ++t) {
         const uint4 ch = nh, cl = nl;
+        const float4 cs0 = ns0, cs1 = ns1;
         if (t + 1 < 4) {
           nh = __ldg(reinterpret_cast<const uint4*>(wline + (t + 1) * 128));
           nl = __ldg(reinterpret_cast<const uint4*>(wline + IL.w_plane + (t + 1) * 128));
+          if (s_ok && g0 + (t + 1) * 8 < a.G) {
+            ns0 = __ldg(reinterpret_cast<const float4*>(sline + (t + 1) * 8));
+            ns1 = __ldg(reinterpret_cast<const float4*>(sline + (t + 1) * 8 + 4));
+          }
         }
         const int gb = g0 + t * 8;            // first of this step's 8 genes
         const uint32_t col = (uint32_t)(cq * 32 + t * 8);
@@ -702,15 +743,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
 #pragma unroll
         for (int i = 0; i < 8; ++i) cs[i] = t_bm;
         if (gb < a.G) {
+          {
+            const float sv[8] = {cs0.x, cs0.y, cs0.z, cs0.w, cs1.x, cs1.y, cs1.z, cs1.w};
 #pragma unroll
-          for (int b = 0; b < MAX_NB; ++b) {
-            if (b < a.nb) {
-              const float* sp = a.smp_s + ((long long)p.s * a.nb + b) * a.G + gb;
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp)), s1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
-              const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            for (int i = 0; i < 8; ++i) cs[i] = fmaf(t_ct[0], sv[i], cs[i]);
+          }
+#pragma unroll 1
+          for (int b = 1; b < a.nb; ++b) {   // further batches: not prefetched
+            const float* sp = a.smp_s + ((long long)p.s * a.nb + b) * a.G + gb;
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp)), s1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
+            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            float tc = 0.f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) cs[i] = fmaf(t_ct[b], sv[i], cs[i]);
-            }
+            for (int bb = 1; bb < MAX_NB; ++bb) tc = (bb == b) ? t_ct[bb] : tc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cs[i] = fmaf(tc, sv[i], cs[i]);
           }
         }
         float Pv[8], Rv[8];
@@ -783,10 +830,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       const int unit = p.rb * 2 + (int)rank;
       return x_img + (((long long)unit * 4 + (warp & 3)) * 16 + cq * 4) * 128 + lane * 4 + (long long)(2 * p.pt) * x_tile;
     };
+    // LOCAL: both halves a whole pair-tile ahead.  GLOBAL (more live registers: the loss): half 0 a pair-tile ahead,
+    // half 1 at the top of its own pair-tile (it has the first half's math and Q store, ~2k cycles, to arrive).
     if (n_outer > 0) {
       const float* xi = x_ptr(cc);
 #pragma unroll
-      for (int v = 0; v < 4; ++v) { xa[v] = *reinterpret_cast<const float4*>(xi + v * 128); xb[v] = *reinterpret_cast<const float4*>(xi + x_tile + v * 128); }
+      for (int v = 0; v < 4; ++v) {
+        xa[v] = *reinterpret_cast<const float4*>(xi + v * 128);
+        if (!GENES) xb[v] = *reinterpret_cast<const float4*>(xi + x_tile + v * 128);
+      }
     }
     for (int oi = 0; oi < n_outer; ++oi) {
       const int st = oi & 1;
@@ -805,6 +857,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       uint32_t R0[16], R1[16];
       float q[16];
       tmem_ld16_issue(taddr, R0);
+      if (GENES) {
+        const float* xi = x_ptr(cc) + x_tile;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) xb[v] = *reinterpret_cast<const float4*>(xi + v * 128);
+      }
       tmem_ld16_wait(R0);
       PT_LAP(3);
       half_math(xa, R0, q);
@@ -826,7 +883,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       if (lane == 0) mbar_arrive_remote(r_rempty[rs]);   // both halves of R are in registers
       PT_LAP(5);
       half_math(xb, R1, q);
-      if (x_early) {
+      if (x_early && !GENES) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) xb[v] = *reinterpret_cast<const float4*>(xnext + x_tile + v * 128);
       }
@@ -841,7 +898,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
           if (!more || cn.rb != cc.rb) flush_block(cc);
           if (more) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) { xa[v] = *reinterpret_cast<const float4*>(xnext + v * 128); xb[v] = *reinterpret_cast<const float4*>(xnext + x_tile + v * 128); }
+            for (int v = 0; v < 4; ++v) xa[v] = *reinterpret_cast<const float4*>(xnext + v * 128);
           }
         } else {
           drain_segment(cc);
