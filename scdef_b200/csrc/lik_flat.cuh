@@ -66,7 +66,7 @@ __host__ __device__ inline FlatSmem plan_flat_smem(int KP) {
   s.st[0] = o; o += s.stage;
   s.st[1] = o; o += s.stage;
   s.q = o; o += 2u * s.q_plane;
-  s.fold = o;
+  s.fold = o; o += (uint32_t)(MAX_NB * 128 * 4);   // GLOBAL, more than one batch: the unit's gene-scale samples of the segment
   s.misc = o;
   s.total = o + 1024u;
   return s;
@@ -496,9 +496,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
         return mbar_test(&mi->w_full[st], par) && mbar_test_remote(&mi->pw_full[st], par) &&
                mbar_test_remote(&mi->r_empty[GENES ? 0 : st], (GENES ? ((uint32_t)oi & 1u) : par) ^ 1u);
       };
-      // The rate GEMM of a pair-tile is issued in CHUNKS of k-steps: the tensor pipe executes in issue order, so a whole
-      // rate GEMM (21 MMAs, ~2k cycles) slipped in ahead would delay the second GEMM of a Q tile that arrives meanwhile
-      // by that much, and with it the release of the single Q buffer the epilogue warps wait for.
+      // The rate GEMM of a pair-tile can be issued in chunks of k-steps (state ks1 / da1 / db1), see MMA1_CHUNK below.
       int ks1 = 0;                 // k-steps of the pending rate GEMM (pair-tile next1) issued so far
       uint64_t da1 = 0, db1 = 0;
       auto issue_mma1 = [&](int oi, int max_steps) {
@@ -537,7 +535,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
         ks1 = 0;
         return true;
       };
-      constexpr int MMA1_CHUNK = 2;   // k-steps (6 MMAs, ~0.6k cycles of tensor pipe) per slipped-in chunk
+      // k-steps per slipped-in chunk.  Measured on a B200 (round 2): chunks of 2 k-steps (so that a Q tile arriving
+      // meanwhile waits ~0.6k instead of ~2k cycles of tensor pipe) made both passes 3 % SLOWER (0.259 -> 0.268 ms LOCAL,
+      // 0.441 -> 0.453 GLOBAL): the pipe is not the resource the epilogue waits for.  So: the whole rate GEMM at once.
+      constexpr int MMA1_CHUNK = 64;
       int next1 = 0;
       for (int u = 0; u < U; ++u) {
         const int oi = u >> 1, h = u & 1, st = oi & 1;
@@ -711,6 +712,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       float t_ct[MAX_NB];
 #pragma unroll
       for (int b = 0; b < MAX_NB; ++b) t_ct[b] = (b < a.nb && kok && a.lik_on) ? own * __ldg(tab + (2 + b) * KP + r) : 0.f;
+      float* sg_sm = reinterpret_cast<float*>(sm + L.fold);
+      if (a.nb > 1) {
+        // gene-scale samples of the unit's 128 genes, batches 1 .. nb-1 (the same for every k0 row): one cooperative copy
+        // per segment.  No warp can be a sub-unit ahead of another (the Q hand-off needs all 16), so nobody still reads
+        // the previous segment's copy here.
+        const int gu = (p.rb * 2 + (int)rank) * UC;
+        for (int i = (int)threadIdx.x; i < a.nb * 128; i += E_THREADS) {
+          const int b = i >> 7, gl = i & 127;
+          sg_sm[i] = (a.lik_on && gu + gl < a.G) ? a.smp_s[((long long)p.s * a.nb + b) * a.G + gu + gl] : 0.f;
+        }
+        named_bar_sync(3, E_THREADS);
+      }
       PT_WAIT(7, pair_wait(&mi->dz_full[0], (uint32_t)p.g & 1u, 13));
       tc_fence_after();
       PT_MARK();
@@ -749,9 +762,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
             for (int i = 0; i < 8; ++i) cs[i] = fmaf(t_ct[0], sv[i], cs[i]);
           }
 #pragma unroll 1
-          for (int b = 1; b < a.nb; ++b) {   // further batches: not prefetched
-            const float* sp = a.smp_s + ((long long)p.s * a.nb + b) * a.G + gb;
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp)), s1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
+          for (int b = 1; b < a.nb; ++b) {   // further batches: from the shared-memory copy made at the top of the fold
+            const float* sp = sg_sm + b * 128 + cq * 32 + t * 8;
+            const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
             const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
             float tc = 0.f;
 #pragma unroll
