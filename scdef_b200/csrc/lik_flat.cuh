@@ -73,6 +73,17 @@ __host__ __device__ inline FlatSmem plan_flat_smem(int KP) {
 }
 
 
+__device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_ftz(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#ifndef SCDEF_MATH_LOCAL
+#define SCDEF_MATH_LOCAL 1
+#endif
+#ifndef SCDEF_MATH_GLOBAL
+#define SCDEF_MATH_GLOBAL 0
+#endif
+constexpr float LN2_F = 0.69314718055994530942f;
+constexpr float LG2_V_HI_M = 49.828777f;   // log2(0.9999e15) = -log2(1.0001e-15) to 1e-8: the margins of V_LO_M / V_HI_M
+
 // 32 lanes x 4 consecutive 32-bit columns (the fold works in groups of four elements to keep its live state small)
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
   uint32_t r0, r1, r2, r3;
@@ -611,10 +622,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
         const float xs[4] = {xv4[v].x, xv4[v].y, xv4[v].z, xv4[v].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float Rv = __uint_as_float(Rr[v * 4 + i]);
-          const bool nz = xs[i] > 0.f;
-          q[v * 4 + i] = nz ? __fdividef(xs[i], Rv) : 0.f;
-          if (WANT_LL) ll += nz ? xs[i] * __logf(Rv) : 0.f;
+          // R >= 1e-30 wherever a count can be non-zero (samples are clipped at 1e-15); the clamp only keeps the padded
+          // rows / columns (R = 0, x = 0) finite, so that x = 0 gives q = 0 and adds 0 to the sum without a select.
+          // One FMNMX, one MUFU.RCP, one FMUL (+ one MUFU.LG2, one FFMA): the raw .ftz approximations, because
+          // __fdividef / __logf wrap the same MUFU in ~6 / ~4 instructions of denormal handling that R never needs.
+          constexpr int MV = GENES ? SCDEF_MATH_GLOBAL : SCDEF_MATH_LOCAL;
+          if (MV > 0) {
+            const float Rv = __uint_as_float(Rr[v * 4 + i]);
+            const bool nz = xs[i] > 0.f;
+            q[v * 4 + i] = nz ? (MV == 2 ? __fdividef(xs[i], Rv) : xs[i] * rcp_ftz(Rv)) : 0.f;
+            if (WANT_LL) ll += nz ? xs[i] * lg2_ftz(Rv) : 0.f;
+            continue;
+          }
+          const float Rc = fmaxf(__uint_as_float(Rr[v * 4 + i]), 1e-35f);
+          q[v * 4 + i] = xs[i] * rcp_ftz(Rc);
+          if (WANT_LL) ll = fmaf(xs[i], lg2_ftz(Rc), ll);   // in units of log 2: scaled once at the end
         }
       }
     };
@@ -782,6 +804,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
           }
         }
         tmem_ld8_wait3(dW, am, al);
+        const bool st_ok = kok && gb < a.G;   // G is a multiple of 8: a step is inside or outside
         const uint32_t hw[4] = {ch.x, ch.y, ch.z, ch.w}, lw[4] = {cl.x, cl.y, cl.z, cl.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -793,9 +816,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
             a1 = a.global_weight * (Pv[i] * t_a1 - own);                       // gw (A - 1), A = P / tau; table: own / tau
           }
           const float tt = fmaf(W, fmaf(a.scale, __uint_as_float(dW[i]), -c1), a1);
-          if (W > V_LO_M && W < V_HI_M && kok && gb + i < a.G) {
+          // inside the sample clip <=> |log2 W| < log2(0.9999e15) (the clip is symmetric in the log; W = 0 of the padding
+          // gives -inf); the second accumulator is kept in units of log 2 and scaled when the block is flushed
+          const float lgW = lg2_ftz(W);
+          if (fabsf(lgW) < LG2_V_HI_M && st_ok) {
             am[i] = __float_as_uint(__uint_as_float(am[i]) + tt);
-            al[i] = __float_as_uint(fmaf(tt, __logf(W), __uint_as_float(al[i])));
+            al[i] = __float_as_uint(fmaf(tt, lgW, __uint_as_float(al[i])));
           }
         }
         tmem_st8(tacc_mu + col, am);
@@ -826,7 +852,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
           for (int i = 0; i < 16; i += 4) {
             if (g0 + t * 16 + i < a.G) {   // G is a multiple of 8
               *reinterpret_cast<float4*>(pm + t * 16 + i) = make_float4(am[i], am[i + 1], am[i + 2], am[i + 3]);
-              *reinterpret_cast<float4*>(pl + t * 16 + i) = make_float4(al[i], al[i + 1], al[i + 2], al[i + 3]);
+              *reinterpret_cast<float4*>(pl + t * 16 + i) = make_float4(LN2_F * al[i], LN2_F * al[i + 1], LN2_F * al[i + 2], LN2_F * al[i + 3]);
             }
           }
         }
@@ -837,20 +863,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
     // this thread's first float4 of 64-column tile t of the count image sits at x_base + t * x_tile
     const long long x_tile = (long long)gm.n_units * (4 * 16 * 128);
     const float* x_img = GENES ? ws.ximg_t : ws.ximg;
+#ifdef SCDEF_LOCAL_XB_AHEAD
+    constexpr bool XB_AHEAD = !GENES;
+#else
+    constexpr bool XB_AHEAD = false;
+#endif
     float4 xa[4], xb[4];   // counts of half 0 / half 1, loaded one pair-tile ahead
     FlatPos cc = cur0;
     auto x_ptr = [&](const FlatPos& p) {
       const int unit = p.rb * 2 + (int)rank;
       return x_img + (((long long)unit * 4 + (warp & 3)) * 16 + cq * 4) * 128 + lane * 4 + (long long)(2 * p.pt) * x_tile;
     };
-    // LOCAL: both halves a whole pair-tile ahead.  GLOBAL (more live registers: the loss): half 0 a pair-tile ahead,
-    // half 1 at the top of its own pair-tile (it has the first half's math and Q store, ~2k cycles, to arrive).
+    // Half 0 a pair-tile ahead, half 1 at the top of its own pair-tile (it has the first half's math and Q store, ~2k
+    // cycles, to arrive): holding both halves a pair-tile ahead costs 16 more live registers and spills in the math.
     if (n_outer > 0) {
       const float* xi = x_ptr(cc);
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         xa[v] = *reinterpret_cast<const float4*>(xi + v * 128);
-        if (!GENES) xb[v] = *reinterpret_cast<const float4*>(xi + x_tile + v * 128);
+        if (XB_AHEAD) xb[v] = *reinterpret_cast<const float4*>(xi + x_tile + v * 128);
       }
     }
     for (int oi = 0; oi < n_outer; ++oi) {
@@ -870,7 +901,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       uint32_t R0[16], R1[16];
       float q[16];
       tmem_ld16_issue(taddr, R0);
-      if (GENES) {
+      if (!XB_AHEAD) {
         const float* xi = x_ptr(cc) + x_tile;
 #pragma unroll
         for (int v = 0; v < 4; ++v) xb[v] = *reinterpret_cast<const float4*>(xi + v * 128);
@@ -896,7 +927,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       if (lane == 0) mbar_arrive_remote(r_rempty[rs]);   // both halves of R are in registers
       PT_LAP(5);
       half_math(xb, R1, q);
-      if (x_early && !GENES) {
+      if (x_early && XB_AHEAD) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) xb[v] = *reinterpret_cast<const float4*>(xnext + x_tile + v * 128);
       }
@@ -920,7 +951,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       cc = cn;
     }
     if (WANT_LL) {
-      double v = warp_sum_d((double)ll);
+      double v = warp_sum_d((double)ll * 0.69314718055994530942);
       if (lane == 0) mi->red[e] = v;
       named_bar_sync(2, E_THREADS);
       if (e == 0 && lane == 0) {

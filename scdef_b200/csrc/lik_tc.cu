@@ -713,7 +713,12 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
   const int g = blockIdx.x * 256 + cgl * 8;
   const int tile = g / TG, cg = (g % TG) / 8;
   const int nkg = KP / 8;
+  __shared__ __align__(16) float sgs[MAX_NB - 1][256];   // gene-scale samples of batches 1 .. nb-1 for the block's 256 genes
   for (int i = tid; i < 128 * (2 + MAX_NB); i += 256) (&rowacc[0][0])[i] = 0.f;
+  for (int i = tid; i < (a.nb - 1) * 256; i += 256) {
+    const int b = 1 + i / 256, gl = i & 255, gg = blockIdx.x * 256 + gl;
+    sgs[b - 1][gl] = gg < a.G ? a.smp_s[((long long)s * a.nb + b) * a.G + gg] : 0.f;
+  }
   __syncthreads();
   if (tile < n_tiles) {
     uint8_t* unit = ws.wimg + ((long long)s * n_tiles + tile) * w_unit;
@@ -764,14 +769,14 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
         atomicAdd(&rowacc[k][0], su);
         atomicAdd(&rowacc[k][1], sw);
       }
-      // (W s_b)[k] += sum over this thread's 8 genes (batch 0's gene-scale samples are held in registers; further
-      // batches come through L1, the same 32 B for every kg)
+      // (W s_b)[k] += sum over this thread's 8 genes (batch 0's gene-scale samples are held in registers, further
+      // batches in shared memory)
       for (int b = 0; b < a.nb; ++b) {
         float d = 0.f;
         if (k < a.K0 && gok) {
           float4 t0 = sv0, t1 = sv1;
           if (b > 0) {
-            const float* sp = a.smp_s + ((long long)s * a.nb + b) * a.G + g;
+            const float* sp = &sgs[b - 1][cgl * 8];
             t0 = *reinterpret_cast<const float4*>(sp); t1 = *reinterpret_cast<const float4*>(sp + 4);
           }
           d = w[0] * t0.x + w[1] * t0.y + w[2] * t0.z + w[3] * t0.w + w[4] * t1.x + w[5] * t1.y + w[6] * t1.z + w[7] * t1.w;
@@ -788,7 +793,7 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
     const int t2 = gg / TG;
     if (t2 < n_tiles) {
       float* st = reinterpret_cast<float*>(ws.wimg + ((long long)s * n_tiles + t2) * w_unit + 2 * w_plane);
-      st[b * TG + (gg % TG)] = gg < a.G ? a.smp_s[((long long)s * a.nb + b) * a.G + gg] : 0.f;
+      st[b * TG + (gg % TG)] = b > 0 ? sgs[b - 1][gl] : (gg < a.G ? a.smp_s[(long long)s * a.nb * a.G + gg] : 0.f);
     }
   }
   __syncthreads();
