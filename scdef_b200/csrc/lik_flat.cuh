@@ -81,6 +81,10 @@ __device__ __forceinline__ float lg2_ftz(float x) { float r; asm("lg2.approx.ftz
 #ifndef SCDEF_MATH_GLOBAL
 #define SCDEF_MATH_GLOBAL 0
 #endif
+#ifndef FOLD_UNROLL
+#define FOLD_UNROLL 4   // measured: 0.375 -> 0.346 ms per GLOBAL launch at C5 against the rolled loop (no register moves for the prefetch rotation)
+#endif
+constexpr int FOLD_UNROLL_N = FOLD_UNROLL;
 constexpr float LN2_F = 0.69314718055994530942f;
 constexpr float LG2_V_HI_M = 49.828777f;   // log2(0.9999e15) = -log2(1.0001e-15) to 1e-8: the margins of V_LO_M / V_HI_M
 
@@ -750,7 +754,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
       tc_fence_after();
       PT_MARK();
       const uint32_t td2 = tmem + FLAT_TMEM_D2_GENES + (lane_base << 16);
-#pragma unroll 1
+#pragma unroll FOLD_UNROLL_N
       for (int t = 0; t < 4; ++t) {
         const uint4 ch = nh, cl = nl;
         const float4 cs0 = ns0, cs1 = ns1;
