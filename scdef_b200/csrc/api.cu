@@ -824,7 +824,10 @@ int scdef_u16_gather_rows(const uint16_t* X, const int64_t* rows, int32_t n_rows
   if (n_rows == 0) return SCDEF_OK;
   if (!rows) return SCDEF_EINVAL;
   const long long total = (long long)n_rows * n_genes;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
   k_u16_gather_rows<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(X, reinterpret_cast<const long long*>(rows), n_rows, n_genes, out);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
