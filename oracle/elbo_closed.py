@@ -24,6 +24,10 @@ from .elbo_ref import LOG_1E_10, LOG_1E6, LOG_1E10, OracleModel
 HALF_LOG_2PI_PLUS_HALF = 0.5 + 0.5 * math.log(2.0 * math.pi)
 
 
+# Hook for operand-precision experiments ONLY (scripts/numerics_probe.py): callable(A, B, which) -> A @ B with the operands
+# rounded to a tensor-core format; None = exact float64 products (every test).
+LIK_GEMM = None
+
 def _np(x, dtype):
     if hasattr(x, "detach"):
         x = x.detach().cpu().numpy()
@@ -189,16 +193,25 @@ def loss_and_grads(model: OracleModel, X, indices, local_params, global_params, 
 
     # ---- Poisson likelihood (A.3; _scdef.py:2096-2136) -------------------------------------
     if lik_on:
-        Rm = z[0].v @ W[0].v  # (S,B,G)
+        Rm = z[0].v @ W[0].v if LIK_GEMM is None else LIK_GEMM(z[0].v, W[0].v, "rate")  # (S,B,G)
         s_cell = np.einsum("nb,sbg->sng", onehot, s.v)
         lam = Rm * c.v * s_cell
         with np.errstate(divide="ignore", invalid="ignore"):
             xlogy = np.where(x[None] > 0, x[None] * np.log(lam), 0.0)
         elbo += scale * (xlogy - lam - gammaln(x + 1.0)[None]).sum((1, 2))
         E = x[None] - lam
-        Q = E / Rm
-        z[0].G += scale * (Q @ np.swapaxes(W[0].v, 1, 2))
-        W[0].G += scale * (np.swapaxes(z[0].v, 1, 2) @ Q)
+        if LIK_GEMM is None:
+            Q = E / Rm
+            z[0].G += scale * (Q @ np.swapaxes(W[0].v, 1, 2))
+            W[0].G += scale * (np.swapaxes(z[0].v, 1, 2) @ Q)
+        else:
+            # numerics experiments (scripts/numerics_probe.py): the kernels' split Q = x/R - c s^T, the x/R part through
+            # the operand-rounding GEMM under test, the rank-1 part exact
+            with np.errstate(divide="ignore", invalid="ignore"):
+                Qx = np.where(x[None] > 0, x[None] / Rm, 0.0)
+            cs = c.v * s_cell
+            z[0].G += scale * (LIK_GEMM(Qx, np.swapaxes(W[0].v, 1, 2), "second") - cs @ np.swapaxes(W[0].v, 1, 2))
+            W[0].G += scale * (LIK_GEMM(np.swapaxes(z[0].v, 1, 2), Qx, "second") - np.swapaxes(z[0].v, 1, 2) @ cs)
         c.G += scale * E.sum(2, keepdims=True) / c.v
         s.G += scale * np.einsum("nb,sng->sbg", onehot, E) / s.v
 
