@@ -604,8 +604,10 @@ def _build_scipy():
 
 def _build_nn():
     m = types.ModuleType("jax.nn")
-    m.one_hot = lambda x, n, dtype=None: _wrap(
-        torch.nn.functional.one_hot(_as_array(x).long(), int(n)).to(_dtype(dtype) or _STATE["dtype"]))
+    def one_hot(x, num_classes, dtype=None):
+        return _wrap(torch.nn.functional.one_hot(_as_array(x).long(), int(num_classes)).to(_dtype(dtype) or _STATE["dtype"]))
+
+    m.one_hot = one_hot
     m.softmax = lambda x, axis=-1: _wrap(torch.softmax(_as_array(x), dim=axis))
     m.relu = lambda x: _wrap(torch.relu(_as_array(x)))
     return m

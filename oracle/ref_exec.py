@@ -65,6 +65,24 @@ class ReferenceRuntime:
     def iscDEF(self):
         return importlib.import_module(f"{_PKG}.models._iscdef").iscDEF
 
+    @property
+    def tools_factor(self):
+        """`scdef.tools.factor` (assign_confident, factor.py:1107-1477): needs inert `scanpy` / `matplotlib.pyplot`."""
+        name = f"{_PKG}.tools.factor"
+        if name not in sys.modules:
+            sys.modules.setdefault(f"{_PKG}.tools", _namespace(f"{_PKG}.tools", os.path.join(REFERENCE_SRC, _PKG, "tools")))
+            self._extra = getattr(self, "_extra", [])
+            if "scanpy" not in sys.modules:
+                sys.modules["scanpy"] = types.ModuleType("scanpy")
+                self._extra.append("scanpy")
+            mpl = sys.modules["matplotlib"]
+            if not hasattr(mpl, "__path__"):
+                mpl.__path__ = []
+            if "matplotlib.pyplot" not in sys.modules:
+                sys.modules["matplotlib.pyplot"] = mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+                self._extra.append("matplotlib.pyplot")
+        return importlib.import_module(name)
+
     def source_lines(self, obj):
         import inspect
 
@@ -101,10 +119,14 @@ def reference_runtime(dtype=torch.float64):
     dont_write = sys.dont_write_bytecode
     sys.dont_write_bytecode = True  # /root/reference is read-only: no __pycache__ there
     with jaxshim.installed(dtype=dtype, extra=parents):
+        rt = None
         try:
-            yield ReferenceRuntime(sys.modules, dtype)
+            rt = ReferenceRuntime(sys.modules, dtype)
+            yield rt
         finally:
             sys.dont_write_bytecode = dont_write
+            for name in getattr(rt, "_extra", []):
+                sys.modules.pop(name, None)
             for name in set(sys.modules) - before:
                 if name == _PKG or name.startswith(_PKG + "."):
                     sys.modules.pop(name, None)

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE — CPU restatement (NumPy) of `scdef.tl.assign_confident`, the post-fit Monte-Carlo
-assignment of cells to layers (`/root/reference/src/scdef/tools/factor.py:1107-1477`).  PARITY UNPINNED: the
-reference's tests hold no golden values for it and its JAX path cannot run in this image; the statements below
+assignment of cells to layers (`/root/reference/src/scdef/tools/factor.py:1107-1477`).  PARITY PIN: the reference's own
+`assign_confident` is executed unmodified under `oracle/jaxshim.py` and must agree with this module on the draws it
+consumed (`tests/test_ref_pin.py::test_restated_assign_confident_equals_the_reference_execution`); the statements below
 follow the reference line by line with the N(0,1) draws injected (`eps[s, n, k]` replaces
 `random.normal(sample_keys[s], mu_k.shape)`, factor.py:1288, 1318).
 

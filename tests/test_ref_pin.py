@@ -320,3 +320,50 @@ def test_layer_ladder_equals_the_reference_method(ref):
         assert geometric_ladder(nf, tf, nl, root=False) == want_nr, (nf, tf, nl)
         n += 1
     assert n > 200
+
+
+@needs_reference
+def test_restated_assign_confident_equals_the_reference_execution(ref):
+    """`tl.assign_confident` (`tools/factor.py:1107-1477`) of the REFERENCE, run on a model whose per-cell blocks were
+    set by hand, against `oracle/tools_ref.py` fed the very draws the reference consumed (`random.normal(sample_keys[s],
+    shape)` of the two `lax.scan` passes: the shim's keys are replayed here)."""
+    from oracle import tools_ref
+
+    rng = np.random.default_rng(5)
+    N, G, Ks, S, tau, level = 90, 40, (6, 3, 1), 64, 0.3, 0.9
+    X = rng.poisson(1.5, (N, G)).astype(float)
+    m = ref.scDEF(ref.adata(X), layer_sizes=list(Ks), seed=3)
+    z = np.array(ref.to_numpy(m.local_params[1]), dtype=np.float64)
+    z[0] = rng.normal(-0.5, 1.0, z[0].shape)
+    z[1] = rng.normal(-1.0, 0.5, z[1].shape)
+    m.local_params[1] = ref.jnp.array(z)
+    m.factor_lists = [np.array([0, 2, 3, 5]), np.array([0, 1, 2]), np.array([0])]     # a filtered bottom layer
+    m.factor_names = [[f"L{l}_{k}" for k in kept] for l, kept in enumerate(m.factor_lists)]
+    ref.tools_factor.assign_confident(m, n_samples=S, tau=tau, credible_level=level)
+    obs = m.adata.obs
+
+    random = ref.random
+    layer_keys = random.split(random.PRNGKey(int(m.seed)), len(Ks))                   # factor.py:1262
+    off = np.concatenate([[0], np.cumsum(Ks)])
+    conf, eff, sd, am = (np.zeros((N, len(Ks))) for _ in range(4))
+    for l, kept in enumerate(m.factor_lists):
+        cols = off[l] + kept
+        keys = random.split(layer_keys[l], S)                                          # 1274
+        eps = np.stack([np.asarray(random.normal(keys[s], shape=(N, len(kept)))) for s in range(S)])
+        st = tools_ref.layer_stats(z[0][:, cols], z[1][:, cols], eps, level)
+        name = m.layer_names[l]
+        for field in ("confidence", "effect_size", "posterior_sd", "winner_mass", "winner_probability", "entropy_confidence"):
+            got = np.asarray(m.adata.obsm[f"confident_{field}"], dtype=float)[:, l]     # factor.py:1452-1457
+            assert np.allclose(got, st[field], rtol=0, atol=2e-6), (name, field, np.abs(got - st[field]).max())
+        assert np.array_equal(np.asarray(m.adata.obsm["confident_argmax_factor"])[:, l], st["argmax"])
+        labels = np.asarray(obs[f"confident_argmax_{name}"]).astype(str)
+        assert np.array_equal(labels, np.asarray(m.factor_names[l], dtype=object)[st["argmax"]].astype(str))
+        conf[:, l], eff[:, l], sd[:, l], am[:, l] = st["confidence"], st["effect_size"], st["posterior_sd"], st["argmax"]
+    sel = tools_ref.select_layers(conf, eff, sd, am.astype(int), [len(k) for k in m.factor_lists], tau)
+    want_layer = np.array([m.layer_names[i] if i >= 0 else "" for i in sel["best_layer_idx"]], dtype=object).astype(str)
+    assert np.array_equal(np.asarray(obs["confident_best_layer"]).astype(str), want_layer)
+    assert np.array_equal(np.asarray(obs["confident_best_layer_idx"]), sel["best_layer_idx"])
+    assert np.array_equal(np.asarray(obs["confident_best_factor_idx"]), sel["best_factor_slot"])
+    assert np.allclose(np.asarray(obs["confident_best_confidence"], dtype=float), sel["best_confidence"], atol=2e-6, equal_nan=True)
+    assert np.allclose(np.asarray(obs["confident_best_effect_size"], dtype=float), sel["best_effect_size"], atol=2e-6, equal_nan=True)
+    assert np.allclose(np.asarray(obs["confident_depth_score"], dtype=float), sel["depth_score"], atol=1e-12, equal_nan=True)
