@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SCDEF_ABI_VERSION 7
+#define SCDEF_ABI_VERSION 8
 #define SCDEF_MAX_LAYERS 8
 
 #define SCDEF_OK 0
@@ -260,6 +260,21 @@ int scdef_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const f
 int scdef_assign_confident(const float* mu, const float* rho, int64_t n_rows, int32_t ld, const int32_t* cols,
                            int32_t n_cols, int32_t n_samples, float quantile_level, uint64_t seed, int32_t stream_id,
                            int64_t row0, const float* eps, float* stats, int32_t* argmax, void* cuda_stream);
+
+/* Monte-Carlo gene scores behind `tl.set_confident_signatures` (src/scdef/tools/factor.py:220-363; layer 0:
+   models/_scdef.py:3975-3989), reduced on the fly instead of materialising the (draws, factors, genes) tensor of
+   `_collect_hierarchy_mc_scores` (factor.py:271-291):
+     score^s[f][g] = sum_r path[s][f][r] * clip(exp(w_mu[rows[r]][g] + exp(w_rho[rows[r]][g]) * eps[s][r][g]), 1e-15, 1e15)
+   (path == NULL: identity, n_factors == n_rows — every factor's own draw).  w_mu / w_rho: the two halves of the W_0 block,
+   (K0, n_genes) row-major; eps: (n_draws, n_rows, n_genes) N(0,1) draws supplied by the caller; path: (n_draws, n_factors, n_rows).
+     mode 0: counts[f][g] += [score > tau[f]]                               (int32 (n_factors, n_genes), zeroed by the caller)
+     mode 1: ref_score[s][f][i] = score at gene ref_idx[f][i]                (ref_idx (n_factors, kmax) int32, -1 = unused)
+     mode 2: rank_count[s][f][i] += #{g : score^s[f][g] > ref_score[s][f][i]} (int32, zeroed by the caller; run mode 1 first)
+   n_rows <= 128, n_factors <= 256. */
+int scdef_signature_scores(const float* w_mu, const float* w_rho, int32_t n_genes, const int32_t* rows, int32_t n_rows,
+                           const float* eps, const float* path, int32_t n_draws, int32_t n_factors, int32_t mode, const float* tau,
+                           int32_t* counts, const int32_t* ref_idx, int32_t kmax, float* ref_score, int32_t* rank_count,
+                           void* cuda_stream);
 
 /* Cold start of a LogNormal block from Gamma draws, on the device (`init_var_params`, _scdef.py:1639-1648 for the z layers):
    m = clip(Gamma(shape, 1) / shape, clip_lo, clip_hi), v = m / var_div, (mu, rho = log sigma) = the LogNormal with mean m and

@@ -126,6 +126,25 @@ class Array(torch.Tensor):
         kwargs = {k: _conv(v) for k, v in kwargs.items()}
         return super().__torch_function__(func, types, args, kwargs)
 
+    def __getitem__(self, idx):
+        # numpy / jax allow negative slice steps (`x.argsort()[::-1][:k]`, _scdef.py:3989); torch does not
+        items = idx if isinstance(idx, tuple) else (idx,)
+        if any(isinstance(i, slice) and i.step is not None and i.step < 0 for i in items):
+            out, dim = self, 0
+            for i in items:
+                if i is None:
+                    out = torch.Tensor.unsqueeze(out, dim)
+                elif isinstance(i, slice) and i.step is not None and i.step < 0:
+                    sel = torch.as_tensor(list(range(*i.indices(out.shape[dim]))), dtype=torch.long)
+                    out = torch.Tensor.index_select(out, dim, sel)
+                elif isinstance(i, slice):
+                    out = torch.Tensor.__getitem__(out, (slice(None),) * dim + (i,))
+                else:
+                    raise IndexError("jaxshim: a negative slice step mixed with non-slice indices is not supported")
+                dim += 1
+            return out
+        return super().__getitem__(idx)
+
     # numpy_array <op> Array lands here because of __array_priority__
     def __rmul__(self, o):
         return torch.mul(self, _conv(o))

@@ -3,7 +3,7 @@ from .anndata_compat import MiniAnnData
 from .model import scDEF
 from .sscdef import sscDEF
 from .iscdef import iscDEF
-from . import tools as tl  # `scdef.tl`: only the device version of `assign_confident` is built
+from . import tools as tl  # `scdef.tl`: device versions of `assign_confident` and `set_confident_signatures`
 
 __all__ = ["scDEF", "sscDEF", "iscDEF", "MiniAnnData", "tl"]
 __version__ = "0.1.0"

@@ -922,6 +922,34 @@ int scdef_assign_confident(const float* mu, const float* rho, int64_t n_rows, in
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 
+int scdef_signature_scores(const float* w_mu, const float* w_rho, int32_t n_genes, const int32_t* rows, int32_t n_rows,
+                           const float* eps, const float* path, int32_t n_draws, int32_t n_factors, int32_t mode, const float* tau,
+                           int32_t* counts, const int32_t* ref_idx, int32_t kmax, float* ref_score, int32_t* rank_count,
+                           void* cuda_stream) {
+  if (!w_mu || !w_rho || !rows || !eps || n_genes < 1 || n_rows < 1 || n_draws < 1 || n_factors < 1) return SCDEF_EINVAL;
+  if (n_rows > SIG_MAX_R || n_factors > SIG_MAX_F) return SCDEF_EUNSUPPORTED;
+  if (!path && n_factors != n_rows) return SCDEF_EINVAL;
+  if (mode == 0 ? (!tau || !counts) : (mode == 1 || mode == 2) ? (!ref_idx || !ref_score || kmax < 1 || (mode == 2 && !rank_count)) : true)
+    return SCDEF_EINVAL;
+  SigArgs a;
+  memset(&a, 0, sizeof(a));
+  a.w_mu = w_mu; a.w_rho = w_rho; a.rows = rows; a.eps = eps; a.path = path; a.tau = tau; a.ref_idx = ref_idx;
+  a.ref_score = ref_score; a.counts = counts; a.rank_count = rank_count;
+  a.R = n_rows; a.G = n_genes; a.S = n_draws; a.F = n_factors; a.kmax = kmax; a.mode = mode;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = (n_genes + SIG_TG - 1) / SIG_TG;
+  int chunks = (2 * sms + tiles - 1) / tiles;          // about two CTAs per SM
+  if (chunks > n_draws) chunks = n_draws;
+  a.draws_per_cta = (n_draws + chunks - 1) / chunks;
+  chunks = (n_draws + a.draws_per_cta - 1) / a.draws_per_cta;
+  const size_t smem = (size_t)(SIG_MAX_R * SIG_TG + SIG_FC * (SIG_MAX_R + 1) + SIG_FC * (SIG_TG + 1)) * sizeof(float);
+  cudaFuncSetAttribute(k_signature_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_signature_scores<<<dim3(tiles, chunks), 256, smem, (cudaStream_t)cuda_stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
+}
+
 int scdef_init_gamma_block(float* mu, float* rho, int64_t n_rows, int32_t n_cols, int32_t ld, float shape, float clip_lo,
                            float clip_hi, float var_div, uint64_t seed, int32_t stream_id, int64_t row0, void* cuda_stream) {
   if (!mu || !rho || n_rows < 0 || n_cols < 1 || ld < n_cols || row0 < 0) return SCDEF_EINVAL;

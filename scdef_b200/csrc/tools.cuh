@@ -266,4 +266,147 @@ __global__ void __launch_bounds__(256) k_init_gamma_block(const InitGammaArgs a)
   }
 }
 
+
+// -----------------------------------------------------------------------------------------
+// tl.set_confident_signatures on the device (`/root/reference/src/scdef/tools/factor.py:220-363`): Monte-Carlo gene
+// scores of the factors of the upper layers,  score^s[f][g] = sum_r path^s[f][r] W_0^s[r][g],  W_0^s = clip(exp(mu +
+// sigma eps^s)) — or, with path == nullptr, the row's own draw (layer 0, `_scdef.py:3975-3989`).  The (S, F, G) score
+// tensor the reference materialises (`_collect_hierarchy_mc_scores`, 271-291) is never stored: a CTA samples one
+// 64-gene tile of W_0^s into shared memory, forms the scores of 32 factors at a time with a register-tiled FP32
+// product, and reduces them on the spot to what the statistics need:
+//   mode 0 COUNT     counts[f][g]        += [score > tau_f]                      (exceedance confidences, 305-308)
+//   mode 1 REFSCORE  ref_score[s][f][i]   = score at gene ref_idx[f][i]          (the signature genes' own scores)
+//   mode 2 RANK      rank_count[s][f][i] += #{g : score[g] > ref_score[s][f][i]}  (gene i is in the draw's top-k list
+//                                                                                 iff its count is < k; 354-357)
+// grid = (gene tiles, draw chunks), 256 threads: thread (fy, gx) owns factors 2 fy, 2 fy + 1 of the chunk and genes
+// 4 gx .. 4 gx + 3 of the tile.
+// -----------------------------------------------------------------------------------------
+struct SigArgs {
+  const float* w_mu; const float* w_rho;   // W_0 halves, (K0_all, G) row-major
+  const int* rows;                         // [R] rows of W_0 behind the path's columns
+  const float* eps;                        // [S][R][G] N(0,1)
+  const float* path;                       // [S][F][R] or nullptr (identity, F == R)
+  const float* tau;                        // [F]            (mode 0)
+  const int* ref_idx;                      // [F][kmax], -1 padded (modes 1, 2)
+  float* ref_score;                        // [S][F][kmax]
+  int* counts;                             // [F][G]         (mode 0)
+  int* rank_count;                         // [S][F][kmax]   (mode 2)
+  int R, G, S, F, kmax, mode, draws_per_cta;
+};
+constexpr int SIG_TG = 64, SIG_FC = 32, SIG_MAX_R = 128, SIG_MAX_F = 256;
+
+__global__ void __launch_bounds__(256) k_signature_scores(const SigArgs a) {
+  extern __shared__ __align__(16) float sig_sm[];
+  float* Wt = sig_sm;                                // [R][SIG_TG]
+  float* Pt = Wt + SIG_MAX_R * SIG_TG;               // [SIG_FC][R + 1]
+  float* Sc = Pt + SIG_FC * (SIG_MAX_R + 1);         // [SIG_FC][SIG_TG + 1]
+  const int tid = threadIdx.x, fy = tid >> 4, gx = tid & 15;
+  const int g0 = blockIdx.x * SIG_TG;
+  const int s_begin = blockIdx.y * a.draws_per_cta, s_end = min(a.S, s_begin + a.draws_per_cta);
+  const int n_fc = (a.F + SIG_FC - 1) / SIG_FC;
+  int cnt[SIG_MAX_F / SIG_FC][2][4];
+#pragma unroll
+  for (int c = 0; c < SIG_MAX_F / SIG_FC; ++c)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cnt[c][i][j] = 0;
+
+  for (int s = s_begin; s < s_end; ++s) {
+    __syncthreads();
+    // the draw's tile of W_0 (lanes along the genes: coalesced)
+    for (int e = tid; e < a.R * SIG_TG; e += 256) {
+      const int r = e / SIG_TG, gl = e - r * SIG_TG, g = g0 + gl;
+      float w = 0.f;
+      if (g < a.G) {
+        const long long o = (long long)a.rows[r] * a.G + g;
+        const float u = a.w_mu[o] + expf(a.w_rho[o]) * a.eps[((long long)s * a.R + r) * a.G + g];
+        w = fminf(fmaxf(expf(u), 1e-15f), 1e15f);
+      }
+      Wt[r * SIG_TG + gl] = w;
+    }
+#pragma unroll 1
+    for (int c = 0; c < n_fc; ++c) {
+      const int f0 = c * SIG_FC;
+      __syncthreads();
+      if (a.path) {
+        for (int e = tid; e < SIG_FC * a.R; e += 256) {
+          const int fl = e / a.R, r = e - fl * a.R;
+          Pt[fl * (SIG_MAX_R + 1) + r] = (f0 + fl < a.F) ? a.path[((long long)s * a.F + f0 + fl) * a.R + r] : 0.f;
+        }
+      }
+      __syncthreads();
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      if (a.path) {
+        const float* p0 = Pt + (2 * fy) * (SIG_MAX_R + 1), * p1 = p0 + (SIG_MAX_R + 1);
+        for (int r = 0; r < a.R; ++r) {
+          const float4 w = *reinterpret_cast<const float4*>(Wt + r * SIG_TG + 4 * gx);
+          const float x0 = p0[r], x1 = p1[r];
+          acc[0][0] = fmaf(x0, w.x, acc[0][0]); acc[0][1] = fmaf(x0, w.y, acc[0][1]);
+          acc[0][2] = fmaf(x0, w.z, acc[0][2]); acc[0][3] = fmaf(x0, w.w, acc[0][3]);
+          acc[1][0] = fmaf(x1, w.x, acc[1][0]); acc[1][1] = fmaf(x1, w.y, acc[1][1]);
+          acc[1][2] = fmaf(x1, w.z, acc[1][2]); acc[1][3] = fmaf(x1, w.w, acc[1][3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int f = f0 + 2 * fy + i;
+          if (f < a.F) {
+            const float4 w = *reinterpret_cast<const float4*>(Wt + f * SIG_TG + 4 * gx);
+            acc[i][0] = w.x; acc[i][1] = w.y; acc[i][2] = w.z; acc[i][3] = w.w;
+          }
+        }
+      }
+      if (a.mode == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int f = f0 + 2 * fy + i;
+          const float t = f < a.F ? a.tau[f] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool hit = f < a.F && g0 + 4 * gx + j < a.G && acc[i][j] > t;
+#pragma unroll
+            for (int cc = 0; cc < SIG_MAX_F / SIG_FC; ++cc) cnt[cc][i][j] += (cc == c && hit) ? 1 : 0;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Sc[(2 * fy + i) * (SIG_TG + 1) + 4 * gx + j] = acc[i][j];
+        __syncthreads();
+        for (int e = tid; e < SIG_FC * a.kmax; e += 256) {
+          const int fl = e / a.kmax, i = e - fl * a.kmax, f = f0 + fl;
+          if (f >= a.F) continue;
+          const int gi = a.ref_idx[(long long)f * a.kmax + i];
+          if (gi < 0) continue;
+          const long long o = ((long long)s * a.F + f) * a.kmax + i;
+          if (a.mode == 1) {
+            if (gi >= g0 && gi < g0 + SIG_TG) a.ref_score[o] = Sc[fl * (SIG_TG + 1) + gi - g0];
+          } else {
+            const float rs = a.ref_score[o];
+            int n = 0;
+            const int gmax = min(SIG_TG, a.G - g0);
+            for (int g = 0; g < gmax; ++g) n += Sc[fl * (SIG_TG + 1) + g] > rs ? 1 : 0;
+            if (n) atomicAdd(&a.rank_count[o], n);
+          }
+        }
+      }
+    }
+  }
+  if (a.mode == 0) {
+#pragma unroll
+    for (int c = 0; c < SIG_MAX_F / SIG_FC; ++c)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int f = c * SIG_FC + 2 * fy + i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int g = g0 + 4 * gx + j;
+          if (f < a.F && g < a.G && cnt[c][i][j]) atomicAdd(&a.counts[(long long)f * a.G + g], cnt[c][i][j]);
+        }
+      }
+  }
+}
+
 }  // namespace scdef

@@ -1,10 +1,14 @@
 """Post-fit tools that the reference runs through JAX (`scdef.tl`) — device versions.
 
-Only `assign_confident` is built: the Monte-Carlo assignment of every cell to the finest layer at which its winning
-factor leads with posterior confidence (`/root/reference/src/scdef/tools/factor.py:1107-1477`).  The per-layer
-statistics (two passes over `n_samples` draws of `q(z)` per cell) run in `scdef_assign_confident`
-(`scdef_b200/csrc/tools.cuh`, one warp per cell); the cross-layer selection rule and the AnnData fields are host code
-with the reference's names and shapes.  No CPU fallback: without CUDA or the shared library this raises.
+* `assign_confident`: the Monte-Carlo assignment of every cell to the finest layer at which its winning factor leads
+  with posterior confidence (`/root/reference/src/scdef/tools/factor.py:1107-1477`).  The per-layer statistics (two
+  passes over `n_samples` draws of `q(z)` per cell) run in `scdef_assign_confident` (`scdef_b200/csrc/tools.cuh`, one
+  warp per cell); the cross-layer selection rule and the AnnData fields are host code with the reference's names.
+* `set_confident_signatures` / `get_stored_confident_signatures` (`factor.py:441-552, 382-438`): gene signatures with
+  posterior confidences for every factor of every layer; the Monte-Carlo gene scores of the upper layers (and the
+  per-draw top-k lists of all layers) are formed and reduced on the device by `scdef_signature_scores`.
+
+No CPU fallback: without CUDA or the shared library these raise.
 """
 from __future__ import annotations
 
@@ -207,3 +211,250 @@ def assign_confident(model, n_samples: int = 500, tau: float = 0.3, credible_lev
         "depth_score": "best_layer_index / max(n_layers - 1, 1); single-layer models use 0",
         "fit_revision": int(getattr(model, "_fit_revision", 0)),
     }
+
+
+# =====================================================================================================================
+# set_confident_signatures (`/root/reference/src/scdef/tools/factor.py:441-552`): gene signatures of every factor of every
+# layer with per-gene posterior confidences, the DE-style combined score and the weighted-Jaccard stability of each list.
+# Layer 0 is closed form (normal approximation, factor.py:1712-1741).  The upper layers need Monte-Carlo gene scores
+# (`_collect_hierarchy_mc_scores`, 271-291: `mc_samples` joint draws of every W_l propagated down to the genes, an
+# (S, F, G) tensor per layer in the reference); here `scdef_signature_scores` forms them tile by tile on the device and
+# reduces them on the spot to exceedance counts and to the ranks of the signature genes (csrc/tools.cuh).
+# =====================================================================================================================
+def _technical_drop_factors(model):
+    factor_obs = model.adata.uns.get("factor_obs") if hasattr(model.adata, "uns") else None      # factor.py:134-139
+    if factor_obs is None or "technical" not in getattr(factor_obs, "columns", ()):
+        return []
+    return factor_obs.index[factor_obs["technical"].astype(bool)].tolist()
+
+
+def _l0_keep_positions(model, drop_factors):
+    drop = set(drop_factors)                                                                      # factor.py:151-159
+    return np.array([i for i, n in enumerate(model.factor_names[0]) if n not in drop], dtype=int)
+
+
+def _layer_term_means(model, layer_idx, l0_keep):
+    """`_get_layer_term_means` (factor.py:182-217) from `model.pmeans`."""
+    names, fl = model.layer_names, [np.asarray(f, dtype=int) for f in model.factor_lists]
+    if layer_idx == 0:
+        return np.asarray(model.pmeans[f"{names[0]}W"], dtype=float)[fl[0]]
+    t = np.asarray(model.pmeans[f"{names[layer_idx]}W"], dtype=float)[fl[layer_idx]][:, fl[layer_idx - 1]]
+    for l in range(layer_idx - 1, 0, -1):
+        t = t.dot(np.asarray(model.pmeans[f"{names[l]}W"], dtype=float)[fl[l]][:, fl[l - 1]])
+    w0 = np.asarray(model.pmeans[f"{names[0]}W"], dtype=float)[fl[0]][l0_keep]
+    return t[:, l0_keep].dot(w0)
+
+
+def _confidence_mean_score(confidences, means, eps: float = 1e-12):
+    confidences, means = np.asarray(confidences, dtype=float), np.asarray(means, dtype=float)   # factor.py:116-131
+    return means * -np.log10(np.clip(1.0 - confidences, eps, 1.0))
+
+
+def _rank_signature(mu, confidences, confidence_threshold, min_effect):
+    keep = confidences >= confidence_threshold                                                    # factor.py:311-322
+    if min_effect is not None:
+        keep = keep & (mu >= min_effect)
+    idx = np.where(keep)[0]
+    if len(idx) > 0:
+        idx = idx[np.argsort(_confidence_mean_score(confidences[idx], mu[idx]))[::-1]]
+    return idx
+
+
+def _lognormal(mu, rho, eps):
+    return torch.clamp(torch.exp(mu + torch.exp(rho) * eps), 1e-15, 1e15)                         # jax_utils.py:6-8
+
+
+def _sig_call(lib, w_mu, w_rho, rows, eps, path, mode, tau=None, counts=None, ref_idx=None, ref_score=None, rank_count=None):
+    S, R, G = (int(x) for x in eps.shape)
+    F = R if path is None else int(path.shape[1])
+    st = C.c_void_p(torch.cuda.current_stream(w_mu.device).cuda_stream)
+    with torch.cuda.device(w_mu.device):
+        rc = lib.scdef_signature_scores(_ptr(w_mu), _ptr(w_rho), G, _ptr(rows), R, _ptr(eps), _ptr(path), S, F, int(mode),
+                                        _ptr(tau), _ptr(counts), _ptr(ref_idx), 0 if ref_idx is None else int(ref_idx.shape[1]),
+                                        _ptr(ref_score), _ptr(rank_count), st)
+    if rc != 0:
+        raise ScdefToolsError(f"scdef_signature_scores failed ({rc}): rows={R}, factors={F}, genes={G}, draws={S}, mode={mode}")
+
+
+def _jaccard_from_ranks(sig_idx, combined, rank_count, ref_idx):
+    """Mean weighted Jaccard (factor.py:41-70, 338-362) from the ranks of the signature genes in every draw: gene i is in
+    the draw's top-k list iff fewer than k genes score above it; the list has exactly k genes, so the genes it holds
+    that are not in the signature number k - |intersection|."""
+    out = []
+    rc = rank_count.cpu().numpy()
+    for f, ref in enumerate(sig_idx):
+        k = len(ref)
+        if k == 0:
+            out.append(float("nan"))
+            continue
+        w = np.asarray(combined[f][:k], dtype=float)
+        if w.size < k:
+            w = np.pad(w, (0, k - w.size), constant_values=0.0)
+        if np.all(w <= 0):
+            w = np.ones(k, dtype=float)
+        w = w / np.sum(w)
+        in_top = rc[:, f, :k] < k                                     # (S, k)
+        inter = in_top.astype(float) @ w
+        n_only = k - in_top.sum(axis=1)
+        out.append(float(np.mean(inter / (1.0 + n_only / float(k)))))
+    return out
+
+
+def _ranks_of_signatures(lib, w_mu, w_rho, rows, eps, path, sig_idx):
+    F = len(sig_idx)
+    kmax = max(1, max((len(s) for s in sig_idx), default=1))
+    ref = np.full((F, kmax), -1, dtype=np.int32)
+    for f, s in enumerate(sig_idx):
+        ref[f, :len(s)] = s
+    ref_d = torch.as_tensor(ref, device=w_mu.device)
+    S = int(eps.shape[0])
+    ref_score = torch.zeros((S, F, kmax), dtype=torch.float32, device=w_mu.device)
+    rank = torch.zeros((S, F, kmax), dtype=torch.int32, device=w_mu.device)
+    _sig_call(lib, w_mu, w_rho, rows, eps, path, 1, ref_idx=ref_d, ref_score=ref_score)
+    _sig_call(lib, w_mu, w_rho, rows, eps, path, 2, ref_idx=ref_d, ref_score=ref_score, rank_count=rank)
+    return rank, ref_d
+
+
+def set_confident_signatures(model, confidence_threshold: float = 0.9, tau_quantile: float = 0.99,
+                             min_effect: Optional[float] = None, mc_samples: int = 100, random_seed: int = 0,
+                             device=None, _eps=None):
+    """Drop-in for `scdef.tl.set_confident_signatures` (same arguments; same structure written to
+    `model.adata.uns['confident_signatures']` and `['factor_signatures']`).
+
+    The N(0,1) draws come from `torch.randn` on the device (generator seeded with `random_seed`), not from JAX's threefry:
+    individual draws differ from the reference's, their distribution is the same.  `_eps` injects them (parity tests):
+    {"w0": (S, R, G), "upper": {l: (S, F_l, F_{l-1})}, "l0": (S, F_0, G)} float32 CUDA tensors."""
+    if not (0.0 < confidence_threshold < 1.0):
+        raise ValueError("confidence_threshold must be in (0, 1).")
+    if not (0.0 < tau_quantile < 1.0):
+        raise ValueError("tau_quantile must be in (0, 1).")
+    if mc_samples <= 0:
+        raise ValueError("mc_samples must be > 0.")
+    if not torch.cuda.is_available():
+        raise ScdefToolsError("set_confident_signatures needs a CUDA device: there is no CPU fallback")
+    from scipy.stats import norm
+
+    lib = _lib.load()
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    S, L = int(mc_samples), int(model.n_layers)
+    names = [str(model.layer_names[i]) for i in range(L)]
+    fl = [np.asarray(model.factor_lists[i], dtype=int) for i in range(L)]
+    term_names = np.asarray(model.adata.var_names)
+    G = int(len(term_names))
+    l0_keep = _l0_keep_positions(model, _technical_drop_factors(model))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(random_seed))
+
+    def randn(key, shape):
+        if _eps is not None:
+            e = _eps[key[0]] if len(key) == 1 else _eps[key[0]][key[1]]
+            assert tuple(e.shape) == tuple(shape) and e.is_cuda and e.dtype == torch.float32
+            return e.contiguous()
+        return torch.randn(shape, generator=gen, device=dev, dtype=torch.float32)
+
+    W = [(torch.as_tensor(np.ascontiguousarray(model.global_params[2 + l][0], dtype=np.float32), device=dev),
+          torch.as_tensor(np.ascontiguousarray(model.global_params[2 + l][1], dtype=np.float32), device=dev)) for l in range(L)]
+    w0_mu, w0_rho = W[0]
+
+    # ---- upper layers: path of every draw down to the kept L0 factors (tiny batched products), then the device kernel ----
+    upper = {}
+    if L > 1 and len(l0_keep) > 0 and all(len(f) > 0 for f in fl):
+        rows = torch.as_tensor((fl[0][l0_keep]).astype(np.int32), device=dev)
+        eps_w0 = randn(("w0",), (S, len(l0_keep), G))
+        paths, path = [], None
+        for l in range(1, L):
+            mu_l = W[l][0][torch.as_tensor(fl[l], device=dev)][:, torch.as_tensor(fl[l - 1], device=dev)]
+            rho_l = W[l][1][torch.as_tensor(fl[l], device=dev)][:, torch.as_tensor(fl[l - 1], device=dev)]
+            w_l = _lognormal(mu_l[None], rho_l[None], randn(("upper", l), (S, len(fl[l]), len(fl[l - 1]))))
+            path = w_l if path is None else torch.bmm(w_l, path)                                  # factor.py:256-259
+            paths.append(path[:, :, torch.as_tensor(l0_keep, device=dev)])
+        path_all = torch.cat(paths, dim=1).contiguous()                                           # (S, sum F_l, R)
+        offs = np.concatenate([[0], np.cumsum([len(fl[l]) for l in range(1, L)])])
+        means_u = [_layer_term_means(model, l, l0_keep) for l in range(1, L)]
+        tau_u = np.concatenate([np.quantile(m, tau_quantile, axis=1) for m in means_u]).astype(np.float32)
+        counts = torch.zeros((path_all.shape[1], G), dtype=torch.int32, device=dev)
+        _sig_call(lib, w0_mu, w0_rho, rows, eps_w0, path_all, 0, tau=torch.as_tensor(tau_u, device=dev), counts=counts)
+        conf_u = counts.cpu().numpy().astype(float) / float(S)                                    # factor.py:308
+        sig_all = []
+        for li, l in enumerate(range(1, L)):
+            for f in range(len(fl[l])):
+                mu = means_u[li][f]
+                sig_all.append(_rank_signature(mu, conf_u[offs[li] + f], confidence_threshold, min_effect))
+        comb_all = []
+        for li, l in enumerate(range(1, L)):
+            for f in range(len(fl[l])):
+                idx = sig_all[offs[li] + f]
+                comb_all.append(_confidence_mean_score(conf_u[offs[li] + f][idx], means_u[li][f][idx]))
+        rank, _ = _ranks_of_signatures(lib, w0_mu, w0_rho, rows, eps_w0, path_all, sig_all)
+        jac_all = _jaccard_from_ranks(sig_all, comb_all, rank, None)
+        for li, l in enumerate(range(1, L)):
+            sl = slice(offs[li], offs[li + 1])
+            upper[l] = (sig_all[sl], [conf_u[offs[li] + f][sig_all[offs[li] + f]] for f in range(len(fl[l]))],
+                        comb_all[sl], jac_all[sl])
+
+    cache = {
+        "fit_revision": int(getattr(model, "_fit_revision", 0)),
+        "params": {"confidence_threshold": float(confidence_threshold), "tau_quantile": float(tau_quantile),
+                   "min_effect": None if min_effect is None else float(min_effect), "mc_samples": int(mc_samples),
+                   "random_seed": int(random_seed)},
+        "by_layer": {},
+    }
+    signatures_flat = {}
+    for l in range(L):
+        fnames = list(model.factor_names[l])
+        if l == 0:
+            means = np.asarray(model.pmeans[f"{names[0]}W"], dtype=float)[fl[0]]                 # factor.py:1712-1741
+            sd = np.sqrt(np.maximum(np.asarray(model.pvars[f"{names[0]}W"], dtype=float)[fl[0]], 0.0) + 1e-12)
+            sig, confs, comb = [], [], []
+            for f in range(len(fl[0])):
+                mu = means[f]
+                conf = norm.cdf((mu - float(np.quantile(mu, tau_quantile))) / sd[f])
+                idx = _rank_signature(mu, conf, confidence_threshold, min_effect)
+                sig.append(idx)
+                confs.append(conf[idx])
+                comb.append(_confidence_mean_score(conf[idx], mu[idx]))
+            if len(fl[0]) > 0:
+                rows0 = torch.as_tensor(fl[0].astype(np.int32), device=dev)
+                eps_l0 = randn(("l0",), (S, len(fl[0]), G))                                       # every factor's own draws
+                rank, _ = _ranks_of_signatures(lib, w0_mu, w0_rho, rows0, eps_l0, None, sig)
+                jac = _jaccard_from_ranks(sig, comb, rank, None)
+            else:
+                jac = []
+        elif l in upper:
+            sig, confs, comb, jac = upper[l]
+        else:
+            sig, confs, comb, jac = [], [], [], []
+        layer = {"layer_name": names[l], "signatures": {}, "confidences": {}, "combined_scores": {}, "signature_confidences": {}}
+        for f, fname in enumerate(fnames):
+            genes = term_names[sig[f]].tolist() if f < len(sig) else []
+            layer["signatures"][fname] = genes
+            layer["confidences"][fname] = np.asarray(confs[f], dtype=float).tolist() if f < len(sig) else []
+            layer["combined_scores"][fname] = np.asarray(comb[f], dtype=float).tolist() if f < len(sig) else []
+            layer["signature_confidences"][fname] = float(jac[f]) if f < len(jac) else float("nan")
+            signatures_flat[fname] = genes
+        cache["by_layer"][str(int(l))] = layer
+    model.adata.uns["confident_signatures"] = cache
+    model.adata.uns["factor_signatures"] = signatures_flat
+    return None
+
+
+def get_stored_confident_signatures(model, layer_idx: int = 0, max_genes: Optional[int] = None, return_confidences: bool = False,
+                                    return_combined_scores: bool = False, return_signature_confidences: bool = False):
+    """`scdef.tl.get_stored_confident_signatures` (factor.py:382-438): read the cache written above."""
+    if layer_idx < 0 or layer_idx >= model.n_layers:
+        raise ValueError(f"layer_idx must be in [0, {model.n_layers - 1}].")
+    cache = model.adata.uns.get("confident_signatures", None)
+    if cache is None:
+        raise KeyError("Confident signatures were not precomputed. Run `tl.set_confident_signatures(model)` first.")
+    if int(cache.get("fit_revision", -1)) != int(getattr(model, "_fit_revision", 0)):
+        raise KeyError("Stored confident signatures are stale for this fitted model. Run `tl.set_confident_signatures(model)` again.")
+    layer = cache["by_layer"][str(int(layer_idx))]
+    cut = (lambda v: v) if max_genes is None else (lambda v: v[: int(max_genes)])
+    out = [{k: cut(list(v)) for k, v in layer["signatures"].items()}]
+    if return_confidences:
+        out.append({k: cut(np.asarray(v, dtype=float)) for k, v in layer["confidences"].items()})
+    if return_combined_scores:
+        out.append({k: cut(np.asarray(v, dtype=float)) for k, v in layer["combined_scores"].items()})
+    if return_signature_confidences:
+        out.append({k: float(v) for k, v in layer.get("signature_confidences", {}).items()})
+    return out[0] if len(out) == 1 else tuple(out)

@@ -367,3 +367,78 @@ def test_restated_assign_confident_equals_the_reference_execution(ref):
     assert np.allclose(np.asarray(obs["confident_best_confidence"], dtype=float), sel["best_confidence"], atol=2e-6, equal_nan=True)
     assert np.allclose(np.asarray(obs["confident_best_effect_size"], dtype=float), sel["best_effect_size"], atol=2e-6, equal_nan=True)
     assert np.allclose(np.asarray(obs["confident_depth_score"], dtype=float), sel["depth_score"], atol=1e-12, equal_nan=True)
+
+
+@needs_reference
+def test_restated_confident_signatures_equal_the_reference_execution(ref):
+    """`tl.set_confident_signatures` (`tools/factor.py:441-552`; helpers 29-363, 1652-1768; `get_signature_sample`,
+    `_scdef.py:3953-3994`) of the REFERENCE on a model with hand-set W blocks, filtered factor lists and one technical
+    L0 factor, against `oracle/tools_ref.py` fed the draws the reference consumed (the shim's key chain is replayed)."""
+    import pandas as pd
+    from oracle import tools_ref as tr
+
+    rng = np.random.default_rng(11)
+    N, G, Ks, S = 50, 64, (6, 4, 2), 20
+    thr, tq = 0.6, 0.9
+    m = ref.scDEF(ref.adata(rng.poisson(1.5, (N, G)).astype(float)), layer_sizes=list(Ks), seed=1)
+    gp = [np.array(p, dtype=np.float64) for p in ref.to_numpy(m.global_params)]
+    for l in range(len(Ks)):
+        gp[2 + l][0] = rng.normal(-1.0, 1.0, gp[2 + l][0].shape)
+        gp[2 + l][1] = rng.normal(-1.5, 0.3, gp[2 + l][1].shape)
+    m.global_params = [ref.jnp.array(p) for p in gp]
+    m.set_posterior_means()
+    m.set_posterior_variances()
+    m.factor_lists = [np.array([0, 1, 3, 4, 5]), np.array([0, 2, 3]), np.array([0, 1])]
+    m.factor_names = [[f"L{l}_{k}" for k in kept] for l, kept in enumerate(m.factor_lists)]
+    m.adata.uns["factor_obs"] = pd.DataFrame({"technical": [n == "L0_3" for l in m.factor_names for n in l]},
+                                             index=[n for l in m.factor_names for n in l])
+    tf = ref.tools_factor
+    tf.set_confident_signatures(m, confidence_threshold=thr, tau_quantile=tq, mc_samples=S, random_seed=7)
+    cache = m.adata.uns["confident_signatures"]
+    genes = {g: i for i, g in enumerate(np.asarray(m.adata.var_names))}
+
+    # ---- the same with the oracle, on the reference's draws --------------------------------------------------------
+    random = ref.random
+    fl = [np.asarray(f) for f in m.factor_lists]
+    l0_keep = np.array([i for i, n in enumerate(m.factor_names[0]) if n != "L0_3"])
+    W_mu, W_rho = [gp[2 + l][0] for l in range(len(Ks))], [gp[2 + l][1] for l in range(len(Ks))]
+    pm = [np.asarray(m.pmeans[f"{m.layer_names[l]}W"], float) for l in range(len(Ks))]
+    pv0 = np.asarray(m.pvars[f"{m.layer_names[0]}W"], float)
+    base = random.PRNGKey(7)
+    upper = {l: [] for l in range(1, len(Ks))}
+    for s in range(S):                                              # factor.py:284-290, 243-266
+        key = random.fold_in(base, s)
+        eps = []
+        key, sk = random.split(key)
+        eps.append(np.asarray(random.normal(sk, shape=(len(fl[0]), G))))
+        for l in range(1, len(Ks)):
+            key, sk = random.split(key)
+            eps.append(np.asarray(random.normal(sk, shape=(len(fl[l]), len(fl[l - 1])))))
+        for l, sc in tr.hierarchy_scores_draw(W_mu, W_rho, fl, l0_keep, eps).items():
+            upper[l].append(sc)
+    for l in range(len(Ks)):
+        means = tr.layer_term_means(pm, fl, l0_keep, l)
+        if l == 0:
+            sig = tr.layer0_confident(means, pv0[fl[0]], thr, tq)
+
+            def scores_of(f):                                        # factor.py:95-110, _scdef.py:3975-3989
+                rows = []
+                for s in range(S):
+                    _, sk = random.split(random.fold_in(base, 0 * 1_000_003 + f * S + s))
+                    e = np.asarray(random.normal(sk, shape=(len(fl[0]), G)))
+                    rows.append(tr.lognormal_draw(W_mu[0][fl[0]], W_rho[0][fl[0]], e)[f])
+                return np.stack(rows)
+        else:
+            mc = np.stack(upper[l])
+            sig = tr.confident_from_scores(means, mc, thr, tq)
+            scores_of = lambda f, mc=mc: mc[:, f, :]
+        combined = [tr.confidence_mean_score(c, means[f][idx]) for f, (idx, c) in enumerate(sig)]
+        jac = tr.jaccard_from_scores([idx for idx, _ in sig], combined, scores_of)
+        got = cache["by_layer"][str(l)]
+        for f, name in enumerate(m.factor_names[l]):
+            want_genes = [genes[g] for g in got["signatures"][name]]
+            assert want_genes == list(sig[f][0]), (l, name)
+            assert np.allclose(got["confidences"][name], sig[f][1], atol=1e-12)
+            assert np.allclose(got["combined_scores"][name], combined[f], rtol=1e-10, atol=1e-12)
+            assert np.isclose(got["signature_confidences"][name], jac[f], atol=1e-12, equal_nan=True), (l, name)
+        assert any(len(idx) > 0 for idx, _ in sig), f"layer {l}: every signature is empty, the case tests nothing"
