@@ -150,6 +150,16 @@ typedef struct scdef_call {
 /* The caller ignores loss_out of this pass (the reference overwrites the local-pass loss with the
    global-pass one, `_scdef.py:3235-3271`): kernels may skip value-only work. */
 #define SCDEF_FLAG_SKIP_LOSS 2
+/* GLOBAL pass only: run the likelihood group before the hierarchy kernel (their outputs are disjoint), so that the W_0
+   gradient — almost all of the buffer a data-parallel caller all-reduces — is final while the rest of the pass still
+   runs.  Results are the same as without the flag up to the order of the float64 loss atomics. */
+#define SCDEF_FLAG_LIK_FIRST 4
+
+/* Data parallelism: `cuda_event` (a cudaEvent_t, or NULL to clear) is recorded on the call's stream by every
+   scdef_elbo_grad(GLOBAL) at the point where grads->W[0] is final (tcgen05 path: before the hierarchy kernel when
+   SCDEF_FLAG_LIK_FIRST is set and before k_finish otherwise; CUDA-core path: at the end of the pass), so the caller can
+   start reducing it on another stream while the rest of the pass runs.  No counterpart in the reference (single device). */
+int scdef_set_w0_grad_event(scdef_ctx* ctx, void* cuda_event);
 
 int scdef_abi_version(void);
 int scdef_ctx_create(const scdef_model_desc* desc, scdef_ctx** out);

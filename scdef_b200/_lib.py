@@ -15,7 +15,7 @@ ABI_VERSION = 8
 PASS_LOCAL, PASS_GLOBAL = 1, 2
 NOISE_PHILOX, NOISE_EXPLICIT = 0, 1
 LIK_AUTO, LIK_SIMT, LIK_TC = 0, 1, 2
-FLAG_REUSE_W0_SAMPLES, FLAG_SKIP_LOSS = 1, 2
+FLAG_REUSE_W0_SAMPLES, FLAG_SKIP_LOSS, FLAG_LIK_FIRST = 1, 2, 4
 
 _f32p = C.c_void_p  # device pointers travel as integers
 
@@ -111,6 +111,7 @@ EXPORTS = [
     "scdef_adam_local_lazy", "scdef_adam_bias_table", "scdef_assignment_counts",
     "scdef_csr_row_stats", "scdef_csr_gather_rows", "scdef_assign_confident", "scdef_init_gamma_block",
     "scdef_u16_row_stats", "scdef_u16_gather_rows", "scdef_count_stats", "scdef_signature_scores",
+    "scdef_set_w0_grad_event",
 ]
 LAZY_CATCHUP, LAZY_UPDATE, LAZY_CATCHUP_ALL = 0, 1, 2
 PROF_KINDS = ["lik", "adam_local_z", "hier", "sample", "wprior", "finish", "adam_global", "priors", "adam_local_c", "lik_main", "lik_main_global"]
@@ -194,6 +195,8 @@ def load():
                                            C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
     lib.scdef_signature_scores.restype = C.c_int
+    lib.scdef_set_w0_grad_event.argtypes = [C.c_void_p, C.c_void_p]
+    lib.scdef_set_w0_grad_event.restype = C.c_int
     lib.scdef_init_gamma_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                            C.c_float, C.c_float, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p]
     lib.scdef_init_gamma_block.restype = C.c_int

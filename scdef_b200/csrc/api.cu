@@ -19,6 +19,7 @@ using namespace scdef;
 constexpr int PROF_RING = 256;
 
 struct scdef_ctx {
+  cudaEvent_t w0_event = nullptr;   // scdef_set_w0_grad_event: recorded in the GLOBAL pass once the W_0 gradient is final
   scdef_model_desc d;
   int L, Kt, K0;
   int K[SCDEF_MAX_LAYERS], off[SCDEF_MAX_LAYERS + 1], out_dim[SCDEF_MAX_LAYERS];
@@ -421,8 +422,12 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     if ((rc = check_launch(ctx, "k_wprior"))) return rc;
   }
 
-  if (B > 0) {
-    // ---- hierarchy ---------------------------------------------------------------------------
+  // ---- hierarchy ---------------------------------------------------------------------------
+  // (its outputs — dELBO/dv of z, of W_l for l >= 1 and of alpha — are disjoint from the likelihood group's in the GLOBAL
+  // pass, so SCDEF_FLAG_LIK_FIRST may run it after that group: the W_0 gradient, 97 % of the data-parallel all-reduce, is
+  // then final a hierarchy kernel earlier)
+  auto run_hier = [&]() -> int {
+    if (B <= 0) return SCDEF_OK;
     HierArgs h;
     memset(&h, 0, sizeof(h));
     h.L = L;
@@ -488,9 +493,10 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       k_hier<<<dim3(chunks, S), HIER_WARPS * 32, smem, st>>>(h, S, loss_out);
     }
     }
-    if ((rc = check_launch(ctx, "k_hier"))) return rc;
-
-  }
+    return check_launch(ctx, "k_hier");
+  };
+  const bool lik_first = pass == SCDEF_PASS_GLOBAL && (call->flags & SCDEF_FLAG_LIK_FIRST);
+  if (!lik_first && (rc = run_hier())) return rc;
 
   // ---- likelihood (+ the whole W_0 path in tcgen05 mode) --------------------------------------------
   {
@@ -552,6 +558,11 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     }
   }
 
+  // the W_0 gradient of the GLOBAL pass is final here on the tcgen05 path (k_tc_w0_final_flat wrote it)
+  const bool w0_final_early = pass == SCDEF_PASS_GLOBAL && tc;
+  if (w0_final_early && ctx->w0_event) cudaEventRecord(ctx->w0_event, st);
+  if (lik_first && (rc = run_hier())) return rc;
+
   // ---- (mu, rho) gradients of the blocks of this pass ------------------------------------------
   {
     BlockTable t;
@@ -580,6 +591,13 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       if ((rc = check_launch(ctx, "k_finish"))) return rc;
     }
   }
+  if (pass == SCDEF_PASS_GLOBAL && ctx->w0_event && !w0_final_early) cudaEventRecord(ctx->w0_event, st);   // CUDA-core path: k_finish wrote it
+  return SCDEF_OK;
+}
+
+int scdef_set_w0_grad_event(scdef_ctx* ctx, void* cuda_event) {
+  if (!ctx) return SCDEF_EINVAL;
+  ctx->w0_event = (cudaEvent_t)cuda_event;
   return SCDEF_OK;
 }
 

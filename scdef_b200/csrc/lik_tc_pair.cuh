@@ -86,6 +86,15 @@ __device__ __noinline__ void pair_stuck(int code, int x, int y, int z) {
 // bounded waits: a protocol error ends in a trap (and a record of which wait it was), not in a hung device
 template <bool REMOTE>
 __device__ __forceinline__ void pair_wait_t(uint64_t* bar, uint32_t parity, int code) {
+#ifdef SCDEF_PAIR_SPIN
+  // A/B switch: poll with the non-blocking test_wait instead of the suspending try_wait
+  if (mbar_test_remote(bar, parity)) return;
+  const long long ts = clock64();
+  while (!mbar_test_remote(bar, parity)) {
+    if (clock64() - ts > PAIR_DEADLINE) pair_stuck(code, (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)parity);
+  }
+  return;
+#endif
   if (mbar_try<REMOTE>(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try<REMOTE>(bar, parity)) {

@@ -12,6 +12,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Optional
 
+import os
+
 import numpy as np
 
 
@@ -44,6 +46,47 @@ def all_reduce_sum(t, shard: ShardInfo):
         return t
     td.all_reduce(t, op=td.ReduceOp.SUM, group=shard.group)
     return t
+
+
+class GradReducer:
+    """Sum of the flat global-gradient buffer over the ranks, once per step (the only collective of the data path).
+
+    The buffer is laid out [small blocks | W_0] (`Engine.glob_grad.split`).  W_0's gradient — 97 % of the bytes — is final
+    before the hierarchy kernel and `k_finish` of the GLOBAL pass have run (`SCDEF_FLAG_LIK_FIRST`,
+    `scdef_set_w0_grad_event`), so its all-reduce is enqueued behind that event and runs on NCCL's stream while the pass
+    finishes; only the all-reduce of the small blocks (~0.1 MB) starts after the pass.  gloo (CPU tests): one plain
+    all-reduce of the whole buffer."""
+
+    def __init__(self, eng, shard: ShardInfo):
+        import torch
+        import torch.distributed as td
+
+        self.eng, self.shard = eng, shard
+        flat, split = eng.glob_grad.flat, eng.glob_grad.split
+        self.overlap = bool(flat.is_cuda and shard.world > 1 and td.get_backend(shard.group) == "nccl" and split is not None
+                            and os.environ.get("SCDEF_DP_OVERLAP", "1") != "0")
+        if self.overlap:
+            self.small, self.w0 = flat[:split], flat[split:]
+            self.side = torch.cuda.Stream(device=flat.device)
+            self.event = eng.w0_grad_event()
+
+    @property
+    def lik_first(self) -> bool:
+        return self.overlap
+
+    def reduce(self):
+        """Call right after the GLOBAL pass has been enqueued on the current stream."""
+        import torch
+        import torch.distributed as td
+
+        if not self.overlap:
+            return all_reduce_sum(self.eng.glob_grad.flat, self.shard)
+        self.side.wait_event(self.event)
+        with torch.cuda.stream(self.side):      # NCCL's stream waits for `side`, i.e. for the W_0 gradient only
+            w_big = td.all_reduce(self.w0, op=td.ReduceOp.SUM, group=self.shard.group, async_op=True)
+        w_small = td.all_reduce(self.small, op=td.ReduceOp.SUM, group=self.shard.group, async_op=True)   # after the whole pass
+        w_big.wait()                             # the compute stream waits for both (no host synchronisation)
+        w_small.wait()
 
 
 def _allreduce_np(a: np.ndarray, shard: ShardInfo, device=None) -> np.ndarray:

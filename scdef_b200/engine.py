@@ -64,14 +64,19 @@ def _block_shapes(n_rows, layer_sizes, n_batches, n_genes):
 class _FlatGroup:
     """A flat float32 buffer carved into named views; every view starts 16-byte aligned."""
 
-    def __init__(self, shapes, device):
+    def __init__(self, shapes, device, last=None):
+        """`last`: name of the block placed at the END of the flat buffer (the views keep the order of `shapes`): the
+        global groups put W0 there, so that "W_0" and "everything else" are two contiguous ranges for the data-parallel
+        all-reduce (dist.GradReducer)."""
         self.names = [n for n, _ in shapes]
-        offs, o = [], 0
-        for _, shp in shapes:
-            offs.append(o)
-            o += (int(np.prod(shp)) + 3) // 4 * 4
+        order = [i for i, (n, _) in enumerate(shapes) if n != last] + [i for i, (n, _) in enumerate(shapes) if n == last]
+        offs, o = [0] * len(shapes), 0
+        for i in order:
+            offs[i] = o
+            o += (int(np.prod(shapes[i][1])) + 3) // 4 * 4
         self.flat = torch.zeros(max(o, 4), dtype=torch.float32, device=device)
         self.views = [self.flat[off : off + int(np.prod(shp))].view(*shp) for off, (_, shp) in zip(offs, shapes)]
+        self.split = offs[self.names.index(last)] if last in self.names else None   # flat[:split] | flat[split:] = the `last` block
 
     def blocks(self, n_layers, local: bool) -> Blocks:
         b = Blocks()
@@ -209,7 +214,8 @@ class Engine:
         self.glob = _FlatGroup(gshapes, dev)
         self.local_m, self.local_v = _FlatGroup(lshapes, dev), _FlatGroup(lshapes, dev)
         self.glob_m, self.glob_v = _FlatGroup(gshapes, dev), _FlatGroup(gshapes, dev)
-        self.glob_grad = _FlatGroup(gshapes, dev)
+        self.glob_grad = _FlatGroup(gshapes, dev, last="W0")   # [small blocks | W_0]: two contiguous all-reduce ranges
+        self._w0_event = None
         self.batch_max = 0
         self.local_grad = None
         self._ensure_batch(int(batch_max))
@@ -326,10 +332,22 @@ class Engine:
                 n.eps_W[l] = w.data_ptr()
         return n
 
+    def w0_grad_event(self) -> torch.cuda.Event:
+        """Event recorded by every GLOBAL pass when the W_0 gradient is final (`scdef_set_w0_grad_event`): lets the
+        data-parallel loop start reducing it while the rest of the pass still runs."""
+        if self._w0_event is None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))   # creates the underlying cudaEvent_t
+            rc = self.lib.scdef_set_w0_grad_event(self.ctx, C.c_void_p(ev.cuda_event))
+            if rc != 0:
+                raise ScdefError(f"scdef_set_w0_grad_event failed ({rc})")
+            self._w0_event = ev
+        return self._w0_event
+
     def elbo_grad(self, which: str, indices: torch.Tensor, noise: NoiseSpec, *, num_samples: int,
                   annealing=1.0, stop_gradients=None, stop_cell_budgets=0.0, stop_gene_budgets=0.0,
                   alpha=1.0, scale=None, global_weight=1.0, X_batch: Optional[torch.Tensor] = None,
-                  lik_impl=_lib.LIK_AUTO, zero_loss=True, reuse_w0=False, want_loss=True):
+                  lik_impl=_lib.LIK_AUTO, zero_loss=True, reuse_w0=False, want_loss=True, lik_first=False):
         """Enqueue loss + gradient (`local_loss_grad` / `global_loss_grad`, `_scdef.py:2848-2849`).
         `indices`: int64 device tensor of this rank's rows.  Results: `self.loss_buf` (device
         double[2]: cell part, global part) and `self.local_grad` / `self.glob_grad`."""
@@ -349,7 +367,8 @@ class Engine:
         call.alpha = float(alpha)
         call.scale = float(scale) if scale is not None else (self.N / max(B, 1))
         call.global_weight = float(global_weight)
-        call.flags = (_lib.FLAG_REUSE_W0_SAMPLES if reuse_w0 else 0) | (0 if want_loss else _lib.FLAG_SKIP_LOSS)
+        call.flags = ((_lib.FLAG_REUSE_W0_SAMPLES if reuse_w0 else 0) | (0 if want_loss else _lib.FLAG_SKIP_LOSS)
+                      | (_lib.FLAG_LIK_FIRST if lik_first else 0))
         keep = []
         if B > 0:
             assert indices.dtype == torch.int64 and indices.is_cuda and indices.is_contiguous()

@@ -801,6 +801,7 @@ class scDEF:
             sigint["old"] = signal.signal(signal.SIGINT, _on_sigint)
         steps_done = 0
         limit = self.max_steps_per_learn
+        reducer = _dist.GradReducer(eng, shard) if shard.world > 1 else None
 
         epochs = range(n_epoch)
         pbar = _tqdm(epochs, disable=shard.rank != 0 or self.logger.level >= 30) if _tqdm is not None else None
@@ -831,9 +832,10 @@ class scDEF:
                         eng.adam_local(idx, float(local_lr), freeze_z_layers)
                     if update_globals:
                         # same rng_input, globals untouched since the local pass: its W_0 sample tiles are reusable
-                        eng.elbo_grad("global", idx, noise, reuse_w0=bool(update_locals), **kw)
-                        if shard.world > 1:
-                            _dist.all_reduce_sum(eng.glob_grad.flat, shard)
+                        eng.elbo_grad("global", idx, noise, reuse_w0=bool(update_locals),
+                                      lik_first=reducer is not None and reducer.lik_first, **kw)
+                        if reducer is not None:
+                            reducer.reduce()   # W_0's share overlaps the tail of the pass (dist.GradReducer)
                         eng.adam_global(float(lr), freeze_w=bool(freeze_w))
                     stream.release()
                     stream.prefetch(it + 1)  # host placement: stage the next minibatch while this step runs

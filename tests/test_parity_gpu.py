@@ -236,3 +236,31 @@ def test_skip_loss_and_reuse_flags_do_not_change_the_gradients(lik_impl):
     eng.elbo_grad("global", idx, spec, reuse_w0=True, **kw)
     assert abs(eng.loss_value() - ref_loss) / abs(ref_loss) < 1e-6
     assert rel_err(eng.glob_grad.flat.cpu().numpy(), ref_g.cpu().numpy()) < 1e-6
+
+
+def test_lik_first_order_of_the_global_pass_gives_the_same_gradients():
+    """`SCDEF_FLAG_LIK_FIRST` (the data-parallel loop sets it so that the W_0 gradient is final before the hierarchy kernel
+    runs) only reorders kernels with disjoint outputs: the gradients are the same (bit-identical where no float atomics
+    are involved), the loss agrees to the order of its float64 atomics, and the W_0 event fires."""
+    X, batch, model, lp, gp = small_problem(300, 136, (24, 6, 1), 2, seed=3)
+    idx = np.random.RandomState(1).permutation(300)[:200]
+    noise = Noise.draw(3, 200, 2, 136, (24, 6, 1), seed=4, dtype=torch.float32)
+    eng = make_engine(X, batch, model, lp, gp)
+    idx_d = torch.as_tensor(idx, dtype=torch.int64, device="cuda")
+    kw = dict(num_samples=3, annealing=1.0, stop_gradients=[0, 0, 0], alpha=model.alpha)
+    ev = eng.w0_grad_event()
+    out = []
+    for lik_first in (False, True):
+        eng.elbo_grad("global", idx_d, noise_to_spec(noise), lik_first=lik_first, **kw)
+        ev.synchronize()
+        torch.cuda.synchronize()
+        out.append((eng.loss_value(), [g.clone() for g in eng.glob_grad.views]))
+    assert abs(out[0][0] - out[1][0]) <= 1e-8 * abs(out[0][0])   # block partial sums reach the float64 total in a different order
+    for i, (a, b) in enumerate(zip(out[0][1], out[1][1])):
+        if i in (0, 2):   # gene scale and W_0: no atomics on their path
+            assert torch.equal(a, b), i
+        else:             # the hierarchy kernel adds its W_l / alpha contributions with float atomics
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * float(a.abs().max())), i
+    split = eng.glob_grad.split
+    assert split is not None and eng.glob_grad.flat[split:].numel() == 2 * 24 * 136       # [small blocks | W_0]
+    assert eng.glob_grad.views[2].data_ptr() == eng.glob_grad.flat[split:].data_ptr()
