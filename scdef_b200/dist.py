@@ -54,8 +54,8 @@ class GradReducer:
     The buffer is laid out [small blocks | W_0] (`Engine.glob_grad.split`).  W_0's gradient — 97 % of the bytes — is final
     before the hierarchy kernel and `k_finish` of the GLOBAL pass have run (`SCDEF_FLAG_LIK_FIRST`,
     `scdef_set_w0_grad_event`), so its all-reduce is enqueued behind that event and runs on NCCL's stream while the pass
-    finishes; only the all-reduce of the small blocks (~0.1 MB) starts after the pass.  gloo (CPU tests): one plain
-    all-reduce of the whole buffer."""
+    finishes; only the all-reduce of the small blocks (~0.1 MB) starts after the pass.  gloo (CPU tests) and more than
+    two ranks (see the measurements below): one plain all-reduce of the whole buffer."""
 
     def __init__(self, eng, shard: ShardInfo):
         import torch
@@ -63,8 +63,12 @@ class GradReducer:
 
         self.eng, self.shard = eng, shard
         flat, split = eng.glob_grad.flat, eng.glob_grad.split
-        self.overlap = bool(flat.is_cuda and shard.world > 1 and td.get_backend(shard.group) == "nccl" and split is not None
-                            and os.environ.get("SCDEF_DP_OVERLAP", "1") != "0")
+        # Measured at C5 on B200s (same box, back to back, ms per step with / without the split): 2 GPUs 1.435 / 1.445,
+        # 4 GPUs 1.429 / 1.427, 8 GPUs 1.466 / 1.460 — beyond two ranks the cost of a collective is its latency, not its
+        # 4 MB, and a second collective costs what the overlap saves.  So: on by default for two ranks only.
+        want = os.environ.get("SCDEF_DP_OVERLAP", "auto")
+        want = shard.world == 2 if want == "auto" else want != "0"
+        self.overlap = bool(flat.is_cuda and shard.world > 1 and td.get_backend(shard.group) == "nccl" and split is not None and want)
         if self.overlap:
             self.small, self.w0 = flat[:split], flat[split:]
             self.side = torch.cuda.Stream(device=flat.device)
