@@ -380,7 +380,11 @@ def run_ours(args):
             del model
             torch.cuda.empty_cache()
             m2 = build(Xh, "host")
-            r2 = timed_learn(m2, per_step_readback=True, P=0)
+            r2 = timed_learn(m2, per_step_readback=not os.environ.get("SCDEF_BENCH_E2E_NO_READBACK"),
+                             P=30 if os.environ.get("SCDEF_BENCH_E2E_PROFILE") else 0)
+            if os.environ.get("SCDEF_BENCH_E2E_PROFILE"):   # debug: per-family kernel times of the host-placement path
+                sys.stderr.write("e2e kernel families: " + json.dumps({k: [round(v[0] / max(v[1], 1), 4), v[2] if len(v) > 2 else None]
+                                                                      for k, v in r2.get("prof_all", {}).items()}) + "\n")
             ms2 = r2["ms"] / K
             e2e = {"value": cells_per_step / (ms2 * 1e-3), "unit": "cells/s",
                    "h2d_bytes_per_step": int((r2["h2d1"] - r2["h2d0"]) / K), "d2h_bytes_per_step": 16,

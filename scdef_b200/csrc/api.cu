@@ -504,7 +504,8 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     const int64_t* idx_x = call->X_batch ? nullptr : call->indices;
     const bool lik_run = lik_on && B > 0;
     if (lik_run && !(call->flags & SCDEF_FLAG_SKIP_LOSS)) {   // a pure loss term: nothing to do when the loss is discarded
-      k_x_lgamma<<<(B + 7) / 8, 256, 0, st>>>(Xp, idx_x, d.x_lgamma_rowsum, call->indices, B, G, scale, loss_out);
+      const long long xlg_warps = d.x_lgamma_rowsum ? (long long)B : (long long)B * ((G + XLG_CHUNK - 1) / XLG_CHUNK);
+      k_x_lgamma<<<(unsigned)((xlg_warps + 7) / 8), 256, 0, st>>>(Xp, idx_x, d.x_lgamma_rowsum, call->indices, B, G, scale, loss_out);
       if ((rc = check_launch(ctx, "k_x_lgamma"))) return rc;
     }
     if (tc) {

@@ -160,29 +160,36 @@ __global__ void __launch_bounds__(256) k_lik_simt(const LikArgs a, int S, double
 }
 
 // - scale * sum_j sum_g lgamma(x_jg + 1): parameter-free part of the Poisson log-pmf
-// (`_scdef.py:2119`).  One warp per minibatch row.  grid = ceil(B/8), block = 256.
+// (`_scdef.py:2119`).  With the per-cell sums precomputed (resident counts): one warp per minibatch row, grid = ceil(B/8).
+// Without them (host placement: the rows arrive per step): one warp per (row, 512-gene chunk), grid = ceil(B*chunks/8) —
+// a warp per whole row left this kernel at 32 CTAs x 157 lgammaf per lane, ~0.09 ms of an otherwise idle GPU per step.
+constexpr int XLG_CHUNK = 512;
 __global__ void __launch_bounds__(256) k_x_lgamma(const float* X, const int64_t* idx_x,
                                                   const float* rowsum, const int64_t* idx_cells,
                                                   int B, int G, float scale, double* loss_out) {
   __shared__ double red[32];
   const int lane = threadIdx.x & 31;
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double val = 0.0;
-  if (j < B) {
-    const long long row = idx_x ? idx_x[j] : j;
-    if (rowsum) {
-      if (lane == 0) val = (double)rowsum[idx_cells[j]];
-    } else {
+  if (rowsum) {
+    if (w < B && lane == 0) val = (double)rowsum[idx_cells[w]];
+  } else {
+    const int chunks = (G + XLG_CHUNK - 1) / XLG_CHUNK;
+    const long long j = w / chunks;
+    const int c = (int)(w - j * chunks);
+    if (j < B) {
+      const long long row = idx_x ? idx_x[j] : j;
+      const int g1 = min(G, (c + 1) * XLG_CHUNK);
       float acc = 0.f;
-      for (int g = lane; g < G; g += 32) {
-        float x = X[row * G + g];
+      for (int g = c * XLG_CHUNK + lane; g < g1; g += 32) {
+        const float x = X[row * G + g];
         if (x > 1.5f) acc += lgammaf(x + 1.f);
       }
       val = (double)acc;
     }
   }
   double tot = block_sum_d(val, red);
-  if (threadIdx.x == 0) atomicAdd(&loss_out[0], tot * (double)scale);
+  if (threadIdx.x == 0 && tot != 0.0) atomicAdd(&loss_out[0], tot * (double)scale);
 }
 
 }  // namespace scdef
