@@ -585,7 +585,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       for (int l = 0; l < L; ++l) add(BLK_Z + l);
     }
     if (t.n > 0) {
-      size_t gx = (max_el * FIN_SPLIT + 255) / 256;
+      size_t gx = (max_el + 31) / 32;   // a CTA per 32 elements of the largest block
       if (gx > (size_t)ctx->sm_count * 16) gx = (size_t)ctx->sm_count * 16;
       ProfScope ps(ctx, SCDEF_PROF_FINISH, st);
       k_finish<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key);

@@ -632,21 +632,25 @@ __global__ void __launch_bounds__(256) k_tc_rowprep(const LikTcArgs a, int* brow
   brow[j] = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
   xoff[j] = (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
 }
-// the same plus the row sums of the minibatch counts, one warp per row (unified pair kernel)
-__global__ void __launch_bounds__(256) k_tc_rowprep_sum(const LikTcArgs a, int* brow, long long* xoff, float* rowsum) {
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+// the same plus the row sums of the minibatch counts, one 128-thread CTA per row (a warp per row left 32 CTAs walking
+// 20 KB rows serially: 10 us per launch; unified pair kernel)
+__global__ void __launch_bounds__(128) k_tc_rowprep_sum(const LikTcArgs a, int* brow, long long* xoff, float* rowsum) {
+  __shared__ float red[4];
+  const int j = blockIdx.x, tid = threadIdx.x;
   if (j >= a.B) return;
   const long long off = (a.idx_x ? a.idx_x[j] : (long long)j) * a.G;
   const float* row = a.X + off;
   float acc = 0.f;
-  for (int g = lane * 4; g < a.G; g += 128) {   // G is a multiple of 8, rows are 16 B aligned
+  for (int g = tid * 4; g < a.G; g += 512) {   // G is a multiple of 8, rows are 16 B aligned
     const float4 v = *reinterpret_cast<const float4*>(row + g);
     acc += (v.x + v.y) + (v.z + v.w);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) {
-    rowsum[j] = acc;
+  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    rowsum[j] = (red[0] + red[1]) + (red[2] + red[3]);
     brow[j] = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
     xoff[j] = off;
   }
@@ -879,11 +883,22 @@ __global__ void __launch_bounds__(1024) k_tc_ctilde(const LikTcArgs a, float* ct
 #pragma unroll
   for (int b = 0; b < MAX_NB; ++b) acc[b] = 0.f;
   if (k < a.K0) {
-    for (int j = rg; j < a.B; j += 8) {
-      const float v = a.smp_c[(long long)s * a.B + j] * a.smp_z0[((long long)s * a.B + j) * a.K0 + k];
-      const int bj = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
+    // four rows per round: the loads of a round are independent, so one latency covers four of them (the loop was a
+    // chain of 32 dependent-latency rounds on 100 CTAs: 20 us per launch)
+    for (int j0 = rg; j0 < a.B; j0 += 32) {
+      float v[4];
+      int bj[4];
 #pragma unroll
-      for (int b = 0; b < MAX_NB; ++b) acc[b] += (b == bj) ? v : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 8 * u;
+        const bool ok = j < a.B;
+        v[u] = ok ? a.smp_c[(long long)s * a.B + j] * a.smp_z0[((long long)s * a.B + j) * a.K0 + k] : 0.f;
+        bj[u] = (ok && a.nb > 1) ? a.batch_id[a.idx[j]] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int b = 0; b < MAX_NB; ++b) acc[b] += (b == bj[u]) ? v[u] : 0.f;
     }
   }
 #pragma unroll
@@ -1274,7 +1289,7 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
     const int nblk = g_sm_count * 4;
     const long long T = (long long)fg.n_rblk * a.S * fg.n_pt;
     pair_stuck_init();
-    k_tc_rowprep_sum<<<(a.B + 7) / 8, 256, 0, st>>>(a, ws.brow, ws.xoff, ws.rowsumx);
+    k_tc_rowprep_sum<<<a.B, 128, 0, st>>>(a, ws.brow, ws.xoff, ws.rowsumx);
     if (!reuse) {
       k_tc_wprep<<<g_sm_count * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
       k_tc_wgen<<<dim3(n_tiles / 4, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit);
