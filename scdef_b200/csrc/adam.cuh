@@ -38,6 +38,7 @@ struct AdamSegTable {
 
 // grid = (blocks, n_segments)
 __global__ void __launch_bounds__(256) k_adam_global(const AdamSegTable tab, const AdamHyper h) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const AdamSeg& sg = tab.s[blockIdx.y];
   const int total = 2 * sg.n_half;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) k_adam_global(const AdamSegTable tab, con
 
 // ---- locals: dense over all N rows; gradient rows come from the minibatch via row_slot -------
 __global__ void k_set_slots(int32_t* row_slot, const int64_t* idx, int B, int clear) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < B) row_slot[idx[j]] = clear ? -1 : j;
 }
@@ -74,6 +76,7 @@ struct AdamLocalArgs {
 // thread per iteration so that six 16-byte loads are in flight before the first dependent use.
 template <int VEC, typename IdxT>
 __global__ void __launch_bounds__(256) k_adam_local(const AdamLocalArgs a, const AdamHyper h) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const IdxT C = (IdxT)a.C, CV = (IdxT)(a.C / VEC);
   const IdxT nvec = (IdxT)a.N * CV;
   const int hsel = blockIdx.y;
@@ -164,6 +167,7 @@ struct AdamLazyPair {
 };
 
 __global__ void __launch_bounds__(256) k_adam_lazy_catchup(const AdamLazyPair pr, AdamHyper h) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const AdamLazyArgs& a = pr.a[blockIdx.z];
   const long long rows = a.idx ? a.B : a.N;
   const long long total = rows * a.C;
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(256) k_adam_lazy_catchup(const AdamLazyPair pr
 
 // applies step `target` with the minibatch gradient to the minibatch rows (already caught up to target-1)
 __global__ void __launch_bounds__(256) k_adam_lazy_update(const AdamLazyPair pr, const AdamHyper h) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const AdamLazyArgs& a = pr.a[blockIdx.z];
   const long long total = (long long)a.B * a.C;
   const long long hoff = (long long)blockIdx.y * a.N * a.C;
@@ -234,6 +239,7 @@ __global__ void __launch_bounds__(256) k_adam_lazy_update(const AdamLazyPair pr,
 }
 
 __global__ void k_set_row_step(int32_t* row_step, const int64_t* idx, long long n, int value) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) row_step[idx ? idx[j] : j] = value;
 }
@@ -251,6 +257,7 @@ struct PostSegTable {
 };
 
 __global__ void __launch_bounds__(256) k_posterior(const PostSegTable tab) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const PostSeg& sg = tab.s[blockIdx.y];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -265,6 +272,7 @@ __global__ void __launch_bounds__(256) k_posterior(const PostSegTable tab) {
 // ---- CSR-resident counts: per-cell constants and minibatch densification (one warp per row) ------
 __global__ void __launch_bounds__(256) k_csr_row_stats(const long long* indptr, const float* data, long long n_rows,
                                                        float* lib, float* lgam) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_rows) return;
@@ -284,6 +292,7 @@ __global__ void __launch_bounds__(256) k_csr_row_stats(const long long* indptr, 
 
 __global__ void __launch_bounds__(256) k_csr_gather_rows(const long long* indptr, const int* indices, const float* data,
                                                          const long long* rows, int n_rows, int G, float* out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const int lane = threadIdx.x & 31;
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (j >= n_rows) return;
@@ -302,6 +311,7 @@ struct AssignArgs {
 };
 
 __global__ void __launch_bounds__(256) k_assignment_counts(const AssignArgs a, unsigned long long* counts) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ unsigned int hist[];
   for (int i = threadIdx.x; i < a.Kt; i += blockDim.x) hist[i] = 0u;
   __syncthreads();
@@ -337,6 +347,7 @@ __global__ void __launch_bounds__(256) k_assignment_counts(const AssignArgs a, u
 // ---- per-cell constants of a resident count matrix ---------------------------------------------
 __global__ void __launch_bounds__(256) k_row_stats(const float* X, long long n_rows, int G, float* lib,
                                                    float* lgam) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_rows) return;
@@ -357,6 +368,7 @@ __global__ void __launch_bounds__(256) k_row_stats(const float* X, long long n_r
 // ---- counts stored as uint16 (half the HBM of float32: 10 GB instead of 20 GB at 1M x 5000) -------------------------
 // per-cell constants, as k_row_stats
 __global__ void __launch_bounds__(256) k_u16_row_stats(const uint16_t* X, long long n_rows, int G, float* lib, float* lgam) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_rows) return;
@@ -375,6 +387,7 @@ __global__ void __launch_bounds__(256) k_u16_row_stats(const uint16_t* X, long l
 }
 // out[j, :] = float(X[rows[j], :]) : the minibatch as the dense float32 X_batch every kernel downstream reads
 __global__ void __launch_bounds__(256) k_u16_gather_rows(const uint16_t* X, const long long* rows, int n_rows, int G, float* out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const long long total = (long long)n_rows * G;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i / G), g = (int)(i - (long long)j * G);
@@ -389,6 +402,7 @@ __global__ void __launch_bounds__(256) k_u16_gather_rows(const uint16_t* X, cons
 template <typename T>
 __global__ void __launch_bounds__(256) k_count_stats(const T* X, const int* batch_id, long long n_rows, int G, int nb,
                                                      double* st, double* gs, float* lib_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ float lib_sm[32];
   __shared__ int b_sm[32];
   const long long r0 = (long long)blockIdx.x * 32;
@@ -437,6 +451,7 @@ __global__ void __launch_bounds__(256) k_count_stats(const T* X, const int* batc
 }
 
 __global__ void __launch_bounds__(256) k_noise_fill(float* out, int S, int per, PhiloxKey key, NoiseTag tag, long long e0) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const long long total = (long long)S * per;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {

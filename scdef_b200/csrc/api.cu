@@ -361,9 +361,9 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
         cta += (int)(((long long)nq[i] * sch + 255) / 256);
       }
       sgrid.cta0[t.n] = cta;
-      if (cta > 0) k_sample_v2<<<(unsigned)cta, 256, 0, st>>>(t, sgrid, S, key, loss_out, gw);
+      if (cta > 0) SCDEF_LAUNCH(k_sample_v2, (unsigned)cta, 256, 0, st, t, sgrid, S, key, loss_out, gw);
     } else {
-      k_sample<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key, loss_out, gw);
+      SCDEF_LAUNCH(k_sample, dim3((unsigned)gx, t.n), 256, 0, st, t, S, key, loss_out, gw);
     }
     if ((rc = check_launch(ctx, "k_sample"))) return rc;
   }
@@ -396,7 +396,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     if (gx > (size_t)ctx->sm_count * 8) gx = (size_t)ctx->sm_count * 8;
     if (gx < 1) gx = 1;
     ProfScope ps(ctx, SCDEF_PROF_PRIORS, st);
-    k_scale_priors<<<dim3((unsigned)gx, 5), 256, 0, st>>>(t, S, loss_out);
+    SCDEF_LAUNCH(k_scale_priors, dim3((unsigned)gx, 5), 256, 0, st, t, S, loss_out);
     if ((rc = check_launch(ctx, "k_scale_priors"))) return rc;
   }
 
@@ -418,7 +418,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     a.weight = gw;
     int warps = S * a.rows;
     ProfScope ps(ctx, SCDEF_PROF_WPRIOR, st);
-    k_wprior<<<(warps + 7) / 8, 256, 0, st>>>(a, S, loss_out);
+    SCDEF_LAUNCH(k_wprior, (warps + 7) / 8, 256, 0, st, a, S, loss_out);
     if ((rc = check_launch(ctx, "k_wprior"))) return rc;
   }
 
@@ -476,7 +476,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       ht.tiles_per_cta = tpc;
       if (smem_t > 48 * 1024) cudaFuncSetAttribute(k_hier_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
       ProfScope ps(ctx, SCDEF_PROF_HIER, st);
-      k_hier_tiled<<<dim3((n_t32 + tpc - 1) / tpc, S), HNT, smem_t, st>>>(ht, S, loss_out);
+      SCDEF_LAUNCH(k_hier_tiled, dim3((n_t32 + tpc - 1) / tpc, S), HNT, smem_t, st, ht, S, loss_out);
     } else {
     // enough CTAs to fill the GPU, at least one round of 8 cells each
     int chunks = (ctx->sm_count * 2 + S - 1) / S;
@@ -490,7 +490,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_hier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     {
       ProfScope ps(ctx, SCDEF_PROF_HIER, st);
-      k_hier<<<dim3(chunks, S), HIER_WARPS * 32, smem, st>>>(h, S, loss_out);
+      SCDEF_LAUNCH(k_hier, dim3(chunks, S), HIER_WARPS * 32, smem, st, h, S, loss_out);
     }
     }
     return check_launch(ctx, "k_hier");
@@ -505,7 +505,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
     const bool lik_run = lik_on && B > 0;
     if (lik_run && !(call->flags & SCDEF_FLAG_SKIP_LOSS)) {   // a pure loss term: nothing to do when the loss is discarded
       const long long xlg_warps = d.x_lgamma_rowsum ? (long long)B : (long long)B * ((G + XLG_CHUNK - 1) / XLG_CHUNK);
-      k_x_lgamma<<<(unsigned)((xlg_warps + 7) / 8), 256, 0, st>>>(Xp, idx_x, d.x_lgamma_rowsum, call->indices, B, G, scale, loss_out);
+      SCDEF_LAUNCH(k_x_lgamma, (unsigned)((xlg_warps + 7) / 8), 256, 0, st, Xp, idx_x, d.x_lgamma_rowsum, call->indices, B, G, scale, loss_out);
       if ((rc = check_launch(ctx, "k_x_lgamma"))) return rc;
     }
     if (tc) {
@@ -553,7 +553,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       {
         ProfScope ps(ctx, SCDEF_PROF_LIK, st);
         ProfScope pm(ctx, pass == SCDEF_PASS_GLOBAL ? SCDEF_PROF_LIK_MAIN_GLOBAL : SCDEF_PROF_LIK_MAIN, st);
-        k_lik_simt<<<grid, 256, smem, st>>>(a, S, loss_out);
+        SCDEF_LAUNCH(k_lik_simt, grid, 256, smem, st, a, S, loss_out);
       }
       if ((rc = check_launch(ctx, "k_lik_simt"))) return rc;
     }
@@ -588,7 +588,7 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       size_t gx = (max_el + 31) / 32;   // a CTA per 32 elements of the largest block
       if (gx > (size_t)ctx->sm_count * 16) gx = (size_t)ctx->sm_count * 16;
       ProfScope ps(ctx, SCDEF_PROF_FINISH, st);
-      k_finish<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t, S, key);
+      SCDEF_LAUNCH(k_finish, dim3((unsigned)gx, t.n), 256, 0, st, t, S, key);
       if ((rc = check_launch(ctx, "k_finish"))) return rc;
     }
   }
@@ -621,7 +621,7 @@ int scdef_adam_local(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blo
   if (N == 0) return SCDEF_OK;
   int rc;
   if (B > 0) {
-    k_set_slots<<<(B + 255) / 256, 256, 0, st>>>(ctx->d.row_slot, indices, B, 0);
+    SCDEF_LAUNCH(k_set_slots, (B + 255) / 256, 256, 0, st, ctx->d.row_slot, indices, B, 0);
     if ((rc = check_launch(ctx, "k_set_slots"))) return rc;
   }
   for (int which = 0; which < 2; ++which) {
@@ -648,15 +648,15 @@ int scdef_adam_local(scdef_ctx* ctx, const scdef_blocks* params, const scdef_blo
     {
       ProfScope ps(ctx, which ? SCDEF_PROF_ADAM_LOCAL : SCDEF_PROF_ADAM_LOCAL_C, st);
       dim3 grid((unsigned)blocks, 2);
-      if (vec4 && small) k_adam_local<4, uint32_t><<<grid, 256, 0, st>>>(a, h);
-      else if (vec4) k_adam_local<4, unsigned long long><<<grid, 256, 0, st>>>(a, h);
-      else if (small) k_adam_local<1, uint32_t><<<grid, 256, 0, st>>>(a, h);
-      else k_adam_local<1, unsigned long long><<<grid, 256, 0, st>>>(a, h);
+      if (vec4 && small) SCDEF_LAUNCH((k_adam_local<4, uint32_t>), grid, 256, 0, st, a, h);
+      else if (vec4) SCDEF_LAUNCH((k_adam_local<4, unsigned long long>), grid, 256, 0, st, a, h);
+      else if (small) SCDEF_LAUNCH((k_adam_local<1, uint32_t>), grid, 256, 0, st, a, h);
+      else SCDEF_LAUNCH((k_adam_local<1, unsigned long long>), grid, 256, 0, st, a, h);
     }
     if ((rc = check_launch(ctx, "k_adam_local"))) return rc;
   }
   if (B > 0) {
-    k_set_slots<<<(B + 255) / 256, 256, 0, st>>>(ctx->d.row_slot, indices, B, 1);
+    SCDEF_LAUNCH(k_set_slots, (B + 255) / 256, 256, 0, st, ctx->d.row_slot, indices, B, 1);
     if ((rc = check_launch(ctx, "k_set_slots(clear)"))) return rc;
   }
   return SCDEF_OK;
@@ -727,15 +727,15 @@ int scdef_adam_local_lazy(scdef_ctx* ctx, int phase, const scdef_blocks* params,
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     ProfScope ps(ctx, SCDEF_PROF_ADAM_LOCAL, st);
-    if (phase == SCDEF_LAZY_UPDATE) k_adam_lazy_update<<<dim3((unsigned)blocks, 2, 2), 256, 0, st>>>(pr, h);
-    else k_adam_lazy_catchup<<<dim3((unsigned)blocks, 2, 2), 256, 0, st>>>(pr, h);
+    if (phase == SCDEF_LAZY_UPDATE) SCDEF_LAUNCH(k_adam_lazy_update, dim3((unsigned)blocks, 2, 2), 256, 0, st, pr, h);
+    else SCDEF_LAUNCH(k_adam_lazy_catchup, dim3((unsigned)blocks, 2, 2), 256, 0, st, pr, h);
   }
   if ((rc = check_launch(ctx, "k_adam_lazy"))) return rc;
   // the rows are now current up to `target`
   {
     const long long rows = phase == SCDEF_LAZY_CATCHUP_ALL ? N : B;
     const int target = phase == SCDEF_LAZY_CATCHUP ? (int)step - 1 : (int)step;
-    k_set_row_step<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(row_step, phase == SCDEF_LAZY_CATCHUP_ALL ? nullptr : indices, rows, target);
+    SCDEF_LAUNCH(k_set_row_step, (unsigned)((rows + 255) / 256), 256, 0, st, row_step, phase == SCDEF_LAZY_CATCHUP_ALL ? nullptr : indices, rows, target);
     if ((rc = check_launch(ctx, "k_set_row_step"))) return rc;
   }
   return SCDEF_OK;
@@ -774,7 +774,7 @@ int scdef_adam_global(scdef_ctx* ctx, const scdef_blocks* params, const scdef_bl
   if (gx > ctx->sm_count * 8) gx = ctx->sm_count * 8;
   {
     ProfScope ps(ctx, SCDEF_PROF_ADAM_GLOBAL, st);
-    k_adam_global<<<dim3(gx, t.n), 256, 0, st>>>(t, h);
+    SCDEF_LAUNCH(k_adam_global, dim3(gx, t.n), 256, 0, st, t, h);
   }
   return check_launch(ctx, "k_adam_global");
 }
@@ -807,15 +807,14 @@ int scdef_posterior(scdef_ctx* ctx, const scdef_blocks* params, const scdef_bloc
   if (t.n == 0) return SCDEF_OK;
   long long gx = (max_n + 255) / 256;
   if (gx > (long long)ctx->sm_count * 16) gx = (long long)ctx->sm_count * 16;
-  k_posterior<<<dim3((unsigned)gx, t.n), 256, 0, st>>>(t);
+  SCDEF_LAUNCH(k_posterior, dim3((unsigned)gx, t.n), 256, 0, st, t);
   return check_launch(ctx, "k_posterior");
 }
 
 int scdef_csr_row_stats(const int64_t* indptr, const float* data, int64_t n_rows, float* lib, float* lgam, void* cuda_stream) {
   if (!indptr || !data || n_rows < 0) return SCDEF_EINVAL;
   if (n_rows == 0) return SCDEF_OK;
-  k_csr_row_stats<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)cuda_stream>>>(
-      reinterpret_cast<const long long*>(indptr), data, n_rows, lib, lgam);
+  SCDEF_LAUNCH(k_csr_row_stats, (unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)cuda_stream, reinterpret_cast<const long long*>(indptr), data, n_rows, lib, lgam);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 
@@ -826,7 +825,7 @@ int scdef_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const f
   if (!rows) return SCDEF_EINVAL;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_rows * n_genes, st);
-  k_csr_gather_rows<<<(n_rows + 7) / 8, 256, 0, st>>>(reinterpret_cast<const long long*>(indptr), indices, data,
+  SCDEF_LAUNCH(k_csr_gather_rows, (n_rows + 7) / 8, 256, 0, st, reinterpret_cast<const long long*>(indptr), indices, data,
                                                       reinterpret_cast<const long long*>(rows), n_rows, n_genes, out);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
@@ -834,7 +833,7 @@ int scdef_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const f
 int scdef_u16_row_stats(const uint16_t* X, int64_t n_rows, int32_t n_genes, float* lib, float* lgam, void* cuda_stream) {
   if (!X || n_rows < 0 || n_genes < 1) return SCDEF_EINVAL;
   if (n_rows == 0) return SCDEF_OK;
-  k_u16_row_stats<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)cuda_stream>>>(X, n_rows, n_genes, lib, lgam);
+  SCDEF_LAUNCH(k_u16_row_stats, (unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)cuda_stream, X, n_rows, n_genes, lib, lgam);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 
@@ -847,7 +846,7 @@ int scdef_u16_gather_rows(const uint16_t* X, const int64_t* rows, int32_t n_rows
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int blocks = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
-  k_u16_gather_rows<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(X, reinterpret_cast<const long long*>(rows), n_rows, n_genes, out);
+  SCDEF_LAUNCH(k_u16_gather_rows, blocks, 256, 0, (cudaStream_t)cuda_stream, X, reinterpret_cast<const long long*>(rows), n_rows, n_genes, out);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 
@@ -860,8 +859,8 @@ int scdef_count_stats(const void* X, int32_t x_is_u16, const int32_t* batch_id, 
   cudaMemsetAsync(gene_sums, 0, sizeof(double) * (size_t)(n_batches + 1) * n_genes, st);
   if (n_rows == 0) return SCDEF_OK;
   const unsigned blocks = (unsigned)((n_rows + 31) / 32);
-  if (x_is_u16) k_count_stats<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)X, batch_id, n_rows, n_genes, n_batches, batch_stats, gene_sums, lib);
-  else k_count_stats<float><<<blocks, 256, 0, st>>>((const float*)X, batch_id, n_rows, n_genes, n_batches, batch_stats, gene_sums, lib);
+  if (x_is_u16) SCDEF_LAUNCH((k_count_stats<uint16_t>), blocks, 256, 0, st, (const uint16_t*)X, batch_id, n_rows, n_genes, n_batches, batch_stats, gene_sums, lib);
+  else SCDEF_LAUNCH((k_count_stats<float>), blocks, 256, 0, st, (const float*)X, batch_id, n_rows, n_genes, n_batches, batch_stats, gene_sums, lib);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 
@@ -879,7 +878,7 @@ int scdef_assignment_counts(scdef_ctx* ctx, const scdef_blocks* params, int64_t*
   for (int l = 0; l < ctx->L; ++l) { a.K[l] = ctx->K[l]; a.off[l] = ctx->off[l]; }
   long long blocks = (N + 7) / 8;
   if (blocks > (long long)ctx->sm_count * 8) blocks = (long long)ctx->sm_count * 8;
-  k_assignment_counts<<<(unsigned)blocks, 256, sizeof(unsigned int) * ctx->Kt, st>>>(a, reinterpret_cast<unsigned long long*>(counts));
+  SCDEF_LAUNCH(k_assignment_counts, (unsigned)blocks, 256, sizeof(unsigned int) * ctx->Kt, st, a, reinterpret_cast<unsigned long long*>(counts));
   return check_launch(ctx, "k_assignment_counts");
 }
 
@@ -901,7 +900,7 @@ int scdef_row_stats(const float* X, int64_t n_rows, int32_t n_genes, float* lib,
   if (!X || n_rows < 0 || n_genes < 1) return SCDEF_EINVAL;
   if (n_rows == 0) return SCDEF_OK;
   long long blocks = (n_rows + 7) / 8;
-  k_row_stats<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(X, n_rows, n_genes, lib, lgam);
+  SCDEF_LAUNCH(k_row_stats, (unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream, X, n_rows, n_genes, lib, lgam);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 
@@ -930,13 +929,13 @@ int scdef_assign_confident(const float* mu, const float* rho, int64_t n_rows, in
   const int quads = (n_cols + 3) / 4;
   if (quads <= 32) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_assign_confident<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_assign_confident<1><<<(unsigned)blocks, 256, smem, st>>>(a);
+    SCDEF_LAUNCH((k_assign_confident<1>), (unsigned)blocks, 256, smem, st, a);
   } else if (quads <= 64) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_assign_confident<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_assign_confident<2><<<(unsigned)blocks, 256, smem, st>>>(a);
+    SCDEF_LAUNCH((k_assign_confident<2>), (unsigned)blocks, 256, smem, st, a);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_assign_confident<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_assign_confident<8><<<(unsigned)blocks, 256, smem, st>>>(a);
+    SCDEF_LAUNCH((k_assign_confident<8>), (unsigned)blocks, 256, smem, st, a);
   }
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
@@ -965,7 +964,7 @@ int scdef_signature_scores(const float* w_mu, const float* w_rho, int32_t n_gene
   chunks = (n_draws + a.draws_per_cta - 1) / a.draws_per_cta;
   const size_t smem = (size_t)(SIG_MAX_R * SIG_TG + SIG_FC * (SIG_MAX_R + 1) + SIG_FC * (SIG_TG + 1)) * sizeof(float);
   cudaFuncSetAttribute(k_signature_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_signature_scores<<<dim3(tiles, chunks), 256, smem, (cudaStream_t)cuda_stream>>>(a);
+  SCDEF_LAUNCH(k_signature_scores, dim3(tiles, chunks), 256, smem, (cudaStream_t)cuda_stream, a);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 
@@ -985,7 +984,7 @@ int scdef_init_gamma_block(float* mu, float* rho, int64_t n_rows, int32_t n_cols
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long blocks = (n_rows * n_cols + 255) / 256;
   if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
-  k_init_gamma_block<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(a);
+  SCDEF_LAUNCH(k_init_gamma_block, (unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream, a);
   return cudaGetLastError() == cudaSuccess ? SCDEF_OK : SCDEF_ECUDA;
 }
 
@@ -1019,7 +1018,7 @@ int scdef_noise_fill(scdef_ctx* ctx, const scdef_noise* noise, int block_kind, i
   long long total = (long long)S * rows * cols;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
-  k_noise_fill<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(out, S, rows * cols, make_key(noise),
+  SCDEF_LAUNCH(k_noise_fill, (unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream, out, S, rows * cols, make_key(noise),
                                                                           make_tag(noise, blk, tag_rows, cols), e0);
   return check_launch(ctx, "k_noise_fill");
 }

@@ -3,10 +3,45 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/scdef_b200.h"
 
 namespace scdef {
+
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A step is ~29 short kernels in one stream; with plain stream order every boundary
+// pays "grid drained -> memory flushed -> next grid scheduled".  Every kernel here starts with `pdl_grid_wait()`
+// (griddepcontrol.wait: returns once the grids this one depends on have completed and their writes are visible) and is
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization, so its blocks are scheduled while the previous
+// grid's last blocks retire.  Nothing is read or written before the wait, so the semantics are those of stream order.
+// SCDEF_NO_PDL=1 launches without the attribute (A/B).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_grid_wait() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+inline bool pdl_enabled() {
+  static const bool on = getenv("SCDEF_NO_PDL") == nullptr;
+  return on;
+}
+template <typename Kern, typename... Args>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+#define SCDEF_LAUNCH(kern, grid, block, smem, st, ...) \
+  (void)::scdef::launch_pdl(kern, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(st), __VA_ARGS__)
+
 
 constexpr float LOG_1E_10 = -23.025850929940457f;  // log(1e-10)  _scdef.py:1835,1837
 constexpr float LOG_1E6 = 13.815510557964274f;     // log(1e6)    _scdef.py:1836

@@ -13,6 +13,7 @@ namespace scdef {
 // -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sample(const BlockTable tab, int S, PhiloxKey key,
                                                 double* loss_out, float global_weight) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ double red[32];
   const BlockDesc& b = tab.b[blockIdx.y];
   const int per = b.rows * b.cols;
@@ -74,6 +75,7 @@ struct SampleGrid {
 
 __global__ void __launch_bounds__(256) k_sample_v2(const BlockTable tab, const SampleGrid sg, int S, PhiloxKey key,
                                                    double* loss_out, float global_weight) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   (void)global_weight;
   __shared__ double red[32];
   int bi = 0;
@@ -151,6 +153,7 @@ constexpr int FIN_SPLIT = 8;  // warps of a CTA that share 32 elements and split
 // element to 8 adjacent lanes: 16 B per sample plane and instruction, half of every sector unused — 30 us per launch
 // at C5 for 41 MB.)
 __global__ void __launch_bounds__(256) k_finish(const BlockTable tab, int S, PhiloxKey key) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   (void)key;
   __shared__ float part[2][FIN_SPLIT][32];
   const BlockDesc& b = tab.b[blockIdx.y];
@@ -222,6 +225,7 @@ struct SimplePriorTable {
 };
 
 __global__ void __launch_bounds__(256) k_scale_priors(const SimplePriorTable tab, int S, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ double red[32];
   const SimplePrior& p = tab.p[blockIdx.y];
   if (!p.active) return;
@@ -266,6 +270,7 @@ struct WPriorArgs {
 };
 
 __global__ void __launch_bounds__(256) k_wprior(const WPriorArgs a, int S, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ double red[32];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -363,6 +368,7 @@ struct HierArgs {
 constexpr int HIER_WARPS = 8;
 
 __global__ void __launch_bounds__(HIER_WARPS * 32) k_hier(const HierArgs a, int S, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ float sm[];
   __shared__ double red[32];
   const int Kt = a.off[a.L];
@@ -518,6 +524,7 @@ constexpr int HT = 32, HLD = 33;
 constexpr int HNW = 16, HNT = HNW * 32;   // warps / threads per CTA of k_hier_tiled (2 CTAs per SM: 32 warps)
 
 __global__ void __launch_bounds__(HNT, 2) k_hier_tiled(const HierTArgs t, int S, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ __align__(16) float sm[];
   __shared__ double red[32];
   const HierArgs& a = t.h;

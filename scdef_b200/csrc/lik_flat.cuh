@@ -133,6 +133,7 @@ constexpr uint32_t FLAT_TMEM_D2_LOCAL = 256, FLAT_TMEM_D2_GENES = 128, FLAT_TMEM
 // Z_own (half = rank) is the CTA's N-half of the rate GEMM's B (K-major); Z_0 / Z_1 are the A operands (MN-major, M = k0) of
 // the CTA's second GEMMs of the two halves.
 __global__ void __launch_bounds__(256) k_tc_zprep_g(const LikTcArgs a, uint8_t* zimg, int KP, int n_ptc) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const FlatSmem L = plan_flat_smem(KP);
   const int nchunk = KP / 8;
   const long long per_pt = 128ll * nchunk;   // (cell of the pair-tile, k0 chunk)
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(256) k_tc_zprep_g(const LikTcArgs a, uint8_t* 
 // minibatch counts -> GLOBAL-orientation image (row = gene, column = cell), same addressing as k_tc_xprep:
 // element (gene = unit*128 + q*32 + lane, cell = tile*64 + v*4 + i) at ((((tile*units + unit)*4 + q)*16 + v)*32 + lane)*4 + i
 __global__ void __launch_bounds__(256) k_tc_xprep_t(const LikTcArgs a, float* ximg, int n_ctiles, int n_units) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const long long total = (long long)n_ctiles * n_units * 4 * 16 * 32;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int lane = (int)(t % 32);               // consecutive threads = consecutive genes of one cell: coalesced reads
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(256) k_tc_xprep_t(const LikTcArgs a, float* xi
 
 // sum_{b,g} colsumX_b[g] log s^s_{b,g}  (the gene-scale part of sum x log Lambda), all samples
 __global__ void __launch_bounds__(256) k_tc_loss_gs(const LikTcArgs a, const float* colsumX, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ double red[32];
   const long long n = (long long)a.S * a.nb * a.G, per = (long long)a.nb * a.G;
   double acc = 0.0;
@@ -210,6 +213,7 @@ __global__ void __launch_bounds__(256) k_tc_loss_gs(const LikTcArgs a, const flo
 //   loss  : - scale / S * (rowsumX_j log c - c dot)
 __global__ void __launch_bounds__(256) k_tc_rank1(const LikTcArgs a, const TcScratch ws, const float* part, int slots_ld,
                                                   long long T, int P, int n_pt, int do_grad, int do_loss, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ double red[32];
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), total = (long long)a.S * a.B;
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(256) k_tc_rank1(const LikTcArgs a, const TcScr
 // W_0: entropy value and the final (mu, rho) gradients from the gene-block slots of the GLOBAL orientation
 __global__ void __launch_bounds__(256) k_tc_w0_final_flat(const LikTcArgs a, const float* part, long long T, int P, int per_rb,
                                                           double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ double red[32];
   const long long n = (long long)a.K0 * a.G;
   const float wH = a.anneal * a.global_weight, invS = 1.f / (float)a.S;
@@ -309,6 +314,7 @@ __global__ void __launch_bounds__(256) k_tc_w0_final_flat(const LikTcArgs a, con
 template <bool GENES, bool WANT_LL, bool MAT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 registers: 112 x 576 threads is refused at launch
     k_lik_flat(const LikTcArgs a, const FlatGeom gm, const TcScratch ws, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ __align__(1024) uint8_t sm[];
   const int KP = gm.KP;
   const FlatSmem L = plan_flat_smem(KP);

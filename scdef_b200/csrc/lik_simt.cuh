@@ -34,6 +34,7 @@ constexpr int LIK_MAX_NB_SMEM = 8;
 
 // grid = (gene tiles, cell tiles, S), block = 256
 __global__ void __launch_bounds__(256) k_lik_simt(const LikArgs a, int S, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ float sm[];
   __shared__ double red[32];
   __shared__ float rowE[LT];
@@ -167,6 +168,7 @@ constexpr int XLG_CHUNK = 512;
 __global__ void __launch_bounds__(256) k_x_lgamma(const float* X, const int64_t* idx_x,
                                                   const float* rowsum, const int64_t* idx_cells,
                                                   int B, int G, float scale, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ double red[32];
   const int lane = threadIdx.x & 31;
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -352,6 +352,7 @@ struct TcScratch {
 // LOCAL pass: CTA = (MC sample s, gene range, cell block).  dz0 accumulates in TMEM over the range.
 // =====================================================================================================
 __global__ void __launch_bounds__(NT, 1) k_lik_tc_local(const LikTcArgs a, const Geom gm, const TcScratch ws, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ __align__(1024) uint8_t sm[];
   const int KP = gm.KP;
   const Smem L = plan_smem(KP);
@@ -451,6 +452,7 @@ __global__ void __launch_bounds__(NT, 1) k_lik_tc_local(const LikTcArgs a, const
 // registers over the chunk; per sample dW = z0^T Q comes from the second MMA.
 // =====================================================================================================
 __global__ void __launch_bounds__(NT, 1) k_lik_tc_global(const LikTcArgs a, const Geom gm, const TcScratch ws, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ __align__(1024) uint8_t sm[];
   const int KP = gm.KP;
   const Smem L = plan_smem(KP);
@@ -620,6 +622,7 @@ __global__ void __launch_bounds__(NT, 1) k_lik_tc_global(const LikTcArgs a, cons
 
 // ---- pre-kernels of the pipelined path -----------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_tc_wprep(const LikTcArgs a, float* wmu, float* wsig) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const long long n = (long long)a.K0 * a.G;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     wmu[i] = fminf(fmaxf(a.mu_W0[i], LOG_1E_10), LOG_1E6);
@@ -627,6 +630,7 @@ __global__ void __launch_bounds__(256) k_tc_wprep(const LikTcArgs a, float* wmu,
   }
 }
 __global__ void __launch_bounds__(256) k_tc_rowprep(const LikTcArgs a, int* brow, long long* xoff) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.B) return;
   brow[j] = a.nb > 1 ? a.batch_id[a.idx[j]] : 0;
@@ -635,6 +639,7 @@ __global__ void __launch_bounds__(256) k_tc_rowprep(const LikTcArgs a, int* brow
 // the same plus the row sums of the minibatch counts, one 128-thread CTA per row (a warp per row left 32 CTAs walking
 // 20 KB rows serially: 10 us per launch; unified pair kernel)
 __global__ void __launch_bounds__(128) k_tc_rowprep_sum(const LikTcArgs a, int* brow, long long* xoff, float* rowsum) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ float red[4];
   const int j = blockIdx.x, tid = threadIdx.x;
   if (j >= a.B) return;
@@ -658,6 +663,7 @@ __global__ void __launch_bounds__(128) k_tc_rowprep_sum(const LikTcArgs a, int* 
 // minibatch counts -> image in which the epilogue's "lane = cell row, 16 B per lane" loads are contiguous:
 // element (row = unit*128 + q*32 + lane, gene = tile*64 + v*4 + i) at ((((tile*units + unit)*4 + q)*16 + v)*32 + lane)*4 + i
 __global__ void __launch_bounds__(256) k_tc_xprep(const LikTcArgs a, float* ximg, int n_tiles, int units) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const long long total = (long long)n_tiles * units * 4 * 16 * 32;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     // decode so that consecutive threads read consecutive genes of one row (coalesced reads)
@@ -676,6 +682,7 @@ __global__ void __launch_bounds__(256) k_tc_xprep(const LikTcArgs a, float* ximg
 
 // z0 samples (S,B,K0) fp32 -> per (s, 128-cell unit) image [hi plane | lo plane] in the canonical layout
 __global__ void __launch_bounds__(256) k_tc_zprep(const LikTcArgs a, uint8_t* zimg, int KP, int units) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const int nchunk = KP / 8;
   const uint32_t z_rs = (uint32_t)nchunk * 128u, z_plane = 16u * z_rs;
   const long long per_unit = (long long)UC * nchunk, total = (long long)a.S * units * per_unit;
@@ -711,6 +718,7 @@ __global__ void __launch_bounds__(256) k_tc_zprep(const LikTcArgs a, uint8_t* zi
 // Also: the per-row sums (sum_g log W, sum_g W) of the W_0 prior, and the gene-scale sample tile.
 __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScratch ws, int KP, int n_tiles, uint32_t w_plane,
                                                  uint32_t w_unit) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ float rowacc[128][2 + MAX_NB];   // per k0 row: sum log W, sum W, sum_g W s_b[g] (the rank-1 vector W s_b)
   const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const int kk = tid & 7, cgl = tid >> 3;
@@ -818,6 +826,7 @@ __global__ void __launch_bounds__(256) k_tc_wgen(const LikTcArgs a, const TcScra
 // With `loss_out` (unified pair kernel) it also adds sum_{b,g} colsumX_b[g] log s_bg, the gene-scale part of sum x log Lambda.
 __global__ void __launch_bounds__(256) k_tc_colw(const LikTcArgs a, const TcScratch ws, int KP, int n_tiles, uint32_t w_plane,
                                                  uint32_t w_unit, double* loss_out = nullptr) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ float csm[];
   __shared__ float red[8];
   float* Wt = csm;                         // [KP][65]
@@ -875,6 +884,7 @@ __global__ void __launch_bounds__(256) k_tc_colw(const LikTcArgs a, const TcScra
 // sample:  sum_j rowsumX_j log c_j - sum_{b,k} ctilde_b[k] (W s_b)[k]   (= sum_n c_n z_n . (W s_b), the sum of all rates).
 __global__ void __launch_bounds__(1024) k_tc_ctilde(const LikTcArgs a, float* ctilde, float* foldtab = nullptr, int KP = 0, int mat = 0,
                                                     const float* rowsumx = nullptr, const float* Ws = nullptr, double* loss_out = nullptr) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ float part[8][MAX_NB][128];
   __shared__ double red[32];
   const int s = blockIdx.x, k = threadIdx.x & 127, rg = threadIdx.x >> 7;
@@ -944,6 +954,7 @@ __global__ void __launch_bounds__(1024) k_tc_ctilde(const LikTcArgs a, float* ct
 
 // colsumX[b][g] = sum_{n in batch b} x_ng ;  grid = ceil(G/64), block = 1024 (gene = tid & 63, 16 row groups)
 __global__ void __launch_bounds__(1024) k_tc_colsum(const LikTcArgs a, float* colsumX) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ float part[16][MAX_NB][64];
   const int gl = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int g = blockIdx.x * 64 + gl;
@@ -974,6 +985,7 @@ __global__ void __launch_bounds__(1024) k_tc_colsum(const LikTcArgs a, float* co
 
 // G_z0[s][j][k] += scale * sum_r part[s][r][j][k]
 __global__ void __launch_bounds__(256) k_tc_dz_reduce(const LikTcArgs a, const float* part, int NG) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const long long per = (long long)a.B * a.K0, total = (long long)a.S * per;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long s = i / per, r = i - s * per;
@@ -986,6 +998,7 @@ __global__ void __launch_bounds__(256) k_tc_dz_reduce(const LikTcArgs a, const f
 // W_0 prior: value (both passes) and the brd / ard gradients (GLOBAL) from the row sums
 // U = sum_g log W, Ws = sum_g W  (`_scdef.py:2014-2028`).  one thread per (s,k)
 __global__ void __launch_bounds__(128) k_tc_w0_prior(const LikTcArgs a, const float* rowstats, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ double red[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double val = 0.0;
@@ -1019,6 +1032,7 @@ __global__ void __launch_bounds__(128) k_tc_w0_prior(const LikTcArgs a, const fl
 // prior's W gradient  t = gw (A - 1 - B W)  is accumulated here into chunk 0 of the partials k_tc_w0_final reduces.
 __global__ void __launch_bounds__(256) k_tc_w0_prior_mat(const LikTcArgs a, const TcScratch ws, int KP, int n_tiles,
                                                          uint32_t w_plane, uint32_t w_unit, double* loss_out, int fold_grad) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ double red[32];
   __shared__ float acc_t[128], acc_o[128];
   const int tile = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
@@ -1068,6 +1082,7 @@ __global__ void __launch_bounds__(256) k_tc_w0_prior_mat(const LikTcArgs a, cons
 // W_0: entropy value (both passes) and, in the GLOBAL pass, the final (mu, rho) gradients from the
 // chunk partials.
 __global__ void __launch_bounds__(256) k_tc_w0_final(const LikTcArgs a, const float* part, int n_chunks, double* loss_out) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   __shared__ double red[32];
   const long long n = (long long)a.K0 * a.G;
   const float wH = a.anneal * a.global_weight, invS = 1.f / (float)a.S;
@@ -1289,46 +1304,46 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
     const int nblk = g_sm_count * 4;
     const long long T = (long long)fg.n_rblk * a.S * fg.n_pt;
     pair_stuck_init();
-    k_tc_rowprep_sum<<<a.B, 128, 0, st>>>(a, ws.brow, ws.xoff, ws.rowsumx);
+    SCDEF_LAUNCH(k_tc_rowprep_sum, a.B, 128, 0, st, a, ws.brow, ws.xoff, ws.rowsumx);
     if (!reuse) {
-      k_tc_wprep<<<g_sm_count * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
-      k_tc_wgen<<<dim3(n_tiles / 4, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit);
+      SCDEF_LAUNCH(k_tc_wprep, g_sm_count * 2, 256, 0, st, a, ws.wmu, ws.wsig);
+      SCDEF_LAUNCH(k_tc_wgen, dim3(n_tiles / 4, a.S), 256, 0, st, a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit);
     }
     auto launch = [&](auto kern) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total);
       if (ev0) cudaEventRecord(ev0, st);
-      kern<<<dim3(2 * fg.P), PIPE_NT, FL.total, st>>>(a, fg, ws, loss_out);
+      SCDEF_LAUNCH(kern, dim3(2 * fg.P), PIPE_NT, FL.total, st, a, fg, ws, loss_out);
       if (ev1 && ev0) cudaEventRecord(ev1, st);
     };
     const int rank1_blocks = (int)(((long long)a.S * a.B + 7) / 8);
     auto loss_terms = [&](bool gene_scale_term) {
-      if (gene_scale_term) k_tc_loss_gs<<<g_sm_count, 256, 0, st>>>(a, ws.colsumX, loss_out);
+      if (gene_scale_term) SCDEF_LAUNCH(k_tc_loss_gs, g_sm_count, 256, 0, st, a, ws.colsumX, loss_out);
       if (matrix_prior)
-        k_tc_w0_prior_mat<<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out, 0);
-      else k_tc_w0_prior<<<(a.S * a.K0 + 127) / 128, 128, 0, st>>>(a, ws.rowstats, loss_out);
+        SCDEF_LAUNCH(k_tc_w0_prior_mat, dim3(n_tiles, a.S), 256, 0, st, a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out, 0);
+      else SCDEF_LAUNCH(k_tc_w0_prior, (a.S * a.K0 + 127) / 128, 128, 0, st, a, ws.rowstats, loss_out);
     };
     if (global_pass) {
-      k_tc_zprep_g<<<nblk, 256, 0, st>>>(a, ws.zimg_g, fg.KP, fg.n_pt);
-      k_tc_xprep_t<<<nblk, 256, 0, st>>>(a, ws.ximg_t, 2 * fg.n_pt, fg.n_units);
-      k_tc_ctilde<<<a.S, 1024, 0, st>>>(a, ws.ctilde, ws.foldtab, fg.KP, matrix_prior ? 1 : 0, ws.rowsumx, ws.Ws, loss_out);
-      k_tc_colsum<<<(a.G + 63) / 64, 1024, 0, st>>>(a, ws.colsumX);
-      k_tc_colw<<<dim3(n_tiles, a.S), 256, (size_t)(fg.KP * 65 + a.nb * fg.KP) * sizeof(float), st>>>(a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out);
+      SCDEF_LAUNCH(k_tc_zprep_g, nblk, 256, 0, st, a, ws.zimg_g, fg.KP, fg.n_pt);
+      SCDEF_LAUNCH(k_tc_xprep_t, nblk, 256, 0, st, a, ws.ximg_t, 2 * fg.n_pt, fg.n_units);
+      SCDEF_LAUNCH(k_tc_ctilde, a.S, 1024, 0, st, a, ws.ctilde, ws.foldtab, fg.KP, matrix_prior ? 1 : 0, ws.rowsumx, ws.Ws, loss_out);
+      SCDEF_LAUNCH(k_tc_colsum, (a.G + 63) / 64, 1024, 0, st, a, ws.colsumX);
+      SCDEF_LAUNCH(k_tc_colw, dim3(n_tiles, a.S), 256, (size_t)(fg.KP * 65 + a.nb * fg.KP) * sizeof(float), st, a, ws, fg.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out);
       if (matrix_prior) launch(k_lik_flat<true, true, true>);
       else launch(k_lik_flat<true, true, false>);
       loss_terms(false);   // the cell-scale terms of the loss came with k_tc_ctilde, the gene-scale term with k_tc_colw
-      k_tc_w0_final_flat<<<g_sm_count * 4, 256, 0, st>>>(a, ws.part, T, fg.P, a.S * fg.n_pt, loss_out);
+      SCDEF_LAUNCH(k_tc_w0_final_flat, g_sm_count * 4, 256, 0, st, a, ws.part, T, fg.P, a.S * fg.n_pt, loss_out);
     } else {
-      k_tc_zprep<<<nblk, 256, 0, st>>>(a, ws.zimg, fg.KP, fg.n_units);
-      k_tc_xprep<<<nblk, 256, 0, st>>>(a, ws.ximg, n_tiles, fg.n_units);
+      SCDEF_LAUNCH(k_tc_zprep, nblk, 256, 0, st, a, ws.zimg, fg.KP, fg.n_units);
+      SCDEF_LAUNCH(k_tc_xprep, nblk, 256, 0, st, a, ws.ximg, n_tiles, fg.n_units);
       if (a.want_loss) launch(k_lik_flat<false, true, false>);
       else launch(k_lik_flat<false, false, false>);
-      k_tc_rank1<<<rank1_blocks, 256, 0, st>>>(a, ws, ws.part, fg.slots, T, fg.P, fg.n_pt, 1, a.want_loss ? 1 : 0, loss_out);
+      SCDEF_LAUNCH(k_tc_rank1, rank1_blocks, 256, 0, st, a, ws, ws.part, fg.slots, T, fg.P, fg.n_pt, 1, a.want_loss ? 1 : 0, loss_out);
       if (a.want_loss) {
-        k_tc_colsum<<<(a.G + 63) / 64, 1024, 0, st>>>(a, ws.colsumX);
+        SCDEF_LAUNCH(k_tc_colsum, (a.G + 63) / 64, 1024, 0, st, a, ws.colsumX);
         loss_terms(true);
         LikTcArgs v = a;
         v.gmu_W0 = nullptr;   // LOCAL pass: the entropy value only
-        k_tc_w0_final_flat<<<g_sm_count * 4, 256, 0, st>>>(v, nullptr, T, fg.P, a.S * fg.n_pt, loss_out);
+        SCDEF_LAUNCH(k_tc_w0_final_flat, g_sm_count * 4, 256, 0, st, v, nullptr, T, fg.P, a.S * fg.n_pt, loss_out);
       }
     }
     const cudaError_t e2 = cudaGetLastError();
@@ -1344,36 +1359,36 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
   // sample W_0 in the kernel; matrix-valued priors walk the tile images instead.
   const bool fold_prior_grad = matrix_prior && global_pass && !a.w0_stopped;
   if (matrix_prior) {
-    k_tc_wprep<<<g_sm_count * 2, 256, 0, st>>>(a, ws.wmu, ws.wsig);
-    k_tc_wgen<<<dim3(n_tiles / 4, a.S), 256, 0, st>>>(a, ws, g.KP, n_tiles, PL.w_plane, PL.w_unit);
+    SCDEF_LAUNCH(k_tc_wprep, g_sm_count * 2, 256, 0, st, a, ws.wmu, ws.wsig);
+    SCDEF_LAUNCH(k_tc_wgen, dim3(n_tiles / 4, a.S), 256, 0, st, a, ws, g.KP, n_tiles, PL.w_plane, PL.w_unit);
     if (fold_prior_grad) cudaMemsetAsync(ws.part, 0, (size_t)g.n_chunks * 2 * a.K0 * a.G * 4, st);
   }
   if (global_pass) {
     if (a.lik_on) {
-      k_tc_ctilde<<<a.S, 1024, 0, st>>>(a, ws.ctilde);
-      k_tc_colsum<<<(a.G + 63) / 64, 1024, 0, st>>>(a, ws.colsumX);
+      SCDEF_LAUNCH(k_tc_ctilde, a.S, 1024, 0, st, a, ws.ctilde, (float*)nullptr, 0, 0, (const float*)nullptr, (const float*)nullptr, (double*)nullptr);
+      SCDEF_LAUNCH(k_tc_colsum, (a.G + 63) / 64, 1024, 0, st, a, ws.colsumX);
     }
     if (!matrix_prior) {
       cudaFuncSetAttribute(k_lik_tc_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
       if (ev0 && a.lik_on) cudaEventRecord(ev0, st);
-      k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(a, g, ws, loss_out);
+      SCDEF_LAUNCH(k_lik_tc_global, g.n_tiles * g.n_chunks, NT, L.total, st, a, g, ws, loss_out);
       if (ev1 && ev0 && a.lik_on) cudaEventRecord(ev1, st);
     }
   } else {
     if (a.lik_on) {
       cudaFuncSetAttribute(k_lik_tc_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
       if (ev0) cudaEventRecord(ev0, st);
-      k_lik_tc_local<<<dim3(a.S * g.NG, g.n_cblocks), NT, L.total, st>>>(a, g, ws, loss_out);
+      SCDEF_LAUNCH(k_lik_tc_local, dim3(a.S * g.NG, g.n_cblocks), NT, L.total, st, a, g, ws, loss_out);
       if (ev1 && ev0) cudaEventRecord(ev1, st);
       const long long total = (long long)a.S * a.B * a.K0;
       const int blocks = (int)((total + 255) / 256 < g_sm_count * 8 ? (total + 255) / 256 : g_sm_count * 8);
-      k_tc_dz_reduce<<<blocks, 256, 0, st>>>(a, ws.part, g.NG);
+      SCDEF_LAUNCH(k_tc_dz_reduce, blocks, 256, 0, st, a, ws.part, g.NG);
     } else if (!matrix_prior) {
       // value only: the GLOBAL kernel without likelihood produces the W_0 row sums
       LikTcArgs v = a;
       v.w0_stopped = 1;
       cudaFuncSetAttribute(k_lik_tc_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-      k_lik_tc_global<<<g.n_tiles * g.n_chunks, NT, L.total, st>>>(v, g, ws, loss_out);
+      SCDEF_LAUNCH(k_lik_tc_global, g.n_tiles * g.n_chunks, NT, L.total, st, v, g, ws, loss_out);
     }
   }
   // LOCAL pass with the loss discarded: the W_0 prior and entropy VALUES are all the kernels below would produce
@@ -1386,9 +1401,9 @@ int lik_tc_launch(const LikTcArgs& a_in, double* loss_out, int sm_count, cudaStr
     return SCDEF_OK;
   }
   if (matrix_prior)
-    k_tc_w0_prior_mat<<<dim3(n_tiles, a.S), 256, 0, st>>>(a, ws, g.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out, fold_prior_grad ? 1 : 0);
-  else k_tc_w0_prior<<<(a.S * a.K0 + 127) / 128, 128, 0, st>>>(a, ws.rowstats, loss_out);
-  k_tc_w0_final<<<g_sm_count * 4, 256, 0, st>>>(a, ws.part, g.n_chunks, loss_out);
+    SCDEF_LAUNCH(k_tc_w0_prior_mat, dim3(n_tiles, a.S), 256, 0, st, a, ws, g.KP, n_tiles, PL.w_plane, PL.w_unit, loss_out, fold_prior_grad ? 1 : 0);
+  else SCDEF_LAUNCH(k_tc_w0_prior, (a.S * a.K0 + 127) / 128, 128, 0, st, a, ws.rowstats, loss_out);
+  SCDEF_LAUNCH(k_tc_w0_final, g_sm_count * 4, 256, 0, st, a, ws.part, g.n_chunks, loss_out);
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     fprintf(stderr, "scdef_b200: lik_tc_launch: %s (smem %u)\n", cudaGetErrorString(err), L.total);

@@ -47,6 +47,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // MAXQ: quads (4 consecutive kept factors) per lane; lane owns quads lane, lane + 32, ...
 template <int MAXQ>
 __global__ void __launch_bounds__(256) k_assign_confident(const ConfidentArgs a) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ float gaps_all[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float* gaps = gaps_all + (size_t)wib * a.S;
@@ -253,6 +254,7 @@ __host__ __device__ inline float philox_gamma(float a, PhiloxKey key, NoiseTag t
 }
 
 __global__ void __launch_bounds__(256) k_init_gamma_block(const InitGammaArgs a) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   const long long total = a.N * a.K;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long n = e / a.K;
@@ -296,6 +298,7 @@ struct SigArgs {
 constexpr int SIG_TG = 64, SIG_FC = 32, SIG_MAX_R = 128, SIG_MAX_F = 256;
 
 __global__ void __launch_bounds__(256) k_signature_scores(const SigArgs a) {
+  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ __align__(16) float sig_sm[];
   float* Wt = sig_sm;                                // [R][SIG_TG]
   float* Pt = Wt + SIG_MAX_R * SIG_TG;               // [SIG_FC][R + 1]
