@@ -23,6 +23,11 @@ __device__ __forceinline__ void pdl_grid_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
 }
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 inline bool pdl_enabled() {
   static const bool on = getenv("SCDEF_NO_PDL") == nullptr;
   return on;

@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(256) k_tc_w0_final_flat(const LikTcArgs a, con
 template <bool GENES, bool WANT_LL, bool MAT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 registers: 112 x 576 threads is refused at launch
     k_lik_flat(const LikTcArgs a, const FlatGeom gm, const TcScratch ws, double* loss_out) {
-  pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ __align__(1024) uint8_t sm[];
   const int KP = gm.KP;
   const FlatSmem L = plan_flat_smem(KP);
@@ -371,6 +370,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PIPE_NT, 1)   // 96 
   tc_fence_after();
   const uint32_t tmem = mi->tmem_base;
   const PipeSmem IL = plan_pipe_smem(KP);   // layout of one W_0 tile image in global memory (k_tc_wgen)
+  // Everything above touched shared and tensor memory only: with programmatic dependent launch it ran while the previous
+  // kernel's last blocks were retiring.  The operands in global memory are complete from here on.
+  pdl_grid_wait();
+  // All CTAs of this persistent grid are resident from the start, so the next kernel's blocks cannot take a slot this
+  // grid still needs: let them be scheduled now (they block in their own griddepcontrol.wait until this grid is done).
+  pdl_launch_dependents();
   auto first_in_seg = [&](int oi, const FlatPos& c) { return c.pt == 0 || oi == 0; };
   auto last_in_seg = [&](int oi, const FlatPos& c) { return c.pt == n_pt - 1 || oi == n_outer - 1; };
 
