@@ -61,11 +61,11 @@ __global__ void __launch_bounds__(256) k_sample(const BlockTable tab, int S, Phi
 }
 
 // -----------------------------------------------------------------------------------------
-// k_sample, second version (opt-in: SCDEF_SAMPLE_V2=1 or scdef_debug_set_sample_impl(2); same draws, same arithmetic,
-// bit-identical samples; NOT YET RUN ON A DEVICE).  k_sample launches ceil(max_elems/4/256) CTAs for EVERY block of the
-// table, so at C5 eleven of the thirteen block rows are thousands of CTAs without work, and every (sample, quad) thread
-// redoes the gather, two integer divisions and an expf(rho) per element.  Here the grid is one dimension sized per
-// block (`SampleGrid.cta0`), a thread owns one quad (4 consecutive elements) for a CHUNK of the S samples and keeps
+// k_sample, second version (the default; SCDEF_SAMPLE_V2=0 selects the first; same draws, same arithmetic, bit-identical
+// samples: `tests/test_variants_gpu.py`).  k_sample launches ceil(max_elems/4/256) CTAs for EVERY block of the table, so
+// at C5 eleven of the thirteen block rows are thousands of CTAs without work, and every (sample, quad) thread redoes the
+// gather, two integer divisions and an expf(rho) per element.  Here the grid is one dimension sized per block
+// (`SampleGrid.cta0`), a thread owns one quad (4 consecutive elements) for a CHUNK of the S samples and keeps
 // (clip(mu), sigma) of its elements in registers.
 // -----------------------------------------------------------------------------------------
 struct SampleGrid {

@@ -1,7 +1,7 @@
 """Device cold start of the z layers (`scdef_init_gamma_block`).  The reference draws its Gamma variates
 with JAX keys, so parity is distributional: the CPU tests draw from the SAME sampler code on the host
 (`scdef_debug_gamma_host`, no CUDA call) and test it against scipy's Gamma distribution and the NumPy path of
-`init_var_params`; the GPU test (pending its first run) checks that the kernel writes what that code draws."""
+`init_var_params`; the GPU test checks that the kernel writes what that code draws."""
 import ctypes
 
 import numpy as np
