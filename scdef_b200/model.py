@@ -773,10 +773,14 @@ class scDEF:
         if (shard.world > 1 and self.epoch_reshard and num_batches > 1 and self.x_placement != "csr"  # CSR rows: static
                 and _dist.epoch_layout(np.arange(n_total), global_batch, counts) is not None):
             migrator = _dist.RowMigrator(shard, counts)
+        # Host placement: a GPU step shorter than the host needs to gather and launch it is fed by two staging threads
+        # (measured at C5 on a B200: S=10, 0.45 ms per step: 0.90 -> 0.62 ms end to end; S=100, 1.35 ms per step: a second
+        # thread only takes the GIL from the launching thread, 1.37 -> 1.43).  Likelihood work per step ~ S B G K0.
+        light_step = float(num_samples) * batch_size * self.n_genes * self.layer_sizes[0] < 4e9
         stream = MinibatchStream(n_total, global_batch, shard, eng.device,
                                  host_X=self.X if self.x_placement == "host" else None,
                                  n_local=self.n_cells, start=start, migrator=migrator,
-                                 tensors_fn=eng.per_cell_tensors)
+                                 tensors_fn=eng.per_cell_tensors, stage=(2, 5, 3) if light_step else (1, 3, 2))
         self._last_stream = stream
         annealing_parameter = float(annealing)
         alpha_f = float(self.alpha)

@@ -20,6 +20,7 @@ from __future__ import annotations
 import time
 
 import os
+from typing import Optional
 
 import numpy as np
 import torch
@@ -29,7 +30,10 @@ from . import dist as _dist
 
 class MinibatchStream:
     def __init__(self, n_total: int, global_batch: int, shard: _dist.ShardInfo, device,
-                 host_X=None, n_local=None, start=None, pinned_slots: int = 3, migrator=None, tensors_fn=None):
+                 host_X=None, n_local=None, start=None, pinned_slots: Optional[int] = None, migrator=None, tensors_fn=None,
+                 stage=(1, 3, 2)):
+        """stage = (staging threads, pinned / device slots, minibatches staged ahead) of the host placement; the
+        environment variables SCDEF_STAGE_WORKERS / _SLOTS / _DEPTH override it."""
         self.n_total, self.gb, self.shard, self.device = int(n_total), int(global_batch), shard, torch.device(device)
         self.rng = np.random.RandomState(0)
         num_complete, leftover = divmod(self.n_total, self.gb)
@@ -53,6 +57,10 @@ class MinibatchStream:
         # gather threads of the host placement: a few per rank, never more than the host has cores for all ranks
         cores = os.cpu_count() or 8
         self._gather_workers = int(os.environ.get("SCDEF_GATHER_THREADS", 1))   # measured: more threads halve the gather (0.42 -> 0.29 ms) but do not shorten the step
+        if pinned_slots is None:
+            pinned_slots = int(os.environ.get("SCDEF_STAGE_SLOTS", stage[1]))
+        self._stage_workers = int(os.environ.get("SCDEF_STAGE_WORKERS", stage[0]))
+        self._stage_depth = int(os.environ.get("SCDEF_STAGE_DEPTH", stage[2]))   # minibatches staged ahead of the running step
         if host_X is not None:
             G = host_X.shape[1]
             cap = min(self.gb, self.n_total)
@@ -244,7 +252,7 @@ class MinibatchStream:
         if self._pool is None:
             from concurrent.futures import ThreadPoolExecutor
 
-            self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="scdef-stage")
+            self._pool = ThreadPoolExecutor(max_workers=self._stage_workers, thread_name_prefix="scdef-stage")
         k = self._slot_i
         self._slot_i = (k + 1) % len(self._slots)
         if self.migrator is not None:
@@ -259,7 +267,7 @@ class MinibatchStream:
         overlap that step's kernels and the main thread's launches."""
         if self.host_X is None:
             return
-        for j in (it, it + 1):
+        for j in range(it, it + self._stage_depth):
             if 0 <= j < self.num_batches and j not in self._staged and len(self._staged) < len(self._slots) - 1:
                 self._stage(j)
 
