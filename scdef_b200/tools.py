@@ -276,7 +276,7 @@ def _sig_call(lib, w_mu, w_rho, rows, eps, path, mode, tau=None, counts=None, re
         raise ScdefToolsError(f"scdef_signature_scores failed ({rc}): rows={R}, factors={F}, genes={G}, draws={S}, mode={mode}")
 
 
-def _jaccard_from_ranks(sig_idx, combined, rank_count, ref_idx):
+def _jaccard_from_ranks(sig_idx, combined, rank_count):
     """Mean weighted Jaccard (factor.py:41-70, 338-362) from the ranks of the signature genes in every draw: gene i is in
     the draw's top-k list iff fewer than k genes score above it; the list has exactly k genes, so the genes it holds
     that are not in the signature number k - |intersection|."""
@@ -312,7 +312,7 @@ def _ranks_of_signatures(lib, w_mu, w_rho, rows, eps, path, sig_idx):
     rank = torch.zeros((S, F, kmax), dtype=torch.int32, device=w_mu.device)
     _sig_call(lib, w_mu, w_rho, rows, eps, path, 1, ref_idx=ref_d, ref_score=ref_score)
     _sig_call(lib, w_mu, w_rho, rows, eps, path, 2, ref_idx=ref_d, ref_score=ref_score, rank_count=rank)
-    return rank, ref_d
+    return rank
 
 
 def set_confident_signatures(model, confidence_threshold: float = 0.9, tau_quantile: float = 0.99,
@@ -385,8 +385,8 @@ def set_confident_signatures(model, confidence_threshold: float = 0.9, tau_quant
             for f in range(len(fl[l])):
                 idx = sig_all[offs[li] + f]
                 comb_all.append(_confidence_mean_score(conf_u[offs[li] + f][idx], means_u[li][f][idx]))
-        rank, _ = _ranks_of_signatures(lib, w0_mu, w0_rho, rows, eps_w0, path_all, sig_all)
-        jac_all = _jaccard_from_ranks(sig_all, comb_all, rank, None)
+        rank = _ranks_of_signatures(lib, w0_mu, w0_rho, rows, eps_w0, path_all, sig_all)
+        jac_all = _jaccard_from_ranks(sig_all, comb_all, rank)
         for li, l in enumerate(range(1, L)):
             sl = slice(offs[li], offs[li + 1])
             upper[l] = (sig_all[sl], [conf_u[offs[li] + f][sig_all[offs[li] + f]] for f in range(len(fl[l]))],
@@ -416,8 +416,8 @@ def set_confident_signatures(model, confidence_threshold: float = 0.9, tau_quant
             if len(fl[0]) > 0:
                 rows0 = torch.as_tensor(fl[0].astype(np.int32), device=dev)
                 eps_l0 = randn(("l0",), (S, len(fl[0]), G))                                       # every factor's own draws
-                rank, _ = _ranks_of_signatures(lib, w0_mu, w0_rho, rows0, eps_l0, None, sig)
-                jac = _jaccard_from_ranks(sig, comb, rank, None)
+                rank = _ranks_of_signatures(lib, w0_mu, w0_rho, rows0, eps_l0, None, sig)
+                jac = _jaccard_from_ranks(sig, comb, rank)
             else:
                 jac = []
         elif l in upper:
