@@ -21,6 +21,12 @@ namespace scdef {
 __device__ __forceinline__ void pdl_grid_wait() {
 #if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef SCDEF_PDL_EARLY
+  // A/B switch: release the dependents as soon as every block of this grid has STARTED (the trigger fires when all blocks
+  // have called it, so no block of this grid is still waiting for a slot the dependents could take).  Measured at C5:
+  // 1.357 ms per step against 1.348 without — the waiting blocks of the next kernels only take room; off by default.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 #endif
 }
 __device__ __forceinline__ void pdl_launch_dependents() {
