@@ -75,6 +75,9 @@ __host__ __device__ inline FlatSmem plan_flat_smem(int KP) {
 
 __device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float lg2_ftz(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// Per-element arithmetic of the epilogue, per orientation (measured on a B200 at C5, ms per launch):
+//   0 = clamp R at 1e-35 and multiply (no select), 1 = select on x > 0 with the raw rcp.approx.ftz, 2 = select with __fdividef.
+//   LOCAL:  0 -> 0.282, 1 -> 0.237, 2 -> 0.243        GLOBAL (also x log2 R): 0 -> 0.375, 1 -> 0.376, 2 -> 0.386
 #ifndef SCDEF_MATH_LOCAL
 #define SCDEF_MATH_LOCAL 1
 #endif
