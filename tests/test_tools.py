@@ -191,3 +191,41 @@ def test_kernel_algorithm_emulated_lane_by_lane_matches_the_oracle(N, K, S, leve
         assert got["argmax"] == want["argmax"][n]
         for name in tools.STAT_NAMES:
             assert got[name] == pytest.approx(float(want[name][n]), abs=2e-5), (name, n)
+
+
+# ---- set_confident_signatures: the host-side algebra around `scdef_signature_scores` (no device needed) --------------
+def test_rank_counts_reproduce_the_top_k_jaccard_of_the_oracle():
+    """The device reports, per draw and signature gene, how many genes score above it; `_jaccard_from_ranks` turns that
+    into the weighted Jaccard of the draw's top-k list (factor.py:41-70, 338-362).  Checked here with NumPy rank counts
+    against the oracle's argsort-based restatement (itself pinned to the executed reference)."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    S, F, G = 12, 5, 90
+    scores = rng.lognormal(size=(S, F, G))
+    sig = [np.sort(rng.choice(G, size=k, replace=False))[::-1].copy() for k in (7, 1, 0, 20, 3)]
+    comb = [rng.uniform(0.1, 2.0, size=len(s)) for s in sig]
+    comb[3][:] = 0.0                                      # all-zero weights fall back to uniform (factor.py:57-58)
+    kmax = max(len(s) for s in sig)
+    rank = np.zeros((S, F, kmax), dtype=np.int32)
+    for s in range(S):
+        for f, ref in enumerate(sig):
+            for i, g in enumerate(ref):
+                rank[s, f, i] = int(np.sum(scores[s, f] > scores[s, f, g]))
+    got = tools._jaccard_from_ranks(sig, comb, torch.as_tensor(rank))
+    want = tools_ref.jaccard_from_scores(sig, comb, lambda f: scores[:, f, :])
+    assert np.isnan(got[2]) and np.isnan(want[2])
+    for f in (0, 1, 3, 4):
+        assert abs(got[f] - want[f]) < 1e-12, f
+
+
+def test_signature_helpers_match_the_oracle_restatement():
+    rng = np.random.default_rng(4)
+    mu, conf = rng.lognormal(size=60), rng.uniform(0, 1, size=60)
+    for min_effect in (None, 1.0):
+        assert np.array_equal(tools._rank_signature(mu, conf, 0.4, min_effect), tools_ref.rank_signature(mu, conf, 0.4, min_effect))
+    assert np.allclose(tools._confidence_mean_score(conf, mu), tools_ref.confidence_mean_score(conf, mu), rtol=0, atol=0)
+    with pytest.raises(ValueError):
+        tools.set_confident_signatures(object(), confidence_threshold=1.5)
+    with pytest.raises(ValueError):
+        tools.set_confident_signatures(object(), mc_samples=0)
