@@ -474,9 +474,15 @@ int scdef_elbo_grad(scdef_ctx* ctx, const scdef_call* call, const scdef_blocks* 
       if (tpc > n_t32) tpc = n_t32;
       ht.h = h;
       ht.tiles_per_cta = tpc;
-      if (smem_t > 48 * 1024) cudaFuncSetAttribute(k_hier_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+      static const bool hier_mma = getenv("SCDEF_HIER_MMA") != nullptr;   // tensor-core form of the three small products (opt-in)
       ProfScope ps(ctx, SCDEF_PROF_HIER, st);
-      SCDEF_LAUNCH(k_hier_tiled, dim3((n_t32 + tpc - 1) / tpc, S), HNT, smem_t, st, ht, S, loss_out);
+      if (hier_mma) {
+        if (smem_t > 48 * 1024) cudaFuncSetAttribute(k_hier_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+        SCDEF_LAUNCH((k_hier_tiled<true>), dim3((n_t32 + tpc - 1) / tpc, S), HNT, smem_t, st, ht, S, loss_out);
+      } else {
+        if (smem_t > 48 * 1024) cudaFuncSetAttribute(k_hier_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+        SCDEF_LAUNCH((k_hier_tiled<false>), dim3((n_t32 + tpc - 1) / tpc, S), HNT, smem_t, st, ht, S, loss_out);
+      }
     } else {
     // enough CTAs to fill the GPU, at least one round of 8 cells each
     int chunks = (ctx->sm_count * 2 + S - 1) / S;

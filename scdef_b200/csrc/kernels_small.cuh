@@ -523,6 +523,40 @@ struct HierTArgs {
 constexpr int HT = 32, HLD = 33;
 constexpr int HNW = 16, HNT = HNW * 32;   // warps / threads per CTA of k_hier_tiled (2 CTAs per SM: 32 warps)
 
+// ---- warp-level tensor-core form of the three small products (template parameter MMA of k_hier_tiled) ----------------
+// mma.sync.m16n8k8 tf32 with both operands split on the fly into tf32 hi + tf32 lo (three products lo*hi + hi*lo + hi*hi:
+// ~2^-21 relative, fp32 accumulate), on the SAME shared-memory tiles as the CUDA-core loops.  g = lane >> 2, t = lane & 3:
+//   A (16 x 8, row): a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4]
+//   B ( 8 x 8, col): b0 = B[t][g], b1 = B[t+4][g]
+//   C (16 x 8)     : c0 = C[g][2t], c1 = C[g][2t+1], c2 = C[g+8][2t], c3 = C[g+8][2t+1]
+// (`tests/test_host.py::test_hier_mma_fragment_maps` replays these index maps in NumPy against a plain product.)
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// C[16 x 8] += A B for one k-step; af / bf return element (row, col) of A / (k, n) of B (0 outside the matrices)
+template <typename FA, typename FB>
+__device__ __forceinline__ void mma_step_3xtf32(float (&c)[4], int lane, FA af, FB bf) {
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t ah[4], al[4], bh[2], bl[2];
+  tf32_split(af(g, t), ah[0], al[0]);
+  tf32_split(af(g + 8, t), ah[1], al[1]);
+  tf32_split(af(g, t + 4), ah[2], al[2]);
+  tf32_split(af(g + 8, t + 4), ah[3], al[3]);
+  tf32_split(bf(t, g), bh[0], bl[0]);
+  tf32_split(bf(t + 4, g), bh[1], bl[1]);
+  mma_tf32_16x8x8(c, al, bh);
+  mma_tf32_16x8x8(c, ah, bl);
+  mma_tf32_16x8x8(c, ah, bh);
+}
+
+template <bool MMA>
 __global__ void __launch_bounds__(HNT, 2) k_hier_tiled(const HierTArgs t, int S, double* loss_out) {
   pdl_grid_wait();   // programmatic dependent launch: inputs of the previous kernel are complete from here on
   extern __shared__ __align__(16) float sm[];
@@ -589,8 +623,24 @@ __global__ void __launch_bounds__(HNT, 2) k_hier_tiled(const HierTArgs t, int S,
       if (has_parent) {
         const int Ku = a.K[l + 1], ld = t.wld[l + 1];
         const float* Wl = Wsm + t.woff[l + 1];
+        if (MMA) {
+          // m[cell][k] = sum_u z[u][cell] W[u][k]:  M = the 32 cells (2 m-tiles), N = Kl, K = Ku; a warp per (m-tile, n-tile)
+          const float* zb = zt + a.off[l + 1] * HLD;
+          const int n_nt = (Kl + 7) / 8;
+          for (int tile = warp; tile < 2 * n_nt; tile += HNW) {
+            const int m0 = (tile & 1) * 16, n0 = (tile >> 1) * 8;
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k0 = 0; k0 < Ku; k0 += 8)
+              mma_step_3xtf32(c, lane,
+                              [&](int r, int kk) { return k0 + kk < Ku ? zb[(k0 + kk) * HLD + m0 + r] : 0.f; },
+                              [&](int kk, int n) { return (k0 + kk < Ku && n0 + n < Kl) ? Wl[(k0 + kk) * ld + n0 + n] : 0.f; });
+            const int g = lane >> 2, tq = lane & 3;
+            if (n0 + 2 * tq < Kl) { Pm[(n0 + 2 * tq) * HLD + m0 + g] = c[0]; Pm[(n0 + 2 * tq) * HLD + m0 + g + 8] = c[2]; }
+            if (n0 + 2 * tq + 1 < Kl) { Pm[(n0 + 2 * tq + 1) * HLD + m0 + g] = c[1]; Pm[(n0 + 2 * tq + 1) * HLD + m0 + g + 8] = c[3]; }
+          }
+        }
         const float* zu = zt + a.off[l + 1] * HLD + lane;
-        for (int k0 = warp * 4; k0 < Kl; k0 += 4 * HNW) {
+        for (int k0 = warp * 4; !MMA && k0 < Kl; k0 += 4 * HNW) {
           float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll 4
           for (int u = 0; u < Ku; ++u) {
@@ -634,7 +684,22 @@ __global__ void __launch_bounds__(HNT, 2) k_hier_tiled(const HierTArgs t, int S,
           // gz_{l+1}[u][cell] += sum_k P_l[k][cell] W_{l+1}[u][k]
           float* gz_par = ((l + 1) & 1) ? gzA : gzB;
           const float* Wl = Wsm + t.woff[l + 1];
-          for (int u0 = warp * 4; u0 < Ku; u0 += 4 * HNW) {
+          if (MMA) {
+            // gz[u][cell] += sum_k P[k][cell] W[u][k]:  M = cells, N = Ku, K = Kl
+            const int n_nt = (Ku + 7) / 8;
+            for (int tile = warp; tile < 2 * n_nt; tile += HNW) {
+              const int m0 = (tile & 1) * 16, n0 = (tile >> 1) * 8;
+              float c[4] = {0.f, 0.f, 0.f, 0.f};
+              for (int k0 = 0; k0 < Kl; k0 += 8)
+                mma_step_3xtf32(c, lane,
+                                [&](int r, int kk) { return k0 + kk < Kl ? Pm[(k0 + kk) * HLD + m0 + r] : 0.f; },
+                                [&](int kk, int n) { return (k0 + kk < Kl && n0 + n < Ku) ? Wl[(n0 + n) * ld + k0 + kk] : 0.f; });
+              const int g = lane >> 2, tq = lane & 3;
+              if (n0 + 2 * tq < Ku) { gz_par[(n0 + 2 * tq) * HLD + m0 + g] += c[0]; gz_par[(n0 + 2 * tq) * HLD + m0 + g + 8] += c[2]; }
+              if (n0 + 2 * tq + 1 < Ku) { gz_par[(n0 + 2 * tq + 1) * HLD + m0 + g] += c[1]; gz_par[(n0 + 2 * tq + 1) * HLD + m0 + g + 8] += c[3]; }
+            }
+          }
+          for (int u0 = warp * 4; !MMA && u0 < Ku; u0 += 4 * HNW) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int k0 = 0; k0 < Kl; k0 += 4) {
               float p[4];
@@ -656,7 +721,26 @@ __global__ void __launch_bounds__(HNT, 2) k_hier_tiled(const HierTArgs t, int S,
           // GW_{l+1}[u][k] += sum_cell z_{l+1}[u][cell] P_l[k][cell]   (lanes on k)
           float* GWl = GWsm + t.woff[l + 1];
           const float* zu = zt + a.off[l + 1] * HLD;
-          for (int u0 = warp * 4; u0 < Ku; u0 += 4 * HNW) {
+          if (MMA) {
+            // GW[u][k] += sum_cell z[u][cell] P[k][cell]:  M = Ku (m-tiles of 16), N = Kl, K = the 32 cells
+            const int n_mt = (Ku + 15) / 16, n_nt = (Kl + 7) / 8;
+            for (int tile = warp; tile < n_mt * n_nt; tile += HNW) {
+              const int m0 = (tile % n_mt) * 16, n0 = (tile / n_mt) * 8;
+              float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int k0 = 0; k0 < HT; k0 += 8)
+                mma_step_3xtf32(c, lane,
+                                [&](int r, int kk) { return m0 + r < Ku ? zu[(m0 + r) * HLD + k0 + kk] : 0.f; },
+                                [&](int kk, int n) { return n0 + n < Kl ? Pm[(n0 + n) * HLD + k0 + kk] : 0.f; });
+              const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int u = m0 + g + (i >> 1) * 8, k = n0 + 2 * tq + (i & 1);
+                if (u < Ku && k < Kl) GWl[u * ld + k] += c[i];
+              }
+            }
+          }
+          for (int u0 = warp * 4; !MMA && u0 < Ku; u0 += 4 * HNW) {
             float acc[4][4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)

@@ -346,3 +346,79 @@ def test_persistent_pair_kernel_work_decomposition():
 
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_flat_plan_check.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "flat plan ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_hier_mma_fragment_maps():
+    """NumPy replay of the tensor-core form of the hierarchy kernel's three small products (`k_hier_tiled<true>`,
+    kernels_small.cuh): per-lane fragment index maps of mma.sync.m16n8k8 (A row-major, B column-major), the tile loops, the
+    zero padding and the stores, on the kernel's shared-memory layouts ([k][cell] with stride 33; W_l [u][ld])."""
+    HLD, HT, HNW = 33, 32, 16
+    rng = np.random.default_rng(0)
+
+    def mma_step(c, af, bf):          # c: (32 lanes, 4); one k-step of C[16 x 8] += A[16 x 8] B[8 x 8]
+        A, Bm = np.zeros((16, 8)), np.zeros((8, 8))
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            A[g, t], A[g + 8, t], A[g, t + 4], A[g + 8, t + 4] = af(g, t), af(g + 8, t), af(g, t + 4), af(g + 8, t + 4)
+            Bm[t, g], Bm[t + 4, g] = bf(t, g), bf(t + 4, g)
+        D = A @ Bm
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            c[lane] += [D[g, 2 * t], D[g, 2 * t + 1], D[g + 8, 2 * t], D[g + 8, 2 * t + 1]]
+
+    for Ku, Kl in ((60, 100), (30, 60), (10, 30), (1, 10)):
+        ld = (Kl + 3) // 4 * 4
+        z = rng.normal(size=(Ku, HLD)); P = rng.normal(size=(Kl, HLD)); W = np.zeros((Ku, ld)); W[:, :Kl] = rng.normal(size=(Ku, Kl))
+        z[:, HT:] = np.nan; P[:, HT:] = np.nan                        # the padding column must never be read
+        # forward: m[k][cell] = sum_u z[u][cell] W[u][k]
+        Pm = np.full((Kl, HLD), np.nan)
+        n_nt = (Kl + 7) // 8
+        for warp in range(HNW):
+            for tile in range(warp, 2 * n_nt, HNW):
+                m0, n0 = (tile & 1) * 16, (tile >> 1) * 8
+                c = np.zeros((32, 4))
+                for k0 in range(0, Ku, 8):
+                    mma_step(c, lambda r, kk: z[k0 + kk, m0 + r] if k0 + kk < Ku else 0.0,
+                             lambda kk, n: W[k0 + kk, n0 + n] if (k0 + kk < Ku and n0 + n < Kl) else 0.0)
+                for lane in range(32):
+                    g, t = lane >> 2, lane & 3
+                    if n0 + 2 * t < Kl:
+                        Pm[n0 + 2 * t, m0 + g], Pm[n0 + 2 * t, m0 + g + 8] = c[lane, 0], c[lane, 2]
+                    if n0 + 2 * t + 1 < Kl:
+                        Pm[n0 + 2 * t + 1, m0 + g], Pm[n0 + 2 * t + 1, m0 + g + 8] = c[lane, 1], c[lane, 3]
+        assert np.allclose(Pm[:, :HT], (z[:, :HT].T @ W[:, :Kl]).T)
+        # backward, LOCAL: gz[u][cell] += sum_k P[k][cell] W[u][k]
+        gz = np.zeros((Ku, HLD))
+        n_nt = (Ku + 7) // 8
+        for warp in range(HNW):
+            for tile in range(warp, 2 * n_nt, HNW):
+                m0, n0 = (tile & 1) * 16, (tile >> 1) * 8
+                c = np.zeros((32, 4))
+                for k0 in range(0, Kl, 8):
+                    mma_step(c, lambda r, kk: P[k0 + kk, m0 + r] if k0 + kk < Kl else 0.0,
+                             lambda kk, n: W[n0 + n, k0 + kk] if (k0 + kk < Kl and n0 + n < Ku) else 0.0)
+                for lane in range(32):
+                    g, t = lane >> 2, lane & 3
+                    if n0 + 2 * t < Ku:
+                        gz[n0 + 2 * t, m0 + g] += c[lane, 0]; gz[n0 + 2 * t, m0 + g + 8] += c[lane, 2]
+                    if n0 + 2 * t + 1 < Ku:
+                        gz[n0 + 2 * t + 1, m0 + g] += c[lane, 1]; gz[n0 + 2 * t + 1, m0 + g + 8] += c[lane, 3]
+        assert np.allclose(gz[:, :HT], W[:, :Kl] @ P[:, :HT])
+        # backward, GLOBAL: GW[u][k] += sum_cell z[u][cell] P[k][cell]
+        GW = np.zeros((Ku, ld))
+        n_mt, n_nt = (Ku + 15) // 16, (Kl + 7) // 8
+        for warp in range(HNW):
+            for tile in range(warp, n_mt * n_nt, HNW):
+                m0, n0 = (tile % n_mt) * 16, (tile // n_mt) * 8
+                c = np.zeros((32, 4))
+                for k0 in range(0, HT, 8):
+                    mma_step(c, lambda r, kk: z[m0 + r, k0 + kk] if m0 + r < Ku else 0.0,
+                             lambda kk, n: P[n0 + n, k0 + kk] if n0 + n < Kl else 0.0)
+                for lane in range(32):
+                    g, t = lane >> 2, lane & 3
+                    for i in range(4):
+                        u, k = m0 + g + (i >> 1) * 8, n0 + 2 * t + (i & 1)
+                        if u < Ku and k < Kl:
+                            GW[u, k] += c[lane, i]
+        assert np.allclose(GW[:, :Kl], z[:, :HT] @ P[:, :HT].T)
+        assert np.all(GW[:, Kl:] == 0)
