@@ -442,3 +442,26 @@ def test_restated_confident_signatures_equal_the_reference_execution(ref):
             assert np.allclose(got["combined_scores"][name], combined[f], rtol=1e-10, atol=1e-12)
             assert np.isclose(got["signature_confidences"][name], jac[f], atol=1e-12, equal_nan=True), (l, name)
         assert any(len(idx) > 0 for idx, _ in sig), f"layer {l}: every signature is empty, the case tests nothing"
+
+
+@needs_reference
+@pytest.mark.parametrize("min_cells_upper,filter_up", [(0.001, True), (2, True), (2, False), (0.5, False), (40, True)])
+def test_restated_upper_layer_filter_equals_the_reference_execution(ref, min_cells_upper, filter_up):
+    """`scDEF.filter_factors(upper_only=True)` (`_scdef.py:3478-3568`, the call `_learn` makes at 3386-3387) of the
+    REFERENCE on hand-set posterior means vs `oracle/host_ref.filter_factors_upper_only` (row f1: the device supplies
+    its arg-max counts through `scdef_assignment_counts`)."""
+    rng = np.random.default_rng(17)
+    N, G, Ks = 60, 30, (6, 4, 2)
+    m = ref.scDEF(ref.adata(rng.poisson(1.0, (N, G)).astype(float)), layer_sizes=list(Ks), seed=0)
+    pz = [rng.gamma(0.3, 1.0, (N, K)) for K in Ks]
+    pz[1][:, 3] = 0.0                                      # a factor nobody is assigned to
+    pW = [None] + [rng.gamma(0.5, 1.0, (Ks[l], Ks[l - 1])) for l in range(1, len(Ks))]
+    for l, name in enumerate(m.layer_names):
+        m.pmeans[f"{name}z"] = pz[l]
+        if l > 0:
+            m.pmeans[f"{name}W"] = pW[l]
+    m.filter_factors(upper_only=True, min_cells_upper=min_cells_upper, filter_up=filter_up, annotate=False)
+    want = host_ref.filter_factors_upper_only(pz, pW, list(Ks), N, min_cells_upper=min_cells_upper, filter_up=filter_up)
+    assert len(m.factor_lists) == len(want)
+    for got, w in zip(m.factor_lists, want):
+        assert np.array_equal(np.asarray(got), np.asarray(w))
