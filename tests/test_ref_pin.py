@@ -465,3 +465,35 @@ def test_restated_upper_layer_filter_equals_the_reference_execution(ref, min_cel
     assert len(m.factor_lists) == len(want)
     for got, w in zip(m.factor_lists, want):
         assert np.array_equal(np.asarray(got), np.asarray(w))
+
+
+@needs_reference
+def test_posterior_summaries_equal_the_reference_execution(ref):
+    """`set_posterior_means` / `set_posterior_variances` (`_scdef.py:3394-3476`, row a9) of the REFERENCE vs this package's
+    host path on the same parameters: same keys (including the `brd` / `wm` / `ard` aliases), same values."""
+    from scdef_b200 import MiniAnnData, scDEF
+
+    rng = np.random.default_rng(23)
+    N, G, Ks = 40, 24, (5, 3, 1)
+    X = rng.poisson(1.0, (N, G)).astype(float)
+    m = ref.scDEF(ref.adata(X), layer_sizes=list(Ks), seed=0)
+    lp = [np.array(p, dtype=np.float64) for p in ref.to_numpy(m.local_params)]
+    gp = [np.array(p, dtype=np.float64) for p in ref.to_numpy(m.global_params)]
+    for p in lp + gp:
+        p[0] = rng.normal(-0.5, 1.0, p[0].shape)
+        p[1] = rng.normal(-1.0, 0.4, p[1].shape)
+    m.local_params = [ref.jnp.array(p) for p in lp]
+    m.global_params = [ref.jnp.array(p) for p in gp]
+    m.set_posterior_means()
+    m.set_posterior_variances()
+
+    mine = scDEF(MiniAnnData(X.astype(np.float32)), layer_sizes=list(Ks), seed=0, logginglevel=30)
+    mine.local_params = [p.astype(np.float32) for p in lp]
+    mine.global_params = [p.astype(np.float32) for p in gp]
+    mine.set_posterior_means()
+    mine.set_posterior_variances()
+    assert set(mine.pmeans) == set(m.pmeans) and set(mine.pvars) == set(m.pvars)
+    for k in m.pmeans:
+        assert np.allclose(np.asarray(mine.pmeans[k], float), np.asarray(ref.to_numpy(m.pmeans[k]), float), rtol=2e-6), k
+    for k in m.pvars:
+        assert np.allclose(np.asarray(mine.pvars[k], float), np.asarray(ref.to_numpy(m.pvars[k]), float), rtol=1e-5), k
